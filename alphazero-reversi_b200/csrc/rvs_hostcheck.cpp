@@ -1,0 +1,32 @@
+// rvs_hostcheck.cpp -- TEST ARTEFACT: compiles the kernels' bit formulas (rvs_board.cuh)
+// with g++ so the CPU-only test tier can compare them with the oracle before any GPU time
+// is spent.  Never loaded by the product package.
+#include "rvs_board.cuh"
+
+using namespace rvs;
+
+extern "C" {
+uint64_t hc_legal(uint64_t P, uint64_t O, int rules) {
+    return rules == RULES_STRICT ? legal_moves<RULES_STRICT>(P, O) : legal_moves<RULES_REF>(P, O);
+}
+uint64_t hc_flips(uint64_t P, uint64_t O, int idx, int rules) {
+    return rules == RULES_STRICT ? flip_mask<RULES_STRICT>(P, O, 1ULL << idx)
+                                 : flip_mask<RULES_REF>(P, O, 1ULL << idx);
+}
+int hc_try_move(uint64_t* black, uint64_t* white, uint8_t* side, uint8_t* flags, int idx, int rules,
+                uint64_t* next_legal) {
+    Board b{*black, *white, *side, *flags};
+    uint64_t nl = 0;
+    bool ok = rules == RULES_STRICT ? try_move<RULES_STRICT>(b, idx, nl) : try_move<RULES_REF>(b, idx, nl);
+    *black = b.black; *white = b.white; *side = b.side; *flags = b.flags; *next_legal = nl;
+    return ok ? 1 : 0;
+}
+int hc_playout(uint64_t* black, uint64_t* white, uint8_t* side, uint8_t* flags, uint64_t stream, int rules) {
+    Board b{*black, *white, *side, *flags};
+    int p = rules == RULES_STRICT ? random_playout<RULES_STRICT>(b, stream) : random_playout<RULES_REF>(b, stream);
+    *black = b.black; *white = b.white; *side = b.side; *flags = b.flags;
+    return p;
+}
+int hc_nth_set_bit(uint64_t m, int k) { return nth_set_bit(m, k); }
+uint64_t hc_stream_seed(uint64_t s, uint64_t a, uint64_t b) { return stream_seed(s, a, b); }
+}
