@@ -1,0 +1,682 @@
+// rvs_engine.cu -- K2 kernels (lockstep batched MCTS), self-play ply / sample kernels, and
+// the engine C ABI.  One warp per game everywhere; grids are G/4 CTAs of 128 threads.
+#include "rvs_engine.cuh"
+
+#include <new>
+
+namespace rvs {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kBlock = 32 * kWarpsPerBlock;
+
+__device__ __forceinline__ void flush_stats(const EngineView& ev, const TreeCtx& cx, unsigned long long lane_steps) {
+    for (int o = 16; o; o >>= 1) lane_steps += __shfl_down_sync(kFull, lane_steps, o);
+    if (cx.lane == 0) {
+        atomicAdd(&ev.stats[ST_SIMS], cx.sims);
+        atomicAdd(&ev.stats[ST_EVALS], cx.evals);
+        atomicAdd(&ev.stats[ST_STEPS], cx.steps + lane_steps);
+        if (cx.overflow) atomicAdd(&ev.stats[ST_OVERFLOW], 1ULL);
+    }
+}
+
+__device__ __forceinline__ void init_root(TreeCtx& cx, int side) {
+    // MCTSNode(1.0, game.current_player, ...) (mcts.py:334-341)
+    if (cx.lane == 0) {
+        cx.hot[0] = make_int4(0, 0, 0, 0);
+        cx.cold[0] = make_int4(__float_as_int(1.0f), -1, (255 << 8) | (side << 16), 0);
+    }
+    cx.n_nodes = 1;
+    __syncwarp();
+}
+
+// evaluator for the fused kernels: fills ws.lm / ws.val, one leaf per lane
+template <int RULES, int EVAL>
+__device__ __forceinline__ void eval_wave(const EngineView& ev, TreeCtx& cx, const WaveScratch& ws, int k, uint64_t game_id,
+                                          uint64_t search_id, int sim_base, unsigned long long& lane_steps) {
+    for (int j = cx.lane; j < k; j += 32) {
+        if (ws.node[j] < 0) continue;
+        const uint16_t sf = ws.sf[j];
+        Board b{ws.black[j], ws.white[j], (uint8_t)(sf & 0xFF), (uint8_t)(sf >> 8)};
+        const uint64_t lm = board_legal<RULES>(b);
+        float v = 0.0f;
+        if (lm) {
+            if (EVAL == RVS_EVAL_E0) {
+                const int nb = popc64(b.black), nw = popc64(b.white);
+                const int d = b.side == 1 ? nb - nw : nw - nb;
+                v = __fdiv_rn((float)d, 64.0f);
+            } else {
+                const int leaf_side = b.side;
+                const uint64_t st = stream_seed(ev.seed, game_id, (search_id << 16) | (uint64_t)(sim_base + j));
+                lane_steps += (unsigned long long)random_playout<RULES>(b, st);
+                const int w = winner_of(b);
+                v = (!is_over(b) || w == 0) ? 0.0f : (w == leaf_side ? 1.0f : -1.0f);
+            }
+        }
+        ws.lm[j] = lm;
+        ws.val[j] = v;
+    }
+    __syncwarp();
+}
+
+// MCTS.search (mcts.py:322-407) with a built-in evaluator, whole search in one launch.
+template <int RULES, int EVAL>
+__global__ void __launch_bounds__(kBlock) search_fused_kernel(EngineView ev, int S, int K) {
+    const int g = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (g >= ev.G) return;
+    TreeCtx cx{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, 1, ev.c_puct, (int)(threadIdx.x & 31), 0, 0, 0, 0};
+    const Board root{ev.black[g], ev.white[g], ev.side[g], ev.flags[g]};
+    const uint64_t game_id = ev.game_id[g];
+    const uint64_t search_id = (uint64_t)ev.ply[g];
+    const WaveScratch ws = scratch_of(ev, g);
+    unsigned long long lane_steps = 0;
+    init_root(cx, root.side);
+    for (int start = 0; start < S; start += K) {
+        const int k = (S - start) < K ? (S - start) : K;
+        select_wave<RULES>(cx, root, ws, k);
+        eval_wave<RULES, EVAL>(ev, cx, ws, k, game_id, search_id, start, lane_steps);
+        process_wave(cx, ws, k, [](int, int) { return 1.0f / 65.0f; });
+    }
+    if (cx.lane == 0) ev.n_nodes[g] = cx.n_nodes;
+    flush_stats(ev, cx, lane_steps);
+}
+
+__global__ void __launch_bounds__(kBlock) begin_search_kernel(EngineView ev) {
+    const int g = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (g >= ev.G) return;
+    TreeCtx cx{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, 1, ev.c_puct, (int)(threadIdx.x & 31), 0, 0, 0, 0};
+    init_root(cx, ev.side[g]);
+    if (cx.lane == 0) ev.n_nodes[g] = 1;
+}
+
+// MCTS._traverse for k simulations per game (external / NN evaluator path)
+template <int RULES>
+__global__ void __launch_bounds__(kBlock) select_kernel(EngineView ev, int k) {
+    const int g = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (g >= ev.G) return;
+    TreeCtx cx{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, ev.n_nodes[g], ev.c_puct, (int)(threadIdx.x & 31), 0, 0, 0, 0};
+    const Board root{ev.black[g], ev.white[g], ev.side[g], ev.flags[g]};
+    const WaveScratch ws = scratch_of(ev, g);
+    select_wave<RULES>(cx, root, ws, k);
+    // legal masks of the leaves (reused by leaf_planes and process)
+    for (int j = cx.lane; j < k; j += 32) {
+        if (ws.node[j] < 0) { ws.lm[j] = 0; continue; }
+        const uint16_t sf = ws.sf[j];
+        const Board b{ws.black[j], ws.white[j], (uint8_t)(sf & 0xFF), (uint8_t)(sf >> 8)};
+        ws.lm[j] = board_legal<RULES>(b);
+    }
+    flush_stats(ev, cx, 0);
+}
+
+// MCTS._process_batch with caller-supplied softmax outputs (mcts.py:596-623).
+// probs [G*k,65], values [G*k], slot = g*k + j.
+__global__ void __launch_bounds__(kBlock) process_probs_kernel(EngineView ev, int k, const float* __restrict__ probs,
+                                                                const float* __restrict__ values) {
+    const int g = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (g >= ev.G) return;
+    TreeCtx cx{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, ev.n_nodes[g], ev.c_puct, (int)(threadIdx.x & 31), 0, 0, 0, 0};
+    const WaveScratch ws = scratch_of(ev, g);
+    const size_t slot0 = (size_t)g * k;
+    for (int j = cx.lane; j < k; j += 32) ws.val[j] = values[slot0 + j];
+    __syncwarp();
+    process_wave(cx, ws, k, [&](int j, int sq) { return probs[(slot0 + j) * 65 + sq]; });
+    if (cx.lane == 0) ev.n_nodes[g] = cx.n_nodes;
+    flush_stats(ev, cx, 0);
+}
+
+// canonical planes of the selected leaves (game.py:131-162), 48 threads x float4 per slot
+__global__ void __launch_bounds__(256) leaf_planes_kernel(EngineView ev, int k, float4* __restrict__ out,
+                                                           uint8_t* __restrict__ valid) {
+    const int64_t total = (int64_t)ev.G * k * 48;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t slot = t / 48;
+        const int r = (int)(t - slot * 48);
+        const int g = (int)(slot / k), j = (int)(slot - (int64_t)g * k);
+        const size_t o = (size_t)g * ev.kmax + j;
+        const uint64_t lm = ev.w_node[o] < 0 ? 0ULL : ev.w_lm[o];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lm) {
+            const bool blk = (ev.w_sf[o] & 0xFF) == 1;
+            const uint64_t P = blk ? ev.w_black[o] : ev.w_white[o], O = blk ? ev.w_white[o] : ev.w_black[o];
+            const int plane = r >> 4, q = r & 15;
+            const uint64_t src = plane == 0 ? P : (plane == 1 ? O : lm);
+            const uint32_t nib = (uint32_t)(src >> (4 * q)) & 15u;
+            v = make_float4((float)(nib & 1), (float)((nib >> 1) & 1), (float)((nib >> 2) & 1), (float)((nib >> 3) & 1));
+        }
+        out[t] = v;
+        if (valid && r == 0) valid[slot] = lm ? 1 : 0;
+    }
+}
+
+// dict MCTS.search returns (mcts.py:406-407) as [G,65] int32
+__global__ void __launch_bounds__(kBlock) root_visits_kernel(EngineView ev, int32_t* __restrict__ out, int n) {
+    const int g = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (g >= n) return;
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < 65; i += 32) out[(size_t)g * 65 + i] = 0;
+    __syncwarp();
+    const int4* hot = ev.hot + (size_t)g * ev.cap;
+    const int4* cold = ev.cold + (size_t)g * ev.cap;
+    const int4 c = cold[0];
+    const int nc = c.z & 0xFF;
+    for (int i = lane; i < nc; i += 32) {
+        const int mv = (cold[c.y + i].z >> 8) & 0xFF;
+        out[(size_t)g * 65 + mv] = hot[c.y + i].x;
+    }
+}
+
+// numpy pairwise sum of 65 doubles (see oracle/rvs_oracle.c np_sum65)
+__device__ inline double np_sum65(const double* a) {
+    double r[8];
+    for (int j = 0; j < 8; j++) r[j] = a[j];
+    for (int i = 8; i < 64; i += 8)
+        for (int j = 0; j < 8; j++) r[j] = __dadd_rn(r[j], a[i + j]);
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    return __dadd_rn(res, a[64]);
+}
+
+// One self-play ply per live slot (self_play.py:80-101, mcts.py:642-694), thread per game.
+template <int RULES>
+__global__ void __launch_bounds__(128) play_kernel(EngineView ev, float temperature, uint8_t* __restrict__ out_moves) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ev.G) return;
+    if (out_moves) out_moves[g] = 255;
+    Board b{ev.black[g], ev.white[g], ev.side[g], ev.flags[g]};
+    if (!ev.live[g] || is_over(b)) return;
+    const int4* hot = ev.hot + (size_t)g * ev.cap;
+    const int4* cold = ev.cold + (size_t)g * ev.cap;
+    double pi[65];
+    for (int i = 0; i < 65; ++i) pi[i] = 0.0;
+    const int4 c = cold[0];
+    const int nc = c.z & 0xFF;
+    long long total = 0;
+    for (int i = 0; i < nc; ++i) total += hot[c.y + i].x;
+    bool all_zero = true;
+    if (total > 0) {
+        for (int i = 0; i < nc; ++i) {
+            const int n = hot[c.y + i].x;
+            const int mv = (cold[c.y + i].z >> 8) & 0xFF;
+            pi[mv] = __ddiv_rn((double)n, (double)total);  // count / total_visits (mcts.py:670)
+            if (n) all_zero = false;
+        }
+    }
+    if (temperature > 0.0f && !all_zero) {  // mcts.py:673-676
+        const double e = __ddiv_rn(1.0, (double)temperature);
+        if (e != 1.0)
+            for (int i = 0; i < 65; ++i) pi[i] = pow(pi[i], e);
+        const double s = np_sum65(pi);
+        for (int i = 0; i < 65; ++i) pi[i] = __ddiv_rn(pi[i], s);
+    }
+    int mv = 0;
+    const int ply = ev.ply[g];
+    if (temperature == 0.0f || all_zero) {  // np.argmax: first maximum (mcts.py:679-681)
+        double best = pi[0];
+        for (int i = 1; i < 65; ++i) if (pi[i] > best) { best = pi[i]; mv = i; }
+    } else {  // np.random.choice: cumsum, normalise by cdf[-1], searchsorted(side='right')
+        uint64_t st = stream_seed(ev.seed, ev.game_id[g], 0x80000000ULL + (uint64_t)ply);
+        const double u = (double)(rng_next(st) >> 11) * (1.0 / 9007199254740992.0);
+        double acc = 0.0;
+        for (int i = 0; i < 65; ++i) acc = __dadd_rn(acc, pi[i]);
+        double run = 0.0;
+        mv = 64;
+        for (int i = 0; i < 65; ++i) {
+            run = __dadd_rn(run, pi[i]);
+            if (__ddiv_rn(run, acc) > u) { mv = i; break; }
+        }
+    }
+    // record the sample BEFORE the move (self_play.py:87-94)
+    if (ply < 64) {
+        const size_t o = (size_t)g * 64 + ply;
+        ev.s_black[o] = b.black; ev.s_white[o] = b.white; ev.s_side[o] = b.side;
+        float* dst = ev.s_pi + o * 65;
+        for (int i = 0; i < 65; ++i) dst[i] = (float)pi[i];
+    }
+    uint64_t nl;
+    if (!try_move<RULES>(b, mv, nl)) {
+        // the reference would spin forever here (SURVEY.md 8(a) A7 hazard); park the slot instead
+        ev.live[g] = 0;
+        atomicAdd(&ev.stats[ST_STALLED], 1ULL);
+        return;
+    }
+    atomicAdd(&ev.stats[ST_STEPS], 1ULL);
+    ev.black[g] = b.black; ev.white[g] = b.white; ev.side[g] = b.side; ev.flags[g] = b.flags;
+    ev.ply[g] = ply + 1;
+    if (out_moves) out_moves[g] = (uint8_t)mv;
+    if (is_over(b)) ev.finished[g] = 1;
+}
+
+// Finished games: z back-fill (self_play.py:117-126), move their samples to the ring, recycle.
+__global__ void __launch_bounds__(kBlock) finalize_kernel(EngineView ev, int recycle) {
+    const int g = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (g >= ev.G) return;
+    if (!ev.finished[g]) return;
+    const int lane = threadIdx.x & 31;
+    const int n = ev.ply[g] < 64 ? ev.ply[g] : 64;
+    const int w = (ev.flags[g] & F_WIN_MASK) >> F_WIN_SHIFT;
+    unsigned long long at = 0;
+    if (lane == 0) at = atomicAdd(ev.ring_count, (unsigned long long)n);
+    at = __shfl_sync(kFull, at, 0);
+    int stored = 0;
+    for (int p = 0; p < n; ++p) {
+        const unsigned long long dst = at + p;
+        if (dst >= (unsigned long long)ev.ring_cap) break;
+        const size_t o = (size_t)g * 64 + p;
+        if (lane == 0) {
+            const int s = ev.s_side[o];
+            ev.r_black[dst] = ev.s_black[o]; ev.r_white[dst] = ev.s_white[o]; ev.r_side[dst] = (uint8_t)s;
+            ev.r_z[dst] = (int8_t)(w == 0 ? 0 : (s == w ? 1 : -1));
+        }
+        for (int i = lane; i < 65; i += 32) ev.r_pi[dst * 65 + i] = ev.s_pi[o * 65 + i];
+        ++stored;
+    }
+    if (lane == 0) {
+        atomicAdd(&ev.stats[ST_FINISHED], 1ULL);
+        atomicAdd(&ev.stats[ST_SAMPLES], (unsigned long long)stored);
+        if (stored < n) atomicAdd(&ev.stats[ST_DROPPED], (unsigned long long)(n - stored));
+        ev.finished[g] = 0;
+        if (recycle) {
+            ev.black[g] = kStartBlack; ev.white[g] = kStartWhite; ev.side[g] = 1; ev.flags[g] = 0;
+            ev.ply[g] = 0;
+            ev.game_id[g] += (uint64_t)ev.G;
+        } else {
+            ev.live[g] = 0;
+        }
+    }
+}
+
+// ring -> trainer format (states [n,3,8,8] f32, pi [n,65] f32, z [n] f32)
+template <int RULES>
+__global__ void __launch_bounds__(256) drain_kernel(EngineView ev, int64_t n, float4* __restrict__ states,
+                                                     float* __restrict__ pi, float* __restrict__ z) {
+    const int64_t total = n * 48;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / 48;
+        const int r = (int)(t - i * 48);
+        const bool blk = ev.r_side[i] == 1;
+        const uint64_t P = blk ? ev.r_black[i] : ev.r_white[i], O = blk ? ev.r_white[i] : ev.r_black[i];
+        const int plane = r >> 4, q = r & 15;
+        const uint64_t src = plane == 0 ? P : (plane == 1 ? O : legal_moves<RULES>(P, O));
+        const uint32_t nib = (uint32_t)(src >> (4 * q)) & 15u;
+        states[t] = make_float4((float)(nib & 1), (float)((nib >> 1) & 1), (float)((nib >> 2) & 1), (float)((nib >> 3) & 1));
+        if (r == 0) z[i] = (float)ev.r_z[i];
+    }
+    const int64_t np = n * 65;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < np; t += (int64_t)gridDim.x * blockDim.x)
+        pi[t] = ev.r_pi[t];
+}
+
+__global__ void reset_games_kernel(EngineView ev) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= ev.G) return;
+    ev.black[g] = kStartBlack; ev.white[g] = kStartWhite; ev.side[g] = 1; ev.flags[g] = 0;
+    ev.game_id[g] = (uint64_t)g; ev.ply[g] = 0; ev.live[g] = 1; ev.finished[g] = 0; ev.n_nodes[g] = 0;
+}
+
+// positions handed in by the caller: derive game_over / winner the way Board would have when the
+// game ended (neither side can move), so that root terminal handling matches mcts.py:567-575.
+template <int RULES>
+__global__ void set_positions_kernel(EngineView ev, const uint64_t* __restrict__ black, const uint64_t* __restrict__ white,
+                                     const uint8_t* __restrict__ side, int n) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    Board b{black[g], white[g], side[g], 0};
+    if (board_legal<RULES>(b) == 0) {
+        Board o = b; o.side = (uint8_t)(3 - b.side);
+        if (board_legal<RULES>(o) == 0) {
+            const int nb = popc64(b.black), nw = popc64(b.white);
+            const int w = nb > nw ? 1 : (nw > nb ? 2 : 0);
+            b.flags = (uint8_t)(F_OVER | (w << F_WIN_SHIFT));
+        }
+    }
+    ev.black[g] = b.black; ev.white[g] = b.white; ev.side[g] = b.side; ev.flags[g] = b.flags;
+    ev.ply[g] = 0; ev.live[g] = 1; ev.finished[g] = 0; ev.n_nodes[g] = 0;
+}
+
+}  // namespace rvs
+
+// ------------------------------------------------------------------------------ C ABI
+using namespace rvs;
+
+namespace {
+
+template <typename T>
+int dalloc(rvs_engine* h, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) > 0 ? count * sizeof(T) : 16);
+    if (e != cudaSuccess) return fail(-100 - (int)e, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    cudaMemset(q, 0, count * sizeof(T));
+    h->allocs[h->n_allocs++] = q;
+    *p = (T*)q;
+    return 0;
+}
+
+int io_stage(rvs_engine* h, size_t bytes, void** out) {
+    if (h->io_stage_cap < bytes) {
+        if (h->io_stage) cudaFree(h->io_stage);
+        h->io_stage = nullptr; h->io_stage_cap = 0;
+        RVS_CUDA(cudaMalloc(&h->io_stage, bytes));
+        h->io_stage_cap = bytes;
+    }
+    *out = h->io_stage;
+    return 0;
+}
+
+inline int games_grid(int G) { return (G + kWarpsPerBlock - 1) / kWarpsPerBlock; }
+
+#define RVS_ENGINE_LAUNCH(h, ...)          \
+    do {                                   \
+        RVS_LAUNCH(__VA_ARGS__);           \
+        (h)->launches++;                   \
+    } while (0)
+
+int check_handle(rvs_engine* h) {
+    if (!h) return fail(-1, "null engine handle");
+    RVS_CUDA(cudaSetDevice(h->cfg.device));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rvs_engine_create(const rvs_engine_config* cfg, rvs_engine** out) {
+    if (!cfg || !out) return fail(-1, "rvs_engine_create: null argument");
+    if (cfg->struct_size != (int)sizeof(rvs_engine_config)) return fail(-1, "rvs_engine_create: struct_size mismatch (%d != %zu)", cfg->struct_size, sizeof(rvs_engine_config));
+    if (cfg->n_games < 1 || cfg->max_sims < 1 || cfg->max_wave < 1 || cfg->max_sims > 65535)
+        return fail(-1, "rvs_engine_create: n_games/max_sims/max_wave out of range");
+    if (cfg->rules != RVS_RULES_REF && cfg->rules != RVS_RULES_STRICT) return fail(-1, "rvs_engine_create: bad rules");
+    if (cfg->evaluator < RVS_EVAL_E0 || cfg->evaluator > RVS_EVAL_NN) return fail(-1, "rvs_engine_create: bad evaluator");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(-2, "rvs_engine_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(-1, "rvs_engine_create: bad device %d", cfg->device);
+    RVS_CUDA(cudaSetDevice(cfg->device));
+    rvs_engine* h = new (std::nothrow) rvs_engine();
+    if (!h) return fail(-3, "out of host memory");
+    h->cfg = *cfg;
+    EngineView& v = h->v;
+    v.G = cfg->n_games;
+    v.kmax = cfg->max_wave;
+    v.cap = cfg->nodes_per_game > 0 ? cfg->nodes_per_game : 2 + 34 * cfg->max_sims;
+    v.c_puct = cfg->c_puct;
+    v.seed = cfg->seed;
+    v.ring_cap = cfg->sample_capacity > 0 ? cfg->sample_capacity : (int64_t)64 * v.G;
+    const size_t G = v.G, GK = G * v.kmax, GN = G * (size_t)v.cap;
+    int rc = 0;
+    if ((rc = dalloc(h, &v.black, G)) || (rc = dalloc(h, &v.white, G)) || (rc = dalloc(h, &v.side, G)) ||
+        (rc = dalloc(h, &v.flags, G)) || (rc = dalloc(h, &v.game_id, G)) || (rc = dalloc(h, &v.ply, G)) ||
+        (rc = dalloc(h, &v.live, G)) || (rc = dalloc(h, &v.finished, G)) || (rc = dalloc(h, &v.hot, GN)) ||
+        (rc = dalloc(h, &v.cold, GN)) || (rc = dalloc(h, &v.n_nodes, G)) || (rc = dalloc(h, &v.w_node, GK)) ||
+        (rc = dalloc(h, &v.w_plen, GK)) || (rc = dalloc(h, &v.w_path, GK * kMaxPath)) || (rc = dalloc(h, &v.w_black, GK)) ||
+        (rc = dalloc(h, &v.w_white, GK)) || (rc = dalloc(h, &v.w_sf, GK)) || (rc = dalloc(h, &v.w_lm, GK)) ||
+        (rc = dalloc(h, &v.w_val, GK)) || (rc = dalloc(h, &v.s_black, G * 64)) || (rc = dalloc(h, &v.s_white, G * 64)) ||
+        (rc = dalloc(h, &v.s_side, G * 64)) || (rc = dalloc(h, &v.s_pi, G * 64 * 65)) ||
+        (rc = dalloc(h, &v.r_black, (size_t)v.ring_cap)) || (rc = dalloc(h, &v.r_white, (size_t)v.ring_cap)) ||
+        (rc = dalloc(h, &v.r_side, (size_t)v.ring_cap)) || (rc = dalloc(h, &v.r_z, (size_t)v.ring_cap)) ||
+        (rc = dalloc(h, &v.r_pi, (size_t)v.ring_cap * 65)) || (rc = dalloc(h, &v.ring_count, 1)) ||
+        (rc = dalloc(h, &v.stats, (size_t)ST_COUNT)) || (rc = dalloc(h, &h->visits, G * 65)) || (rc = dalloc(h, &h->moves, G))) {
+        rvs_engine_destroy(h);
+        return rc;
+    }
+    reset_games_kernel<<<(v.G + 127) / 128, 128>>>(v);
+    g_launches.fetch_add(1);
+    h->launches++;
+    e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        rvs_engine_destroy(h);
+        return fail(-100 - (int)e, "rvs_engine_create: %s", cudaGetErrorString(e));
+    }
+    *out = h;
+    return 0;
+}
+
+int rvs_engine_destroy(rvs_engine* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < h->n_allocs; ++i) cudaFree(h->allocs[i]);
+    if (h->io_stage) cudaFree(h->io_stage);
+    if (h->ext_probs) cudaFree(h->ext_probs);
+    if (h->ext_values) cudaFree(h->ext_values);
+    if (h->ext_planes) cudaFree(h->ext_planes);
+    if (h->ext_valid) cudaFree(h->ext_valid);
+    if (h->net) rvs_net_destroy(h->net);
+    delete h;
+    return 0;
+}
+
+int rvs_engine_reset(rvs_engine* h, void* stream) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    RVS_ENGINE_LAUNCH(h, reset_games_kernel, (h->v.G + 127) / 128, 128, 0, s, h->v);
+    RVS_CUDA(cudaMemsetAsync(h->v.ring_count, 0, 8, s));
+    h->searching = false;
+    return 0;
+}
+
+int rvs_engine_set_positions(rvs_engine* h, const uint64_t* black, const uint64_t* white, const uint8_t* side, int32_t n,
+                             int mem, void* stream) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (n < 0 || n > h->v.G || (n > 0 && (!black || !white || !side))) return fail(-1, "rvs_engine_set_positions: bad arguments");
+    if (n == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint64_t *db = black, *dw = white;
+    const uint8_t* ds = side;
+    if (mem == RVS_MEM_HOST) {
+        void* st = nullptr;
+        const size_t nb = (size_t)n * 8;
+        if ((rc = io_stage(h, 2 * nb + n, &st))) return rc;
+        RVS_CUDA(cudaMemcpyAsync(st, black, nb, cudaMemcpyHostToDevice, s));
+        RVS_CUDA(cudaMemcpyAsync((char*)st + nb, white, nb, cudaMemcpyHostToDevice, s));
+        RVS_CUDA(cudaMemcpyAsync((char*)st + 2 * nb, side, n, cudaMemcpyHostToDevice, s));
+        db = (const uint64_t*)st; dw = (const uint64_t*)((char*)st + nb); ds = (const uint8_t*)((char*)st + 2 * nb);
+    }
+    if (h->cfg.rules == RVS_RULES_STRICT)
+        RVS_ENGINE_LAUNCH(h, set_positions_kernel<RULES_STRICT>, (n + 127) / 128, 128, 0, s, h->v, db, dw, ds, n);
+    else
+        RVS_ENGINE_LAUNCH(h, set_positions_kernel<RULES_REF>, (n + 127) / 128, 128, 0, s, h->v, db, dw, ds, n);
+    h->searching = false;
+    return 0;
+}
+
+int rvs_engine_get_positions(rvs_engine* h, uint64_t* black, uint64_t* white, uint8_t* side, uint8_t* flags, int32_t n,
+                             int mem, void* stream) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (n < 0 || n > h->v.G) return fail(-1, "rvs_engine_get_positions: bad n");
+    cudaStream_t s = (cudaStream_t)stream;
+    const cudaMemcpyKind kind = mem == RVS_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (black) RVS_CUDA(cudaMemcpyAsync(black, h->v.black, (size_t)n * 8, kind, s));
+    if (white) RVS_CUDA(cudaMemcpyAsync(white, h->v.white, (size_t)n * 8, kind, s));
+    if (side) RVS_CUDA(cudaMemcpyAsync(side, h->v.side, n, kind, s));
+    if (flags) RVS_CUDA(cudaMemcpyAsync(flags, h->v.flags, n, kind, s));
+    if (mem == RVS_MEM_HOST) RVS_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int rvs_engine_search(rvs_engine* h, int32_t num_sims, int32_t wave, void* stream) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (num_sims < 1 || num_sims > h->cfg.max_sims) return fail(-1, "rvs_engine_search: num_sims %d outside [1,%d]", num_sims, h->cfg.max_sims);
+    if (wave < 1 || wave > h->cfg.max_wave) return fail(-1, "rvs_engine_search: wave %d outside [1,%d]", wave, h->cfg.max_wave);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = games_grid(h->v.G);
+    const bool strict = h->cfg.rules == RVS_RULES_STRICT;
+    switch (h->cfg.evaluator) {
+    case RVS_EVAL_E0:
+        if (strict) RVS_ENGINE_LAUNCH(h, (search_fused_kernel<RULES_STRICT, RVS_EVAL_E0>), grid, kBlock, 0, s, h->v, num_sims, wave);
+        else RVS_ENGINE_LAUNCH(h, (search_fused_kernel<RULES_REF, RVS_EVAL_E0>), grid, kBlock, 0, s, h->v, num_sims, wave);
+        break;
+    case RVS_EVAL_ROLLOUT:
+        if (strict) RVS_ENGINE_LAUNCH(h, (search_fused_kernel<RULES_STRICT, RVS_EVAL_ROLLOUT>), grid, kBlock, 0, s, h->v, num_sims, wave);
+        else RVS_ENGINE_LAUNCH(h, (search_fused_kernel<RULES_REF, RVS_EVAL_ROLLOUT>), grid, kBlock, 0, s, h->v, num_sims, wave);
+        break;
+    case RVS_EVAL_NN:
+        return rvs_net_search(h, num_sims, wave, s);
+    default:
+        return fail(-1, "rvs_engine_search: evaluator EXTERNAL needs begin_search/select/process");
+    }
+    h->searching = false;
+    return 0;
+}
+
+int rvs_engine_begin_search(rvs_engine* h, void* stream) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    RVS_ENGINE_LAUNCH(h, begin_search_kernel, games_grid(h->v.G), kBlock, 0, (cudaStream_t)stream, h->v);
+    h->searching = true;
+    h->cur_k = 0;
+    return 0;
+}
+
+int rvs_engine_select(rvs_engine* h, int32_t k, void* stream) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!h->searching) return fail(-1, "rvs_engine_select: call rvs_engine_begin_search first");
+    if (k < 1 || k > h->cfg.max_wave) return fail(-1, "rvs_engine_select: k %d outside [1,%d]", k, h->cfg.max_wave);
+    if (h->cur_k != 0) return fail(-1, "rvs_engine_select: previous wave not processed");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->cfg.rules == RVS_RULES_STRICT) RVS_ENGINE_LAUNCH(h, select_kernel<RULES_STRICT>, games_grid(h->v.G), kBlock, 0, s, h->v, k);
+    else RVS_ENGINE_LAUNCH(h, select_kernel<RULES_REF>, games_grid(h->v.G), kBlock, 0, s, h->v, k);
+    h->cur_k = k;
+    return 0;
+}
+
+int rvs_engine_leaf_planes(rvs_engine* h, float* out_planes, uint8_t* out_valid, int mem, void* stream) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (h->cur_k == 0) return fail(-1, "rvs_engine_leaf_planes: no selected wave");
+    if (!out_planes) return fail(-1, "rvs_engine_leaf_planes: null output");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t slots = (int64_t)h->v.G * h->cur_k;
+    float* dp = out_planes;
+    uint8_t* dv = out_valid;
+    if (mem == RVS_MEM_HOST) {
+        const size_t need = (size_t)h->v.G * h->cfg.max_wave;
+        if (!h->ext_planes) RVS_CUDA(cudaMalloc(&h->ext_planes, need * 192 * sizeof(float)));
+        if (!h->ext_valid) RVS_CUDA(cudaMalloc(&h->ext_valid, need));
+        dp = h->ext_planes;
+        dv = h->ext_valid;
+    }
+    RVS_ENGINE_LAUNCH(h, leaf_planes_kernel, grid_for(slots * 48, 256), 256, 0, s, h->v, h->cur_k, (float4*)dp, dv);
+    if (mem == RVS_MEM_HOST) {
+        RVS_CUDA(cudaMemcpyAsync(out_planes, dp, slots * 192 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        if (out_valid) RVS_CUDA(cudaMemcpyAsync(out_valid, dv, slots, cudaMemcpyDeviceToHost, s));
+        RVS_CUDA(cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
+int rvs_engine_process(rvs_engine* h, const float* probs, const float* values, int mem, void* stream) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (h->cur_k == 0) return fail(-1, "rvs_engine_process: no selected wave");
+    if (!probs || !values) return fail(-1, "rvs_engine_process: null input");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t slots = (int64_t)h->v.G * h->cur_k;
+    const float *dp = probs, *dv = values;
+    if (mem == RVS_MEM_HOST) {
+        const size_t need = (size_t)h->v.G * h->cfg.max_wave;
+        if (!h->ext_probs) RVS_CUDA(cudaMalloc(&h->ext_probs, need * 65 * sizeof(float)));
+        if (!h->ext_values) RVS_CUDA(cudaMalloc(&h->ext_values, need * sizeof(float)));
+        RVS_CUDA(cudaMemcpyAsync(h->ext_probs, probs, slots * 65 * sizeof(float), cudaMemcpyHostToDevice, s));
+        RVS_CUDA(cudaMemcpyAsync(h->ext_values, values, slots * sizeof(float), cudaMemcpyHostToDevice, s));
+        dp = h->ext_probs;
+        dv = h->ext_values;
+    }
+    RVS_ENGINE_LAUNCH(h, process_probs_kernel, games_grid(h->v.G), kBlock, 0, s, h->v, h->cur_k, dp, dv);
+    h->cur_k = 0;
+    return 0;
+}
+
+int rvs_engine_root_visits(rvs_engine* h, int32_t* out, int32_t n, int mem, void* stream) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!out || n < 0 || n > h->v.G) return fail(-1, "rvs_engine_root_visits: bad arguments");
+    if (n == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    int32_t* d = mem == RVS_MEM_HOST ? h->visits : out;
+    RVS_ENGINE_LAUNCH(h, root_visits_kernel, games_grid(n), kBlock, 0, s, h->v, d, n);
+    if (mem == RVS_MEM_HOST) {
+        RVS_CUDA(cudaMemcpyAsync(out, d, (size_t)n * 65 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        RVS_CUDA(cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
+int rvs_engine_play(rvs_engine* h, float temperature, int recycle, uint8_t* out_moves, int mem, void* stream) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (temperature < 0.0f) return fail(-1, "rvs_engine_play: negative temperature");
+    cudaStream_t s = (cudaStream_t)stream;
+    uint8_t* dm = out_moves ? (mem == RVS_MEM_HOST ? h->moves : out_moves) : nullptr;
+    if (h->cfg.rules == RVS_RULES_STRICT) RVS_ENGINE_LAUNCH(h, play_kernel<RULES_STRICT>, (h->v.G + 127) / 128, 128, 0, s, h->v, temperature, dm);
+    else RVS_ENGINE_LAUNCH(h, play_kernel<RULES_REF>, (h->v.G + 127) / 128, 128, 0, s, h->v, temperature, dm);
+    RVS_ENGINE_LAUNCH(h, finalize_kernel, games_grid(h->v.G), kBlock, 0, s, h->v, recycle);
+    if (out_moves && mem == RVS_MEM_HOST) {
+        RVS_CUDA(cudaMemcpyAsync(out_moves, dm, h->v.G, cudaMemcpyDeviceToHost, s));
+        RVS_CUDA(cudaStreamSynchronize(s));
+    }
+    h->searching = false;
+    return 0;
+}
+
+int rvs_engine_drain_samples(rvs_engine* h, float* states, float* pi, float* z, int64_t capacity, int64_t* out_count,
+                             int mem, void* stream) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!out_count) return fail(-1, "rvs_engine_drain_samples: null out_count");
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long cnt = 0;
+    RVS_CUDA(cudaMemcpyAsync(&cnt, h->v.ring_count, 8, cudaMemcpyDeviceToHost, s));
+    RVS_CUDA(cudaStreamSynchronize(s));
+    int64_t n = (int64_t)cnt < h->v.ring_cap ? (int64_t)cnt : h->v.ring_cap;
+    *out_count = n;
+    if (n == 0) return 0;
+    if (!states || !pi || !z) return fail(-1, "rvs_engine_drain_samples: null output");
+    if (capacity < n) return fail(-4, "rvs_engine_drain_samples: capacity %lld < %lld samples pending", (long long)capacity, (long long)n);
+    float *ds = states, *dp = pi, *dz = z;
+    const size_t bs = (size_t)n * 192 * 4, bp = (size_t)n * 65 * 4, bz = (size_t)n * 4;
+    if (mem == RVS_MEM_HOST) {
+        void* st = nullptr;
+        if ((rc = io_stage(h, bs + bp + bz, &st))) return rc;
+        ds = (float*)st; dp = (float*)((char*)st + bs); dz = (float*)((char*)st + bs + bp);
+    }
+    const int grid = grid_for(n * 65, 256);
+    if (h->cfg.rules == RVS_RULES_STRICT) RVS_ENGINE_LAUNCH(h, drain_kernel<RULES_STRICT>, grid, 256, 0, s, h->v, n, (float4*)ds, dp, dz);
+    else RVS_ENGINE_LAUNCH(h, drain_kernel<RULES_REF>, grid, 256, 0, s, h->v, n, (float4*)ds, dp, dz);
+    RVS_CUDA(cudaMemsetAsync(h->v.ring_count, 0, 8, s));
+    if (mem == RVS_MEM_HOST) {
+        RVS_CUDA(cudaMemcpyAsync(states, ds, bs, cudaMemcpyDeviceToHost, s));
+        RVS_CUDA(cudaMemcpyAsync(pi, dp, bp, cudaMemcpyDeviceToHost, s));
+        RVS_CUDA(cudaMemcpyAsync(z, dz, bz, cudaMemcpyDeviceToHost, s));
+        RVS_CUDA(cudaStreamSynchronize(s));
+    }
+    return 0;
+}
+
+int rvs_engine_stats_get(rvs_engine* h, rvs_engine_stats* out, void* stream) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!out) return fail(-1, "rvs_engine_stats_get: null output");
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long st[ST_COUNT];
+    RVS_CUDA(cudaMemcpyAsync(st, h->v.stats, sizeof(st), cudaMemcpyDeviceToHost, s));
+    int nn[1] = {0};
+    (void)nn;
+    RVS_CUDA(cudaStreamSynchronize(s));
+    out->sims = (int64_t)st[ST_SIMS];
+    out->evals = (int64_t)st[ST_EVALS];
+    out->board_steps = (int64_t)st[ST_STEPS];
+    out->nodes = 0;
+    out->games_finished = (int64_t)st[ST_FINISHED];
+    out->samples = (int64_t)st[ST_SAMPLES];
+    out->launches = h->launches;
+    out->overflow = (int64_t)(st[ST_OVERFLOW] + st[ST_DROPPED] + st[ST_STALLED]);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+// rvs_engine.cuh -- host-side engine object shared by rvs_engine.cu (tree kernels + C ABI) and
+// rvs_net.cu (K4 network).  All pointers are device memory owned by the engine.
+#pragma once
+#include "rvs_common.cuh"
+#include "rvs_tree.cuh"
+
+namespace rvs {
+
+enum : int { ST_SIMS = 0, ST_EVALS, ST_STEPS, ST_FINISHED, ST_SAMPLES, ST_OVERFLOW, ST_DROPPED, ST_STALLED, ST_COUNT };
+
+struct NetState;  // rvs_net.cu
+
+// POD view passed to kernels by value
+struct EngineView {
+    int G, cap, kmax;
+    float c_puct;
+    uint64_t seed;
+    // game state per slot
+    uint64_t* black; uint64_t* white; uint8_t* side; uint8_t* flags;
+    uint64_t* game_id; int* ply; uint8_t* live; uint8_t* finished;
+    // trees
+    int4* hot; int4* cold; int* n_nodes;
+    // wave scratch [G*kmax]
+    int* w_node; int* w_plen; int* w_path; uint64_t* w_black; uint64_t* w_white; uint16_t* w_sf;
+    uint64_t* w_lm; float* w_val;
+    // per-slot sample staging [G*64]
+    uint64_t* s_black; uint64_t* s_white; uint8_t* s_side; float* s_pi;  // s_pi [G*64*65]
+    // completed-sample ring [ring_cap]
+    int64_t ring_cap;
+    uint64_t* r_black; uint64_t* r_white; uint8_t* r_side; int8_t* r_z; float* r_pi;
+    unsigned long long* ring_count;
+    unsigned long long* stats;  // [ST_COUNT]
+};
+
+__device__ __forceinline__ WaveScratch scratch_of(const EngineView& ev, int g) {
+    const size_t o = (size_t)g * ev.kmax;
+    return WaveScratch{ev.w_node + o, ev.w_plen + o, ev.w_path + o * kMaxPath, ev.w_black + o, ev.w_white + o,
+                       ev.w_sf + o,   ev.w_lm + o,   ev.w_val + o};
+}
+
+}  // namespace rvs
+
+struct rvs_engine {
+    rvs_engine_config cfg;
+    rvs::EngineView v;
+    int cur_k = 0;          // wave size of the last select (external path)
+    bool searching = false;
+    float* ext_probs = nullptr;   // staging for host-side probs/values/planes of the external path
+    float* ext_values = nullptr;
+    float* ext_planes = nullptr;
+    uint8_t* ext_valid = nullptr;
+    int32_t* visits = nullptr;    // [G*65] scratch for root_visits with host output
+    uint8_t* moves = nullptr;     // [G]
+    void* io_stage = nullptr;     // staging for set/get positions, drain (grow-only)
+    size_t io_stage_cap = 0;
+    int64_t launches = 0;
+    rvs::NetState* net = nullptr;
+    void* allocs[64];
+    int n_allocs = 0;
+};
+
+// K4 hooks implemented in rvs_net.cu
+int rvs_net_search(rvs_engine* h, int32_t num_sims, int32_t wave, cudaStream_t s);
+void rvs_net_destroy(rvs::NetState* n);

@@ -1,0 +1,131 @@
+"""Engine: the lockstep batched MCTS / self-play engine handle (rvs_engine_* in rvs_b200.h)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+class Engine:
+    """One engine per device.  Not thread-safe (one host thread per handle)."""
+
+    def __init__(self, n_games, max_sims, max_wave=64, evaluator=L.EVAL_E0, c_puct=1.0, rules=L.RULES_REF,
+                 seed=0, device=0, nodes_per_game=0, net_blocks=0, net_filters=0, sample_capacity=0):
+        cfg = L.EngineConfig(C.sizeof(L.EngineConfig), device, n_games, max_sims, max_wave, rules, evaluator,
+                             c_puct, seed, nodes_per_game, net_blocks, net_filters, sample_capacity)
+        self._h = C.c_void_p()
+        L.check(L.lib().rvs_engine_create(C.byref(cfg), C.byref(self._h)))
+        self.n_games, self.max_sims, self.max_wave = n_games, max_sims, max_wave
+        self.evaluator, self.rules, self.device = evaluator, rules, device
+        self.cur_k = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            L.lib().rvs_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _s(stream):
+        return stream if stream is not None else L.current_stream()
+
+    def reset(self, stream=None):
+        L.check(L.lib().rvs_engine_reset(self._h, self._s(stream)))
+
+    def set_positions(self, black, white, side, stream=None):
+        mem = L.mem_of(black, white, side)
+        L.check(L.lib().rvs_engine_set_positions(self._h, L.ptr(black)[0], L.ptr(white)[0], L.ptr(side)[0],
+                                                 len(black), mem, self._s(stream)))
+
+    def get_positions(self, n=None, stream=None):
+        n = self.n_games if n is None else n
+        b = np.empty(n, dtype=np.uint64)
+        w = np.empty(n, dtype=np.uint64)
+        s = np.empty(n, dtype=np.uint8)
+        f = np.empty(n, dtype=np.uint8)
+        L.check(L.lib().rvs_engine_get_positions(self._h, b.ctypes.data, w.ctypes.data, s.ctypes.data,
+                                                 f.ctypes.data, n, L.MEM_HOST, self._s(stream)))
+        return b, w, s, f
+
+    def search(self, num_sims, wave, stream=None):
+        L.check(L.lib().rvs_engine_search(self._h, num_sims, wave, self._s(stream)))
+
+    # ---- external-evaluator path (MCTS._traverse / _process_batch split at model.predict) ----
+    def begin_search(self, stream=None):
+        L.check(L.lib().rvs_engine_begin_search(self._h, self._s(stream)))
+
+    def select(self, k, stream=None):
+        L.check(L.lib().rvs_engine_select(self._h, k, self._s(stream)))
+        self.cur_k = k
+
+    def leaf_planes(self, device=None, stream=None):
+        """([n_games*k,3,8,8] f32, [n_games*k] uint8 valid) as numpy (device=None) or torch CUDA tensors"""
+        n = self.n_games * self.cur_k
+        if device is None:
+            planes = np.empty((n, 3, 8, 8), dtype=np.float32)
+            valid = np.empty(n, dtype=np.uint8)
+            mem = L.MEM_HOST
+        else:
+            import torch
+            planes = torch.empty((n, 3, 8, 8), dtype=torch.float32, device=device)
+            valid = torch.empty(n, dtype=torch.uint8, device=device)
+            mem = L.MEM_DEVICE
+        L.check(L.lib().rvs_engine_leaf_planes(self._h, L.ptr(planes)[0], L.ptr(valid)[0], mem, self._s(stream)))
+        return planes, valid
+
+    def process(self, probs, values, stream=None):
+        mem = L.mem_of(probs, values)
+        L.check(L.lib().rvs_engine_process(self._h, L.ptr(probs)[0], L.ptr(values)[0], mem, self._s(stream)))
+        self.cur_k = 0
+
+    def root_visits(self, n=None, device=None, stream=None):
+        n = self.n_games if n is None else n
+        if device is None:
+            out = np.empty((n, 65), dtype=np.int32)
+            mem = L.MEM_HOST
+        else:
+            import torch
+            out = torch.empty((n, 65), dtype=torch.int32, device=device)
+            mem = L.MEM_DEVICE
+        L.check(L.lib().rvs_engine_root_visits(self._h, L.ptr(out)[0], n, mem, self._s(stream)))
+        return out
+
+    def play(self, temperature=1.0, recycle=True, want_moves=False, stream=None):
+        mv = np.empty(self.n_games, dtype=np.uint8) if want_moves else None
+        L.check(L.lib().rvs_engine_play(self._h, float(temperature), 1 if recycle else 0,
+                                        None if mv is None else mv.ctypes.data, L.MEM_HOST, self._s(stream)))
+        return mv
+
+    def drain_samples(self, capacity=None, device=None, stream=None):
+        """completed-game samples (states [n,3,8,8] f32, pi [n,65] f32, z [n] f32)"""
+        cap = capacity if capacity is not None else 64 * self.n_games
+        cnt = C.c_int64(0)
+        if device is None:
+            st = np.empty((cap, 3, 8, 8), dtype=np.float32)
+            pi = np.empty((cap, 65), dtype=np.float32)
+            z = np.empty(cap, dtype=np.float32)
+            mem = L.MEM_HOST
+        else:
+            import torch
+            st = torch.empty((cap, 3, 8, 8), dtype=torch.float32, device=device)
+            pi = torch.empty((cap, 65), dtype=torch.float32, device=device)
+            z = torch.empty(cap, dtype=torch.float32, device=device)
+            mem = L.MEM_DEVICE
+        L.check(L.lib().rvs_engine_drain_samples(self._h, L.ptr(st)[0], L.ptr(pi)[0], L.ptr(z)[0], cap,
+                                                 C.byref(cnt), mem, self._s(stream)))
+        n = cnt.value
+        return st[:n], pi[:n], z[:n]
+
+    def stats(self, stream=None):
+        st = L.EngineStats()
+        L.check(L.lib().rvs_engine_stats_get(self._h, C.byref(st), self._s(stream)))
+        return {k: getattr(st, k) for k, _ in L.EngineStats._fields_}
+
+    def load_weights(self, flat, stream=None):
+        L.check(L.lib().rvs_engine_load_weights(self._h, L.ptr(flat)[0], flat.numel() if hasattr(flat, "numel") else flat.size,
+                                                L.ptr(flat)[1], self._s(stream)))

@@ -1,0 +1,146 @@
+"""Drop-in mirror of the reference's self-play generator (src/self_play/self_play.py:15-219).
+
+`SelfPlay(model, args).generate_games(n)` returns the same list of dicts
+(`states`, `action_probs`, `current_players`, `values`) and `generate_training_data(n)` the same
+stacked arrays the trainer consumes (src/trainer/pipeline.py:163-169, 226-228).
+
+Two execution modes, chosen by args['num_parallel_games'] (an argument the reference accepts and
+ignores, self_play.py:30):
+  * absent / 1  -> game-by-game through the MCTS mirror with numpy move sampling: reproduces the
+                   reference bit for bit under the same np.random seed.
+  * > 1         -> lockstep batched self-play on the device (Engine.search + Engine.play):
+                   thousands of games advance one ply per step, samples stay in HBM until drained.
+"""
+import os
+import time
+from typing import Dict, List
+
+import numpy as np
+
+from . import _lib as L
+from .engine import Engine
+from .game import ReversiGame
+from .mcts import MCTS
+
+
+class SelfPlay:
+    def __init__(self, model, args: dict):
+        self.model = model
+        self.args = args
+        self._builtin = getattr(model, "evaluator", None)
+        if self._builtin is None:
+            self.device = next(model.parameters()).device
+            self.model.to(self.device)
+            self.model.eval()
+        else:
+            self.device = None
+        self.mcts = MCTS(model=model, c_puct=args.get("c_puct", 1.0),
+                         num_simulations=args.get("num_simulations", 800),
+                         batch_size=args.get("batch_size", 64))
+        self.save_dir = args.get("save_dir", None)
+        if self.save_dir:
+            os.makedirs(self.save_dir, exist_ok=True)
+        self.verbose = args.get("verbose", False)
+
+    # ------------------------------------------------------------------ sequential (bit-exact)
+    def _play_one(self) -> Dict:
+        game = ReversiGame()
+        gd = {"states": [], "action_probs": [], "current_players": [], "values": []}
+        T = self.args.get("temperature", 1.0)
+        while not game.is_game_over():  # self_play.py:80-101
+            action, action_probs = self.mcts.get_action_probs(game, temperature=T)
+            gd["states"].append(game.get_canonical_state())
+            gd["current_players"].append(game.current_player)
+            gd["action_probs"].append(action_probs)
+            row, col = action
+            if not game.make_move(row, col):
+                # the reference would loop forever here; fail loudly instead
+                raise RuntimeError(f"self-play selected an illegal move {action}; "
+                                   "num_simulations must exceed the MCTS wave size")
+            self.mcts.update_with_move(action)
+        winner = game.get_winner()
+        for player in gd["current_players"]:  # self_play.py:117-126
+            gd["values"].append(0.0 if winner == 0 else (1.0 if player == winner else -1.0))
+        return gd
+
+    # ------------------------------------------------------------------ batched (device)
+    def _play_batched(self, num_games: int, parallel: int) -> List[Dict]:
+        if self._builtin is None:
+            raise L.RvsError("batched self-play needs a built-in evaluator (UniformDiscDiff, UniformRollout or "
+                             "RvsNetwork); wrap external torch models with MCTS/SelfPlay in sequential mode")
+        S = self.args.get("num_simulations", 800)
+        K = self.args.get("batch_size", 64)
+        T = self.args.get("temperature", 1.0)
+        slots = min(parallel, num_games)
+        eng = Engine(slots, S, K, evaluator=self._builtin, c_puct=self.args.get("c_puct", 1.0),
+                     seed=self.args.get("seed", getattr(self.model, "seed", 0)),
+                     sample_capacity=64 * max(slots, 1) * 2)
+        if hasattr(self.model, "attach"):
+            self.model.attach(eng)
+        games: List[Dict] = []
+        collected = 0
+        while len(games) < num_games:
+            eng.search(S, K)
+            eng.play(T, recycle=True)  # finished slots restart at once; surplus games are discarded
+            st = eng.stats()
+            if st["overflow"]:
+                raise L.RvsError(f"engine error counters non-zero: {st}")
+            if st["games_finished"] > collected:
+                collected = st["games_finished"]
+                states, pi, z = eng.drain_samples()
+                games.extend(_split_games(states, pi, z))
+        eng.close()
+        return games[:num_games]
+
+    # ------------------------------------------------------------------ reference API
+    def generate_games(self, num_games: int) -> List[Dict]:
+        parallel = int(self.args.get("num_parallel_games", 1) or 1)
+        if parallel > 1:
+            all_games = self._play_batched(num_games, parallel)
+        else:
+            all_games = []
+            for game_idx in range(num_games):
+                t0 = time.time()
+                gd = self._play_one()
+                all_games.append(gd)
+                if self.verbose:
+                    print(f"Game {game_idx + 1} completed in {time.time() - t0:.1f}s, {len(gd['states'])} states")
+        if self.save_dir:
+            import torch
+            from datetime import datetime
+            ts = datetime.now().strftime("%Y%m%d_%H%M%S")
+            for i, gd in enumerate(all_games):  # self_play.py:129-131
+                torch.save(gd, os.path.join(self.save_dir, f"game_{ts}_{i}.pt"))
+        return all_games
+
+    def generate_training_data(self, num_games: int):
+        games = self.generate_games(num_games)
+        all_states, all_probs, all_values = [], [], []
+        for g in games:
+            all_states.extend(g.get("states", []))
+            all_probs.extend(g.get("action_probs", []))
+            all_values.extend(g.get("values", []))
+        if not all_states or not all_probs or not all_values:
+            return None
+        return {"states": np.array(all_states, dtype=np.float32),
+                "action_probs": np.array(all_probs, dtype=np.float32),
+                "values": np.array(all_values, dtype=np.float32).reshape(-1, 1)}
+
+
+def _split_games(states, pi, z) -> List[Dict]:
+    """the ring stores each finished game's plies contiguously, ply 0 first: split on start positions"""
+    states = np.asarray(states)
+    pi = np.asarray(pi)
+    z = np.asarray(z)
+    games, cur = [], None
+    for i in range(len(states)):
+        s = states[i]
+        is_start = s[0].sum() == 2 and s[1].sum() == 2
+        if is_start or cur is None:
+            cur = {"states": [], "action_probs": [], "current_players": [], "values": []}
+            games.append(cur)
+        cur["states"].append(s)
+        cur["action_probs"].append(pi[i].astype(np.float64))
+        cur["values"].append(float(z[i]))
+        cur["current_players"].append(0)  # side to move is implicit in the canonical planes
+    return games

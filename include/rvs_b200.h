@@ -1,0 +1,189 @@
+/*
+ * rvs_b200.h -- C ABI of the B200-native Reversi self-play hot path (librvs_b200.so).
+ *
+ * The reference (RandomMike1280/AlphaZero-Reversi) has no plugin / FFI interface on this
+ * path: the boundary is its Python class API (ReversiGame, MCTS, SelfPlay).  Each entry
+ * point below names the reference method(s) it replaces (paths relative to the reference
+ * root); the Python mirror classes in alphazero-reversi_b200/ bind them with ctypes, and
+ * INTEGRATION.md shows the same binding added to the reference itself.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; rvs_last_error() gives a
+ *     thread-local message.  No C++ exception crosses the boundary.
+ *   - `mem` selects where the caller's bulk pointers live: RVS_MEM_DEVICE (CUDA device
+ *     pointers, e.g. torch.Tensor.data_ptr()) or RVS_MEM_HOST (plain host memory; the
+ *     library stages through pinned buffers and the copies run on `stream`).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls with
+ *     RVS_MEM_HOST outputs synchronise the stream before returning; device-only calls
+ *     are asynchronous.
+ *   - the caller owns every buffer it passes; engine handles own their internal HBM
+ *     pools.  A handle is bound to one device and is not thread-safe.
+ *   - squares are indices row*8+col (bit index of the reference bitboards,
+ *     src/game/board.py:49,170); side 1 = BLACK, 2 = WHITE (board.py:22-23).
+ */
+#ifndef RVS_B200_H
+#define RVS_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVS_MEM_DEVICE 0
+#define RVS_MEM_HOST 1
+
+#define RVS_RULES_REF 0    /* bug-compatible with src/game/board.py (graded) */
+#define RVS_RULES_STRICT 1 /* true Othello */
+
+/* flags byte of a position: bit0 game over, bits1-2 winner (0 draw, 1 black, 2 white),
+ * bit3 the last move was followed by an auto-pass (board.py:242-249) */
+#define RVS_FLAG_OVER 1
+#define RVS_FLAG_WINNER_SHIFT 1
+#define RVS_FLAG_WINNER_MASK 6
+#define RVS_FLAG_PASSED 8
+
+#define RVS_PLANES_F32_NCHW 0  /* [n,3,8,8] float32: ReversiGame.get_canonical_state */
+#define RVS_PLANES_BF16_NHWC 1 /* [n,8,8,16] bf16, channels 3..15 zero: K4 network input */
+
+#define RVS_EVAL_E0 0       /* deterministic: prior f32(1/65), value (own-opp)/64 */
+#define RVS_EVAL_ROLLOUT 1  /* uniform prior, value = one uniform random playout */
+#define RVS_EVAL_EXTERNAL 2 /* caller evaluates leaves (any model.predict duck type) */
+#define RVS_EVAL_NN 3       /* built-in bf16 ResNet on tcgen05 (K4) */
+
+const char *rvs_last_error(void);
+int rvs_version(void);
+/* number of kernels this library has launched since load (bench.py "gpu_launches") */
+int64_t rvs_launch_count(void);
+
+/* ---- K1: stateless board operations ------------------------------------------------ */
+
+/* Board.get_valid_moves (src/game/board.py:70-133) for n positions -> legal bit masks */
+int rvs_legal_masks(const uint64_t *black, const uint64_t *white, const uint8_t *side,
+                    uint64_t *out_mask, int64_t n, int rules, int mem, void *stream);
+
+/* flip scan of Board.make_move / _get_flipped_pieces (board.py:190-219, 295-348) */
+int rvs_flip_masks(const uint64_t *black, const uint64_t *white, const uint8_t *side,
+                   const uint8_t *move, uint64_t *out_flip, int64_t n, int rules, int mem,
+                   void *stream);
+
+/* ReversiGame.make_move (src/game/game.py:36-70 -> board.py:135-251) in place on n
+ * positions: ok[i]=0 and the position is untouched when the game is over or the square is
+ * not in the legal mask.  out_next_legal (optional) = legal mask of the side to move next. */
+int rvs_apply_moves(uint64_t *black, uint64_t *white, uint8_t *side, uint8_t *flags,
+                    const uint8_t *move, uint8_t *ok, uint64_t *out_next_legal, int64_t n,
+                    int rules, int mem, void *stream);
+
+/* n uniform-random games from the start position (BASELINE config 1); game g uses RNG
+ * stream (seed, first_game+g).  Any output pointer may be NULL.  *out_total_plies (host)
+ * receives the number of board-steps played. */
+int rvs_random_playouts(int64_t n_games, uint64_t seed, uint64_t first_game, int rules,
+                        uint64_t *out_black, uint64_t *out_white, uint8_t *out_winner,
+                        uint8_t *out_plies, int64_t *out_total_plies, int mem, void *stream);
+
+/* perft under the reference's auto-pass semantics; *out_count is a host pointer */
+int rvs_perft(uint64_t black, uint64_t white, int side, int depth, int rules,
+              uint64_t *out_count, void *stream);
+
+/* ---- K3: leaf encoding ------------------------------------------------------------- */
+
+/* ReversiGame.get_canonical_state (game.py:131-162) */
+int rvs_encode_planes(const uint64_t *black, const uint64_t *white, const uint8_t *side,
+                      void *out, int64_t n, int layout, int rules, int mem, void *stream);
+
+/* ---- K2(+K3+K4): lockstep batched MCTS engine --------------------------------------- */
+
+typedef struct rvs_engine rvs_engine;
+
+typedef struct rvs_engine_config {
+    int32_t struct_size; /* sizeof(rvs_engine_config) */
+    int32_t device;
+    int32_t n_games;        /* concurrent game slots on this device */
+    int32_t max_sims;       /* upper bound of num_simulations (sizes the node pools) */
+    int32_t max_wave;       /* upper bound of the per-game wave (MCTS batch_size) */
+    int32_t rules;
+    int32_t evaluator;
+    float c_puct;           /* MCTS(c_puct=...)  src/mcts/mcts.py:197 */
+    uint64_t seed;
+    int32_t nodes_per_game; /* 0 = worst case 2 + 34*max_sims */
+    int32_t net_blocks;     /* RVS_EVAL_NN: AlphaZeroNetwork(num_res_blocks, num_filters) */
+    int32_t net_filters;
+    int32_t sample_capacity; /* self-play sample ring, 0 = 64*n_games */
+} rvs_engine_config;
+
+typedef struct rvs_engine_stats {
+    int64_t sims;        /* simulations run (root-to-leaf traversals) */
+    int64_t evals;       /* leaf evaluations requested from the evaluator */
+    int64_t board_steps; /* moves applied (tree descent + rollouts + played moves) */
+    int64_t nodes;       /* tree nodes allocated */
+    int64_t games_finished;
+    int64_t samples;     /* samples recorded */
+    int64_t launches;    /* kernels launched by this engine */
+    int64_t overflow;    /* node-pool overflows (must stay 0) */
+} rvs_engine_stats;
+
+int rvs_engine_create(const rvs_engine_config *cfg, rvs_engine **out);
+int rvs_engine_destroy(rvs_engine *h);
+
+/* every slot back to the start position with a fresh game id (ReversiGame(), game.py:14-26) */
+int rvs_engine_reset(rvs_engine *h, void *stream);
+/* root positions for slots [0,n): MCTS.search(game) takes the caller's game (mcts.py:322) */
+int rvs_engine_set_positions(rvs_engine *h, const uint64_t *black, const uint64_t *white,
+                             const uint8_t *side, int32_t n, int mem, void *stream);
+int rvs_engine_get_positions(rvs_engine *h, uint64_t *black, uint64_t *white, uint8_t *side,
+                             uint8_t *flags, int32_t n, int mem, void *stream);
+
+/* MCTS.search (src/mcts/mcts.py:322-407) for all slots with a built-in evaluator:
+ * fresh root, num_sims simulations in waves of `wave` (= MCTS batch_size). */
+int rvs_engine_search(rvs_engine *h, int32_t num_sims, int32_t wave, void *stream);
+
+/* The same search split at the evaluator (RVS_EVAL_EXTERNAL): begin -> repeat { select k
+ * leaves per game; caller evaluates rvs_engine_leaf_planes(); process } .  This is
+ * MCTS._traverse (mcts.py:409-444) / MCTS._process_batch (mcts.py:544-623). */
+int rvs_engine_begin_search(rvs_engine *h, void *stream);
+int rvs_engine_select(rvs_engine *h, int32_t k, void *stream);
+/* canonical planes of the leaves selected last, [n_games*k, 3,8,8] f32 (slot-major); leaves
+ * that need no evaluation (terminal hits) are all-zero.  out_valid (optional, uint8
+ * [n_games*k]) marks leaves whose evaluation will be consumed. */
+int rvs_engine_leaf_planes(rvs_engine *h, float *out_planes, uint8_t *out_valid, int mem,
+                           void *stream);
+/* probs [n_games*k,65] f32 = softmax(logits) (mcts.py:596), values [n_games*k] f32 */
+int rvs_engine_process(rvs_engine *h, const float *probs, const float *values, int mem,
+                       void *stream);
+
+/* root child visit counts by square, [n,65] int32 (index 64 = pass, always 0): the dict
+ * MCTS.search returns (mcts.py:406-407) */
+int rvs_engine_root_visits(rvs_engine *h, int32_t *out, int32_t n, int mem, void *stream);
+
+/* One self-play ply for every live slot (src/self_play/self_play.py:80-101): pi from the
+ * root visits (MCTS.get_action_probs, mcts.py:660-676), move choice (argmax if
+ * temperature==0 else inverse-CDF sampling), sample record, make_move; finished games get
+ * z back-filled (self_play.py:117-126) and, if recycle!=0, the slot restarts.
+ * out_moves (optional, uint8 [n_games]) receives the squares played (255 = idle slot). */
+int rvs_engine_play(rvs_engine *h, float temperature, int recycle, uint8_t *out_moves, int mem,
+                    void *stream);
+
+/* completed-game samples in the trainer's format (self_play.py:72-77, pipeline.py:226-228):
+ * states [cap,3,8,8] f32, pi [cap,65] f32, z [cap] f32.  Returns up to `capacity` samples
+ * and removes them from the ring. */
+int rvs_engine_drain_samples(rvs_engine *h, float *states, float *pi, float *z, int64_t capacity,
+                             int64_t *out_count, int mem, void *stream);
+
+int rvs_engine_stats_get(rvs_engine *h, rvs_engine_stats *out, void *stream);
+
+/* ---- K4: network -------------------------------------------------------------------- */
+
+/* Loads AlphaZeroNetwork weights (src/model/network.py:33-69) given as the flat f32
+ * concatenation of the state_dict tensors in canonical key order (see
+ * alphazero-reversi_b200/network.py: pack_state_dict); BN is folded here. */
+int rvs_engine_load_weights(rvs_engine *h, const float *flat, int64_t n_floats, int mem,
+                            void *stream);
+/* AlphaZeroNetwork.predict (network.py:136-158) on packed positions: logits [n,65] f32,
+ * value [n] f32 (bf16 tensor-core compute, f32 accumulate) */
+int rvs_engine_predict(rvs_engine *h, const uint64_t *black, const uint64_t *white,
+                       const uint8_t *side, int64_t n, float *out_logits, float *out_value,
+                       int mem, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
