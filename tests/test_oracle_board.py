@@ -38,7 +38,7 @@ def test_perft_ref(golden):
 
 
 def test_perft_strict():
-    # true Othello counts; depth 9 = 3005288 from the literature
+    # true Othello counts
     exp = [4, 12, 56, 244, 1396, 8200, 55092, 390216]
     for d, e in enumerate(exp, start=1):
         assert orc.perft(d, orc.RULES_STRICT) == e
