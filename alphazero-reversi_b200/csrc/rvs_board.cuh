@@ -212,14 +212,179 @@ RVS_HD uint64_t rng_next(uint64_t& s) {
 }
 RVS_HD int rng_pick(uint64_t r, int n) { return (int)(((r >> 32) * (uint64_t)n) >> 32); }
 
+// playout move picker: PCG-RXS-M-XS-32 seeded from a 64-bit stream id (~9 SASS instructions per
+// draw instead of ~25 for splitmix64); move = k-th legal square with k = (r * n) >> 32
+RVS_HD uint32_t roll_init(uint64_t stream) { return (uint32_t)(stream ^ (stream >> 32)); }
+RVS_HD uint32_t roll_next(uint32_t& s) {
+    s = s * 747796405u + 2891336453u;
+    const uint32_t w = ((s >> ((s >> 28u) + 4u)) ^ s) * 277803737u;
+    return (w >> 22u) ^ w;
+}
+RVS_HD int roll_pick(uint32_t r, int n) { return (int)(((uint64_t)r * (uint64_t)n) >> 32); }
+
+// ---- direction-sliced formulas (warp-cooperative board ops) ---------------------------------
+// In the tree kernels one warp owns one game, so a scalar apply_move would leave 31 lanes idle.
+// Instead lane l evaluates direction (l & 7) of the flip / move-generation scan and the warp
+// ORs the eight partial masks with two REDUX instructions (coop_* below).  To keep every lane
+// on the same instruction stream, "negative" directions (>>) run on bit-reversed boards with
+// a left shift: brev(x >> s) == brev(x) << s.  The per-direction functions are plain
+// host/device code so the CPU test tier checks OR_d part(d) == oracle.
+RVS_HD uint64_t brev64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __brevll(x);
+#else
+    x = ((x >> 1) & 0x5555555555555555ULL) | ((x & 0x5555555555555555ULL) << 1);
+    x = ((x >> 2) & 0x3333333333333333ULL) | ((x & 0x3333333333333333ULL) << 2);
+    x = ((x >> 4) & 0x0F0F0F0F0F0F0F0FULL) | ((x & 0x0F0F0F0F0F0F0F0FULL) << 4);
+    return __builtin_bswap64(x);
+#endif
+}
+
+struct DirLane {
+    int s;          // |shift| in {1, 7, 8, 9}
+    bool neg;       // direction is a right shift -> work on bit-reversed boards
+    uint64_t fm;    // flip scan: mask of cells a line may pass through / close on (working domain)
+    uint64_t gm;    // move generation: mask applied to the opponent set (working domain)
+};
+
+template <int RULES>
+RVS_HD DirLane make_dir(int d) {
+    // d: 0 +1(E) 1 -1(W) 2 +8(S) 3 -8(N) 4 +9(SE) 5 -9(NW) 6 +7(SW) 7 -7(NE)
+    DirLane L;
+    const int a = d >> 1;
+    L.s = a == 0 ? 1 : (a == 1 ? 8 : (a == 2 ? 9 : 7));
+    L.neg = d & 1;
+    uint64_t fm, gm;
+    if (RULES == RULES_REF) {
+        fm = a == 0 ? kNotA : (a == 1 ? kAll : (a == 2 ? kNotH : kNotA));  // edge_masks.get(abs(d)) (board.py:196-208)
+        gm = kAll;                                                         // no file masks (board.py:102-124)
+    } else {
+        // landing file: east-ish steps (+1,+9,-7) never land on col 0, west-ish (-1,-9,+7) never on col 7
+        const bool east = (d == 0 || d == 4 || d == 7);
+        fm = a == 1 ? kAll : (east ? kNotA : kNotH);
+        gm = a == 1 ? kAll : (kNotA & kNotH);
+    }
+    L.fm = L.neg ? brev64(fm) : fm;
+    L.gm = L.neg ? brev64(gm) : gm;
+    return L;
+}
+
+RVS_HD uint64_t to_dom(uint64_t x, bool neg) { return neg ? brev64(x) : x; }
+
+// contribution of one direction to Board.get_valid_moves; Pd/Od in the lane's working domain,
+// result in the normal domain
+RVS_HD uint64_t legal_part(const DirLane& L, uint64_t Pd, uint64_t Od) {
+    const uint64_t E = ~(Pd | Od), Om = Od & L.gm;
+    const int s = L.s;
+    uint64_t c = (Pd << s) & Om;
+    c |= (c << s) & Om;
+    const uint64_t Om2 = Om & (Om << s);
+    c |= (c << (2 * s)) & Om2;
+    c |= (c << (2 * s)) & Om2;
+    return to_dom((c << s) & E, L.neg);
+}
+
+// contribution of one direction to the flip scan for the move bit `mvd` (working domain)
+RVS_HD uint64_t flip_part(const DirLane& L, uint64_t Pd, uint64_t Od, uint64_t mvd) {
+    const uint64_t Om = Od & L.fm, Pm = Pd & L.fm;
+    const int s = L.s;
+    uint64_t x = (mvd << s) & Om;
+    x |= (x << s) & Om;
+    const uint64_t Om2 = Om & (Om << s);
+    x |= (x << (2 * s)) & Om2;
+    x |= (x << (2 * s)) & Om2;
+    const uint64_t end = (x << s) & ~x & Pm;
+    return to_dom(end ? x : 0ULL, L.neg);
+}
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ uint64_t warp_or64(uint64_t x) {
+    const unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)x);
+    const unsigned hi = __reduce_or_sync(0xffffffffu, (unsigned)(x >> 32));
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// A position held by the warp: every lane keeps the mover's / opponent's discs in ITS OWN
+// working domain (bit-reversed for right-shift directions), so a ply costs one brev of the
+// reduced flip mask instead of re-reversing both boards.  popcounts are domain independent.
+struct CoopBoard {
+    uint64_t Pd, Od;  // side to move / opponent, lane domain
+    int side;         // 1 BLACK, 2 WHITE
+    int flags;        // F_OVER | winner | F_PASSED like Board::flags
+};
+
+__device__ __forceinline__ CoopBoard coop_load(const DirLane& L, const Board& b) {
+    const bool blk = b.side == 1;
+    return CoopBoard{to_dom(blk ? b.black : b.white, L.neg), to_dom(blk ? b.white : b.black, L.neg), b.side, b.flags};
+}
+// normal-domain view (every lane gets the same Board)
+__device__ __forceinline__ Board coop_store(const DirLane& L, const CoopBoard& c) {
+    const uint64_t P = to_dom(c.Pd, L.neg), O = to_dom(c.Od, L.neg);
+    return Board{c.side == 1 ? P : O, c.side == 1 ? O : P, (uint8_t)c.side, (uint8_t)c.flags};
+}
+
+// Board.get_valid_moves for the side to move, by the whole warp (normal domain, warp-uniform)
+__device__ __forceinline__ uint64_t coop_legal(const DirLane& L, const CoopBoard& c) {
+    return warp_or64(legal_part(L, c.Pd, c.Od));
+}
+
+// k-th set bit of a warp-uniform mask, lanes test bits (lane) and (lane+32) in parallel
+__device__ __forceinline__ int coop_nth_set_bit(uint64_t m, int k, int lane) {
+    const unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
+    const unsigned lt = (1u << lane) - 1u;
+    const int nlo = __popc(lo);
+    const bool hit_lo = ((lo >> lane) & 1u) && __popc(lo & lt) == k;
+    const bool hit_hi = ((hi >> lane) & 1u) && (nlo + __popc(hi & lt)) == k;
+    const unsigned blo = __ballot_sync(0xffffffffu, hit_lo), bhi = __ballot_sync(0xffffffffu, hit_hi);
+    return blo ? (__ffs(blo) - 1) : (31 + __ffs(bhi));
+}
+
+// apply_move() by the whole warp (board.py:181-251).  Returns the legal mask of the side to move
+// afterwards (0 when the game is over); every lane computes the same side / flags.
+__device__ __forceinline__ uint64_t coop_apply_move(const DirLane& L, CoopBoard& c, int idx) {
+    const uint64_t mvd = 1ULL << (L.neg ? 63 - idx : idx);
+    const uint64_t f = warp_or64(flip_part(L, c.Pd, c.Od, mvd));
+    const uint64_t fd = to_dom(f, L.neg);
+    const uint64_t P = c.Pd ^ (mvd | fd), O = c.Od ^ fd;
+    uint64_t lm = warp_or64(legal_part(L, O, P));  // opponent to move
+    if (lm) {                                      // warp-uniform branch
+        c.Pd = O; c.Od = P; c.side = 3 - c.side; c.flags = 0;
+        return lm;
+    }
+    c.Pd = P; c.Od = O;                            // auto-pass (board.py:242-249)
+    lm = warp_or64(legal_part(L, P, O));
+    c.flags = F_PASSED;
+    if (lm == 0) {
+        const int np = popc64(P), no = popc64(O);
+        const int nb = c.side == 1 ? np : no, nw = c.side == 1 ? no : np;
+        const int w = nb > nw ? 1 : (nw > nb ? 2 : 0);
+        c.flags = F_PASSED | F_OVER | (w << F_WIN_SHIFT);
+    }
+    return lm;
+}
+
+// random_playout() by the whole warp from a position whose legal mask `lm` is known
+__device__ __forceinline__ int coop_random_playout(const DirLane& L, CoopBoard& c, uint64_t lm, uint64_t stream, int lane) {
+    int plies = 0;
+    uint32_t rs = roll_init(stream);
+    while (lm) {
+        const int k = roll_pick(roll_next(rs), popc64(lm));
+        lm = coop_apply_move(L, c, coop_nth_set_bit(lm, k, lane));
+        ++plies;
+    }
+    return plies;
+}
+#endif
+
 // one uniform random playout to the end (config 1 / rollout evaluator); returns plies
 template <int RULES>
 RVS_HD int random_playout(Board& b, uint64_t stream) {
     int plies = 0;
     if (is_over(b)) return 0;
     uint64_t lm = board_legal<RULES>(b);
+    uint32_t rs = roll_init(stream);
     while (lm) {
-        const int k = rng_pick(rng_next(stream), popc64(lm));
+        const int k = roll_pick(roll_next(rs), popc64(lm));
         apply_move<RULES>(b, nth_set_bit(lm, k), lm);
         ++plies;
     }

@@ -12,9 +12,11 @@ constexpr int kBlock = 32 * kWarpsPerBlock;
 __device__ __forceinline__ void flush_stats(const EngineView& ev, const TreeCtx& cx, unsigned long long lane_steps) {
     for (int o = 16; o; o >>= 1) lane_steps += __shfl_down_sync(kFull, lane_steps, o);
     if (cx.lane == 0) {
-        atomicAdd(&ev.stats[ST_SIMS], cx.sims);
-        atomicAdd(&ev.stats[ST_EVALS], cx.evals);
-        atomicAdd(&ev.stats[ST_STEPS], cx.steps + lane_steps);
+        atomicAdd(&ev.stats[ST_SIMS], (unsigned long long)cx.sims);
+        atomicAdd(&ev.stats[ST_EVALS], (unsigned long long)cx.evals);
+        atomicAdd(&ev.stats[ST_STEPS], (unsigned long long)cx.steps + lane_steps);
+        atomicAdd(&ev.stats[ST_BYTES], (unsigned long long)cx.bytes);
+        atomicAdd(&ev.stats[ST_NODES], (unsigned long long)cx.created);
         if (cx.overflow) atomicAdd(&ev.stats[ST_OVERFLOW], 1ULL);
     }
 }
@@ -29,10 +31,33 @@ __device__ __forceinline__ void init_root(TreeCtx& cx, int side) {
     __syncwarp();
 }
 
-// evaluator for the fused kernels: fills ws.lm / ws.val, one leaf per lane
+// evaluator for the fused kernels: fills ws.lm / ws.val.
+// Small waves (k <= kCoopWave): the warp evaluates the leaves one after another with the
+// direction-sliced board ops (every lane busy on one rollout).  Large waves: one leaf per lane.
+constexpr int kCoopWave = 4;
+
 template <int RULES, int EVAL>
 __device__ __forceinline__ void eval_wave(const EngineView& ev, TreeCtx& cx, const WaveScratch& ws, int k, uint64_t game_id,
                                           uint64_t search_id, int sim_base, unsigned long long& lane_steps) {
+    if (EVAL == RVS_EVAL_ROLLOUT && k <= kCoopWave) {
+        for (int j = 0; j < k; ++j) {
+            if (ws.node[j] < 0) continue;  // warp-uniform
+            const uint16_t sf = ws.sf[j];
+            CoopBoard b = coop_load(cx.dir, Board{ws.black[j], ws.white[j], (uint8_t)(sf & 0xFF), (uint8_t)(sf >> 8)});
+            const uint64_t lm = coop_legal(cx.dir, b);
+            float v = 0.0f;
+            if (lm) {
+                const int leaf_side = b.side;
+                const uint64_t st = stream_seed(ev.seed, game_id, (search_id << 16) | (uint64_t)(sim_base + j));
+                cx.steps += (unsigned)coop_random_playout(cx.dir, b, lm, st, cx.lane);
+                const int w = (b.flags & F_WIN_MASK) >> F_WIN_SHIFT;
+                v = (!(b.flags & F_OVER) || w == 0) ? 0.0f : (w == leaf_side ? 1.0f : -1.0f);
+            }
+            if (cx.lane == 0) { ws.lm[j] = lm; ws.val[j] = v; }
+        }
+        __syncwarp();
+        return;
+    }
     for (int j = cx.lane; j < k; j += 32) {
         if (ws.node[j] < 0) continue;
         const uint16_t sf = ws.sf[j];
@@ -63,7 +88,7 @@ template <int RULES, int EVAL>
 __global__ void __launch_bounds__(kBlock) search_fused_kernel(EngineView ev, int S, int K) {
     const int g = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (g >= ev.G) return;
-    TreeCtx cx{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, 1, ev.c_puct, (int)(threadIdx.x & 31), 0, 0, 0, 0};
+    TreeCtx cx{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, 1, ev.c_puct, (int)(threadIdx.x & 31), 0, 0, 0, 0, 0, 0, make_dir<RULES>(threadIdx.x & 7)};
     const Board root{ev.black[g], ev.white[g], ev.side[g], ev.flags[g]};
     const uint64_t game_id = ev.game_id[g];
     const uint64_t search_id = (uint64_t)ev.ply[g];
@@ -72,7 +97,7 @@ __global__ void __launch_bounds__(kBlock) search_fused_kernel(EngineView ev, int
     init_root(cx, root.side);
     for (int start = 0; start < S; start += K) {
         const int k = (S - start) < K ? (S - start) : K;
-        select_wave<RULES>(cx, root, ws, k);
+        select_wave(cx, root, ws, k);
         eval_wave<RULES, EVAL>(ev, cx, ws, k, game_id, search_id, start, lane_steps);
         process_wave(cx, ws, k, [](int, int) { return 1.0f / 65.0f; });
     }
@@ -80,10 +105,30 @@ __global__ void __launch_bounds__(kBlock) search_fused_kernel(EngineView ev, int
     flush_stats(ev, cx, lane_steps);
 }
 
+// MCTS.search with batch_size == 1 and a built-in evaluator: every simulation is register
+// resident (path one node per lane, position in the warp's CoopBoard), no wave scratch.
+template <int RULES, int EVAL>
+__global__ void __launch_bounds__(kBlock, 7) search_k1_kernel(EngineView ev, int S) {
+    const int g = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (g >= ev.G) return;
+    TreeCtx cx{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, 1, ev.c_puct, (int)(threadIdx.x & 31), 0, 0, 0, 0, 0, 0, make_dir<RULES>(threadIdx.x & 7)};
+    const Board root{ev.black[g], ev.white[g], ev.side[g], ev.flags[g]};
+    const uint64_t game_id = ev.game_id[g];
+    const uint64_t search_id = (uint64_t)ev.ply[g];
+    init_root(cx, root.side);
+    const CoopBoard root_c = coop_load(cx.dir, root);
+    for (int sim = 0; sim < S; ++sim) {
+        const uint64_t st = EVAL == RVS_EVAL_ROLLOUT ? stream_seed(ev.seed, game_id, (search_id << 16) | (uint64_t)sim) : 0ULL;
+        simulate_one<EVAL>(cx, root_c, st);
+    }
+    if (cx.lane == 0) ev.n_nodes[g] = cx.n_nodes;
+    flush_stats(ev, cx, 0);
+}
+
 __global__ void __launch_bounds__(kBlock) begin_search_kernel(EngineView ev) {
     const int g = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (g >= ev.G) return;
-    TreeCtx cx{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, 1, ev.c_puct, (int)(threadIdx.x & 31), 0, 0, 0, 0};
+    TreeCtx cx{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, 1, ev.c_puct, (int)(threadIdx.x & 31), 0, 0, 0, 0, 0, 0, DirLane{}};
     init_root(cx, ev.side[g]);
     if (cx.lane == 0) ev.n_nodes[g] = 1;
 }
@@ -93,10 +138,10 @@ template <int RULES>
 __global__ void __launch_bounds__(kBlock) select_kernel(EngineView ev, int k) {
     const int g = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (g >= ev.G) return;
-    TreeCtx cx{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, ev.n_nodes[g], ev.c_puct, (int)(threadIdx.x & 31), 0, 0, 0, 0};
+    TreeCtx cx{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, ev.n_nodes[g], ev.c_puct, (int)(threadIdx.x & 31), 0, 0, 0, 0, 0, 0, make_dir<RULES>(threadIdx.x & 7)};
     const Board root{ev.black[g], ev.white[g], ev.side[g], ev.flags[g]};
     const WaveScratch ws = scratch_of(ev, g);
-    select_wave<RULES>(cx, root, ws, k);
+    select_wave(cx, root, ws, k);
     // legal masks of the leaves (reused by leaf_planes and process)
     for (int j = cx.lane; j < k; j += 32) {
         if (ws.node[j] < 0) { ws.lm[j] = 0; continue; }
@@ -113,7 +158,7 @@ __global__ void __launch_bounds__(kBlock) process_probs_kernel(EngineView ev, in
                                                                 const float* __restrict__ values) {
     const int g = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (g >= ev.G) return;
-    TreeCtx cx{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, ev.n_nodes[g], ev.c_puct, (int)(threadIdx.x & 31), 0, 0, 0, 0};
+    TreeCtx cx{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, ev.n_nodes[g], ev.c_puct, (int)(threadIdx.x & 31), 0, 0, 0, 0, 0, 0, DirLane{}};
     const WaveScratch ws = scratch_of(ev, g);
     const size_t slot0 = (size_t)g * k;
     for (int j = cx.lane; j < k; j += 32) ws.val[j] = values[slot0 + j];
@@ -505,6 +550,15 @@ int rvs_engine_search(rvs_engine* h, int32_t num_sims, int32_t wave, void* strea
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = games_grid(h->v.G);
     const bool strict = h->cfg.rules == RVS_RULES_STRICT;
+    if (wave == 1 && (h->cfg.evaluator == RVS_EVAL_E0 || h->cfg.evaluator == RVS_EVAL_ROLLOUT)) {
+        const bool e0 = h->cfg.evaluator == RVS_EVAL_E0;
+        if (strict && e0) RVS_ENGINE_LAUNCH(h, (search_k1_kernel<RULES_STRICT, RVS_EVAL_E0>), grid, kBlock, 0, s, h->v, num_sims);
+        else if (strict) RVS_ENGINE_LAUNCH(h, (search_k1_kernel<RULES_STRICT, RVS_EVAL_ROLLOUT>), grid, kBlock, 0, s, h->v, num_sims);
+        else if (e0) RVS_ENGINE_LAUNCH(h, (search_k1_kernel<RULES_REF, RVS_EVAL_E0>), grid, kBlock, 0, s, h->v, num_sims);
+        else RVS_ENGINE_LAUNCH(h, (search_k1_kernel<RULES_REF, RVS_EVAL_ROLLOUT>), grid, kBlock, 0, s, h->v, num_sims);
+        h->searching = false;
+        return 0;
+    }
     switch (h->cfg.evaluator) {
     case RVS_EVAL_E0:
         if (strict) RVS_ENGINE_LAUNCH(h, (search_fused_kernel<RULES_STRICT, RVS_EVAL_E0>), grid, kBlock, 0, s, h->v, num_sims, wave);
@@ -671,7 +725,8 @@ int rvs_engine_stats_get(rvs_engine* h, rvs_engine_stats* out, void* stream) {
     out->sims = (int64_t)st[ST_SIMS];
     out->evals = (int64_t)st[ST_EVALS];
     out->board_steps = (int64_t)st[ST_STEPS];
-    out->nodes = 0;
+    out->nodes = (int64_t)st[ST_NODES];
+    out->tree_bytes = (int64_t)st[ST_BYTES];
     out->games_finished = (int64_t)st[ST_FINISHED];
     out->samples = (int64_t)st[ST_SAMPLES];
     out->launches = h->launches;

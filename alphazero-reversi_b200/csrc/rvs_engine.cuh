@@ -6,7 +6,7 @@
 
 namespace rvs {
 
-enum : int { ST_SIMS = 0, ST_EVALS, ST_STEPS, ST_FINISHED, ST_SAMPLES, ST_OVERFLOW, ST_DROPPED, ST_STALLED, ST_COUNT };
+enum : int { ST_SIMS = 0, ST_EVALS, ST_STEPS, ST_FINISHED, ST_SAMPLES, ST_OVERFLOW, ST_DROPPED, ST_STALLED, ST_BYTES, ST_NODES, ST_COUNT };
 
 struct NetState;  // rvs_net.cu
 

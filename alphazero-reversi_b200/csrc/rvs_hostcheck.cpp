@@ -27,6 +27,24 @@ int hc_playout(uint64_t* black, uint64_t* white, uint8_t* side, uint8_t* flags, 
     *black = b.black; *white = b.white; *side = b.side; *flags = b.flags;
     return p;
 }
+// direction-sliced variants: OR over the eight DirLane parts (what the warp computes with REDUX)
+uint64_t hc_legal_sliced(uint64_t P, uint64_t O, int rules) {
+    uint64_t v = 0;
+    for (int d = 0; d < 8; ++d) {
+        const DirLane L = rules == RULES_STRICT ? make_dir<RULES_STRICT>(d) : make_dir<RULES_REF>(d);
+        v |= legal_part(L, to_dom(P, L.neg), to_dom(O, L.neg));
+    }
+    return v;
+}
+uint64_t hc_flips_sliced(uint64_t P, uint64_t O, int idx, int rules) {
+    uint64_t v = 0;
+    for (int d = 0; d < 8; ++d) {
+        const DirLane L = rules == RULES_STRICT ? make_dir<RULES_STRICT>(d) : make_dir<RULES_REF>(d);
+        const uint64_t mvd = L.neg ? (1ULL << (63 - idx)) : (1ULL << idx);
+        v |= flip_part(L, to_dom(P, L.neg), to_dom(O, L.neg), mvd);
+    }
+    return v;
+}
 int hc_nth_set_bit(uint64_t m, int k) { return nth_set_bit(m, k); }
 uint64_t hc_stream_seed(uint64_t s, uint64_t a, uint64_t b) { return stream_seed(s, a, b); }
 }

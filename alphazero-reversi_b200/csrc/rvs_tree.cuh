@@ -54,7 +54,11 @@ struct TreeCtx {
     float c_puct;
     int lane;
     int overflow;
-    unsigned long long steps, sims, evals;
+    // per-launch, per-game counters (32 bit is ample: <= 65535 sims x 64 plies)
+    unsigned steps, sims, evals;
+    unsigned bytes;    // algorithmic HBM bytes (DESIGN.md 'K2 roofline'): 32 B per row touched
+    unsigned created;  // child nodes created
+    DirLane dir;                 // this lane's direction slice for the warp-cooperative board ops
 };
 
 // per-game wave scratch (global memory), slot j in [0, wave)
@@ -97,18 +101,19 @@ __device__ __forceinline__ void backup_path(TreeCtx& cx, int p0, int p1, int ple
             cx.hot[n] = h;
         }
     }
+    cx.bytes += 32u * (unsigned)plen;  // hot row read + write per path node
     __syncwarp();
 }
 
 // MCTS._traverse (mcts.py:409-444).  Returns the leaf node; lane d holds path node d in
 // p0 (d<32) / p1 (d>=32); `b` is advanced to the leaf position; `leaf_vlf` = leaf's vlf word.
-template <int RULES>
-__device__ __forceinline__ int select_one(TreeCtx& cx, Board& b, int& p0, int& p1, int& plen, int& leaf_vlf) {
+__device__ __forceinline__ int select_one(TreeCtx& cx, CoopBoard& b, int& p0, int& p1, int& plen, int& leaf_vlf) {
     int node = 0;
     p0 = 0; p1 = 0;  // path[0] = root (node 0) for lane 0; other lanes overwritten as we descend
     plen = 1;
     int4 h = cx.hot[0];
     int4 c = cx.cold[0];
+    cx.bytes += 32;  // root rows
     const unsigned key_floor = ordered_key(-INFINITY);
     while (true) {
         const int nchild = c.z & 0xFF;
@@ -117,6 +122,7 @@ __device__ __forceinline__ int select_one(TreeCtx& cx, Board& b, int& p0, int& p
         if (cx.lane == 0) reinterpret_cast<int*>(&cx.hot[node])[2] = h.z;
         const float sq = __fsqrt_rn((float)h.x);  // == f32(math.sqrt(N)) (double rounding is innocuous)
         const int fc = c.y;
+        cx.bytes += 32u * (unsigned)nchild;  // hot + cold row of every child scanned
         unsigned best_key = key_floor;
         int best_i = -1;
         int4 bh = h, bc = c;
@@ -151,8 +157,7 @@ __device__ __forceinline__ int select_one(TreeCtx& cx, Board& b, int& p0, int& p
             }
         }
         if (best_i < 0) { cx.overflow |= 2; break; }  // reference would raise (next_node is None)
-        uint64_t nl;
-        apply_move<RULES>(b, (bc.z >> 8) & 0xFF, nl);  // game.make_move(*next_move) (mcts.py:439)
+        coop_apply_move(cx.dir, b, (bc.z >> 8) & 0xFF);  // game.make_move(*next_move) (mcts.py:439)
         ++cx.steps;
         node = fc + best_i;
         h = bh;
@@ -191,6 +196,8 @@ __device__ __forceinline__ void expand_node(TreeCtx& cx, int node, uint64_t lm, 
         cx.cold[node] = c;
     }
     cx.n_nodes += nc;
+    cx.created += (unsigned)nc;
+    cx.bytes += 32u * (unsigned)nc;  // rows written
     __syncwarp();
 }
 
@@ -214,21 +221,68 @@ __device__ __forceinline__ void store_leaf(const WaveScratch& ws, int j, int lan
 
 // One wave of selections (mcts.py:355-386): k traversals from the root; a traversal that ends
 // on a terminal-flagged node is backed up at once (mcts.py:364-366) and leaves slot j empty.
-template <int RULES>
 __device__ __forceinline__ void select_wave(TreeCtx& cx, const Board& root, const WaveScratch& ws, int k) {
+    const CoopBoard root_c = coop_load(cx.dir, root);
     for (int j = 0; j < k; ++j) {
-        Board b = root;
+        CoopBoard b = root_c;
         int p0, p1, plen, vlf;
-        const int node = select_one<RULES>(cx, b, p0, p1, plen, vlf);
+        const int node = select_one(cx, b, p0, p1, plen, vlf);
         ++cx.sims;
         if (vlf & kTerminal) {
             backup_path(cx, p0, p1, plen, term_value_of(vlf));
             if (cx.lane == 0) ws.node[j] = -1;
         } else {
-            store_leaf(ws, j, cx.lane, node, p0, p1, plen, b);
+            store_leaf(ws, j, cx.lane, node, p0, p1, plen, coop_store(cx.dir, b));
         }
     }
     __syncwarp();
+}
+
+// terminal leaf found at evaluation time (mcts.py:567-579): flag it with its ABSOLUTE value
+// (+1 black won, -1 white won, 0 draw / not over) and back that value up
+__device__ __forceinline__ void mark_terminal_and_backup(TreeCtx& cx, int node, int flags, int p0, int p1, int plen) {
+    const int w = (flags & F_WIN_MASK) >> F_WIN_SHIFT;
+    const int code = !(flags & F_OVER) ? 0 : (w == 1 ? 1 : (w == 2 ? 2 : 0));
+    if (cx.lane == 0) {
+        int* z = &reinterpret_cast<int*>(&cx.hot[node])[2];
+        *z = (*z & ~(3 << kTermShift)) | kTerminal | (code << kTermShift);
+    }
+    __syncwarp();
+    backup_path(cx, p0, p1, plen, code == 1 ? 1.0f : (code == 2 ? -1.0f : 0.0f));
+}
+
+// One whole simulation with wave size 1 (MCTS(batch_size=1): select -> evaluate -> expand ->
+// backup), entirely in registers: the path lives one node per lane, the leaf position stays in
+// the warp's CoopBoard and the rollout continues from it.  Identical results to
+// select_wave/eval/process_wave with k == 1.
+template <int EVAL>
+__device__ __forceinline__ void simulate_one(TreeCtx& cx, const CoopBoard& root_c, uint64_t stream_for_sim) {
+    CoopBoard b = root_c;
+    int p0, p1, plen, vlf;
+    const int node = select_one(cx, b, p0, p1, plen, vlf);
+    ++cx.sims;
+    if (vlf & kTerminal) {  // mcts.py:364-366
+        backup_path(cx, p0, p1, plen, term_value_of(vlf));
+        return;
+    }
+    const uint64_t lm = coop_legal(cx.dir, b);
+    if (lm == 0) {
+        mark_terminal_and_backup(cx, node, b.flags, p0, p1, plen);
+        return;
+    }
+    float v;
+    if (EVAL == RVS_EVAL_E0) {
+        v = __fdiv_rn((float)(popc64(b.Pd) - popc64(b.Od)), 64.0f);
+    } else {
+        const int leaf_side = b.side;
+        CoopBoard r = b;
+        cx.steps += (unsigned)coop_random_playout(cx.dir, r, lm, stream_for_sim, cx.lane);
+        const int w = (r.flags & F_WIN_MASK) >> F_WIN_SHIFT;
+        v = (!(r.flags & F_OVER) || w == 0) ? 0.0f : (w == leaf_side ? 1.0f : -1.0f);
+    }
+    ++cx.evals;
+    expand_node(cx, node, lm, [](int) { return 1.0f / 65.0f; });
+    backup_path(cx, p0, p1, plen, v);
 }
 
 // MCTS._process_batch (mcts.py:544-623) for one game's wave.  ws.lm / ws.val must be filled
@@ -239,17 +293,9 @@ __device__ __forceinline__ void process_wave(TreeCtx& cx, const WaveScratch& ws,
     for (int j = 0; j < k; ++j) {
         const int node = ws.node[j];
         if (node < 0 || ws.lm[j] != 0) continue;
-        const int fl = ws.sf[j] >> 8;
-        const int w = (fl & F_WIN_MASK) >> F_WIN_SHIFT;
-        const int code = !(fl & F_OVER) ? 0 : (w == 1 ? 1 : (w == 2 ? 2 : 0));
-        if (cx.lane == 0) {
-            int* z = &reinterpret_cast<int*>(&cx.hot[node])[2];
-            *z = (*z & ~(3 << kTermShift)) | kTerminal | (code << kTermShift);
-        }
-        __syncwarp();
         int p0, p1, plen;
         load_path(ws, j, cx.lane, p0, p1, plen);
-        backup_path(cx, p0, p1, plen, code == 1 ? 1.0f : (code == 2 ? -1.0f : 0.0f));
+        mark_terminal_and_backup(cx, node, ws.sf[j] >> 8, p0, p1, plen);
     }
     for (int j = 0; j < k; ++j) {
         const int node = ws.node[j];

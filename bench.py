@@ -1,0 +1,393 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the self-play hot path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--wave 1]
+
+Workload (config.workload): BASELINE.json configs[1] -- batched pure MCTS (uniform prior, one
+uniform-random rollout per leaf for the value), 100 simulations per move, 4096 concurrent games
+per GPU, reference rules.  A *step* is one self-play ply of all games on the GPU: a full
+100-simulation search of every game (one fused kernel) followed by move sampling, sample
+recording, make_move and recycling of finished games (play + finalize kernels).
+
+  value   MCTS simulations per second, whole job (all ranks), inputs resident in HBM
+  e2e     the same searches through the C ABI with HOST buffers: every step uploads 4096
+          positions (pinned host memory) and downloads the [4096,65] visit-count policies
+  roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md "Measurement"
+
+`--impl reference` times the CPU restatement of the reference path (oracle/, kind "port": the
+reference itself is pure Python and /root/reference does not exist on the GPU box) with all host
+threads on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_GAMES = 4096
+N_SIMS = 100
+METRIC = "mcts_sims_per_sec"
+UNIT = "sims/s"
+# algorithmic HBM bytes per simulation of the fused search kernel (DESIGN.md "K2 roofline"):
+#   32 B per child row scanned on the way down + 32 B per path node at backup (hot row read +
+#   write) + 32 B per child row created + 24 B leaf record; the rollout itself is register
+#   resident (0 B).  Measured per run from the engine's counters, see algorithmic_bytes().
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def position_pool(az, n, seed):
+    """realistic root positions for the e2e / reference legs: uniform-random games cut at a random
+    ply, generated on the GPU (rvs_random_playouts stops are final; use rvs_apply_moves loop)"""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    bl = np.full(n, 0x0000000810000000, dtype=np.uint64)
+    wh = np.full(n, 0x0000001008000000, dtype=np.uint64)
+    sd = np.ones(n, dtype=np.uint8)
+    fl = np.zeros(n, dtype=np.uint8)
+    cut = rng.integers(0, 56, n)
+    for ply in range(56):
+        lm = az.board_ops.legal_masks(bl, wh, sd)
+        mv = np.full(n, 255, dtype=np.uint8)
+        live = (cut > ply) & (lm != 0) & ((fl & 1) == 0)
+        idx = np.nonzero(live)[0]
+        r = rng.integers(0, 64, len(idx))
+        for j, i in enumerate(idx):  # r-th set bit (mod popcount)
+            m = int(lm[i])
+            bits = [b for b in range(64) if (m >> b) & 1]
+            mv[i] = bits[r[j] % len(bits)]
+        az.board_ops.apply_moves(bl, wh, sd, fl, mv, want_legal=False)
+    return bl, wh, sd
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import alphazero_reversi_b200 as az
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lib = az._lib.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    wave = args.wave
+    eng = az.Engine(N_GAMES, N_SIMS, max(wave, 64), evaluator=az.EVAL_ROLLOUT, c_puct=1.0, seed=1000 + rank, device=local)
+
+    def step(e):
+        e.search(N_SIMS, wave, stream=stream)
+        e.play(1.0, recycle=True, stream=stream)
+
+    # steady state of a self-play farm: games are spread uniformly over all phases.  Start every
+    # slot from a random-playout position cut at a random ply (the slots then recycle naturally);
+    # with all games at the same ply the rollout length -- and the step time -- would be a
+    # function of the ply instead of the workload.
+    pb0, pw0, ps0 = position_pool(az, N_GAMES, 99 + rank)
+    eng.set_positions(pb0, pw0, ps0, stream=stream)
+    for _ in range(max(args.warmup, 3) + args.presteps):
+        step(eng)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    s0 = eng.stats()
+    l0 = lib.rvs_launch_count()
+    ks = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        ks[i][0].record()
+        eng.search(N_SIMS, wave, stream=stream)
+        ks[i][1].record()
+        eng.play(1.0, recycle=True, stream=stream)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    s1 = eng.stats()
+    launches = lib.rvs_launch_count() - l0
+    kernel_ms = sum(a.elapsed_time(b) for a, b in ks) / args.steps
+    d = {k: s1[k] - s0[k] for k in s1}
+    if s1["overflow"]:
+        raise SystemExit(f"engine error counters non-zero: {s1}")
+
+    # ---- e2e: C ABI with host buffers (pinned), H2D + D2H inside the timed region ----------
+    pool_steps = 4
+    pb, pw, ps = position_pool(az, N_GAMES * pool_steps, 7 + rank)
+    hb = torch.empty(N_GAMES * pool_steps, dtype=torch.int64).pin_memory()
+    hw = torch.empty_like(hb).pin_memory()
+    hs = torch.empty(N_GAMES * pool_steps, dtype=torch.uint8).pin_memory()
+    hb.numpy()[:] = pb.view(np.int64)
+    hw.numpy()[:] = pw.view(np.int64)
+    hs.numpy()[:] = ps
+    hv = torch.empty((N_GAMES, 65), dtype=torch.int32).pin_memory()
+    eng2 = az.Engine(N_GAMES, N_SIMS, max(wave, 64), evaluator=az.EVAL_ROLLOUT, c_puct=1.0, seed=2000 + rank, device=local)
+
+    def e2e_step(i):
+        o = (i % pool_steps) * N_GAMES
+        az._lib.check(lib.rvs_engine_set_positions(eng2._h, hb[o:].data_ptr(), hw[o:].data_ptr(), hs[o:].data_ptr(),
+                                                   N_GAMES, az._lib.MEM_HOST, stream))
+        az._lib.check(lib.rvs_engine_search(eng2._h, N_SIMS, wave, stream))
+        az._lib.check(lib.rvs_engine_root_visits(eng2._h, hv.data_ptr(), N_GAMES, az._lib.MEM_HOST, stream))
+
+    for i in range(3):
+        e2e_step(i)
+    e2e_steps = max(4, args.steps // 2)
+    barrier()
+    t0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    f1.record()
+    torch.cuda.synchronize()
+    e2e_wall = (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e_ms = max(f0.elapsed_time(f1), e2e_wall)
+    assert int(hv.numpy().sum()) > 0
+
+    # ---- config-1 side metric: register-resident uniform-random playouts ------------------
+    n_po = 1 << 20
+    az.board_ops.random_playouts(n_po, 1, outputs=False, stream=stream)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    *_, po_steps = az.board_ops.random_playouts(n_po, 2 + rank, outputs=False, stream=stream)
+    g1.record()
+    torch.cuda.synchronize()
+    po_ms = g0.elapsed_time(g1)
+
+    # ---- reductions over ranks --------------------------------------------------------------
+    vals = torch.tensor([ms, e2e_ms, kernel_ms], dtype=torch.float64, device=dev)
+    sums = torch.tensor([d["sims"], d["board_steps"], d["evals"], float(launches), e2e_steps * N_GAMES * N_SIMS,
+                         po_steps / (po_ms * 1e-3)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    ms, e2e_ms, kernel_ms = vals.tolist()
+    sims, bsteps, evals, launches_all, e2e_sims, po_rate = sums.tolist()
+
+    if rank == 0:
+        hbm, which = peaks()
+        # algorithmic bytes of the fused search kernel per launch (this rank), from its counters
+        tree_bytes = algorithmic_bytes(d)
+        achieved = tree_bytes / (kernel_ms * 1e-3) / 1e9
+        out = {
+            "metric": METRIC, "value": sims / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3) + args.presteps, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64+f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: pure MCTS, uniform prior + uniform-random rollout value, 100 sims/move, "
+                                   "4096 concurrent games per GPU, REF rules, self-play with recycling",
+                       "games_per_gpu": N_GAMES, "sims_per_move": N_SIMS, "wave": wave, "c_puct": 1.0, "temperature": 1.0,
+                       "parallelism": f"games sharded x{world}, no data-path collective",
+                       "cache": "node pools 446 MB per GPU (> 126 MB L2), rewritten every step"},
+            "board_steps_per_sec": bsteps / (ms * 1e-3),
+            "unique_evals_per_sec": evals / (ms * 1e-3),
+            "playout_board_steps_per_sec": po_rate,
+            "e2e": {"value": e2e_sims / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": N_GAMES * 17,
+                    "d2h_bytes_per_step": N_GAMES * 65 * 4, "steps": e2e_steps},
+            "gpu_launches": int(launches_all),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                         "traffic": args.traffic, "peak_source": which, "kernel": "search_fused_kernel<REF,ROLLOUT>",
+                         "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / (ms / args.steps),
+                         "note": "latency/issue-bound integer kernel: rollouts are register resident; see DESIGN.md"},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline(wave, threads=os.cpu_count() or 1, budget_s=12.0)
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def algorithmic_bytes(d):
+    """algorithmic HBM bytes of ONE search launch (this rank): the engine counts 32 B for every
+    node row the search must touch (children scanned, path rows read+written at backup, rows
+    created) -- DESIGN.md 'K2 roofline'; rollouts are register resident and count 0 B."""
+    steps = max(1, d["launches"] // 3)  # 3 launches per step: search, play, finalize
+    return d["tree_bytes"] / steps
+
+
+def cpu_baseline(wave, threads, budget_s):
+    """oracle port timed on the host cores: searches of the same workload on a bounded sample"""
+    import numpy as np
+    import orc
+    n = 256
+    rng = np.random.default_rng(3)
+    bl, wh, wi, pl = orc.random_playouts(1, 1)  # warm the library
+    pos_b = np.full(n, orc.START[0], dtype=np.uint64)
+    pos_w = np.full(n, orc.START[1], dtype=np.uint64)
+    pos_s = np.ones(n, dtype=np.uint8)
+    # mid-game roots: play k random plies with the oracle
+    import ctypes as C
+    L = orc.lib()
+    for i in range(n):
+        b = orc.make_board(*orc.START)
+        st = L.orc_stream_seed(11, i, 0)
+        for _ in range(int(rng.integers(0, 56))):
+            if b.over:
+                break
+            lm = L.orc_board_legal(C.byref(b), 0)
+            bits = [q for q in range(64) if (lm >> q) & 1]
+            st = orc.mix64(st + 1)
+            L.orc_apply(C.byref(b), bits[st % len(bits)], 0)
+        pos_b[i], pos_w[i], pos_s[i] = b.black, b.white, b.side
+    t0 = time.perf_counter()
+    sims = steps = 0
+    rounds = 0
+    while time.perf_counter() - t0 < budget_s:
+        v, ev, st = orc.search_batch(pos_b, pos_w, pos_s, N_SIMS, wave, evaluator=orc.EVAL_ROLLOUT, seed=rounds,
+                                     threads=threads)
+        sims += n * N_SIMS
+        steps += st
+        rounds += 1
+    dt = time.perf_counter() - t0
+    return {"value": sims / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "board_steps_per_sec": steps / dt,
+            "sample": f"{rounds} x {n} mid-game roots x {N_SIMS} sims (wave {wave}), C oracle (oracle/rvs_oracle.c), "
+                      f"{threads} host threads, {dt:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    import numpy as np
+    import orc
+    import ctypes as C
+    n = 512  # bounded sample of the 4096-game step
+    rng = np.random.default_rng(3)
+    L = orc.lib()
+    pos_b = np.zeros(n, dtype=np.uint64); pos_w = np.zeros(n, dtype=np.uint64); pos_s = np.ones(n, dtype=np.uint8)
+    for i in range(n):
+        b = orc.make_board(*orc.START)
+        st = L.orc_stream_seed(11, i, 0)
+        for _ in range(int(rng.integers(0, 56))):
+            if b.over:
+                break
+            lm = L.orc_board_legal(C.byref(b), 0)
+            bits = [q for q in range(64) if (lm >> q) & 1]
+            st = orc.mix64(st + 1)
+            L.orc_apply(C.byref(b), bits[st % len(bits)], 0)
+        pos_b[i], pos_w[i], pos_s[i] = b.black, b.white, b.side
+    for w in range(max(args.warmup, 1)):
+        orc.search_batch(pos_b, pos_w, pos_s, N_SIMS, args.wave, seed=w, threads=threads)
+    t0 = time.perf_counter()
+    steps_total = 0
+    for k in range(args.steps):
+        _, _, st = orc.search_batch(pos_b, pos_w, pos_s, N_SIMS, args.wave, seed=100 + k, threads=threads)
+        steps_total += st
+    dt = time.perf_counter() - t0
+    v = args.steps * n * N_SIMS / dt
+    sample = (f"{args.steps} steps x {n} mid-game roots x {N_SIMS} sims (wave {args.wave}), C oracle port of the "
+              f"reference path, {threads} host threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64+f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: pure MCTS, uniform prior + uniform-random rollout value, 100 sims/move, "
+                               f"bounded sample of {n} of the 4096 games per step", "sims_per_move": N_SIMS,
+                   "wave": args.wave},
+        "board_steps_per_sec": steps_total / dt,
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--presteps", type=int, default=5, help="untimed plies that spread games over all phases")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--wave", type=int, default=1, help="MCTS batch_size per game (reference default 64)")
+    ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per launch of the search kernel")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

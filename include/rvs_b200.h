@@ -114,11 +114,12 @@ typedef struct rvs_engine_stats {
     int64_t sims;        /* simulations run (root-to-leaf traversals) */
     int64_t evals;       /* leaf evaluations requested from the evaluator */
     int64_t board_steps; /* moves applied (tree descent + rollouts + played moves) */
-    int64_t nodes;       /* tree nodes allocated */
+    int64_t nodes;       /* child nodes created by expansions */
     int64_t games_finished;
     int64_t samples;     /* samples recorded */
     int64_t launches;    /* kernels launched by this engine */
-    int64_t overflow;    /* node-pool overflows (must stay 0) */
+    int64_t overflow;    /* node-pool overflows + dropped samples + stalled slots (must stay 0) */
+    int64_t tree_bytes;  /* algorithmic HBM bytes of the tree kernels: 32 B per node row touched */
 } rvs_engine_stats;
 
 int rvs_engine_create(const rvs_engine_config *cfg, rvs_engine **out);

@@ -17,6 +17,8 @@
 #define NOT_A 0xFEFEFEFEFEFEFEFEULL /* bit (r*8+c) with c != 0 */
 #define NOT_H 0x7F7F7F7F7F7F7F7FULL /* c != 7 */
 
+static __thread int64_t g_steps = 0; /* moves applied by this thread (bench accounting) */
+
 static inline uint64_t sh(uint64_t x, int s) { return s > 0 ? (x << s) : (x >> (-s)); }
 static inline int popc(uint64_t x) { return __builtin_popcountll(x); }
 
@@ -126,6 +128,7 @@ int orc_apply(orc_board *b, int idx, int rules) {
     uint64_t f = orc_flips(P, O, idx, rules);
     P ^= mv | f;
     O ^= f;
+    g_steps++;
     if (b->side == 1) { b->black = P; b->white = O; } else { b->white = P; b->black = O; }
     b->side = (uint8_t)(3 - b->side);
     b->passes = 0;
@@ -191,12 +194,20 @@ static inline int nth_set_bit(uint64_t m, int k) {
     return __builtin_ctzll(m);
 }
 
+/* playout move picker: PCG-RXS-M-XS-32 seeded from the 64-bit stream id (DESIGN.md "RNG") */
+static inline uint32_t roll_next(uint32_t *s) {
+    *s = *s * 747796405u + 2891336453u;
+    uint32_t w = ((*s >> ((*s >> 28u) + 4u)) ^ *s) * 277803737u;
+    return (w >> 22u) ^ w;
+}
+
 int orc_random_playout(orc_board *b, uint64_t stream, int rules) {
     int plies = 0;
+    uint32_t rs = (uint32_t)(stream ^ (stream >> 32));
     while (!b->over) {
         uint64_t lm = orc_board_legal(b, rules);
         if (lm == 0) break; /* only for hand-made positions that never auto-passed */
-        int k = rng_pick(rng_next(&stream), popc(lm));
+        int k = (int)(((uint64_t)roll_next(&rs) * (uint64_t)popc(lm)) >> 32);
         orc_apply(b, nth_set_bit(lm, k), rules);
         plies++;
     }
@@ -294,15 +305,30 @@ int orc_mcts_search(const orc_board *root, int num_sims, int wave, float c_puct,
                     float *root_w, int64_t *n_evals) {
     otree t;
     t.cap = 2 + num_sims * 34;
-    t.nodes = (onode *)malloc(sizeof(onode) * (size_t)t.cap);
+    if (wave < 1) wave = 1;
+    /* per-thread grow-only scratch (a malloc/free pair per search serialises host threads) */
+    static __thread onode *tl_nodes = 0; static __thread int tl_cap = 0;
+    static __thread oleaf *tl_leaves = 0; static __thread orc_board *tl_lb = 0;
+    static __thread float *tl_probs = 0, *tl_values = 0; static __thread int *tl_lidx = 0;
+    static __thread int tl_wave = 0;
+    if (tl_cap < t.cap) { free(tl_nodes); tl_nodes = (onode *)malloc(sizeof(onode) * (size_t)t.cap); tl_cap = t.cap; }
+    if (tl_wave < wave) {
+        free(tl_leaves); free(tl_lb); free(tl_probs); free(tl_values); free(tl_lidx);
+        tl_leaves = (oleaf *)malloc(sizeof(oleaf) * (size_t)wave);
+        tl_lb = (orc_board *)malloc(sizeof(orc_board) * (size_t)wave);
+        tl_probs = (float *)malloc(sizeof(float) * 65 * (size_t)wave);
+        tl_values = (float *)malloc(sizeof(float) * (size_t)wave);
+        tl_lidx = (int *)malloc(sizeof(int) * (size_t)wave);
+        tl_wave = wave;
+    }
+    t.nodes = tl_nodes;
     t.n = 0;
     t.c_puct = c_puct;
-    if (wave < 1) wave = 1;
-    oleaf *leaves = (oleaf *)malloc(sizeof(oleaf) * (size_t)wave);
-    orc_board *lb = (orc_board *)malloc(sizeof(orc_board) * (size_t)wave);
-    float *probs = (float *)malloc(sizeof(float) * 65 * (size_t)wave);
-    float *values = (float *)malloc(sizeof(float) * (size_t)wave);
-    int *lidx = (int *)malloc(sizeof(int) * (size_t)wave);
+    oleaf *leaves = tl_leaves;
+    orc_board *lb = tl_lb;
+    float *probs = tl_probs;
+    float *values = tl_values;
+    int *lidx = tl_lidx;
     int64_t evals = 0;
     int rc = 0;
 
@@ -413,7 +439,6 @@ int orc_mcts_search(const orc_board *root, int num_sims, int wave, float c_puct,
         rc = t.n;
     }
     if (n_evals) *n_evals = evals;
-    free(t.nodes); free(leaves); free(lb); free(probs); free(values); free(lidx);
     return rc;
 }
 
@@ -488,4 +513,33 @@ int orc_self_play_game(int num_sims, int wave, float c_puct, int rules, int eval
         out[i].z = b.winner == 0 ? 0 : (out[i].side == b.winner ? 1 : -1);
     if (winner) *winner = b.winner;
     return ply;
+}
+
+/* bench helper: the same search over n root positions on the calling thread (the benchmark
+ * splits a batch over host threads).  game ids game0..game0+n-1; *steps += moves applied. */
+int orc_search_batch(const uint64_t *black, const uint64_t *white, const uint8_t *side, int n,
+                     int num_sims, int wave, float c_puct, int rules, int evaluator, uint64_t seed,
+                     uint64_t game0, uint64_t search_id, int32_t *visits, int64_t *evals,
+                     int64_t *steps) {
+    int64_t ev = 0, e1 = 0;
+    g_steps = 0;
+    for (int i = 0; i < n; i++) {
+        orc_board b = {black[i], white[i], side[i], 0, 0, 0};
+        if (orc_board_legal(&b, rules) == 0) {
+            orc_board o = b;
+            o.side = (uint8_t)(3 - b.side);
+            if (orc_board_legal(&o, rules) == 0) {
+                int nb = popc(b.black), nw = popc(b.white);
+                b.over = 1;
+                b.winner = nb > nw ? 1 : nw > nb ? 2 : 0;
+            }
+        }
+        int rc = orc_mcts_search(&b, num_sims, wave, c_puct, rules, evaluator, 0, 0, seed,
+                                 game0 + (uint64_t)i, search_id, visits + (size_t)i * 65, 0, 0, &e1);
+        if (rc < 0) return rc;
+        ev += e1;
+    }
+    if (evals) *evals = ev;
+    if (steps) *steps = g_steps;
+    return 0;
 }

@@ -63,6 +63,12 @@ int orc_mcts_search(const orc_board *root, int num_sims, int wave, float c_puct,
                     uint64_t game_id, uint64_t search_id, int32_t *visits, int32_t *root_n,
                     float *root_w, int64_t *n_evals);
 
+/* bench helper: orc_mcts_search over n roots on the calling thread */
+int orc_search_batch(const uint64_t *black, const uint64_t *white, const uint8_t *side, int n,
+                     int num_sims, int wave, float c_puct, int rules, int evaluator, uint64_t seed,
+                     uint64_t game0, uint64_t search_id, int32_t *visits, int64_t *evals,
+                     int64_t *steps);
+
 /* MCTS.get_action_probs pi (mcts.py:660-676): f64 pi[65] from visit counts */
 void orc_action_probs(const int32_t *visits, double temperature, double *pi65);
 

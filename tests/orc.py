@@ -77,6 +77,9 @@ def lib():
         L.orc_self_play_game.restype = i32
         L.orc_self_play_game.argtypes = [i32, i32, C.c_float, i32, i32, EVAL_FN, C.c_void_p, u64,
                                          u64, C.c_double, C.POINTER(Sample), i32, u8p]
+        L.orc_search_batch.restype = i32
+        L.orc_search_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, i32, i32, i32, C.c_float, i32, i32,
+                                       u64, u64, u64, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         _lib = L
     return _lib
 
@@ -210,3 +213,34 @@ def t1_hash_value(b, w, s):
     own, opp = own_opp(b, w, s)
     h = mix64((own * 0x9E3779B97F4A7C15) ^ mix64(opp))
     return h
+
+
+def search_batch(black, white, side, num_sims, wave, c_puct=1.0, rules=RULES_REF, evaluator=EVAL_ROLLOUT,
+                 seed=0, game0=0, search_id=0, threads=1):
+    """oracle search over a batch of roots, split over `threads` host threads (ctypes drops the GIL).
+    Returns (visits [n,65] int32, evals, board_steps)."""
+    from concurrent.futures import ThreadPoolExecutor
+    n = len(black)
+    black = np.ascontiguousarray(black, dtype=np.uint64)
+    white = np.ascontiguousarray(white, dtype=np.uint64)
+    side = np.ascontiguousarray(side, dtype=np.uint8)
+    vis = np.zeros((n, 65), dtype=np.int32)
+    L = lib()
+    bounds = np.linspace(0, n, max(1, threads) + 1).astype(int)
+
+    def work(t):
+        lo, hi = int(bounds[t]), int(bounds[t + 1])
+        ev, st = C.c_int64(0), C.c_int64(0)
+        if hi > lo:
+            rc = L.orc_search_batch(black[lo:].ctypes.data, white[lo:].ctypes.data, side[lo:].ctypes.data, hi - lo,
+                                    num_sims, wave, c_puct, rules, evaluator, seed, game0 + lo, search_id,
+                                    vis[lo:].ctypes.data, C.byref(ev), C.byref(st))
+            if rc:
+                raise RuntimeError(f"orc_search_batch rc={rc}")
+        return ev.value, st.value
+    if threads <= 1:
+        res = [work(0)]
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            res = list(ex.map(work, range(threads)))
+    return vis, sum(r[0] for r in res), sum(r[1] for r in res)

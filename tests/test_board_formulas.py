@@ -30,6 +30,10 @@ def hc():
                               C.POINTER(C.c_uint8), C.c_int, C.c_int, C.POINTER(C.c_uint64)]
     L.hc_playout.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint8),
                              C.POINTER(C.c_uint8), C.c_uint64, C.c_int]
+    L.hc_legal_sliced.restype = C.c_uint64
+    L.hc_legal_sliced.argtypes = [C.c_uint64, C.c_uint64, C.c_int]
+    L.hc_flips_sliced.restype = C.c_uint64
+    L.hc_flips_sliced.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int]
     L.hc_nth_set_bit.argtypes = [C.c_uint64, C.c_int]
     L.hc_stream_seed.restype = C.c_uint64
     L.hc_stream_seed.argtypes = [C.c_uint64] * 3
@@ -73,6 +77,25 @@ def test_flips_on_every_empty_square(hc, rules):
             idx = (E & -E).bit_length() - 1
             E &= E - 1
             assert hc.hc_flips(P, O, idx, rules) == orc.flips(P, O, idx, rules)
+
+
+@pytest.mark.parametrize("rules", [orc.RULES_REF, orc.RULES_STRICT])
+def test_direction_sliced_formulas_match_oracle(hc, rules):
+    """the warp-cooperative path: per-direction parts (bit-reversed boards for right shifts) ORed"""
+    for P, O in rand_positions(12000, 31 + rules):
+        assert hc.hc_legal_sliced(P, O, rules) == orc.legal(P, O, rules)
+        E = ~(P | O) & orc.M64
+        k = 0
+        while E and k < 12:
+            idx = (E & -E).bit_length() - 1
+            E &= E - 1
+            k += 1
+            assert hc.hc_flips_sliced(P, O, idx, rules) == orc.flips(P, O, idx, rules)
+        m = orc.legal(P, O, rules)
+        while m:
+            idx = (m & -m).bit_length() - 1
+            m &= m - 1
+            assert hc.hc_flips_sliced(P, O, idx, rules) == orc.flips(P, O, idx, rules)
 
 
 @pytest.mark.parametrize("rules", [orc.RULES_REF, orc.RULES_STRICT])
