@@ -220,14 +220,12 @@ __device__ inline double np_sum65(const double* a) {
     return __dadd_rn(res, a[64]);
 }
 
-// One self-play ply per live slot (self_play.py:80-101, mcts.py:642-694), thread per game.
+// One self-play ply of slot g by ONE thread (self_play.py:80-101, mcts.py:642-694): pi from the
+// root visit counts, move choice, sample record, make_move.  Returns the square played or 255.
 template <int RULES>
-__global__ void __launch_bounds__(128) play_kernel(EngineView ev, float temperature, uint8_t* __restrict__ out_moves) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= ev.G) return;
-    if (out_moves) out_moves[g] = 255;
+__device__ __noinline__ int play_game(const EngineView& ev, int g, float temperature) {
     Board b{ev.black[g], ev.white[g], ev.side[g], ev.flags[g]};
-    if (!ev.live[g] || is_over(b)) return;
+    if (!ev.live[g] || is_over(b)) return 255;
     const int4* hot = ev.hot + (size_t)g * ev.cap;
     const int4* cold = ev.cold + (size_t)g * ev.cap;
     double pi[65];
@@ -281,23 +279,30 @@ __global__ void __launch_bounds__(128) play_kernel(EngineView ev, float temperat
         // the reference would spin forever here (SURVEY.md 8(a) A7 hazard); park the slot instead
         ev.live[g] = 0;
         atomicAdd(&ev.stats[ST_STALLED], 1ULL);
-        return;
+        return 255;
     }
     atomicAdd(&ev.stats[ST_STEPS], 1ULL);
     ev.black[g] = b.black; ev.white[g] = b.white; ev.side[g] = b.side; ev.flags[g] = b.flags;
     ev.ply[g] = ply + 1;
-    if (out_moves) out_moves[g] = (uint8_t)mv;
     if (is_over(b)) ev.finished[g] = 1;
+    return mv;
 }
 
-// Finished games: z back-fill (self_play.py:117-126), move their samples to the ring, recycle.
-__global__ void __launch_bounds__(kBlock) finalize_kernel(EngineView ev, int recycle) {
-    const int g = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+template <int RULES>
+__global__ void __launch_bounds__(128) play_kernel(EngineView ev, float temperature, uint8_t* __restrict__ out_moves) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= ev.G) return;
+    const int mv = play_game<RULES>(ev, g, temperature);
+    if (out_moves) out_moves[g] = (uint8_t)mv;
+}
+
+// Finished game of slot g, by its warp: z back-fill (self_play.py:117-126), samples to the ring,
+// recycle or park the slot.
+__device__ __forceinline__ void finalize_game(const EngineView& ev, int g, int lane, int recycle) {
     if (!ev.finished[g]) return;
-    const int lane = threadIdx.x & 31;
     const int n = ev.ply[g] < 64 ? ev.ply[g] : 64;
     const int w = (ev.flags[g] & F_WIN_MASK) >> F_WIN_SHIFT;
+    __syncwarp();
     unsigned long long at = 0;
     if (lane == 0) at = atomicAdd(ev.ring_count, (unsigned long long)n);
     at = __shfl_sync(kFull, at, 0);
@@ -326,6 +331,50 @@ __global__ void __launch_bounds__(kBlock) finalize_kernel(EngineView ev, int rec
         } else {
             ev.live[g] = 0;
         }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kBlock) finalize_kernel(EngineView ev, int recycle) {
+    const int g = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (g >= ev.G) return;
+    finalize_game(ev, g, threadIdx.x & 31, recycle);
+}
+
+// Persistent self-play (SelfPlay.generate_games, self_play.py:66-131, with MCTS batch_size 1):
+// every warp keeps playing plies of its slot -- search (S register-resident simulations), move
+// choice + sample record, make_move, game end + recycling -- until the launch-wide budget of
+// game-plies is used up.  Games desynchronise freely, so the launch is work-conserving: no warp
+// waits at a per-ply barrier for the slowest (early-game, long-rollout) positions.
+template <int RULES, int EVAL>
+__global__ void __launch_bounds__(kBlock, 7) selfplay_k1_kernel(EngineView ev, int S, float temperature,
+                                                               unsigned long long budget, int recycle) {
+    const int g = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (g >= ev.G) return;
+    const int lane = threadIdx.x & 31;
+    while (true) {
+        if (!ev.live[g]) break;
+        const Board root{ev.black[g], ev.white[g], ev.side[g], ev.flags[g]};
+        if (is_over(root)) break;
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(ev.ply_counter, 1ULL);
+        t = __shfl_sync(kFull, t, 0);
+        if (t >= budget) break;
+        TreeCtx cx{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, 1, ev.c_puct, lane, 0, 0, 0, 0, 0, 0, make_dir<RULES>(lane & 7)};
+        const uint64_t game_id = ev.game_id[g];
+        const uint64_t search_id = (uint64_t)ev.ply[g];
+        init_root(cx, root.side);
+        const CoopBoard root_c = coop_load(cx.dir, root);
+        for (int sim = 0; sim < S; ++sim) {
+            const uint64_t st = EVAL == RVS_EVAL_ROLLOUT ? stream_seed(ev.seed, game_id, (search_id << 16) | (uint64_t)sim) : 0ULL;
+            simulate_one<EVAL>(cx, root_c, st);
+        }
+        if (lane == 0) ev.n_nodes[g] = cx.n_nodes;
+        flush_stats(ev, cx, 0);
+        __syncwarp();
+        if (lane == 0) play_game<RULES>(ev, g, temperature);
+        __syncwarp();
+        finalize_game(ev, g, lane, recycle);
     }
 }
 
@@ -459,7 +508,7 @@ int rvs_engine_create(const rvs_engine_config* cfg, rvs_engine** out) {
         (rc = dalloc(h, &v.s_side, G * 64)) || (rc = dalloc(h, &v.s_pi, G * 64 * 65)) ||
         (rc = dalloc(h, &v.r_black, (size_t)v.ring_cap)) || (rc = dalloc(h, &v.r_white, (size_t)v.ring_cap)) ||
         (rc = dalloc(h, &v.r_side, (size_t)v.ring_cap)) || (rc = dalloc(h, &v.r_z, (size_t)v.ring_cap)) ||
-        (rc = dalloc(h, &v.r_pi, (size_t)v.ring_cap * 65)) || (rc = dalloc(h, &v.ring_count, 1)) ||
+        (rc = dalloc(h, &v.r_pi, (size_t)v.ring_cap * 65)) || (rc = dalloc(h, &v.ring_count, 1)) || (rc = dalloc(h, &v.ply_counter, 1)) ||
         (rc = dalloc(h, &v.stats, (size_t)ST_COUNT)) || (rc = dalloc(h, &h->visits, G * 65)) || (rc = dalloc(h, &h->moves, G))) {
         rvs_engine_destroy(h);
         return rc;
@@ -674,6 +723,26 @@ int rvs_engine_play(rvs_engine* h, float temperature, int recycle, uint8_t* out_
         RVS_CUDA(cudaMemcpyAsync(out_moves, dm, h->v.G, cudaMemcpyDeviceToHost, s));
         RVS_CUDA(cudaStreamSynchronize(s));
     }
+    h->searching = false;
+    return 0;
+}
+
+int rvs_engine_selfplay(rvs_engine* h, int32_t num_sims, float temperature, int64_t plies, int recycle, void* stream) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (num_sims < 1 || num_sims > h->cfg.max_sims) return fail(-1, "rvs_engine_selfplay: num_sims %d outside [1,%d]", num_sims, h->cfg.max_sims);
+    if (plies < 0 || temperature < 0.0f) return fail(-1, "rvs_engine_selfplay: bad arguments");
+    if (h->cfg.evaluator != RVS_EVAL_E0 && h->cfg.evaluator != RVS_EVAL_ROLLOUT)
+        return fail(-1, "rvs_engine_selfplay: needs a built-in in-kernel evaluator (E0 or ROLLOUT); use search+play for NN");
+    cudaStream_t s = (cudaStream_t)stream;
+    RVS_CUDA(cudaMemsetAsync(h->v.ply_counter, 0, 8, s));
+    const int grid = games_grid(h->v.G);
+    const bool strict = h->cfg.rules == RVS_RULES_STRICT, e0 = h->cfg.evaluator == RVS_EVAL_E0;
+    const unsigned long long budget = (unsigned long long)plies;
+    if (strict && e0) RVS_ENGINE_LAUNCH(h, (selfplay_k1_kernel<RULES_STRICT, RVS_EVAL_E0>), grid, kBlock, 0, s, h->v, num_sims, temperature, budget, recycle);
+    else if (strict) RVS_ENGINE_LAUNCH(h, (selfplay_k1_kernel<RULES_STRICT, RVS_EVAL_ROLLOUT>), grid, kBlock, 0, s, h->v, num_sims, temperature, budget, recycle);
+    else if (e0) RVS_ENGINE_LAUNCH(h, (selfplay_k1_kernel<RULES_REF, RVS_EVAL_E0>), grid, kBlock, 0, s, h->v, num_sims, temperature, budget, recycle);
+    else RVS_ENGINE_LAUNCH(h, (selfplay_k1_kernel<RULES_REF, RVS_EVAL_ROLLOUT>), grid, kBlock, 0, s, h->v, num_sims, temperature, budget, recycle);
     h->searching = false;
     return 0;
 }

@@ -29,6 +29,7 @@ struct EngineView {
     int64_t ring_cap;
     uint64_t* r_black; uint64_t* r_white; uint8_t* r_side; int8_t* r_z; float* r_pi;
     unsigned long long* ring_count;
+    unsigned long long* ply_counter;  // game-plies claimed in the current persistent self-play launch
     unsigned long long* stats;  // [ST_COUNT]
 };
 

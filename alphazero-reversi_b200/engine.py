@@ -101,6 +101,11 @@ class Engine:
                                         None if mv is None else mv.ctypes.data, L.MEM_HOST, self._s(stream)))
         return mv
 
+    def selfplay(self, num_sims, plies, temperature=1.0, recycle=True, stream=None):
+        """persistent self-play launch: `plies` game-plies in total over all slots (wave 1)"""
+        L.check(L.lib().rvs_engine_selfplay(self._h, num_sims, float(temperature), int(plies), 1 if recycle else 0,
+                                            self._s(stream)))
+
     def drain_samples(self, capacity=None, device=None, stream=None):
         """completed-game samples (states [n,3,8,8] f32, pi [n,65] f32, z [n] f32)"""
         cap = capacity if capacity is not None else 64 * self.n_games

@@ -148,9 +148,15 @@ def run_ours(args):
     wave = args.wave
     eng = az.Engine(N_GAMES, N_SIMS, max(wave, 64), evaluator=az.EVAL_ROLLOUT, c_puct=1.0, seed=1000 + rank, device=local)
 
+    persistent = wave == 1 and not args.lockstep
+    ppl = max(1, args.steps_per_launch)
+
     def step(e):
-        e.search(N_SIMS, wave, stream=stream)
-        e.play(1.0, recycle=True, stream=stream)
+        if persistent:  # one work-conserving launch = one step = N_GAMES game-plies
+            e.selfplay(N_SIMS, plies=N_GAMES, temperature=1.0, recycle=True, stream=stream)
+        else:
+            e.search(N_SIMS, wave, stream=stream)
+            e.play(1.0, recycle=True, stream=stream)
 
     # steady state of a self-play farm: games are spread uniformly over all phases.  Start every
     # slot from a random-playout position cut at a random ply (the slots then recycle naturally);
@@ -171,11 +177,22 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for i in range(args.steps):
-        ks[i][0].record()
-        eng.search(N_SIMS, wave, stream=stream)
-        ks[i][1].record()
-        eng.play(1.0, recycle=True, stream=stream)
+    if persistent:
+        # K steps = K x N_GAMES game-plies, issued as persistent launches of `ppl` steps each
+        done = 0
+        while done < args.steps:
+            n = min(ppl, args.steps - done)
+            ks[done][0].record()
+            eng.selfplay(N_SIMS, plies=N_GAMES * n, temperature=1.0, recycle=True, stream=stream)
+            ks[done][1].record()
+            done += n
+        ks = [ks[i] for i in range(0, args.steps, ppl)]
+    else:
+        for i in range(args.steps):
+            ks[i][0].record()
+            eng.search(N_SIMS, wave, stream=stream)
+            ks[i][1].record()
+            eng.play(1.0, recycle=True, stream=stream)
     e1.record()
     torch.cuda.synchronize()
     barrier()
@@ -183,8 +200,9 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     s1 = eng.stats()
     launches = lib.rvs_launch_count() - l0
-    kernel_ms = sum(a.elapsed_time(b) for a, b in ks) / args.steps
+    kernel_ms = sum(a.elapsed_time(b) for a, b in ks) / len(ks)  # average launch duration of the dominant kernel
     d = {k: s1[k] - s0[k] for k in s1}
+    d["n_search_launches"] = len(ks)
     if s1["overflow"]:
         raise SystemExit(f"engine error counters non-zero: {s1}")
 
@@ -255,6 +273,7 @@ def run_ours(args):
             "config": {"workload": "configs[1]: pure MCTS, uniform prior + uniform-random rollout value, 100 sims/move, "
                                    "4096 concurrent games per GPU, REF rules, self-play with recycling",
                        "games_per_gpu": N_GAMES, "sims_per_move": N_SIMS, "wave": wave, "c_puct": 1.0, "temperature": 1.0,
+                       "schedule": ("persistent work-conserving self-play launches" if persistent else "lockstep search+play per ply"),
                        "parallelism": f"games sharded x{world}, no data-path collective",
                        "cache": "node pools 446 MB per GPU (> 126 MB L2), rewritten every step"},
             "board_steps_per_sec": bsteps / (ms * 1e-3),
@@ -264,8 +283,10 @@ def run_ours(args):
                     "d2h_bytes_per_step": N_GAMES * 65 * 4, "steps": e2e_steps},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": args.traffic, "peak_source": which, "kernel": "search_fused_kernel<REF,ROLLOUT>",
-                         "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / (ms / args.steps),
+                         "traffic": args.traffic, "peak_source": which, "kernel": ("selfplay_k1_kernel<REF,ROLLOUT>" if persistent else
+                                    ("search_k1_kernel<REF,ROLLOUT>" if wave == 1 else "search_fused_kernel<REF,ROLLOUT>")),
+                         "steps_per_launch": ppl if persistent else 1,
+                         "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms * len(ks) / ms,
                          "note": "latency/issue-bound integer kernel: rollouts are register resident; see DESIGN.md"},
             "clocks": clocks,
         }
@@ -280,8 +301,7 @@ def algorithmic_bytes(d):
     """algorithmic HBM bytes of ONE search launch (this rank): the engine counts 32 B for every
     node row the search must touch (children scanned, path rows read+written at backup, rows
     created) -- DESIGN.md 'K2 roofline'; rollouts are register resident and count 0 B."""
-    steps = max(1, d["launches"] // 3)  # 3 launches per step: search, play, finalize
-    return d["tree_bytes"] / steps
+    return d["tree_bytes"] / max(1, d["n_search_launches"])
 
 
 def cpu_baseline(wave, threads, budget_s):
@@ -380,6 +400,9 @@ def main():
     ap.add_argument("--presteps", type=int, default=5, help="untimed plies that spread games over all phases")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--wave", type=int, default=1, help="MCTS batch_size per game (reference default 64)")
+    ap.add_argument("--steps-per-launch", type=int, default=10,
+                    help="persistent self-play: steps (x4096 game-plies) per launch")
+    ap.add_argument("--lockstep", action="store_true", help="wave 1 through search+play launches per ply")
     ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per launch of the search kernel")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

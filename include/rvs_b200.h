@@ -163,6 +163,14 @@ int rvs_engine_root_visits(rvs_engine *h, int32_t *out, int32_t n, int mem, void
 int rvs_engine_play(rvs_engine *h, float temperature, int recycle, uint8_t *out_moves, int mem,
                     void *stream);
 
+/* Persistent self-play (SelfPlay.generate_games, self_play.py:66-131, with MCTS batch_size 1 and a
+ * built-in evaluator): ONE launch in which every slot keeps playing plies -- search, move choice,
+ * sample record, make_move, game end, recycling -- until `plies` game-plies have been played in
+ * total.  Work conserving: slots do not wait for each other between plies.  Per-game results are
+ * identical to repeating rvs_engine_search(num_sims, 1) + rvs_engine_play. */
+int rvs_engine_selfplay(rvs_engine *h, int32_t num_sims, float temperature, int64_t plies,
+                        int recycle, void *stream);
+
 /* completed-game samples in the trainer's format (self_play.py:72-77, pipeline.py:226-228):
  * states [cap,3,8,8] f32, pi [cap,65] f32, z [cap] f32.  Returns up to `capacity` samples
  * and removes them from the ring. */

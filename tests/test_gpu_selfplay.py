@@ -84,3 +84,45 @@ def test_batched_selfplay_api_with_recycling(az):
     # pi mass only on legal squares (plane 2)
     legal = data["states"][:, 2].reshape(-1, 64) > 0.5
     assert not (data["action_probs"][:, :64][~legal] > 0).any()
+
+
+@pytest.mark.parametrize("evaluator,S,T", [(1, 100, 1.0), (0, 60, 1.0), (1, 40, 0.0)])
+def test_persistent_selfplay_kernel_vs_oracle(az, evaluator, S, T):
+    """rvs_engine_selfplay (one work-conserving launch, games desynchronised) must emit exactly the
+    samples of the lockstep path / the oracle: per-game RNG streams do not depend on scheduling"""
+    n = 64
+    eng = az.Engine(n, S, 1, evaluator=evaluator, seed=321)
+    eng.selfplay(S, plies=n * 64, temperature=T, recycle=False)
+    st = eng.stats()
+    assert st["overflow"] == 0 and st["games_finished"] == n
+    states, pi, z = eng.drain_samples()
+    got = {}
+    i = 0
+    while i < len(states):
+        j = i + 1
+        while j < len(states) and not (states[j][0].sum() == 2 and states[j][1].sum() == 2):
+            j += 1
+        got[states[i:j].tobytes()] = (pi[i:j], z[i:j])
+        i = j
+    total = 0
+    for g in range(n):
+        samples, win = orc.self_play_game(S, 1, evaluator=evaluator, seed=321, game_id=g, temperature=T)
+        total += len(samples)
+        key = np.array([orc.planes(s.black, s.white, s.side) for s in samples], dtype=np.float32).tobytes()
+        assert key in got, g
+        gpi, gz = got[key]
+        assert np.array_equal(gpi, np.array([orc.action_probs(np.array(s.visits[:]), T).astype(np.float32) for s in samples]))
+        assert np.array_equal(gz, np.array([s.z for s in samples], dtype=np.float32))
+    assert len(states) == total == st["samples"]
+
+
+def test_persistent_selfplay_budget_and_recycling(az):
+    n, S = 128, 30
+    eng = az.Engine(n, S, 1, evaluator=az.EVAL_ROLLOUT, seed=5)
+    eng.selfplay(S, plies=n * 100, temperature=1.0, recycle=True)
+    st = eng.stats()
+    assert st["overflow"] == 0
+    assert st["sims"] == n * 100 * S            # exactly the budgeted game-plies were searched
+    assert st["games_finished"] >= n            # ~60 plies per game: every slot recycled at least once
+    states, pi, z = eng.drain_samples()
+    assert len(states) == st["samples"] and np.allclose(pi.sum(axis=1), 1.0, atol=1e-5)
