@@ -13,6 +13,14 @@ from .game import Board, ReversiGame
 from .mcts import MCTS, UniformDiscDiff, UniformRollout
 from .self_play import SelfPlay
 
+
+def __getattr__(name):  # torch-dependent members are imported lazily
+    if name in ("AlphaZeroNetwork", "RvsNetwork", "pack_state_dict", "network"):
+        import importlib
+        network = importlib.import_module(__name__ + ".network")
+        return network if name == "network" else getattr(network, name)
+    raise AttributeError(name)
+
 __all__ = ["Board", "ReversiGame", "MCTS", "SelfPlay", "Engine", "board_ops", "UniformDiscDiff",
            "UniformRollout", "RvsError", "RULES_REF", "RULES_STRICT", "EVAL_E0", "EVAL_ROLLOUT",
            "EVAL_EXTERNAL", "EVAL_NN"]

@@ -1,18 +1,466 @@
-// rvs_net.cu -- K4: AlphaZeroNetwork inference (placeholder until the tcgen05 tower lands).
+// rvs_net.cu -- K4: AlphaZeroNetwork inference (reference: src/model/network.py:33-117) and the
+// NN-evaluated lockstep search (MCTS._process_batch with model.predict, src/mcts/mcts.py:544-623).
+//
+// Data layout: activations NHWC bf16 [B][8][8][C]; conv weights BN-folded bf16 [tap][Cout][Cin]
+// (tap = ky*3+kx, K-major for both GEMM operands); biases and the two small heads in f32.
+//   conv_tower_*     3x3 convolutions C->C: implicit GEMM on tcgen05 (rvs_conv_tc.cuh)
+//   conv3x3_direct   first layer (3->C, K = 27) and bring-up/debug path: CUDA cores
+//   heads_kernel     policy 1x1 conv + FC + softmax, value 1x1 conv + FC + FC + tanh (fp32)
 #include "rvs_engine.cuh"
+
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include "rvs_conv_tc.cuh"
+
+namespace rvs {
+
+struct ConvLayer {
+    __nv_bfloat16* w = nullptr;  // [9][Cout][Cin]
+    float* bias = nullptr;       // [Cout]
+    int cin = 0, cout = 0;
+    ConvTcPlan tc;               // tensor-core plan (TMA descriptors), valid when cin == cout
+};
+
+struct NetState {
+    int blocks = 0, C = 0;
+    int64_t max_batch = 0;
+    ConvLayer conv0;
+    ConvLayer* tower = nullptr;  // 2*blocks layers
+    // heads (BN folded), f32
+    float *pw = nullptr, *pb = nullptr;      // policy conv [2][C], bias [2]
+    float *pfw = nullptr, *pfb = nullptr;    // policy fc [65][128], [65]
+    float *vw = nullptr, *vb = nullptr;      // value conv [C], bias [1]
+    float *v1w = nullptr, *v1b = nullptr;    // fc1 [256][64], [256]
+    float *v2w = nullptr, *v2b = nullptr;    // fc2 [256], [1]
+    // activations
+    __nv_bfloat16 *x0 = nullptr, *a = nullptr, *b = nullptr, *c = nullptr;  // x0 [B][64][16]; a,b,c [B][64][C]
+    float *probs = nullptr, *logits = nullptr, *values = nullptr;          // [B][65], [B][65], [B]
+    float* flat = nullptr;  // staging of the raw state_dict
+    bool loaded = false;
+    bool force_direct = false;  // RVS_NET_DIRECT=1: run the tower on the CUDA-core kernel (debug)
+    void* allocs[64];
+    int n_allocs = 0;
+};
+
+namespace {
+
+template <typename T>
+int nalloc(NetState* n, T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) > 0 ? count * sizeof(T) : 16);
+    if (e != cudaSuccess) return fail(-100 - (int)e, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    cudaMemset(q, 0, count * sizeof(T));
+    n->allocs[n->n_allocs++] = q;
+    *p = (T*)q;
+    return 0;
+}
+
+// ---- weight folding (eval-mode BatchNorm, eps 1e-5, network.py:19-21,48) ---------------------
+// w [Cout][Cin][3][3] f32 + bn{gamma,beta,mean,var}[Cout] -> wf [9][Cout][CinPad] bf16, bias[Cout]
+__global__ void fold_conv3x3_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ mean,
+                                    const float* __restrict__ var, int cout, int cin, int cin_pad,
+                                    __nv_bfloat16* __restrict__ wf, float* __restrict__ bias) {
+    const int total = 9 * cout * cin_pad;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int ci = t % cin_pad, co = (t / cin_pad) % cout, tap = t / (cin_pad * cout);
+        const float scale = gamma[co] / sqrtf(var[co] + 1e-5f);
+        float v = 0.f;
+        if (ci < cin) v = w[((size_t)co * cin + ci) * 9 + tap] * scale;
+        wf[t] = __float2bfloat16(v);
+        if (tap == 0 && ci == 0) bias[co] = beta[co] - mean[co] * scale;
+    }
+}
+// 1x1 conv [Cout][Cin] + bn -> f32 folded
+__global__ void fold_conv1x1_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ mean,
+                                    const float* __restrict__ var, int cout, int cin, float* __restrict__ wf,
+                                    float* __restrict__ bias) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < cout * cin; t += gridDim.x * blockDim.x) {
+        const int co = t / cin;
+        const float scale = gamma[co] / sqrtf(var[co] + 1e-5f);
+        wf[t] = w[t] * scale;
+        if (t % cin == 0) bias[co] = beta[co] - mean[co] * scale;
+    }
+}
+
+// ---- direct 3x3 convolution on CUDA cores ----------------------------------------------------
+// one CTA per board: the board's input (with a zero halo) lives in shared memory; thread t owns
+// output channel (t % COUT_T) and a group of pixels; weights stream from L2 as 16-byte vectors.
+// out = relu(conv(in) + bias [+ residual])
+template <int CIN>
+__global__ void __launch_bounds__(256) conv3x3_direct_kernel(const __nv_bfloat16* __restrict__ in,
+                                                              const __nv_bfloat16* __restrict__ w,
+                                                              const float* __restrict__ bias,
+                                                              const __nv_bfloat16* __restrict__ residual,
+                                                              __nv_bfloat16* __restrict__ out, int cout, int relu) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // [10][10][CIN]
+    const int board = blockIdx.x;
+    const uint4* gin = reinterpret_cast<const uint4*>(in + (size_t)board * 64 * CIN);
+    constexpr int V = CIN / 8;  // uint4 per pixel
+    for (int i = threadIdx.x; i < 100 * V; i += blockDim.x) {
+        const int p = i / V, v = i % V;
+        const int y = p / 10 - 1, x = p % 10 - 1;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (y >= 0 && y < 8 && x >= 0 && x < 8) val = gin[(y * 8 + x) * V + v];
+        reinterpret_cast<uint4*>(sx)[i] = val;
+    }
+    __syncthreads();
+    const int groups = blockDim.x / cout;  // cout in {64,128,256} -> 4, 2 or 1 pixel groups
+    const int co = threadIdx.x % cout, grp = threadIdx.x / cout;
+    const int ppg = 64 / groups;           // pixels per group
+    {
+        for (int p0 = grp * ppg; p0 < (grp + 1) * ppg; p0 += 16) {
+            float acc[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+            for (int tap = 0; tap < 9; ++tap) {
+                const int dy = tap / 3, dx = tap % 3;  // halo-shifted: input (y+dy, x+dx) in padded coords
+                const uint4* wrow = reinterpret_cast<const uint4*>(w + ((size_t)tap * cout + co) * CIN);
+                for (int v = 0; v < V; ++v) {
+                    const uint4 wv = wrow[v];
+                    const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wv);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int p = p0 + i, y = p >> 3, x = p & 7;
+                        const uint4 xv = reinterpret_cast<const uint4*>(sx)[((y + dy) * 10 + (x + dx)) * V + v];
+                        const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(&xv);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 a = __bfloat1622float2(x2[q]), b = __bfloat1622float2(w2[q]);
+                            acc[i] = fmaf(a.x, b.x, acc[i]);
+                            acc[i] = fmaf(a.y, b.y, acc[i]);
+                        }
+                    }
+                }
+            }
+            const float bv = bias[co];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const size_t o = ((size_t)board * 64 + p0 + i) * cout + co;
+                float r = acc[i] + bv;
+                if (residual) r += __bfloat162float(residual[o]);
+                if (relu) r = fmaxf(r, 0.f);
+                out[o] = __float2bfloat16(r);
+            }
+        }
+    }
+}
+
+// ---- heads (network.py:103-117) + softmax (mcts.py:596), one CTA (256 threads) per board ------
+__global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restrict__ x, int C,
+                                                     const float* __restrict__ pw, const float* __restrict__ pb,
+                                                     const float* __restrict__ pfw, const float* __restrict__ pfb,
+                                                     const float* __restrict__ vw, const float* __restrict__ vb,
+                                                     const float* __restrict__ v1w, const float* __restrict__ v1b,
+                                                     const float* __restrict__ v2w, const float* __restrict__ v2b,
+                                                     float* __restrict__ logits, float* __restrict__ probs,
+                                                     float* __restrict__ values) {
+    __shared__ float feat[192];   // [0,128): policy planes channel-major (ch*64+px); [128,192): value plane
+    __shared__ float hid[256];
+    __shared__ float lg[65];
+    __shared__ float red[2];
+    const int board = blockIdx.x, t = threadIdx.x;
+    const __nv_bfloat16* xb = x + (size_t)board * 64 * C;
+    if (t < 192) {  // 1x1 convs + BN + ReLU
+        const int px = t & 63, j = t >> 6;  // j: 0,1 policy channels; 2 value channel
+        const float* wv = j < 2 ? pw + j * C : vw;
+        float acc = 0.f;
+        const __nv_bfloat162* xr = reinterpret_cast<const __nv_bfloat162*>(xb + (size_t)px * C);
+        for (int c = 0; c < C / 2; ++c) {
+            const float2 a = __bfloat1622float2(xr[c]);
+            acc = fmaf(a.x, wv[2 * c], acc);
+            acc = fmaf(a.y, wv[2 * c + 1], acc);
+        }
+        acc += j < 2 ? pb[j] : vb[0];
+        feat[j * 64 + px] = fmaxf(acc, 0.f);
+    }
+    __syncthreads();
+    if (t < 65) {  // policy_fc: view(batch,-1) is channel-major (network.py:107)
+        float acc = pfb[t];
+        const float* wr = pfw + t * 128;
+        for (int i = 0; i < 128; ++i) acc = fmaf(wr[i], feat[i], acc);
+        lg[t] = acc;
+        if (logits) logits[(size_t)board * 65 + t] = acc;
+    }
+    {  // value_fc1 + ReLU
+        float acc = v1b[t];
+        const float* wr = v1w + t * 64;
+        for (int i = 0; i < 64; ++i) acc = fmaf(wr[i], feat[128 + i], acc);
+        hid[t] = fmaxf(acc, 0.f);
+    }
+    __syncthreads();
+    if (t < 32) {  // warp 0: softmax over the 65 logits; value_fc2 + tanh
+        float m = fmaxf(lg[t], lg[t + 32]);
+        if (t == 0) m = fmaxf(m, lg[64]);
+        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const float e0 = expf(lg[t] - m), e1 = expf(lg[t + 32] - m), e2 = t == 0 ? expf(lg[64] - m) : 0.f;
+        float s = e0 + e1 + e2;
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (probs) {
+            float* pr = probs + (size_t)board * 65;
+            pr[t] = e0 / s;
+            pr[t + 32] = e1 / s;
+            if (t == 0) pr[64] = e2 / s;
+        }
+        float acc = 0.f;
+        for (int i = t; i < 256; i += 32) acc = fmaf(v2w[i], hid[i], acc);
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (t == 0) values[board] = tanhf(acc + v2b[0]);
+    }
+    (void)red;
+}
+
+// K3 fused for the engine: canonical planes of the selected leaves straight into the network's
+// bf16 NHWC input buffer (16 channels, 3 used); slots that need no evaluation are zeroed.
+__global__ void __launch_bounds__(256) encode_leaves_kernel(EngineView ev, int k, uint4* __restrict__ out) {
+    const int64_t total = (int64_t)ev.G * k * 64;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t slot = t >> 6;
+        const int sq = (int)(t & 63);
+        const int g = (int)(slot / k), j = (int)(slot - (int64_t)g * k);
+        const size_t o = (size_t)g * ev.kmax + j;
+        const uint64_t lm = ev.w_node[o] < 0 ? 0ULL : ev.w_lm[o];
+        uint32_t c01 = 0, c2 = 0;
+        if (lm) {
+            const bool blk = (ev.w_sf[o] & 0xFF) == 1;
+            const uint64_t P = blk ? ev.w_black[o] : ev.w_white[o], O = blk ? ev.w_white[o] : ev.w_black[o];
+            const uint32_t one = 0x3F80u;
+            c01 = (((P >> sq) & 1) ? one : 0u) | ((((O >> sq) & 1) ? one : 0u) << 16);
+            c2 = ((lm >> sq) & 1) ? one : 0u;
+        }
+        out[2 * t] = make_uint4(c01, c2, 0u, 0u);
+        out[2 * t + 1] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+template <int RULES>
+__global__ void __launch_bounds__(256) encode_positions_kernel(const uint64_t* __restrict__ black,
+                                                                const uint64_t* __restrict__ white,
+                                                                const uint8_t* __restrict__ side, int64_t n,
+                                                                uint4* __restrict__ out) {
+    const int64_t total = n * 64;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t >> 6;
+        const int sq = (int)(t & 63);
+        const bool blk = side[i] == 1;
+        const uint64_t P = blk ? black[i] : white[i], O = blk ? white[i] : black[i];
+        const uint64_t L = legal_moves<RULES>(P, O);
+        const uint32_t one = 0x3F80u;
+        out[2 * t] = make_uint4((((P >> sq) & 1) ? one : 0u) | ((((O >> sq) & 1) ? one : 0u) << 16),
+                                ((L >> sq) & 1) ? one : 0u, 0u, 0u);
+        out[2 * t + 1] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+int launch_direct(const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
+                  int64_t B, int relu, cudaStream_t s) {
+    const int threads = 256;
+    if (L.cout > 256 || 256 % L.cout != 0) return fail(-6, "direct conv: unsupported cout %d", L.cout);
+    if (L.cin == 16) {
+        RVS_LAUNCH(conv3x3_direct_kernel<16>, (int)B, threads, 100 * 16 * 2, s, in, L.w, L.bias, residual, out, L.cout, relu);
+    } else if (L.cin == 64) {
+        RVS_LAUNCH(conv3x3_direct_kernel<64>, (int)B, threads, 100 * 64 * 2, s, in, L.w, L.bias, residual, out, L.cout, relu);
+    } else if (L.cin == 128) {
+        RVS_LAUNCH(conv3x3_direct_kernel<128>, (int)B, threads, 100 * 128 * 2, s, in, L.w, L.bias, residual, out, L.cout, relu);
+    } else if (L.cin == 256) {
+        static bool attr = false;
+        if (!attr) {
+            RVS_CUDA(cudaFuncSetAttribute(conv3x3_direct_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 256 * 2));
+            attr = true;
+        }
+        RVS_LAUNCH(conv3x3_direct_kernel<256>, (int)B, threads, 100 * 256 * 2, s, in, L.w, L.bias, residual, out, L.cout, relu);
+    } else {
+        return fail(-6, "direct conv: unsupported cin %d", L.cin);
+    }
+    return 0;
+}
+
+}  // namespace
+
+// forward pass on B boards whose bf16 planes are already in n->x0; results in n->probs/logits/values
+int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s) {
+    NetState* n = h->net;
+    if (!n || !n->loaded) return fail(-7, "network weights not loaded: call rvs_engine_load_weights first");
+    if (B > n->max_batch) return fail(-7, "network batch %lld exceeds capacity %lld", (long long)B, (long long)n->max_batch);
+    if (B == 0) return 0;
+    int rc;
+    if ((rc = launch_direct(n->conv0, n->x0, nullptr, n->a, B, 1, s))) return rc;  // network.py:97
+    __nv_bfloat16 *x = n->a, *t = n->b, *y = n->c;
+    for (int i = 0; i < n->blocks; ++i) {  // ResBlock (network.py:23-28)
+        const ConvLayer& c1 = n->tower[2 * i];
+        const ConvLayer& c2 = n->tower[2 * i + 1];
+        if (n->force_direct || !c1.tc.valid) {
+            if ((rc = launch_direct(c1, x, nullptr, t, B, 1, s))) return rc;
+            if ((rc = launch_direct(c2, t, x, y, B, 1, s))) return rc;
+        } else {
+            if ((rc = conv_tc_launch(c1.tc, x, nullptr, t, c1.bias, B, s))) return rc;
+            if ((rc = conv_tc_launch(c2.tc, t, x, y, c2.bias, B, s))) return rc;
+            h->launches += 0;
+        }
+        __nv_bfloat16* tmp = x; x = y; y = tmp;
+    }
+    RVS_LAUNCH(heads_kernel, (int)B, 256, 0, s, x, n->C, n->pw, n->pb, n->pfw, n->pfb, n->vw, n->vb, n->v1w, n->v1b,
+               n->v2w, n->v2b, want_logits ? n->logits : nullptr, n->probs, n->values);
+    return 0;
+}
+
+int net_create(rvs_engine* h) {
+    if (h->net) return 0;
+    const int blocks = h->cfg.net_blocks, C = h->cfg.net_filters;
+    if (blocks < 1 || blocks > 40 || (C != 64 && C != 128 && C != 256))
+        return fail(-1, "network: net_blocks in [1,40] and net_filters in {64,128,256} required (got %d, %d)", blocks, C);
+    NetState* n = new NetState();
+    h->net = n;
+    n->blocks = blocks;
+    n->C = C;
+    n->max_batch = (int64_t)h->v.G * h->cfg.max_wave;
+    n->force_direct = getenv("RVS_NET_DIRECT") && atoi(getenv("RVS_NET_DIRECT")) != 0;
+    const size_t B = (size_t)n->max_batch;
+    int rc = 0;
+    n->tower = new ConvLayer[2 * blocks];
+    if ((rc = nalloc(n, &n->conv0.w, (size_t)9 * C * 16)) || (rc = nalloc(n, &n->conv0.bias, (size_t)C))) return rc;
+    n->conv0.cin = 16; n->conv0.cout = C;
+    // one contiguous slab for the tower weights so that a single TMA descriptor family covers it
+    for (int i = 0; i < 2 * blocks; ++i) {
+        ConvLayer& L = n->tower[i];
+        L.cin = C; L.cout = C;
+        if ((rc = nalloc(n, &L.w, (size_t)9 * C * C)) || (rc = nalloc(n, &L.bias, (size_t)C))) return rc;
+    }
+    if ((rc = nalloc(n, &n->pw, (size_t)2 * C)) || (rc = nalloc(n, &n->pb, 2)) || (rc = nalloc(n, &n->pfw, 65 * 128)) ||
+        (rc = nalloc(n, &n->pfb, 65)) || (rc = nalloc(n, &n->vw, (size_t)C)) || (rc = nalloc(n, &n->vb, 1)) ||
+        (rc = nalloc(n, &n->v1w, 256 * 64)) || (rc = nalloc(n, &n->v1b, 256)) || (rc = nalloc(n, &n->v2w, 256)) ||
+        (rc = nalloc(n, &n->v2b, 1)) || (rc = nalloc(n, &n->x0, B * 64 * 16)) || (rc = nalloc(n, &n->a, B * 64 * C)) ||
+        (rc = nalloc(n, &n->b, B * 64 * C)) || (rc = nalloc(n, &n->c, B * 64 * C)) || (rc = nalloc(n, &n->probs, B * 65)) ||
+        (rc = nalloc(n, &n->logits, B * 65)) || (rc = nalloc(n, &n->values, B)))
+        return rc;
+    return 0;
+}
+
+int64_t net_param_floats(int blocks, int C) {
+    int64_t n = (int64_t)C * 27 + 4 * C;
+    n += (int64_t)blocks * 2 * ((int64_t)C * C * 9 + 4 * C);
+    n += 2 * C + 8 + 65 * 128 + 65;
+    n += C + 4 + 256 * 64 + 256 + 256 + 1;
+    return n;
+}
+
+}  // namespace rvs
 
 using namespace rvs;
 
-int rvs_net_search(rvs_engine*, int32_t, int32_t, cudaStream_t) {
-    return fail(-5, "RVS_EVAL_NN: network kernels are not built into this library yet");
+void rvs_net_destroy(rvs::NetState* n) {
+    if (!n) return;
+    for (int i = 0; i < n->n_allocs; ++i) cudaFree(n->allocs[i]);
+    if (n->flat) cudaFree(n->flat);
+    for (int i = 0; i < 2 * n->blocks; ++i) conv_tc_destroy(n->tower[i].tc);
+    delete[] n->tower;
+    delete n;
 }
-void rvs_net_destroy(rvs::NetState*) {}
+
+// MCTS.search with the built-in network: per wave  select -> encode (K3) -> tower + heads (K4)
+// -> expand/backup with the softmax priors (K2).  No host round trip inside the loop.
+int rvs_net_search(rvs_engine* h, int32_t num_sims, int32_t wave, cudaStream_t s) {
+    int rc;
+    if ((rc = net_create(h))) return rc;
+    if (!h->net->loaded) return fail(-7, "RVS_EVAL_NN: call rvs_engine_load_weights before rvs_engine_search");
+    if ((rc = rvs_engine_begin_search(h, s))) return rc;
+    for (int start = 0; start < num_sims; start += wave) {
+        const int k = num_sims - start < wave ? num_sims - start : wave;
+        if ((rc = rvs_engine_select(h, k, s))) return rc;
+        const int64_t B = (int64_t)h->v.G * k;
+        RVS_LAUNCH(encode_leaves_kernel, grid_for(B * 64, 256), 256, 0, s, h->v, k, (uint4*)h->net->x0);
+        h->launches++;
+        if ((rc = net_forward(h, B, false, s))) return rc;
+        if ((rc = rvs_engine_process(h, h->net->probs, h->net->values, RVS_MEM_DEVICE, s))) return rc;
+    }
+    h->searching = false;
+    return 0;
+}
 
 extern "C" {
-int rvs_engine_load_weights(rvs_engine*, const float*, int64_t, int, void*) {
-    return fail(-5, "rvs_engine_load_weights: network kernels are not built into this library yet");
+
+int rvs_engine_load_weights(rvs_engine* h, const float* flat, int64_t n_floats, int mem, void* stream) {
+    if (!h) return fail(-1, "null engine handle");
+    RVS_CUDA(cudaSetDevice(h->cfg.device));
+    int rc;
+    if ((rc = net_create(h))) return rc;
+    NetState* n = h->net;
+    const int C = n->C, blocks = n->blocks;
+    const int64_t need = net_param_floats(blocks, C);
+    if (!flat || n_floats != need)
+        return fail(-1, "rvs_engine_load_weights: expected %lld floats for %dx%d, got %lld", (long long)need, blocks, C, (long long)n_floats);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!n->flat) RVS_CUDA(cudaMalloc(&n->flat, need * sizeof(float)));
+    RVS_CUDA(cudaMemcpyAsync(n->flat, flat, need * sizeof(float), mem == RVS_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+    const float* p = n->flat;
+    auto take = [&](int64_t k) { const float* q = p; p += k; return q; };
+    {
+        const float* w = take((int64_t)C * 27);
+        const float *g = take(C), *b = take(C), *m = take(C), *v = take(C);
+        RVS_LAUNCH(fold_conv3x3_kernel, 64, 256, 0, s, w, g, b, m, v, C, 3, 16, n->conv0.w, n->conv0.bias);
+    }
+    for (int i = 0; i < 2 * blocks; ++i) {
+        const float* w = take((int64_t)C * C * 9);
+        const float *g = take(C), *b = take(C), *m = take(C), *v = take(C);
+        RVS_LAUNCH(fold_conv3x3_kernel, 592, 256, 0, s, w, g, b, m, v, C, C, C, n->tower[i].w, n->tower[i].bias);
+    }
+    {
+        const float* w = take(2 * C);
+        const float *g = take(2), *b = take(2), *m = take(2), *v = take(2);
+        RVS_LAUNCH(fold_conv1x1_kernel, 4, 128, 0, s, w, g, b, m, v, 2, C, n->pw, n->pb);
+        RVS_CUDA(cudaMemcpyAsync(n->pfw, take(65 * 128), 65 * 128 * 4, cudaMemcpyDeviceToDevice, s));
+        RVS_CUDA(cudaMemcpyAsync(n->pfb, take(65), 65 * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    {
+        const float* w = take(C);
+        const float *g = take(1), *b = take(1), *m = take(1), *v = take(1);
+        RVS_LAUNCH(fold_conv1x1_kernel, 2, 128, 0, s, w, g, b, m, v, 1, C, n->vw, n->vb);
+        RVS_CUDA(cudaMemcpyAsync(n->v1w, take(256 * 64), 256 * 64 * 4, cudaMemcpyDeviceToDevice, s));
+        RVS_CUDA(cudaMemcpyAsync(n->v1b, take(256), 256 * 4, cudaMemcpyDeviceToDevice, s));
+        RVS_CUDA(cudaMemcpyAsync(n->v2w, take(256), 256 * 4, cudaMemcpyDeviceToDevice, s));
+        RVS_CUDA(cudaMemcpyAsync(n->v2b, take(1), 4, cudaMemcpyDeviceToDevice, s));
+    }
+    for (int i = 0; i < 2 * blocks; ++i) {
+        if ((rc = conv_tc_plan(n->tower[i].tc, n->tower[i].w, C, n->max_batch))) return rc;
+    }
+    RVS_CUDA(cudaStreamSynchronize(s));
+    n->loaded = true;
+    return 0;
 }
-int rvs_engine_predict(rvs_engine*, const uint64_t*, const uint64_t*, const uint8_t*, int64_t, float*, float*, int, void*) {
-    return fail(-5, "rvs_engine_predict: network kernels are not built into this library yet");
+
+int rvs_engine_predict(rvs_engine* h, const uint64_t* black, const uint64_t* white, const uint8_t* side, int64_t n_pos,
+                       float* out_logits, float* out_value, int mem, void* stream) {
+    if (!h) return fail(-1, "null engine handle");
+    RVS_CUDA(cudaSetDevice(h->cfg.device));
+    if (!h->net || !h->net->loaded) return fail(-7, "rvs_engine_predict: weights not loaded");
+    if (n_pos < 0 || (n_pos > 0 && (!black || !white || !side || !out_logits || !out_value))) return fail(-1, "rvs_engine_predict: bad arguments");
+    NetState* n = h->net;
+    cudaStream_t s = (cudaStream_t)stream;
+    std::unique_lock<std::mutex> lk(g_stage_mu, std::defer_lock);
+    if (mem == RVS_MEM_HOST) lk.lock();
+    for (int64_t off = 0; off < n_pos; off += n->max_batch) {
+        const int64_t B = n_pos - off < n->max_batch ? n_pos - off : n->max_batch;
+        Arg ab, aw, as;
+        int rc;
+        if ((rc = arg_in(ab, black + off, B * 8, mem, 0, s)) || (rc = arg_in(aw, white + off, B * 8, mem, 1, s)) ||
+            (rc = arg_in(as, side + off, B, mem, 2, s)))
+            return rc;
+        if (h->cfg.rules == RVS_RULES_STRICT)
+            RVS_LAUNCH(encode_positions_kernel<RULES_STRICT>, grid_for(B * 64, 256), 256, 0, s, (const uint64_t*)ab.dev,
+                       (const uint64_t*)aw.dev, (const uint8_t*)as.dev, B, (uint4*)n->x0);
+        else
+            RVS_LAUNCH(encode_positions_kernel<RULES_REF>, grid_for(B * 64, 256), 256, 0, s, (const uint64_t*)ab.dev,
+                       (const uint64_t*)aw.dev, (const uint8_t*)as.dev, B, (uint4*)n->x0);
+        if ((rc = net_forward(h, B, true, s))) return rc;
+        const cudaMemcpyKind kind = mem == RVS_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+        RVS_CUDA(cudaMemcpyAsync(out_logits + off * 65, n->logits, B * 65 * 4, kind, s));
+        RVS_CUDA(cudaMemcpyAsync(out_value + off, n->values, B * 4, kind, s));
+        if (mem == RVS_MEM_HOST) RVS_CUDA(cudaStreamSynchronize(s));
+    }
+    return 0;
 }
-}
+
+}  // extern "C"

@@ -132,5 +132,21 @@ class Engine:
         return {k: getattr(st, k) for k, _ in L.EngineStats._fields_}
 
     def load_weights(self, flat, stream=None):
+        """flat f32 state_dict (network.pack_state_dict); BN folding + bf16 packing happen on device"""
         L.check(L.lib().rvs_engine_load_weights(self._h, L.ptr(flat)[0], flat.numel() if hasattr(flat, "numel") else flat.size,
                                                 L.ptr(flat)[1], self._s(stream)))
+
+    def predict(self, black, white, side, stream=None):
+        """AlphaZeroNetwork.predict on packed positions -> (logits [n,65] f32, value [n] f32)"""
+        n = len(black)
+        if hasattr(black, "data_ptr"):
+            import torch
+            logits = torch.empty((n, 65), dtype=torch.float32, device=black.device)
+            value = torch.empty(n, dtype=torch.float32, device=black.device)
+        else:
+            logits = np.empty((n, 65), dtype=np.float32)
+            value = np.empty(n, dtype=np.float32)
+        mem = L.mem_of(black, white, side, logits, value)
+        L.check(L.lib().rvs_engine_predict(self._h, L.ptr(black)[0], L.ptr(white)[0], L.ptr(side)[0], n,
+                                           L.ptr(logits)[0], L.ptr(value)[0], mem, self._s(stream)))
+        return logits, value

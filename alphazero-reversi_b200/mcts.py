@@ -70,7 +70,10 @@ class MCTS:
             ev = self._builtin if self._builtin is not None else L.EVAL_EXTERNAL
             self._engine = Engine(1, self.num_simulations, max(1, self.batch_size), evaluator=ev,
                                   c_puct=self.c_puct, rules=self.rules, seed=getattr(self.model, "seed", 0),
-                                  device=self._cuda_device)
+                                  device=self._cuda_device, net_blocks=getattr(self.model, "net_blocks", 0),
+                                  net_filters=getattr(self.model, "net_filters", 0))
+            if hasattr(self.model, "attach"):
+                self.model.attach(self._engine)
             self._engine_key = key
         return self._engine
 

@@ -74,7 +74,8 @@ class SelfPlay:
         slots = min(parallel, num_games)
         eng = Engine(slots, S, K, evaluator=self._builtin, c_puct=self.args.get("c_puct", 1.0),
                      seed=self.args.get("seed", getattr(self.model, "seed", 0)),
-                     sample_capacity=64 * max(slots, 1) * 2)
+                     sample_capacity=64 * max(slots, 1) * 2, net_blocks=getattr(self.model, "net_blocks", 0),
+                     net_filters=getattr(self.model, "net_filters", 0))
         if hasattr(self.model, "attach"):
             self.model.attach(eng)
         games: List[Dict] = []

@@ -50,3 +50,15 @@ class StubModel:
             else:
                 raise ValueError("T2 priors are table-driven: use the Engine external path")
         return torch.from_numpy(logits).to(dev), torch.from_numpy(values).to(dev)
+
+
+def perturb_bn(model, seed):
+    """restates oracle/gen_golden.py:perturb_bn (non-trivial BN statistics, unsaturated value head)"""
+    gen = torch.Generator().manual_seed(seed)
+    for name, m in model.named_modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=gen) * 0.2)
+            m.running_var.copy_(torch.rand(m.num_features, generator=gen) * 1.5 + 0.25)
+            m.weight.data.copy_(torch.rand(m.num_features, generator=gen) * 0.5 + 0.5)
+            m.bias.data.copy_(torch.randn(m.num_features, generator=gen) * 0.1)
+    model.value_fc2.weight.data.mul_(0.05)
