@@ -55,12 +55,13 @@ def test_predict_vs_reference_golden(az, golden, tag, nb, nf, variant):
         planes = torch.from_numpy(az.board_ops.encode_planes(bl, wh, sd))
         tl, tv = net(planes)
     assert np.allclose(tl.numpy(), ref_l, atol=2e-3, rtol=1e-3)
-    if variant == "bn":
-        base_l = np.abs(g[f"{tag}_bn_logits_autocast"] - ref_l).max()
-        base_v = np.abs(g[f"{tag}_bn_values_autocast"] - ref_v).max()
-    else:
-        base_l = 0.02 * np.abs(ref_l).max()
-        base_v = 0.015
+    # calibration baseline: torch's own bf16 autocast of the same module against its fp32 output
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        al, av = net(planes)
+    base_l = np.abs(al.float().numpy() - ref_l).max()
+    base_v = np.abs(av.float().numpy() - ref_v).max()
+    if variant == "bn":  # the recorded autocast outputs of the reference agree with the live ones
+        assert abs(base_l - np.abs(g[f"{tag}_bn_logits_autocast"] - ref_l).max()) < 0.05
     err_l = np.abs(logits - ref_l).max()
     err_p = np.abs(_softmax(logits) - _softmax(ref_l)).max()
     err_v = np.abs(value - ref_v).max()
