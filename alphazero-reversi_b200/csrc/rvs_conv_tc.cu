@@ -1,17 +1,360 @@
-// rvs_conv_tc.cu -- placeholder: the tcgen05 implicit-GEMM convolution lands here.
+// rvs_conv_tc.cu -- 3x3 convolution C->C (+ folded BN bias, optional residual, ReLU) as an
+// implicit GEMM on the 5th-generation tensor cores: TMA -> shared memory -> tcgen05.mma -> TMEM ->
+// tcgen05.ld epilogue.  sm_100a only.
+//
+// GEMM view per CTA:  D[128 pixels, 64 couts] += A_tap[128 pixels, cin] * W_tap[64 couts, cin]^T
+//   M = 128 = one "tile" = two boards, rows ordered (y, board, x): with this order a vertical tap
+//       shift dy is a shift by 16 rows = 2048 B, i.e. a whole number of 1024-byte swizzle atoms.
+//   N = 64 couts per CTA (C/64 CTAs share a pixel tile); its 9 x C/64 weight tiles (8 KB each) are
+//       loaded ONCE and stay resident in shared memory for the whole persistent CTA.
+//   K = 9 taps x cin, consumed as 3 (dx) x C/64 stages; each stage is ONE TMA box of the
+//       activations: 10 rows of y (halo -1..8) x 2 boards x 8 x (shifted by dx) x 64 channels,
+//       out-of-bounds rows/columns zero-filled by the TMA unit = the convolution's zero padding.
+//       The three vertical taps of that dx reuse the same box at row offsets 0 / 16 / 32.
+// Activations live in HBM in the same tiled order [tile][y][board][x][c] (rvs_conv_tc.cuh:
+// act_row), so accumulator row r of a tile is simply row r of the output tile.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2-5 = epilogue (TMEM lane quarter = warp_id % 4).  Two 64-column accumulators in TMEM
+// ping-pong so that the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "rvs_conv_tc.cuh"
+
+#include <cuda.h>
+
 #include "rvs_common.cuh"
 
 namespace rvs {
-int conv_tc_plan(ConvTcPlan& plan, const __nv_bfloat16*, int C, int64_t max_batch) {
+
+namespace {
+
+constexpr int kTileRows = 128;              // pixels per tile (2 boards)
+constexpr int kNT = 64;                     // couts per CTA
+constexpr int kABytes = 10 * 2 * 8 * 128;   // one activation stage: 160 rows x 128 B
+constexpr int kWBytes = kNT * 128;          // one weight tile: 64 rows x 128 B
+constexpr int kThreads = 192;
+
+struct Impl {
+    CUtensorMap w_map;
+    const void* act_ptr[4] = {nullptr, nullptr, nullptr, nullptr};
+    CUtensorMap act_map[4];
+    int n_act = 0;
+};
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode() {
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeFn)p;
+    }
+    return fn;
+}
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, one elected thread
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (=1, unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 (1024 B between 8-row groups) | [46,48) version = 1 (sm_100)
+//   [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16
+// [10,13)=1, A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kNT >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
+
+template <int C>
+struct Cfg {
+    static constexpr int KC = C / 64;                      // 64-channel k chunks
+    static constexpr int NSPLIT = C / kNT;                 // CTAs sharing one pixel tile
+    static constexpr int W_TILES = 9 * KC;
+    static constexpr int STAGES = C == 64 ? 4 : 3;
+    static constexpr int SMEM = W_TILES * kWBytes + STAGES * kABytes + 1024 /*align*/ + 512 /*barriers, bias*/;
+};
+
+template <int C>
+__global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap a_map,
+                                                                  const __grid_constant__ CUtensorMap w_map,
+                                                                  const __nv_bfloat16* __restrict__ residual,
+                                                                  __nv_bfloat16* __restrict__ out,
+                                                                  const float* __restrict__ bias, int n_tiles) {
+    using K = Cfg<C>;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-B alignment
+    unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t w_s = base;
+    const uint32_t a_s = base + K::W_TILES * kWBytes;
+    unsigned char* tail = gen + K::W_TILES * kWBytes + K::STAGES * kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);   // full[S], empty[S], wfull, acc_full[2], acc_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 128);
+    float* sbias = reinterpret_cast<float*>(tail + 192);  // [64]
+    const uint32_t bar0 = smem_u32(bars);
+    auto FULL = [&](int s) { return bar0 + 8u * s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (K::STAGES + s); };
+    const uint32_t WFULL = bar0 + 8u * (2 * K::STAGES);
+    auto ACC_FULL = [&](int a) { return bar0 + 8u * (2 * K::STAGES + 1 + a); };
+    auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (2 * K::STAGES + 3 + a); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_split = blockIdx.x % K::NSPLIT;
+    const int tile0 = blockIdx.x / K::NSPLIT;
+    const int tile_step = gridDim.x / K::NSPLIT;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < K::STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        mbar_init(WFULL, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(ACC_FULL(a), 1); mbar_init(ACC_EMPTY(a), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < kNT) sbias[threadIdx.x] = bias[n_split * kNT + threadIdx.x];
+    if (warp == 1) {  // TMEM: 2 accumulators x 64 fp32 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer =====
+            mbar_expect_tx(WFULL, K::W_TILES * kWBytes);
+            for (int tap = 0; tap < 9; ++tap)
+                for (int kc = 0; kc < K::KC; ++kc)
+                    tma_load_2d(&w_map, WFULL, w_s + (tap * K::KC + kc) * kWBytes, kc * 64, tap * C + n_split * kNT);
+            int stage = 0, phase = 0;
+            for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+                for (int dx = 0; dx < 3; ++dx)
+                    for (int kc = 0; kc < K::KC; ++kc) {
+                        mbar_wait(EMPTY(stage), phase ^ 1);
+                        mbar_expect_tx(FULL(stage), kABytes);
+                        tma_load_5d(&a_map, FULL(stage), a_s + stage * kABytes, kc * 64, dx - 1, 0, -1, tile);
+                        if (++stage == K::STAGES) { stage = 0; phase ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer =====
+            mbar_wait(WFULL, 0);
+            int stage = 0, phase = 0, it = 0;
+            for (int tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
+                const int acc = it & 1;
+                mbar_wait(ACC_EMPTY(acc), ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(acc * kNT);
+                uint32_t accum = 0;
+                for (int dx = 0; dx < 3; ++dx)
+                    for (int kc = 0; kc < K::KC; ++kc) {
+                        mbar_wait(FULL(stage), phase);
+                        tc_fence_after();
+                        const uint32_t a0 = a_s + stage * kABytes;
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy) {
+                            const uint32_t wt = w_s + ((dy * 3 + dx) * K::KC + kc) * kWBytes;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {  // 4 x (K = 16 bf16 = 32 B) inside the 128-B swizzle atom
+                                tc_mma(d, make_desc(a0 + dy * 2048 + k * 32), make_desc(wt + k * 32), kIdesc, accum);
+                                accum = 1;
+                            }
+                        }
+                        tc_commit(EMPTY(stage));  // the stage is free once these MMAs have read it
+                        if (++stage == K::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                tc_commit(ACC_FULL(acc));
+            }
+        }
+    } else {  // ===== epilogue: TMEM -> registers -> (+bias, +residual, ReLU) -> bf16 -> HBM =====
+        const int q = warp & 3;             // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;      // accumulator row = output row inside the tile
+        int it = 0;
+        for (int tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
+            const int acc = it & 1;
+            mbar_wait(ACC_FULL(acc), (it >> 1) & 1);
+            tc_fence_after();
+            uint32_t v[64];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kNT);
+            tc_ld32(taddr, v);
+            tc_ld32(taddr + 32, v + 32);
+            tc_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ACC_EMPTY(acc));  // accumulator may be overwritten now
+            const size_t off = ((size_t)tile * kTileRows + row) * C + (size_t)n_split * kNT;
+            uint4* optr = reinterpret_cast<uint4*>(out + off);
+            const uint4* rptr = residual ? reinterpret_cast<const uint4*>(residual + off) : nullptr;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[c8 * 8 + i]) + sbias[c8 * 8 + i];
+                if (rptr) {
+                    const uint4 r = rptr[c8];
+                    const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 t = __bfloat1622float2(r2[i]);
+                        f[2 * i] += t.x;
+                        f[2 * i + 1] += t.y;
+                    }
+                }
+                uint4 o;
+                __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(fmaxf(f[2 * i], 0.f), fmaxf(f[2 * i + 1], 0.f));
+                optr[c8] = o;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
+    }
+}
+
+int encode_act_map(CUtensorMap* m, const void* ptr, int C, int64_t n_tiles) {
+    EncodeFn enc = get_encode();
+    if (!enc) return fail(-9, "cuTensorMapEncodeTiled entry point not available");
+    // tiled activation layout [tile][y][board][x][c]  (dims innermost first)
+    const cuuint64_t dims[5] = {(cuuint64_t)C, 8, 2, 8, (cuuint64_t)n_tiles};
+    const cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * 8, (cuuint64_t)C * 2 * 16, (cuuint64_t)C * 2 * 128};
+    const cuuint32_t box[5] = {64, 8, 2, 10, 1};
+    const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-9, "cuTensorMapEncodeTiled(activations) failed: %d", (int)r);
+    return 0;
+}
+
+}  // namespace
+
+int conv_tc_plan(ConvTcPlan& plan, const __nv_bfloat16* w, int C, int64_t max_batch) {
     plan.valid = false;
     plan.C = C;
     plan.max_batch = max_batch;
+    if (C != 64 && C != 128) return 0;  // 256 filters: resident weights do not fit; direct path
+    EncodeFn enc = get_encode();
+    if (!enc) return fail(-9, "cuTensorMapEncodeTiled entry point not available");
+    Impl* im = plan.impl ? static_cast<Impl*>(plan.impl) : new Impl();
+    plan.impl = im;
+    im->n_act = 0;
+    // weights [9*C rows (tap, cout)][C cin] bf16, box = 64 cin x 64 couts
+    const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)9 * C};
+    const cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    const cuuint32_t box[2] = {64, kNT};
+    const cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(&im->w_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(w), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-9, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+    plan.valid = true;
     return 0;
 }
-int conv_tc_launch(const ConvTcPlan&, const __nv_bfloat16*, const __nv_bfloat16*, __nv_bfloat16*, const float*, int64_t,
-                   cudaStream_t) {
-    return fail(-8, "tcgen05 convolution not built");
+
+int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
+                   const float* bias, int64_t B, cudaStream_t s) {
+    if (!plan.valid || !plan.impl) return fail(-8, "tcgen05 convolution: no plan");
+    Impl* im = static_cast<Impl*>(plan.impl);
+    int slot = -1;
+    for (int i = 0; i < im->n_act; ++i)
+        if (im->act_ptr[i] == in) slot = i;
+    if (slot < 0) {
+        if (im->n_act == 4) im->n_act = 0;
+        slot = im->n_act++;
+        int rc = encode_act_map(&im->act_map[slot], in, plan.C, (plan.max_batch + 1) / 2);
+        if (rc) return rc;
+        im->act_ptr[slot] = in;
+    }
+    const int n_tiles = (int)((B + 1) / 2);
+    const int C = plan.C;
+    const int nsplit = C / kNT;
+    int ctas = n_tiles * nsplit < kNumSMs ? n_tiles * nsplit : (kNumSMs / nsplit) * nsplit;
+    if (C == 64) {
+        static bool attr = false;
+        if (!attr) { RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM)); attr = true; }
+        RVS_LAUNCH(conv3x3_tc_kernel<64>, ctas, kThreads, Cfg<64>::SMEM, s, im->act_map[slot], im->w_map, residual, out, bias, n_tiles);
+    } else {
+        static bool attr = false;
+        if (!attr) { RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM)); attr = true; }
+        RVS_LAUNCH(conv3x3_tc_kernel<128>, ctas, kThreads, Cfg<128>::SMEM, s, im->act_map[slot], im->w_map, residual, out, bias, n_tiles);
+    }
+    return 0;
 }
-void conv_tc_destroy(ConvTcPlan&) {}
+
+void conv_tc_destroy(ConvTcPlan& plan) {
+    if (plan.impl) delete static_cast<Impl*>(plan.impl);
+    plan.impl = nullptr;
+    plan.valid = false;
+}
+
 }  // namespace rvs

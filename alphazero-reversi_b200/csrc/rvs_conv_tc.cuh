@@ -6,6 +6,12 @@
 
 namespace rvs {
 
+// Activation layout in HBM, shared by every K4 kernel: [tile][y][board-in-tile][x][c] bf16 with
+// tile = board / 2.  Row index (in units of C channels) of pixel px = y*8+x of `board`:
+__host__ __device__ inline size_t act_row(int64_t board, int px) {
+    return (size_t)(board >> 1) * 128 + (size_t)(px >> 3) * 16 + (size_t)(board & 1) * 8 + (size_t)(px & 7);
+}
+
 struct ConvTcPlan {
     bool valid = false;
     int C = 0;

@@ -89,7 +89,7 @@ __global__ void fold_conv1x1_kernel(const float* __restrict__ w, const float* __
 // one CTA per board: the board's input (with a zero halo) lives in shared memory; thread t owns
 // output channel (t % COUT_T) and a group of pixels; weights stream from L2 as 16-byte vectors.
 // out = relu(conv(in) + bias [+ residual])
-template <int CIN>
+template <int CIN, bool PLAIN_IN>
 __global__ void __launch_bounds__(256) conv3x3_direct_kernel(const __nv_bfloat16* __restrict__ in,
                                                               const __nv_bfloat16* __restrict__ w,
                                                               const float* __restrict__ bias,
@@ -98,13 +98,16 @@ __global__ void __launch_bounds__(256) conv3x3_direct_kernel(const __nv_bfloat16
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // [10][10][CIN]
     const int board = blockIdx.x;
-    const uint4* gin = reinterpret_cast<const uint4*>(in + (size_t)board * 64 * CIN);
+    const uint4* gin = reinterpret_cast<const uint4*>(in);
     constexpr int V = CIN / 8;  // uint4 per pixel
     for (int i = threadIdx.x; i < 100 * V; i += blockDim.x) {
         const int p = i / V, v = i % V;
         const int y = p / 10 - 1, x = p % 10 - 1;
         uint4 val = make_uint4(0, 0, 0, 0);
-        if (y >= 0 && y < 8 && x >= 0 && x < 8) val = gin[(y * 8 + x) * V + v];
+        if (y >= 0 && y < 8 && x >= 0 && x < 8) {
+            const size_t row = PLAIN_IN ? (size_t)board * 64 + (y * 8 + x) : act_row(board, y * 8 + x);
+            val = gin[row * V + v];
+        }
         reinterpret_cast<uint4*>(sx)[i] = val;
     }
     __syncthreads();
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(256) conv3x3_direct_kernel(const __nv_bfloat16
             const float bv = bias[co];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                const size_t o = ((size_t)board * 64 + p0 + i) * cout + co;
+                const size_t o = act_row(board, p0 + i) * cout + co;
                 float r = acc[i] + bv;
                 if (residual) r += __bfloat162float(residual[o]);
                 if (relu) r = fmaxf(r, 0.f);
@@ -163,12 +166,12 @@ __global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restr
     __shared__ float lg[65];
     __shared__ float red[2];
     const int board = blockIdx.x, t = threadIdx.x;
-    const __nv_bfloat16* xb = x + (size_t)board * 64 * C;
+
     if (t < 192) {  // 1x1 convs + BN + ReLU
         const int px = t & 63, j = t >> 6;  // j: 0,1 policy channels; 2 value channel
         const float* wv = j < 2 ? pw + j * C : vw;
         float acc = 0.f;
-        const __nv_bfloat162* xr = reinterpret_cast<const __nv_bfloat162*>(xb + (size_t)px * C);
+        const __nv_bfloat162* xr = reinterpret_cast<const __nv_bfloat162*>(x + act_row(board, px) * C);
         for (int c = 0; c < C / 2; ++c) {
             const float2 a = __bfloat1622float2(xr[c]);
             acc = fmaf(a.x, wv[2 * c], acc);
@@ -260,18 +263,18 @@ int launch_direct(const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat
     const int threads = 256;
     if (L.cout > 256 || 256 % L.cout != 0) return fail(-6, "direct conv: unsupported cout %d", L.cout);
     if (L.cin == 16) {
-        RVS_LAUNCH(conv3x3_direct_kernel<16>, (int)B, threads, 100 * 16 * 2, s, in, L.w, L.bias, residual, out, L.cout, relu);
+        RVS_LAUNCH((conv3x3_direct_kernel<16, true>), (int)B, threads, 100 * 16 * 2, s, in, L.w, L.bias, residual, out, L.cout, relu);
     } else if (L.cin == 64) {
-        RVS_LAUNCH(conv3x3_direct_kernel<64>, (int)B, threads, 100 * 64 * 2, s, in, L.w, L.bias, residual, out, L.cout, relu);
+        RVS_LAUNCH((conv3x3_direct_kernel<64, false>), (int)B, threads, 100 * 64 * 2, s, in, L.w, L.bias, residual, out, L.cout, relu);
     } else if (L.cin == 128) {
-        RVS_LAUNCH(conv3x3_direct_kernel<128>, (int)B, threads, 100 * 128 * 2, s, in, L.w, L.bias, residual, out, L.cout, relu);
+        RVS_LAUNCH((conv3x3_direct_kernel<128, false>), (int)B, threads, 100 * 128 * 2, s, in, L.w, L.bias, residual, out, L.cout, relu);
     } else if (L.cin == 256) {
         static bool attr = false;
         if (!attr) {
-            RVS_CUDA(cudaFuncSetAttribute(conv3x3_direct_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 256 * 2));
+            RVS_CUDA(cudaFuncSetAttribute(conv3x3_direct_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 256 * 2));
             attr = true;
         }
-        RVS_LAUNCH(conv3x3_direct_kernel<256>, (int)B, threads, 100 * 256 * 2, s, in, L.w, L.bias, residual, out, L.cout, relu);
+        RVS_LAUNCH((conv3x3_direct_kernel<256, false>), (int)B, threads, 100 * 256 * 2, s, in, L.w, L.bias, residual, out, L.cout, relu);
     } else {
         return fail(-6, "direct conv: unsupported cin %d", L.cin);
     }
@@ -318,7 +321,7 @@ int net_create(rvs_engine* h) {
     n->C = C;
     n->max_batch = (int64_t)h->v.G * h->cfg.max_wave;
     n->force_direct = getenv("RVS_NET_DIRECT") && atoi(getenv("RVS_NET_DIRECT")) != 0;
-    const size_t B = (size_t)n->max_batch;
+    const size_t B = (size_t)((n->max_batch + 1) / 2) * 2;  // whole tiles of two boards
     int rc = 0;
     n->tower = new ConvLayer[2 * blocks];
     if ((rc = nalloc(n, &n->conv0.w, (size_t)9 * C * 16)) || (rc = nalloc(n, &n->conv0.bias, (size_t)C))) return rc;

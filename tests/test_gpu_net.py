@@ -60,15 +60,16 @@ def test_predict_vs_reference_golden(az, golden, tag, nb, nf, variant):
         al, av = net(planes)
     base_l = np.abs(al.float().numpy() - ref_l).max()
     base_v = np.abs(av.float().numpy() - ref_v).max()
+    base_p = np.abs(_softmax(al.float().numpy()) - _softmax(ref_l)).max()
     if variant == "bn":  # the recorded autocast outputs of the reference agree with the live ones
         assert abs(base_l - np.abs(g[f"{tag}_bn_logits_autocast"] - ref_l).max()) < 0.05
     err_l = np.abs(logits - ref_l).max()
     err_p = np.abs(_softmax(logits) - _softmax(ref_l)).max()
     err_v = np.abs(value - ref_v).max()
     print(f"{tag} {variant}: logits err {err_l:.4f} (autocast {base_l:.4f}) rel-L2 "
-          f"{np.linalg.norm(logits - ref_l) / np.linalg.norm(ref_l):.4f} priors {err_p:.5f} value {err_v:.5f} (autocast {base_v:.5f})")
+          f"{np.linalg.norm(logits - ref_l) / np.linalg.norm(ref_l):.4f} priors {err_p:.5f} (autocast {base_p:.5f}) value {err_v:.5f} (autocast {base_v:.5f})")
     assert err_l <= max(2 * base_l, 0.05)
-    assert err_p <= 2e-2
+    assert err_p <= max(2 * base_p, 2e-2)
     assert err_v <= max(2 * base_v, 3e-2)
     eng.close()
 
@@ -159,3 +160,42 @@ def test_mcts_and_selfplay_with_rvs_network(az):
     sp = az.SelfPlay(rn, {"num_simulations": 16, "batch_size": 1, "temperature": 1.0, "num_parallel_games": 32})
     data = sp.generate_training_data(40)
     assert data["states"].shape[1:] == (3, 8, 8) and np.allclose(data["action_probs"].sum(axis=1), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("nb,nf,n", [(1, 64, 2), (1, 128, 2), (1, 64, 1500), (1, 128, 1501), (2, 128, 37), (5, 128, 512)])
+def test_tcgen05_tower_matches_direct_kernel(az, nb, nf, n):
+    """the tensor-core implicit GEMM (TMA + tcgen05 + TMEM) against the CUDA-core direct kernel on
+    the same bf16 weights/activations: only the f32 summation order differs"""
+    import os
+    net = _build(az, nb, nf, "bn")
+    rn = az.RvsNetwork.from_module(net)
+    bl, wh, wi, pl = orc.random_playouts(n, 77)
+    rng = np.random.default_rng(1)
+    # random (not necessarily reachable) disc sets exercise every input pattern
+    occ = rng.integers(0, 2**64, n, dtype=np.uint64)
+    pick = rng.integers(0, 2**64, n, dtype=np.uint64)
+    bl, wh = occ & pick, occ & ~pick
+    sd = rng.integers(1, 3, n).astype(np.uint8)
+    outs = {}
+    for mode in ("1", "0"):
+        os.environ["RVS_NET_DIRECT"] = mode
+        eng = az.Engine(n, 8, 1, evaluator=az.EVAL_NN, net_blocks=nb, net_filters=nf)
+        rn.attach(eng)
+        outs[mode] = eng.predict(bl, wh, sd)
+        eng.close()
+    os.environ.pop("RVS_NET_DIRECT")
+    dl = np.abs(outs["1"][0] - outs["0"][0]).max()
+    dv = np.abs(outs["1"][1] - outs["0"][1]).max()
+    scale = np.abs(outs["1"][0]).max()
+    # both against the fp32 torch module: deep towers amplify bf16 rounding differences, so the
+    # criterion is "the tensor-core path is as close to fp32 as the direct path", plus near-equality
+    # for shallow towers where no amplification happens
+    with torch.no_grad():
+        tl, tv = net(torch.from_numpy(az.board_ops.encode_planes(bl, wh, sd)))
+    e_dir = np.abs(outs["1"][0] - tl.numpy()).max()
+    e_tc = np.abs(outs["0"][0] - tl.numpy()).max()
+    print(f"{nb}x{nf} n={n}: direct vs tcgen05 logits max diff {dl:.5f} (scale {scale:.2f}) value diff {dv:.5f}; "
+          f"vs fp32: direct {e_dir:.5f} tcgen05 {e_tc:.5f}")
+    assert e_tc <= 1.5 * e_dir + 0.01
+    if nb == 1:
+        assert dl <= 0.004 * max(scale, 1.0) and dv <= 0.01
