@@ -29,12 +29,14 @@ struct NetState {
     ConvLayer* tower = nullptr;  // 2*blocks layers
     // heads (BN folded), f32
     float *pw = nullptr, *pb = nullptr;      // policy conv [2][C], bias [2]
-    float *pfw = nullptr, *pfb = nullptr;    // policy fc [65][128], [65]
+    float *pfw = nullptr, *pfb = nullptr;    // policy fc TRANSPOSED [128][65], [65]
     float *vw = nullptr, *vb = nullptr;      // value conv [C], bias [1]
-    float *v1w = nullptr, *v1b = nullptr;    // fc1 [256][64], [256]
+    float *v1w = nullptr, *v1b = nullptr;    // fc1 TRANSPOSED [64][256], [256]
+    float *w0f = nullptr, *b0f = nullptr;    // first conv for the bit-plane kernel: [27][C] f32, [C]
+    uint64_t* bits = nullptr;                // [B][3] own / opponent / legal bit planes (K3 output)
     float *v2w = nullptr, *v2b = nullptr;    // fc2 [256], [1]
     // activations
-    __nv_bfloat16 *x0 = nullptr, *a = nullptr, *b = nullptr, *c = nullptr;  // x0 [B][64][16]; a,b,c [B][64][C]
+    __nv_bfloat16 *a = nullptr, *b = nullptr, *c = nullptr;  // [tile][y][board][x][C] (act_row)
     float *probs = nullptr, *logits = nullptr, *values = nullptr;          // [B][65], [B][65], [B]
     float* flat = nullptr;  // staging of the raw state_dict
     bool loaded = false;
@@ -152,90 +154,190 @@ __global__ void __launch_bounds__(256) conv3x3_direct_kernel(const __nv_bfloat16
     }
 }
 
-// ---- heads (network.py:103-117) + softmax (mcts.py:596), one CTA (256 threads) per board ------
-__global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restrict__ x, int C,
+// ---- heads (network.py:103-117) + softmax (mcts.py:596) ---------------------------------------
+// One CTA (256 threads) evaluates kHB = 8 boards: (1) the three 1x1 convolutions + BN + ReLU, one
+// thread per pixel streaming its C channels with 16-byte loads; (2) policy_fc (65 rows) and
+// value_fc1 (256 rows) with TRANSPOSED weights so that consecutive threads read consecutive
+// addresses, each weight reused for the 8 boards; (3) one warp per board: softmax over the 65
+// logits (no legal-move masking: mcts.py:596 applies the plain softmax), value_fc2 + tanh.
+constexpr int kHB = 8;
+__global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restrict__ x, int C, int64_t B,
                                                      const float* __restrict__ pw, const float* __restrict__ pb,
-                                                     const float* __restrict__ pfw, const float* __restrict__ pfb,
+                                                     const float* __restrict__ pfwT, const float* __restrict__ pfb,
                                                      const float* __restrict__ vw, const float* __restrict__ vb,
-                                                     const float* __restrict__ v1w, const float* __restrict__ v1b,
+                                                     const float* __restrict__ v1wT, const float* __restrict__ v1b,
                                                      const float* __restrict__ v2w, const float* __restrict__ v2b,
                                                      float* __restrict__ logits, float* __restrict__ probs,
                                                      float* __restrict__ values) {
-    __shared__ float feat[192];   // [0,128): policy planes channel-major (ch*64+px); [128,192): value plane
-    __shared__ float hid[256];
-    __shared__ float lg[65];
-    __shared__ float red[2];
-    const int board = blockIdx.x, t = threadIdx.x;
-
-    if (t < 192) {  // 1x1 convs + BN + ReLU
-        const int px = t & 63, j = t >> 6;  // j: 0,1 policy channels; 2 value channel
-        const float* wv = j < 2 ? pw + j * C : vw;
-        float acc = 0.f;
-        const __nv_bfloat162* xr = reinterpret_cast<const __nv_bfloat162*>(x + act_row(board, px) * C);
-        for (int c = 0; c < C / 2; ++c) {
-            const float2 a = __bfloat1622float2(xr[c]);
-            acc = fmaf(a.x, wv[2 * c], acc);
-            acc = fmaf(a.y, wv[2 * c + 1], acc);
+    __shared__ float w1x1[3 * 256];        // [3][C] (C <= 256)
+    __shared__ float feat[kHB][192];       // [0,128): policy planes channel-major (ch*64+px); [128,192): value plane
+    __shared__ float hid[kHB][256];
+    __shared__ float lg[kHB][68];
+    const int t = threadIdx.x;
+    const int64_t board0 = (int64_t)blockIdx.x * kHB;
+    for (int i = t; i < 3 * C; i += 256) w1x1[i] = i < 2 * C ? pw[i] : vw[i - 2 * C];
+    __syncthreads();
+    for (int p = t; p < kHB * 64; p += 256) {  // (1) 1x1 convs
+        const int bi = p >> 6, px = p & 63;
+        const int64_t board = board0 + bi;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        if (board < B) {
+            const uint4* xr = reinterpret_cast<const uint4*>(x + act_row(board, px) * C);
+            for (int v = 0; v < C / 8; ++v) {
+                const uint4 q = xr[v];
+                const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __bfloat1622float2(q2[i]);
+                    const int c = v * 8 + 2 * i;
+                    a0 = fmaf(f.x, w1x1[c], a0); a0 = fmaf(f.y, w1x1[c + 1], a0);
+                    a1 = fmaf(f.x, w1x1[C + c], a1); a1 = fmaf(f.y, w1x1[C + c + 1], a1);
+                    a2 = fmaf(f.x, w1x1[2 * C + c], a2); a2 = fmaf(f.y, w1x1[2 * C + c + 1], a2);
+                }
+            }
         }
-        acc += j < 2 ? pb[j] : vb[0];
-        feat[j * 64 + px] = fmaxf(acc, 0.f);
+        feat[bi][px] = fmaxf(a0 + pb[0], 0.f);
+        feat[bi][64 + px] = fmaxf(a1 + pb[1], 0.f);
+        feat[bi][128 + px] = fmaxf(a2 + vb[0], 0.f);
     }
     __syncthreads();
-    if (t < 65) {  // policy_fc: view(batch,-1) is channel-major (network.py:107)
-        float acc = pfb[t];
-        const float* wr = pfw + t * 128;
-        for (int i = 0; i < 128; ++i) acc = fmaf(wr[i], feat[i], acc);
-        lg[t] = acc;
-        if (logits) logits[(size_t)board * 65 + t] = acc;
+    {  // (2a) value_fc1 + ReLU: row t of [256][64], transposed weights [64][256]
+        float acc[kHB];
+#pragma unroll
+        for (int b = 0; b < kHB; ++b) acc[b] = v1b[t];
+        for (int i = 0; i < 64; ++i) {
+            const float w = v1wT[i * 256 + t];
+#pragma unroll
+            for (int b = 0; b < kHB; ++b) acc[b] = fmaf(w, feat[b][128 + i], acc[b]);
+        }
+#pragma unroll
+        for (int b = 0; b < kHB; ++b) hid[b][t] = fmaxf(acc[b], 0.f);
     }
-    {  // value_fc1 + ReLU
-        float acc = v1b[t];
-        const float* wr = v1w + t * 64;
-        for (int i = 0; i < 64; ++i) acc = fmaf(wr[i], feat[128 + i], acc);
-        hid[t] = fmaxf(acc, 0.f);
+    if (t < 65) {  // (2b) policy_fc: view(batch,-1) is channel-major (network.py:107); weights [128][65]
+        float acc[kHB];
+#pragma unroll
+        for (int b = 0; b < kHB; ++b) acc[b] = pfb[t];
+        for (int i = 0; i < 128; ++i) {
+            const float w = pfwT[i * 65 + t];
+#pragma unroll
+            for (int b = 0; b < kHB; ++b) acc[b] = fmaf(w, feat[b][i], acc[b]);
+        }
+#pragma unroll
+        for (int b = 0; b < kHB; ++b) lg[b][t] = acc[b];
     }
     __syncthreads();
-    if (t < 32) {  // warp 0: softmax over the 65 logits; value_fc2 + tanh
-        float m = fmaxf(lg[t], lg[t + 32]);
-        if (t == 0) m = fmaxf(m, lg[64]);
-        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        const float e0 = expf(lg[t] - m), e1 = expf(lg[t + 32] - m), e2 = t == 0 ? expf(lg[64] - m) : 0.f;
-        float s = e0 + e1 + e2;
-        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (probs) {
-            float* pr = probs + (size_t)board * 65;
-            pr[t] = e0 / s;
-            pr[t + 32] = e1 / s;
-            if (t == 0) pr[64] = e2 / s;
+    {  // (3) warp w <-> board w
+        const int w = t >> 5, l = t & 31;
+        const int64_t board = board0 + w;
+        if (board < B) {
+            float m = fmaxf(lg[w][l], lg[w][l + 32]);
+            if (l == 0) m = fmaxf(m, lg[w][64]);
+            for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            const float e0 = expf(lg[w][l] - m), e1 = expf(lg[w][l + 32] - m), e2 = l == 0 ? expf(lg[w][64] - m) : 0.f;
+            float s = e0 + e1 + e2;
+            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (probs) {
+                float* pr = probs + (size_t)board * 65;
+                pr[l] = e0 / s;
+                pr[l + 32] = e1 / s;
+                if (l == 0) pr[64] = e2 / s;
+            }
+            if (logits) {
+                float* lo = logits + (size_t)board * 65;
+                lo[l] = lg[w][l];
+                lo[l + 32] = lg[w][l + 32];
+                if (l == 0) lo[64] = lg[w][64];
+            }
+            float acc = 0.f;
+            for (int i = l; i < 256; i += 32) acc = fmaf(v2w[i], hid[w][i], acc);
+            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (l == 0) values[board] = tanhf(acc + v2b[0]);
         }
-        float acc = 0.f;
-        for (int i = t; i < 256; i += 32) acc = fmaf(v2w[i], hid[i], acc);
-        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (t == 0) values[board] = tanhf(acc + v2b[0]);
     }
-    (void)red;
 }
 
-// K3 fused for the engine: canonical planes of the selected leaves straight into the network's
-// bf16 NHWC input buffer (16 channels, 3 used); slots that need no evaluation are zeroed.
-__global__ void __launch_bounds__(256) encode_leaves_kernel(EngineView ev, int k, uint4* __restrict__ out) {
-    const int64_t total = (int64_t)ev.G * k * 64;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t slot = t >> 6;
-        const int sq = (int)(t & 63);
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < rows * cols; t += gridDim.x * blockDim.x)
+        out[(t % cols) * rows + t / cols] = in[t];
+}
+
+// first layer folded for the bit-plane kernel: w [C][3][3][3] -> wf [tap*3+plane][C] f32
+__global__ void fold_conv0_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  const float* __restrict__ mean, const float* __restrict__ var, int C,
+                                  float* __restrict__ wf, float* __restrict__ bias) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 27 * C; t += gridDim.x * blockDim.x) {
+        const int co = t % C, tp = t / C, tap = tp / 3, plane = tp % 3;
+        const float scale = gamma[co] / sqrtf(var[co] + 1e-5f);
+        wf[t] = w[((size_t)co * 3 + plane) * 9 + tap] * scale;
+        if (tp == 0) bias[co] = beta[co] - mean[co] * scale;
+    }
+}
+
+// K3 + first convolution fused (network.py:97): the network input is never materialised.  The
+// three input planes are bit masks (own discs, opponent discs, legal squares), so the 3->C 3x3
+// convolution is, per output pixel, a sum of at most 27 weight rows selected by neighbour bits.
+// One CTA (256 threads) per tile of two boards: thread = (tile row, half of the couts).
+template <int C>
+__global__ void __launch_bounds__(256) conv0_bits_kernel(const uint64_t* __restrict__ bits /*[B][3]*/, int64_t B,
+                                                          const float* __restrict__ wf, const float* __restrict__ bias,
+                                                          __nv_bfloat16* __restrict__ out) {
+    __shared__ __align__(16) float sw[27 * C];
+    __shared__ __align__(16) float sb[C];
+    for (int i = threadIdx.x; i < 27 * C; i += 256) sw[i] = wf[i];
+    for (int i = threadIdx.x; i < C; i += 256) sb[i] = bias[i];
+    __syncthreads();
+    constexpr int H = C / 2;                 // couts per thread
+    const int row = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int y = row >> 4, b = (row >> 3) & 1, x = row & 7;
+    const int64_t board = (int64_t)blockIdx.x * 2 + b;
+    uint64_t pl[3] = {0, 0, 0};
+    if (board < B) { pl[0] = bits[board * 3]; pl[1] = bits[board * 3 + 1]; pl[2] = bits[board * 3 + 2]; }
+    float acc[H];
+#pragma unroll
+    for (int i = 0; i < H; ++i) acc[i] = sb[half * H + i];
+    for (int tap = 0; tap < 9; ++tap) {
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        if (yy < 0 || yy > 7 || xx < 0 || xx > 7) continue;
+        const int sq = yy * 8 + xx;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            if ((pl[p] >> sq) & 1) {
+                const float4* wr = reinterpret_cast<const float4*>(sw + (tap * 3 + p) * C + half * H);
+#pragma unroll
+                for (int i = 0; i < H / 4; ++i) {
+                    const float4 w4 = wr[i];
+                    acc[4 * i] += w4.x; acc[4 * i + 1] += w4.y; acc[4 * i + 2] += w4.z; acc[4 * i + 3] += w4.w;
+                }
+            }
+        }
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + ((size_t)blockIdx.x * 128 + row) * C + half * H);
+#pragma unroll
+    for (int i = 0; i < H / 8; ++i) {
+        uint4 q;
+        __nv_bfloat162* q2 = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            q2[j] = __floats2bfloat162_rn(fmaxf(acc[8 * i + 2 * j], 0.f), fmaxf(acc[8 * i + 2 * j + 1], 0.f));
+        o[i] = q;
+    }
+}
+
+// K3 for the engine: (own, opponent, legal) bit planes of the selected leaves, consumed by the
+// fused first convolution; slots that need no evaluation are zeroed.
+__global__ void __launch_bounds__(256) encode_leaves_kernel(EngineView ev, int k, uint64_t* __restrict__ out) {
+    const int64_t total = (int64_t)ev.G * k;
+    for (int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; slot < total; slot += (int64_t)gridDim.x * blockDim.x) {
         const int g = (int)(slot / k), j = (int)(slot - (int64_t)g * k);
         const size_t o = (size_t)g * ev.kmax + j;
         const uint64_t lm = ev.w_node[o] < 0 ? 0ULL : ev.w_lm[o];
-        uint32_t c01 = 0, c2 = 0;
+        uint64_t P = 0, O = 0;
         if (lm) {
             const bool blk = (ev.w_sf[o] & 0xFF) == 1;
-            const uint64_t P = blk ? ev.w_black[o] : ev.w_white[o], O = blk ? ev.w_white[o] : ev.w_black[o];
-            const uint32_t one = 0x3F80u;
-            c01 = (((P >> sq) & 1) ? one : 0u) | ((((O >> sq) & 1) ? one : 0u) << 16);
-            c2 = ((lm >> sq) & 1) ? one : 0u;
+            P = blk ? ev.w_black[o] : ev.w_white[o];
+            O = blk ? ev.w_white[o] : ev.w_black[o];
         }
-        out[2 * t] = make_uint4(c01, c2, 0u, 0u);
-        out[2 * t + 1] = make_uint4(0u, 0u, 0u, 0u);
+        out[slot * 3] = P; out[slot * 3 + 1] = O; out[slot * 3 + 2] = lm;
     }
 }
 
@@ -243,18 +345,11 @@ template <int RULES>
 __global__ void __launch_bounds__(256) encode_positions_kernel(const uint64_t* __restrict__ black,
                                                                 const uint64_t* __restrict__ white,
                                                                 const uint8_t* __restrict__ side, int64_t n,
-                                                                uint4* __restrict__ out) {
-    const int64_t total = n * 64;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = t >> 6;
-        const int sq = (int)(t & 63);
+                                                                uint64_t* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const bool blk = side[i] == 1;
         const uint64_t P = blk ? black[i] : white[i], O = blk ? white[i] : black[i];
-        const uint64_t L = legal_moves<RULES>(P, O);
-        const uint32_t one = 0x3F80u;
-        out[2 * t] = make_uint4((((P >> sq) & 1) ? one : 0u) | ((((O >> sq) & 1) ? one : 0u) << 16),
-                                ((L >> sq) & 1) ? one : 0u, 0u, 0u);
-        out[2 * t + 1] = make_uint4(0u, 0u, 0u, 0u);
+        out[i * 3] = P; out[i * 3 + 1] = O; out[i * 3 + 2] = legal_moves<RULES>(P, O);
     }
 }
 
@@ -283,14 +378,19 @@ int launch_direct(const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat
 
 }  // namespace
 
-// forward pass on B boards whose bf16 planes are already in n->x0; results in n->probs/logits/values
+// forward pass on B boards whose bit planes are already in n->bits; results in n->probs/logits/values
 int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s) {
     NetState* n = h->net;
     if (!n || !n->loaded) return fail(-7, "network weights not loaded: call rvs_engine_load_weights first");
     if (B > n->max_batch) return fail(-7, "network batch %lld exceeds capacity %lld", (long long)B, (long long)n->max_batch);
     if (B == 0) return 0;
     int rc;
-    if ((rc = launch_direct(n->conv0, n->x0, nullptr, n->a, B, 1, s))) return rc;  // network.py:97
+    {  // network.py:97, fused with the leaf encoding
+        const int tiles = (int)((B + 1) / 2);
+        if (n->C == 64) RVS_LAUNCH(conv0_bits_kernel<64>, tiles, 256, 0, s, n->bits, B, n->w0f, n->b0f, n->a);
+        else if (n->C == 128) RVS_LAUNCH(conv0_bits_kernel<128>, tiles, 256, 0, s, n->bits, B, n->w0f, n->b0f, n->a);
+        else RVS_LAUNCH(conv0_bits_kernel<256>, tiles, 256, 0, s, n->bits, B, n->w0f, n->b0f, n->a);
+    }
     __nv_bfloat16 *x = n->a, *t = n->b, *y = n->c;
     for (int i = 0; i < n->blocks; ++i) {  // ResBlock (network.py:23-28)
         const ConvLayer& c1 = n->tower[2 * i];
@@ -305,7 +405,7 @@ int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s) {
         }
         __nv_bfloat16* tmp = x; x = y; y = tmp;
     }
-    RVS_LAUNCH(heads_kernel, (int)B, 256, 0, s, x, n->C, n->pw, n->pb, n->pfw, n->pfb, n->vw, n->vb, n->v1w, n->v1b,
+    RVS_LAUNCH(heads_kernel, (int)((B + kHB - 1) / kHB), 256, 0, s, x, n->C, B, n->pw, n->pb, n->pfw, n->pfb, n->vw, n->vb, n->v1w, n->v1b,
                n->v2w, n->v2b, want_logits ? n->logits : nullptr, n->probs, n->values);
     return 0;
 }
@@ -335,7 +435,7 @@ int net_create(rvs_engine* h) {
     if ((rc = nalloc(n, &n->pw, (size_t)2 * C)) || (rc = nalloc(n, &n->pb, 2)) || (rc = nalloc(n, &n->pfw, 65 * 128)) ||
         (rc = nalloc(n, &n->pfb, 65)) || (rc = nalloc(n, &n->vw, (size_t)C)) || (rc = nalloc(n, &n->vb, 1)) ||
         (rc = nalloc(n, &n->v1w, 256 * 64)) || (rc = nalloc(n, &n->v1b, 256)) || (rc = nalloc(n, &n->v2w, 256)) ||
-        (rc = nalloc(n, &n->v2b, 1)) || (rc = nalloc(n, &n->x0, B * 64 * 16)) || (rc = nalloc(n, &n->a, B * 64 * C)) ||
+        (rc = nalloc(n, &n->v2b, 1)) || (rc = nalloc(n, &n->bits, B * 3)) || (rc = nalloc(n, &n->w0f, (size_t)27 * C)) || (rc = nalloc(n, &n->b0f, (size_t)C)) || (rc = nalloc(n, &n->a, B * 64 * C)) ||
         (rc = nalloc(n, &n->b, B * 64 * C)) || (rc = nalloc(n, &n->c, B * 64 * C)) || (rc = nalloc(n, &n->probs, B * 65)) ||
         (rc = nalloc(n, &n->logits, B * 65)) || (rc = nalloc(n, &n->values, B)))
         return rc;
@@ -374,7 +474,7 @@ int rvs_net_search(rvs_engine* h, int32_t num_sims, int32_t wave, cudaStream_t s
         const int k = num_sims - start < wave ? num_sims - start : wave;
         if ((rc = rvs_engine_select(h, k, s))) return rc;
         const int64_t B = (int64_t)h->v.G * k;
-        RVS_LAUNCH(encode_leaves_kernel, grid_for(B * 64, 256), 256, 0, s, h->v, k, (uint4*)h->net->x0);
+        RVS_LAUNCH(encode_leaves_kernel, grid_for(B, 256), 256, 0, s, h->v, k, h->net->bits);
         h->launches++;
         if ((rc = net_forward(h, B, false, s))) return rc;
         if ((rc = rvs_engine_process(h, h->net->probs, h->net->values, RVS_MEM_DEVICE, s))) return rc;
@@ -404,6 +504,7 @@ int rvs_engine_load_weights(rvs_engine* h, const float* flat, int64_t n_floats, 
         const float* w = take((int64_t)C * 27);
         const float *g = take(C), *b = take(C), *m = take(C), *v = take(C);
         RVS_LAUNCH(fold_conv3x3_kernel, 64, 256, 0, s, w, g, b, m, v, C, 3, 16, n->conv0.w, n->conv0.bias);
+        RVS_LAUNCH(fold_conv0_kernel, 16, 256, 0, s, w, g, b, m, v, C, n->w0f, n->b0f);
     }
     for (int i = 0; i < 2 * blocks; ++i) {
         const float* w = take((int64_t)C * C * 9);
@@ -414,14 +515,14 @@ int rvs_engine_load_weights(rvs_engine* h, const float* flat, int64_t n_floats, 
         const float* w = take(2 * C);
         const float *g = take(2), *b = take(2), *m = take(2), *v = take(2);
         RVS_LAUNCH(fold_conv1x1_kernel, 4, 128, 0, s, w, g, b, m, v, 2, C, n->pw, n->pb);
-        RVS_CUDA(cudaMemcpyAsync(n->pfw, take(65 * 128), 65 * 128 * 4, cudaMemcpyDeviceToDevice, s));
+        RVS_LAUNCH(transpose_kernel, 32, 256, 0, s, take(65 * 128), n->pfw, 65, 128);
         RVS_CUDA(cudaMemcpyAsync(n->pfb, take(65), 65 * 4, cudaMemcpyDeviceToDevice, s));
     }
     {
         const float* w = take(C);
         const float *g = take(1), *b = take(1), *m = take(1), *v = take(1);
         RVS_LAUNCH(fold_conv1x1_kernel, 2, 128, 0, s, w, g, b, m, v, 1, C, n->vw, n->vb);
-        RVS_CUDA(cudaMemcpyAsync(n->v1w, take(256 * 64), 256 * 64 * 4, cudaMemcpyDeviceToDevice, s));
+        RVS_LAUNCH(transpose_kernel, 64, 256, 0, s, take(256 * 64), n->v1w, 256, 64);
         RVS_CUDA(cudaMemcpyAsync(n->v1b, take(256), 256 * 4, cudaMemcpyDeviceToDevice, s));
         RVS_CUDA(cudaMemcpyAsync(n->v2w, take(256), 256 * 4, cudaMemcpyDeviceToDevice, s));
         RVS_CUDA(cudaMemcpyAsync(n->v2b, take(1), 4, cudaMemcpyDeviceToDevice, s));
@@ -452,11 +553,11 @@ int rvs_engine_predict(rvs_engine* h, const uint64_t* black, const uint64_t* whi
             (rc = arg_in(as, side + off, B, mem, 2, s)))
             return rc;
         if (h->cfg.rules == RVS_RULES_STRICT)
-            RVS_LAUNCH(encode_positions_kernel<RULES_STRICT>, grid_for(B * 64, 256), 256, 0, s, (const uint64_t*)ab.dev,
-                       (const uint64_t*)aw.dev, (const uint8_t*)as.dev, B, (uint4*)n->x0);
+            RVS_LAUNCH(encode_positions_kernel<RULES_STRICT>, grid_for(B, 256), 256, 0, s, (const uint64_t*)ab.dev,
+                       (const uint64_t*)aw.dev, (const uint8_t*)as.dev, B, n->bits);
         else
-            RVS_LAUNCH(encode_positions_kernel<RULES_REF>, grid_for(B * 64, 256), 256, 0, s, (const uint64_t*)ab.dev,
-                       (const uint64_t*)aw.dev, (const uint8_t*)as.dev, B, (uint4*)n->x0);
+            RVS_LAUNCH(encode_positions_kernel<RULES_REF>, grid_for(B, 256), 256, 0, s, (const uint64_t*)ab.dev,
+                       (const uint64_t*)aw.dev, (const uint8_t*)as.dev, B, n->bits);
         if ((rc = net_forward(h, B, true, s))) return rc;
         const cudaMemcpyKind kind = mem == RVS_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
         RVS_CUDA(cudaMemcpyAsync(out_logits + off * 65, n->logits, B * 65 * 4, kind, s));
