@@ -1,0 +1,61 @@
+"""Multi-GPU plumbing for sharded self-play: games are independent, so every rank
+owns a contiguous block of game slots with its own trees, RNG streams and sample ring; the only
+exchanges are a weight broadcast per generation and a replay-sample gather.  Both are plain
+torch.distributed collectives (NCCL over NVLink on the GPU box, gloo in the CPU test tier) and
+neither is inside the search loop.
+
+The reference has no counterpart: its `num_parallel_games` is accepted and ignored
+(src/self_play/self_play.py:30) and `torch.distributed` is imported but unused (src/mcts/mcts.py:11).
+"""
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_games: int, rank: int, world: int) -> Tuple[int, int]:
+    """contiguous block of global game ids owned by `rank`: (first_game, count); sizes differ by <= 1"""
+    base, rem = divmod(n_games, world)
+    count = base + (1 if rank < rem else 0)
+    first = rank * base + min(rank, rem)
+    return first, count
+
+
+def rank_seed(seed: int, rank: int) -> int:
+    """per-rank engine seed so that shards draw disjoint RNG streams"""
+    return (seed * 0x9E3779B97F4A7C15 + (rank + 1) * 0xD1B54A32D192ED03) & 0x7FFFFFFFFFFFFFFF
+
+
+def broadcast_weights(flat: torch.Tensor, src: int = 0) -> torch.Tensor:
+    """trainer rank -> every self-play rank; `flat` = network.pack_state_dict(...)[0] (in place)"""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(flat, src=src)
+    return flat
+
+
+def gather_samples(states: torch.Tensor, pi: torch.Tensor, z: torch.Tensor, dst: int = 0):
+    """variable-length (states [n,3,8,8], pi [n,65], z [n]) from every rank -> concatenated on `dst`
+    (None elsewhere).  Counts are all-gathered first, payloads padded to the maximum count."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return states, pi, z
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = states.device
+    n = torch.tensor([states.shape[0]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    mx = max(max(counts), 1)
+    # one packed row per sample: 192 planes + 65 pi + 1 z
+    row = torch.zeros((mx, 258), dtype=torch.float32, device=dev)
+    k = states.shape[0]
+    if k:
+        row[:k, :192] = states.reshape(k, 192)
+        row[:k, 192:257] = pi
+        row[:k, 257] = z
+    bufs = [torch.empty_like(row) for _ in range(world)] if rank == dst else None
+    dist.gather(row, bufs, dst=dst)
+    if rank != dst:
+        return None
+    parts = [bufs[r][:counts[r]] for r in range(world)]
+    allr = torch.cat(parts, dim=0)
+    return allr[:, :192].reshape(-1, 3, 8, 8), allr[:, 192:257].contiguous(), allr[:, 257].contiguous()

@@ -251,6 +251,53 @@ def run_ours(args):
     torch.cuda.synchronize()
     po_ms = g0.elapsed_time(g1)
 
+    # ---- config-3 side metric: ResNet 5x128 (default_config.json) NN-evaluated self-play ------
+    nn = None
+    if not args.no_nn:
+        torch.manual_seed(42)
+        net = az.AlphaZeroNetwork(8, 5, 128).eval()  # random-init weights of the reference architecture
+        rn = az.RvsNetwork.from_module(net)
+        if dist is not None:  # config 5: the trainer rank broadcasts the packed weights over NCCL
+            from alphazero_reversi_b200 import dist as azd
+            wdev = rn.flat.to(dev) if rank == 0 else torch.zeros_like(rn.flat, device=dev)
+            azd.broadcast_weights(wdev, src=0)
+            rn = az.RvsNetwork(wdev, rn.net_blocks, rn.net_filters)
+        eng3 = az.Engine(N_GAMES, N_SIMS, 1, evaluator=az.EVAL_NN, c_puct=1.0, seed=3000 + rank, device=local,
+                         net_blocks=5, net_filters=128)
+        rn.attach(eng3)
+        eng3.set_positions(pb0, pw0, ps0, stream=stream)
+        for _ in range(2):
+            eng3.search(N_SIMS, 1, stream=stream); eng3.play(1.0, recycle=True, stream=stream)
+        torch.cuda.synchronize()
+        t0s = eng3.stats()
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nn_steps = 3
+        n0.record()
+        for _ in range(nn_steps):
+            eng3.search(N_SIMS, 1, stream=stream); eng3.play(1.0, recycle=True, stream=stream)
+        n1.record()
+        torch.cuda.synchronize()
+        nn_ms = n0.elapsed_time(n1)
+        t1s = eng3.stats()
+        flops_per_eval = 2 * (64 * 27 * 128 + 2 * 5 * 64 * 9 * 128 * 128 + 64 * 128 * 2 + 128 * 65 + 64 * 128 + 64 * 256 + 256)
+        batch_evals = nn_steps * N_SIMS * N_GAMES  # the tower runs on every slot of every wave
+        nn = {"sims_per_sec": (t1s["sims"] - t0s["sims"]) / (nn_ms * 1e-3),
+              "consumed_evals_per_sec": (t1s["evals"] - t0s["evals"]) / (nn_ms * 1e-3),
+              "network_evals_per_sec": batch_evals / (nn_ms * 1e-3), "ms_per_step": nn_ms / nn_steps,
+              "tflops": batch_evals * flops_per_eval / (nn_ms * 1e-3) / 1e12, "flops_per_eval": flops_per_eval}
+        eng3.close()
+
+    # ---- config 5: replay samples of the timed self-play gathered to rank 0 (outside the timing) --
+    gathered = None
+    st_, pi_, z_ = eng.drain_samples(device=dev)
+    if dist is not None:
+        from alphazero_reversi_b200 import dist as azd
+        cap = min(int(st_.shape[0]), 8192)
+        res = azd.gather_samples(st_[:cap].contiguous(), pi_[:cap].contiguous(), z_[:cap].contiguous(), dst=0)
+        gathered = None if res is None else int(res[0].shape[0])
+    else:
+        gathered = int(st_.shape[0])
+
     # ---- reductions over ranks --------------------------------------------------------------
     vals = torch.tensor([ms, e2e_ms, kernel_ms], dtype=torch.float64, device=dev)
     sums = torch.tensor([d["sims"], d["board_steps"], d["evals"], float(launches), e2e_steps * N_GAMES * N_SIMS,
@@ -282,6 +329,7 @@ def run_ours(args):
             "e2e": {"value": e2e_sims / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": N_GAMES * 17,
                     "d2h_bytes_per_step": N_GAMES * 65 * 4, "steps": e2e_steps},
             "gpu_launches": int(launches_all),
+            "samples_gathered_rank0": gathered,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": args.traffic, "peak_source": which, "kernel": ("selfplay_k1_kernel<REF,ROLLOUT>" if persistent else
                                     ("search_k1_kernel<REF,ROLLOUT>" if wave == 1 else "search_fused_kernel<REF,ROLLOUT>")),
@@ -290,6 +338,13 @@ def run_ours(args):
                          "note": "latency/issue-bound integer kernel: rollouts are register resident; see DESIGN.md"},
             "clocks": clocks,
         }
+        if nn is not None:
+            pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1412.9) \
+                if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1400.0
+            nn["roofline"] = {"bound": "tensor", "achieved": nn["tflops"], "peak": pk, "unit": "TFLOP/s",
+                              "frac": nn["tflops"] / pk, "note": "whole search step incl. tree kernels; rank 0"}
+            nn["config"] = "configs[2]: ResNet 5x128 self-play, 100 sims/move, 4096 games, bf16, random-init weights, wave 1"
+            out["nn"] = nn
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(wave, threads=os.cpu_count() or 1, budget_s=12.0)
         print(json.dumps(out))
@@ -405,6 +460,7 @@ def main():
     ap.add_argument("--lockstep", action="store_true", help="wave 1 through search+play launches per ply")
     ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per launch of the search kernel")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-nn", action="store_true", help="skip the config-3 (ResNet) side measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
