@@ -799,7 +799,9 @@ int rvs_engine_stats_get(rvs_engine* h, rvs_engine_stats* out, void* stream) {
     out->games_finished = (int64_t)st[ST_FINISHED];
     out->samples = (int64_t)st[ST_SAMPLES];
     out->launches = h->launches;
-    out->overflow = (int64_t)(st[ST_OVERFLOW] + st[ST_DROPPED] + st[ST_STALLED]);
+    out->overflow = (int64_t)st[ST_OVERFLOW];
+    out->samples_dropped = (int64_t)st[ST_DROPPED];
+    out->stalled = (int64_t)st[ST_STALLED];
     return 0;
 }
 

@@ -17,6 +17,7 @@ class Engine:
         L.check(L.lib().rvs_engine_create(C.byref(cfg), C.byref(self._h)))
         self.n_games, self.max_sims, self.max_wave = n_games, max_sims, max_wave
         self.evaluator, self.rules, self.device = evaluator, rules, device
+        self.sample_capacity = sample_capacity if sample_capacity > 0 else 64 * n_games
         self.cur_k = 0
 
     def close(self):
@@ -108,7 +109,7 @@ class Engine:
 
     def drain_samples(self, capacity=None, device=None, stream=None):
         """completed-game samples (states [n,3,8,8] f32, pi [n,65] f32, z [n] f32)"""
-        cap = capacity if capacity is not None else 64 * self.n_games
+        cap = capacity if capacity is not None else self.sample_capacity
         cnt = C.c_int64(0)
         if device is None:
             st = np.empty((cap, 3, 8, 8), dtype=np.float32)

@@ -121,7 +121,7 @@ class MCTS:
                 eng.process(probs, values)
         visits = eng.root_visits(1)[0]
         st = eng.stats()
-        if st["overflow"]:
+        if st["overflow"] or st["stalled"] or st["samples_dropped"]:
             raise L.RvsError("MCTS engine reported a node-pool overflow / stalled slot")
         self.root = _Root(visits)
         # children exist for every legal square once the root was expanded (mcts.py:406-407)

@@ -84,7 +84,7 @@ class SelfPlay:
             eng.search(S, K)
             eng.play(T, recycle=True)  # finished slots restart at once; surplus games are discarded
             st = eng.stats()
-            if st["overflow"]:
+            if st["overflow"] or st["stalled"] or st["samples_dropped"]:
                 raise L.RvsError(f"engine error counters non-zero: {st}")
             if st["games_finished"] > collected:
                 collected = st["games_finished"]

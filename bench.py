@@ -63,7 +63,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -146,7 +146,8 @@ def run_ours(args):
     lib = az._lib.lib()
     stream = torch.cuda.current_stream().cuda_stream
     wave = args.wave
-    eng = az.Engine(N_GAMES, N_SIMS, max(wave, 64), evaluator=az.EVAL_ROLLOUT, c_puct=1.0, seed=1000 + rank, device=local)
+    eng = az.Engine(N_GAMES, N_SIMS, max(wave, 64), evaluator=az.EVAL_ROLLOUT, c_puct=1.0, seed=1000 + rank, device=local,
+                    sample_capacity=(args.steps + args.warmup + args.presteps + 72) * N_GAMES)
 
     persistent = wave == 1 and not args.lockstep
     ppl = max(1, args.steps_per_launch)
@@ -203,7 +204,7 @@ def run_ours(args):
     kernel_ms = sum(a.elapsed_time(b) for a, b in ks) / len(ks)  # average launch duration of the dominant kernel
     d = {k: s1[k] - s0[k] for k in s1}
     d["n_search_launches"] = len(ks)
-    if s1["overflow"]:
+    if s1["overflow"] or s1["samples_dropped"] or s1["stalled"]:
         raise SystemExit(f"engine error counters non-zero: {s1}")
 
     # ---- e2e: C ABI with host buffers (pinned), H2D + D2H inside the timed region ----------
@@ -450,7 +451,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--presteps", type=int, default=5, help="untimed plies that spread games over all phases")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

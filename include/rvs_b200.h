@@ -118,8 +118,10 @@ typedef struct rvs_engine_stats {
     int64_t games_finished;
     int64_t samples;     /* samples recorded */
     int64_t launches;    /* kernels launched by this engine */
-    int64_t overflow;    /* node-pool overflows + dropped samples + stalled slots (must stay 0) */
+    int64_t overflow;    /* node-pool / path overflows (must stay 0) */
     int64_t tree_bytes;  /* algorithmic HBM bytes of the tree kernels: 32 B per node row touched */
+    int64_t samples_dropped; /* samples lost because the ring was full (drain more often) */
+    int64_t stalled;     /* slots parked after an illegal move choice (num_sims <= wave hazard) */
 } rvs_engine_stats;
 
 int rvs_engine_create(const rvs_engine_config *cfg, rvs_engine **out);
