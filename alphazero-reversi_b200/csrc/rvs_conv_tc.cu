@@ -20,6 +20,7 @@
 #include "rvs_conv_tc.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "rvs_common.cuh"
 
@@ -35,6 +36,8 @@ constexpr int kThreads = 192;
 
 struct Impl {
     CUtensorMap w_map;
+    CUtensorMap w_map2;   // box of C/2 weight rows for the 2-CTA kernel
+    bool two_sm = true;
     const void* act_ptr[4] = {nullptr, nullptr, nullptr, nullptr};
     CUtensorMap act_map[4];
     int n_act = 0;
@@ -281,6 +284,241 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const __grid_co
     }
 }
 
+
+// =============================================================================================
+// 2-CTA variant (cta_group::2).  Profiling the 1-CTA kernel showed the tensor pipe busy 73 % of
+// the time at only 31 % of its throughput: with N = 64 every MMA streams 4 KB of A + 2 KB of B
+// from shared memory for 32 cycles of math (192 B/cycle > the 128 B/cycle SMEM port).  Here a CTA
+// pair computes D[256 px, C couts]: each CTA supplies its own 128-pixel tile (A) and HALF of the
+// weight rows (B, still resident), so one MMA reads 4 KB + 2 KB per CTA for 64 cycles of math
+// (96 B/cycle) and every activation byte is fetched once per cout instead of twice.
+//   * both CTAs run a TMA producer (own A tile, own W half) that signals the LEADER's barriers
+//     (cp.async.bulk.tensor ... .cta_group::2 with the peer bit of the barrier address cleared);
+//   * only the leader (cluster rank 0) issues tcgen05.mma.cta_group::2 and commits with
+//     .multicast::cluster so that "stage free" / "accumulator ready" arrive in both CTAs;
+//   * both CTAs run the epilogue on their own TMEM (128 lanes x C columns, double buffered); the
+//     peer's epilogue warps arrive remotely on the leader's "accumulator free" barrier.
+// =============================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // cute::Sm100MmaPeerBitMask: address of the same offset in the even CTA
+__device__ __forceinline__ void tma2_load_2d(const CUtensorMap* map, uint32_t leader_bar, uint32_t dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(leader_bar & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_5d(const CUtensorMap* map, uint32_t leader_bar, uint32_t dst, int c0, int c1, int c2,
+                                             int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+        "l"(map), "r"(leader_bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tc2_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void tc2_commit_mc(uint32_t bar) {  // arrive on `bar` in BOTH CTAs of the pair
+    asm volatile(
+        "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}" ::"r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {  // arrive on the leader CTA's barrier from either CTA
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquire at cluster scope
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+template <int C>
+struct Cfg2 {
+    static constexpr int KC = C / 64;
+    static constexpr int NH = C / 2;                        // weight rows (couts) held by each CTA
+    static constexpr int W_TILE = NH * 128;                 // bytes of one (tap, kc) weight tile per CTA
+    static constexpr int W_TILES = 9 * KC;
+    static constexpr int STAGES = C == 64 ? 6 : 3;
+    static constexpr int TMEM_COLS = 2 * C;                 // two accumulators of C fp32 columns
+    static constexpr int SMEM = W_TILES * W_TILE + STAGES * kABytes + 1024 + 1024;
+    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+};
+
+template <int C>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap w_map,
+                   const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
+                   const float* __restrict__ bias, int n_tiles) {
+    using K = Cfg2<C>;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t w_s = base;
+    const uint32_t a_s = base + K::W_TILES * K::W_TILE;
+    unsigned char* tail = gen + K::W_TILES * K::W_TILE + K::STAGES * kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 192);
+    float* sbias = reinterpret_cast<float*>(tail + 256);  // [C] <= 256 floats
+    const uint32_t bar0 = smem_u32(bars);
+    auto FULL = [&](int s) { return bar0 + 8u * s; };                       // used in the leader
+    auto EMPTY = [&](int s) { return bar0 + 8u * (K::STAGES + s); };        // both CTAs (multicast commit)
+    const uint32_t WFULL = bar0 + 8u * (2 * K::STAGES);                     // leader
+    auto ACC_FULL = [&](int a) { return bar0 + 8u * (2 * K::STAGES + 1 + a); };   // both CTAs
+    auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (2 * K::STAGES + 3 + a); };  // leader, 8 arrivals
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int n_iters = (n_tiles + 2 * n_pairs - 1) / (2 * n_pairs);  // same trip count in both CTAs of a pair
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < K::STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        mbar_init(WFULL, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(ACC_FULL(a), 1); mbar_init(ACC_EMPTY(a), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < C; i += kThreads) sbias[i] = bias[i];
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(K::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // barriers of both CTAs are initialised before anyone signals across the pair
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer (both CTAs) =====
+            if (rank == 0) mbar_expect_tx(WFULL, 2 * K::W_TILES * K::W_TILE);  // both halves report to the leader
+            for (int tap = 0; tap < 9; ++tap)
+                for (int kc = 0; kc < K::KC; ++kc)
+                    tma2_load_2d(&w_map, WFULL, w_s + (tap * K::KC + kc) * K::W_TILE, kc * 64, tap * C + (int)rank * K::NH);
+            int stage = 0, phase = 0;
+            for (int it = 0; it < n_iters; ++it) {
+                const int tile = (it * n_pairs + pair) * 2 + (int)rank;  // may be >= n_tiles: TMA zero-fills
+                for (int dx = 0; dx < 3; ++dx)
+                    for (int kc = 0; kc < K::KC; ++kc) {
+                        mbar_wait_cluster(EMPTY(stage), phase ^ 1);
+                        if (rank == 0) mbar_expect_tx(FULL(stage), 2 * kABytes);
+                        tma2_load_5d(&a_map, FULL(stage), a_s + stage * kABytes, kc * 64, dx - 1, 0, -1, tile);
+                        if (++stage == K::STAGES) { stage = 0; phase ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {  // ===== MMA issuer (leader only) =====
+            mbar_wait_cluster(WFULL, 0);
+            int stage = 0, phase = 0;
+            for (int it = 0; it < n_iters; ++it) {
+                const int acc = it & 1;
+                mbar_wait_cluster(ACC_EMPTY(acc), ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(acc * C);
+                uint32_t accum = 0;
+                for (int dx = 0; dx < 3; ++dx)
+                    for (int kc = 0; kc < K::KC; ++kc) {
+                        mbar_wait_cluster(FULL(stage), phase);
+                        tc_fence_after();
+                        const uint32_t a0 = a_s + stage * kABytes;
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy) {
+                            const uint32_t wt = w_s + ((dy * 3 + dx) * K::KC + kc) * K::W_TILE;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                tc2_mma(d, make_desc(a0 + dy * 2048 + k * 32), make_desc(wt + k * 32), K::IDESC, accum);
+                                accum = 1;
+                            }
+                        }
+                        tc2_commit_mc(EMPTY(stage));
+                        if (++stage == K::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                tc2_commit_mc(ACC_FULL(acc));
+            }
+        }
+    } else {  // ===== epilogue (both CTAs, own tile) =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        for (int it = 0; it < n_iters; ++it) {
+            const int acc = it & 1;
+            const int tile = (it * n_pairs + pair) * 2 + (int)rank;
+            mbar_wait_cluster(ACC_FULL(acc), (it >> 1) & 1);
+            tc_fence_after();
+            const size_t off = ((size_t)tile * kTileRows + row) * C;
+            const bool live = tile < n_tiles;
+#pragma unroll 1
+            for (int h = 0; h < C / 64; ++h) {  // 64 columns at a time keeps the register footprint at v[64]
+                uint32_t v[64];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C + h * 64);
+                tc_ld32(taddr, v);
+                tc_ld32(taddr + 32, v + 32);
+                tc_wait_ld();
+                if (h == C / 64 - 1) {  // all TMEM reads of this accumulator are done
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(ACC_EMPTY(acc));
+                }
+                if (live) {
+                    uint4* optr = reinterpret_cast<uint4*>(out + off + h * 64);
+                    const uint4* rptr = residual ? reinterpret_cast<const uint4*>(residual + off + h * 64) : nullptr;
+#pragma unroll
+                    for (int c8 = 0; c8 < 8; ++c8) {
+                        float f[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[c8 * 8 + i]) + sbias[h * 64 + c8 * 8 + i];
+                        if (rptr) {
+                            const uint4 r = rptr[c8];
+                            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float2 t = __bfloat1622float2(r2[i]);
+                                f[2 * i] += t.x;
+                                f[2 * i + 1] += t.y;
+                            }
+                        }
+                        uint4 o;
+                        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(fmaxf(f[2 * i], 0.f), fmaxf(f[2 * i + 1], 0.f));
+                        optr[c8] = o;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the peer's shared memory / TMEM stay valid until the leader's MMAs are done
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(K::TMEM_COLS));
+    }
+}
+
 int encode_act_map(CUtensorMap* m, const void* ptr, int C, int64_t n_tiles) {
     EncodeFn enc = get_encode();
     if (!enc) return fail(-9, "cuTensorMapEncodeTiled entry point not available");
@@ -317,6 +555,12 @@ int conv_tc_plan(ConvTcPlan& plan, const __nv_bfloat16* w, int C, int64_t max_ba
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(-9, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+    const cuuint32_t box2[2] = {64, (cuuint32_t)(C / 2)};
+    r = enc(&im->w_map2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(w), dims, strides, box2, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-9, "cuTensorMapEncodeTiled(weights, 2-CTA) failed: %d", (int)r);
+    im->two_sm = !(getenv("RVS_CONV_1SM") && atoi(getenv("RVS_CONV_1SM")) != 0);
     plan.valid = true;
     return 0;
 }
@@ -337,6 +581,20 @@ int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_b
     }
     const int n_tiles = (int)((B + 1) / 2);
     const int C = plan.C;
+    if (im->two_sm) {  // CTA pairs: grid = 2 x pairs, at most one CTA per SM
+        int pairs = (n_tiles + 1) / 2;
+        if (pairs > kNumSMs / 2) pairs = kNumSMs / 2;
+        if (C == 64) {
+            static bool attr = false;
+            if (!attr) { RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<64>::SMEM)); attr = true; }
+            RVS_LAUNCH(conv3x3_tc2_kernel<64>, 2 * pairs, kThreads, Cfg2<64>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles);
+        } else {
+            static bool attr = false;
+            if (!attr) { RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<128>::SMEM)); attr = true; }
+            RVS_LAUNCH(conv3x3_tc2_kernel<128>, 2 * pairs, kThreads, Cfg2<128>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles);
+        }
+        return 0;
+    }
     const int nsplit = C / kNT;
     int ctas = n_tiles * nsplit < kNumSMs ? n_tiles * nsplit : (kNumSMs / nsplit) * nsplit;
     if (C == 64) {

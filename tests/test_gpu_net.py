@@ -177,13 +177,18 @@ def test_tcgen05_tower_matches_direct_kernel(az, nb, nf, n):
     bl, wh = occ & pick, occ & ~pick
     sd = rng.integers(1, 3, n).astype(np.uint8)
     outs = {}
-    for mode in ("1", "0"):
-        os.environ["RVS_NET_DIRECT"] = mode
+    # "1": CUDA-core direct kernel; "0": tcgen05 2-CTA (cta_group::2) kernel; "1sm": 1-CTA kernel
+    for mode in ("1", "0", "1sm"):
+        os.environ["RVS_NET_DIRECT"] = "1" if mode == "1" else "0"
+        os.environ["RVS_CONV_1SM"] = "1" if mode == "1sm" else "0"
         eng = az.Engine(n, 8, 1, evaluator=az.EVAL_NN, net_blocks=nb, net_filters=nf)
         rn.attach(eng)
         outs[mode] = eng.predict(bl, wh, sd)
         eng.close()
     os.environ.pop("RVS_NET_DIRECT")
+    os.environ.pop("RVS_CONV_1SM")
+    # both tensor-core variants run the same MMAs in the same K order: identical results
+    assert np.array_equal(outs["0"][0], outs["1sm"][0]) and np.array_equal(outs["0"][1], outs["1sm"][1])
     dl = np.abs(outs["1"][0] - outs["0"][0]).max()
     dv = np.abs(outs["1"][1] - outs["0"][1]).max()
     scale = np.abs(outs["1"][0]).max()
