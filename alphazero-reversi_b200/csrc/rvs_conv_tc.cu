@@ -362,9 +362,9 @@ struct Cfg2 {
     static constexpr int NH = C / 2;                        // weight rows (couts) held by each CTA
     static constexpr int W_TILE = NH * 128;                 // bytes of one (tap, kc) weight tile per CTA
     static constexpr int W_TILES = 9 * KC;
-    static constexpr int STAGES = C == 64 ? 6 : 3;
+    static constexpr int STAGES = C == 64 ? 6 : 4;           // C = 128: 144 KB weights + 4 x 20 KB = 224 KB
     static constexpr int TMEM_COLS = 2 * C;                 // two accumulators of C fp32 columns
-    static constexpr int SMEM = W_TILES * W_TILE + STAGES * kABytes + 1024 + 1024;
+    static constexpr int SMEM = W_TILES * W_TILE + STAGES * kABytes + 1024 /*align*/ + 1280 /*barriers, bias*/;
     static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 };
 
@@ -466,12 +466,23 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
         for (int it = 0; it < n_iters; ++it) {
             const int acc = it & 1;
             const int tile = (it * n_pairs + pair) * 2 + (int)rank;
-            mbar_wait_cluster(ACC_FULL(acc), (it >> 1) & 1);
-            tc_fence_after();
             const size_t off = ((size_t)tile * kTileRows + row) * C;
             const bool live = tile < n_tiles;
-#pragma unroll 1
-            for (int h = 0; h < C / 64; ++h) {  // 64 columns at a time keeps the register footprint at v[64]
+            // residual row prefetched into registers BEFORE waiting for the accumulator: its HBM/L2
+            // latency hides behind the MMAs of this tile instead of extending the epilogue
+            uint4 res[C / 8];
+            if (residual && live) {
+                const uint4* rptr = reinterpret_cast<const uint4*>(residual + off);
+#pragma unroll
+                for (int i = 0; i < C / 8; ++i) res[i] = rptr[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < C / 8; ++i) res[i] = make_uint4(0, 0, 0, 0);
+            }
+            mbar_wait_cluster(ACC_FULL(acc), (it >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < C / 64; ++h) {  // 64 columns at a time keeps the TMEM staging at v[64]
                 uint32_t v[64];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C + h * 64);
                 tc_ld32(taddr, v);
@@ -484,21 +495,18 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
                 }
                 if (live) {
                     uint4* optr = reinterpret_cast<uint4*>(out + off + h * 64);
-                    const uint4* rptr = residual ? reinterpret_cast<const uint4*>(residual + off + h * 64) : nullptr;
 #pragma unroll
                     for (int c8 = 0; c8 < 8; ++c8) {
                         float f[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[c8 * 8 + i]) + sbias[h * 64 + c8 * 8 + i];
-                        if (rptr) {
-                            const uint4 r = rptr[c8];
-                            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+                        const uint4 r = res[h * 8 + c8];
+                        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float2 t = __bfloat1622float2(r2[i]);
-                                f[2 * i] += t.x;
-                                f[2 * i + 1] += t.y;
-                            }
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 t = __bfloat1622float2(r2[i]);
+                            f[2 * i] += t.x;
+                            f[2 * i + 1] += t.y;
                         }
                         uint4 o;
                         __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
