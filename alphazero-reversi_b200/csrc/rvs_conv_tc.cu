@@ -121,6 +121,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
 }
+// 256-bit global accesses (LDG/STG.E.ENL2.256 on sm_100a): one full 32-byte sector per instruction
+__device__ __forceinline__ void ldg256(const void* p, uint32_t* v) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t* v) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor, K-major, SWIZZLE_128B (cute::UMMA::SmemDescriptor):
@@ -470,14 +481,13 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
             const bool live = tile < n_tiles;
             // residual row prefetched into registers BEFORE waiting for the accumulator: its HBM/L2
             // latency hides behind the MMAs of this tile instead of extending the epilogue
-            uint4 res[C / 8];
+            uint32_t res[C / 2];  // C bf16 = C/2 words, as C/16 256-bit loads
             if (residual && live) {
-                const uint4* rptr = reinterpret_cast<const uint4*>(residual + off);
 #pragma unroll
-                for (int i = 0; i < C / 8; ++i) res[i] = rptr[i];
+                for (int i = 0; i < C / 16; ++i) ldg256(residual + off + i * 16, res + i * 8);
             } else {
 #pragma unroll
-                for (int i = 0; i < C / 8; ++i) res[i] = make_uint4(0, 0, 0, 0);
+                for (int i = 0; i < C / 2; ++i) res[i] = 0u;
             }
             mbar_wait_cluster(ACC_FULL(acc), (it >> 1) & 1);
             tc_fence_after();
@@ -494,25 +504,20 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
                     if (lane == 0) mbar_arrive_leader(ACC_EMPTY(acc));
                 }
                 if (live) {
-                    uint4* optr = reinterpret_cast<uint4*>(out + off + h * 64);
 #pragma unroll
-                    for (int c8 = 0; c8 < 8; ++c8) {
-                        float f[8];
+                    for (int c16 = 0; c16 < 4; ++c16) {  // 16 couts = one 32-byte sector of bf16
+                        uint32_t o[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[c8 * 8 + i]) + sbias[h * 64 + c8 * 8 + i];
-                        const uint4 r = res[h * 8 + c8];
-                        const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float2 t = __bfloat1622float2(r2[i]);
-                            f[2 * i] += t.x;
-                            f[2 * i + 1] += t.y;
+                        for (int i = 0; i < 8; ++i) {
+                            const int col = c16 * 16 + 2 * i;
+                            const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&res[h * 32 + c16 * 8 + i]);
+                            const float2 t = __bfloat1622float2(r2);
+                            const float f0 = __uint_as_float(v[col]) + sbias[h * 64 + col] + t.x;
+                            const float f1 = __uint_as_float(v[col + 1]) + sbias[h * 64 + col + 1] + t.y;
+                            const __nv_bfloat162 ob = __floats2bfloat162_rn(fmaxf(f0, 0.f), fmaxf(f1, 0.f));
+                            o[i] = *reinterpret_cast<const uint32_t*>(&ob);
                         }
-                        uint4 o;
-                        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(fmaxf(f[2 * i], 0.f), fmaxf(f[2 * i + 1], 0.f));
-                        optr[c8] = o;
+                        stg256(out + off + h * 64 + c16 * 16, o);
                     }
                 }
             }

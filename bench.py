@@ -314,6 +314,10 @@ def run_ours(args):
         # algorithmic bytes of the fused search kernel per launch (this rank), from its counters
         tree_bytes = algorithmic_bytes(d)
         achieved = tree_bytes / (kernel_ms * 1e-3) / 1e9
+        traffic = args.traffic  # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
+        tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
+        if traffic is None and persistent and os.path.exists(tpath):
+            traffic = json.load(open(tpath))["selfplay_k1_kernel"]["dram_bytes_per_step"] * min(ppl, args.steps)
         out = {
             "metric": METRIC, "value": sims / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3) + args.presteps, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -332,7 +336,7 @@ def run_ours(args):
             "gpu_launches": int(launches_all),
             "samples_gathered_rank0": gathered,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": args.traffic, "peak_source": which, "kernel": ("selfplay_k1_kernel<REF,ROLLOUT>" if persistent else
+                         "traffic": traffic, "peak_source": which, "kernel": ("selfplay_k1_kernel<REF,ROLLOUT>" if persistent else
                                     ("search_k1_kernel<REF,ROLLOUT>" if wave == 1 else "search_fused_kernel<REF,ROLLOUT>")),
                          "steps_per_launch": ppl if persistent else 1,
                          "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms * len(ks) / ms,
