@@ -310,6 +310,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const __grid_co
 //   * both CTAs run the epilogue on their own TMEM (128 lanes x C columns, double buffered); the
 //     peer's epilogue warps arrive remotely on the leader's "accumulator free" barrier.
 // =============================================================================================
+// programmatic dependent launch: the next layer's prologue (barrier init, TMEM alloc, 144 KB of
+// weights) overlaps the tail of this layer; activations are only touched after pdl_wait()
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -422,6 +427,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
     cluster_sync_all();  // barriers of both CTAs are initialised before anyone signals across the pair
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) pdl_launch_dependents();
 
     if (warp == 0) {
         if (lane == 0) {  // ===== TMA producer (both CTAs) =====
@@ -429,6 +435,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
             for (int tap = 0; tap < 9; ++tap)
                 for (int kc = 0; kc < K::KC; ++kc)
                     tma2_load_2d(&w_map, WFULL, w_s + (tap * K::KC + kc) * K::W_TILE, kc * 64, tap * C + (int)rank * K::NH);
+            pdl_wait();  // weights are constants; activations come from the previous layer
             int stage = 0, phase = 0;
             for (int it = 0; it < n_iters; ++it) {
                 const int tile = (it * n_pairs + pair) * 2 + (int)rank;  // may be >= n_tiles: TMA zero-fills
@@ -474,6 +481,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
     } else {  // ===== epilogue (both CTAs, own tile) =====
         const int q = warp & 3;
         const int row = q * 32 + lane;
+        pdl_wait();
         for (int it = 0; it < n_iters; ++it) {
             const int acc = it & 1;
             const int tile = (it * n_pairs + pair) * 2 + (int)rank;
@@ -530,6 +538,24 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(K::TMEM_COLS));
     }
+}
+
+template <typename Kern>
+int launch_pdl(Kern kern, int grid, int smem, cudaStream_t s, const CUtensorMap& a_map, const CUtensorMap& w_map,
+               const __nv_bfloat16* residual, __nv_bfloat16* out, const float* bias, int n_tiles) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RVS_CUDA(cudaLaunchKernelEx(&cfg, kern, a_map, w_map, residual, out, bias, n_tiles));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
 }
 
 int encode_act_map(CUtensorMap* m, const void* ptr, int C, int64_t n_tiles) {
@@ -600,11 +626,11 @@ int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_b
         if (C == 64) {
             static bool attr = false;
             if (!attr) { RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<64>::SMEM)); attr = true; }
-            RVS_LAUNCH(conv3x3_tc2_kernel<64>, 2 * pairs, kThreads, Cfg2<64>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles);
+            return launch_pdl(conv3x3_tc2_kernel<64>, 2 * pairs, Cfg2<64>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles);
         } else {
             static bool attr = false;
             if (!attr) { RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<128>::SMEM)); attr = true; }
-            RVS_LAUNCH(conv3x3_tc2_kernel<128>, 2 * pairs, kThreads, Cfg2<128>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles);
+            return launch_pdl(conv3x3_tc2_kernel<128>, 2 * pairs, Cfg2<128>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles);
         }
         return 0;
     }

@@ -276,50 +276,50 @@ __global__ void fold_conv0_kernel(const float* __restrict__ w, const float* __re
 // K3 + first convolution fused (network.py:97): the network input is never materialised.  The
 // three input planes are bit masks (own discs, opponent discs, legal squares), so the 3->C 3x3
 // convolution is, per output pixel, a sum of at most 27 weight rows selected by neighbour bits.
-// One CTA (256 threads) per tile of two boards: thread = (tile row, half of the couts).
+// One warp per output pixel, lanes across the output channels (C/32 each): the bit tests are
+// warp-uniform (no divergence), only set bits cost work, and a warp writes one contiguous row.
 template <int C>
 __global__ void __launch_bounds__(256) conv0_bits_kernel(const uint64_t* __restrict__ bits /*[B][3]*/, int64_t B,
                                                           const float* __restrict__ wf, const float* __restrict__ bias,
                                                           __nv_bfloat16* __restrict__ out) {
+    constexpr int PER = C / 32;  // couts per lane: 2, 4 or 8
     __shared__ __align__(16) float sw[27 * C];
-    __shared__ __align__(16) float sb[C];
     for (int i = threadIdx.x; i < 27 * C; i += 256) sw[i] = wf[i];
-    for (int i = threadIdx.x; i < C; i += 256) sb[i] = bias[i];
     __syncthreads();
-    constexpr int H = C / 2;                 // couts per thread
-    const int row = threadIdx.x & 127, half = threadIdx.x >> 7;
-    const int y = row >> 4, b = (row >> 3) & 1, x = row & 7;
-    const int64_t board = (int64_t)blockIdx.x * 2 + b;
-    uint64_t pl[3] = {0, 0, 0};
-    if (board < B) { pl[0] = bits[board * 3]; pl[1] = bits[board * 3 + 1]; pl[2] = bits[board * 3 + 2]; }
-    float acc[H];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float bv[PER];
 #pragma unroll
-    for (int i = 0; i < H; ++i) acc[i] = sb[half * H + i];
-    for (int tap = 0; tap < 9; ++tap) {
-        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-        if (yy < 0 || yy > 7 || xx < 0 || xx > 7) continue;
-        const int sq = yy * 8 + xx;
+    for (int i = 0; i < PER; ++i) bv[i] = bias[lane * PER + i];
+    // one CTA per tile of two boards = 128 rows; warp w handles rows w, w+8, ...
+    const int64_t tile = blockIdx.x;
+    const uint64_t* b0 = bits + tile * 6;
+    const bool h0 = tile * 2 < B, h1 = tile * 2 + 1 < B;
+    const uint64_t a0 = h0 ? b0[0] : 0ULL, a1 = h0 ? b0[1] : 0ULL, a2 = h0 ? b0[2] : 0ULL;
+    const uint64_t c0 = h1 ? b0[3] : 0ULL, c1 = h1 ? b0[4] : 0ULL, c2 = h1 ? b0[5] : 0ULL;
+    for (int row = warp; row < 128; row += 8) {
+        const int y = row >> 4, b = (row >> 3) & 1, x = row & 7;
+        const uint64_t pl[3] = {b ? c0 : a0, b ? c1 : a1, b ? c2 : a2};
+        float acc[PER];
 #pragma unroll
-        for (int p = 0; p < 3; ++p) {
-            if ((pl[p] >> sq) & 1) {
-                const float4* wr = reinterpret_cast<const float4*>(sw + (tap * 3 + p) * C + half * H);
+        for (int i = 0; i < PER; ++i) acc[i] = bv[i];
 #pragma unroll
-                for (int i = 0; i < H / 4; ++i) {
-                    const float4 w4 = wr[i];
-                    acc[4 * i] += w4.x; acc[4 * i + 1] += w4.y; acc[4 * i + 2] += w4.z; acc[4 * i + 3] += w4.w;
+        for (int tap = 0; tap < 9; ++tap) {
+            const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+            if (yy < 0 || yy > 7 || xx < 0 || xx > 7) continue;  // warp-uniform
+            const int sq = yy * 8 + xx;
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+                if ((pl[p] >> sq) & 1) {                         // warp-uniform
+                    const float* wr = sw + (tap * 3 + p) * C + lane * PER;
+#pragma unroll
+                    for (int i = 0; i < PER; ++i) acc[i] += wr[i];
                 }
             }
         }
-    }
-    uint4* o = reinterpret_cast<uint4*>(out + ((size_t)blockIdx.x * 128 + row) * C + half * H);
+        __nv_bfloat16* o = out + ((size_t)tile * 128 + row) * C + lane * PER;
 #pragma unroll
-    for (int i = 0; i < H / 8; ++i) {
-        uint4 q;
-        __nv_bfloat162* q2 = reinterpret_cast<__nv_bfloat162*>(&q);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            q2[j] = __floats2bfloat162_rn(fmaxf(acc[8 * i + 2 * j], 0.f), fmaxf(acc[8 * i + 2 * j + 1], 0.f));
-        o[i] = q;
+        for (int i = 0; i < PER; i += 2)
+            *reinterpret_cast<__nv_bfloat162*>(o + i) = __floats2bfloat162_rn(fmaxf(acc[i], 0.f), fmaxf(acc[i + 1], 0.f));
     }
 }
 
