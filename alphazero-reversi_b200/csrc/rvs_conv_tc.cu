@@ -38,6 +38,7 @@ struct Impl {
     CUtensorMap w_map;
     CUtensorMap w_map2;   // box of C/2 weight rows for the 2-CTA kernel
     bool two_sm = true;
+    int cin = 0;
     const void* act_ptr[4] = {nullptr, nullptr, nullptr, nullptr};
     CUtensorMap act_map[4];
     int n_act = 0;
@@ -372,24 +373,24 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     } while (!done);
 }
 
-template <int C>
+template <int C, int CIN>
 struct Cfg2 {
-    static constexpr int KC = C / 64;
+    static constexpr int KC = CIN / 64;
     static constexpr int NH = C / 2;                        // weight rows (couts) held by each CTA
     static constexpr int W_TILE = NH * 128;                 // bytes of one (tap, kc) weight tile per CTA
     static constexpr int W_TILES = 9 * KC;
-    static constexpr int STAGES = C == 64 ? 6 : 4;           // C = 128: 144 KB weights + 4 x 20 KB = 224 KB
+    static constexpr int STAGES = (C == 128 && CIN == 128) ? 4 : 6;  // 128->128: 144 KB weights + 4 x 20 KB = 224 KB
     static constexpr int TMEM_COLS = 2 * C;                 // two accumulators of C fp32 columns
     static constexpr int SMEM = W_TILES * W_TILE + STAGES * kABytes + 1024 /*align*/ + 1280 /*barriers, bias*/;
     static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 };
 
-template <int C>
+template <int C, int CIN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap w_map,
                    const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
                    const float* __restrict__ bias, int n_tiles) {
-    using K = Cfg2<C>;
+    using K = Cfg2<C, CIN>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -558,7 +559,7 @@ int launch_pdl(Kern kern, int grid, int smem, cudaStream_t s, const CUtensorMap&
     return 0;
 }
 
-int encode_act_map(CUtensorMap* m, const void* ptr, int C, int64_t n_tiles) {
+int encode_act_map(CUtensorMap* m, const void* ptr, int C /*channels of this buffer*/, int64_t n_tiles) {
     EncodeFn enc = get_encode();
     if (!enc) return fail(-9, "cuTensorMapEncodeTiled entry point not available");
     // tiled activation layout [tile][y][board][x][c]  (dims innermost first)
@@ -575,19 +576,21 @@ int encode_act_map(CUtensorMap* m, const void* ptr, int C, int64_t n_tiles) {
 
 }  // namespace
 
-int conv_tc_plan(ConvTcPlan& plan, const __nv_bfloat16* w, int C, int64_t max_batch) {
+int conv_tc_plan(ConvTcPlan& plan, const __nv_bfloat16* w, int C, int64_t max_batch, int cin) {
     plan.valid = false;
     plan.C = C;
     plan.max_batch = max_batch;
-    if (C != 64 && C != 128) return 0;  // 256 filters: resident weights do not fit; direct path
+    if (cin <= 0) cin = C;
+    if (!((C == 64 && cin == 64) || (C == 128 && (cin == 128 || cin == 64)))) return 0;  // 256 filters: resident weights do not fit; direct path
     EncodeFn enc = get_encode();
     if (!enc) return fail(-9, "cuTensorMapEncodeTiled entry point not available");
     Impl* im = plan.impl ? static_cast<Impl*>(plan.impl) : new Impl();
     plan.impl = im;
     im->n_act = 0;
-    // weights [9*C rows (tap, cout)][C cin] bf16, box = 64 cin x 64 couts
-    const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)9 * C};
-    const cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    im->cin = cin;
+    // weights [9*C rows (tap, cout)][cin] bf16, box = 64 cin x 64 couts
+    const cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)9 * C};
+    const cuuint64_t strides[1] = {(cuuint64_t)cin * 2};
     const cuuint32_t box[2] = {64, kNT};
     const cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&im->w_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(w), dims, strides, box, es,
@@ -614,7 +617,7 @@ int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_b
     if (slot < 0) {
         if (im->n_act == 4) im->n_act = 0;
         slot = im->n_act++;
-        int rc = encode_act_map(&im->act_map[slot], in, plan.C, (plan.max_batch + 1) / 2);
+        int rc = encode_act_map(&im->act_map[slot], in, im->cin, (plan.max_batch + 1) / 2);
         if (rc) return rc;
         im->act_ptr[slot] = in;
     }
@@ -625,15 +628,20 @@ int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_b
         if (pairs > kNumSMs / 2) pairs = kNumSMs / 2;
         if (C == 64) {
             static bool attr = false;
-            if (!attr) { RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<64>::SMEM)); attr = true; }
-            return launch_pdl(conv3x3_tc2_kernel<64>, 2 * pairs, Cfg2<64>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles);
+            if (!attr) { RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<64, 64>::SMEM)); attr = true; }
+            return launch_pdl(conv3x3_tc2_kernel<64, 64>, 2 * pairs, Cfg2<64, 64>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles);
+        } else if (im->cin == 64) {  // first layer of a 128-filter tower: 64 (3 used) -> 128
+            static bool attr = false;
+            if (!attr) { RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<128, 64>::SMEM)); attr = true; }
+            return launch_pdl(conv3x3_tc2_kernel<128, 64>, 2 * pairs, Cfg2<128, 64>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles);
         } else {
             static bool attr = false;
-            if (!attr) { RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<128>::SMEM)); attr = true; }
-            return launch_pdl(conv3x3_tc2_kernel<128>, 2 * pairs, Cfg2<128>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles);
+            if (!attr) { RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<128, 128>::SMEM)); attr = true; }
+            return launch_pdl(conv3x3_tc2_kernel<128, 128>, 2 * pairs, Cfg2<128, 128>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles);
         }
         return 0;
     }
+    if (im->cin != C) return fail(-8, "1-CTA tcgen05 convolution supports cin == cout only");
     const int nsplit = C / kNT;
     int ctas = n_tiles * nsplit < kNumSMs ? n_tiles * nsplit : (kNumSMs / nsplit) * nsplit;
     if (C == 64) {

@@ -19,8 +19,8 @@ struct ConvTcPlan {
     void* impl = nullptr;
 };
 
-// builds the TMA descriptors for one layer's folded weights [9][C][C] bf16
-int conv_tc_plan(ConvTcPlan& plan, const __nv_bfloat16* w, int C, int64_t max_batch);
+// builds the TMA descriptors for one layer's folded weights [9][C][cin] bf16 (cin = C by default)
+int conv_tc_plan(ConvTcPlan& plan, const __nv_bfloat16* w, int C, int64_t max_batch, int cin = 0);
 // out = relu(conv3x3(in) + bias [+ residual]) on B boards, NHWC bf16
 int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
                    const float* bias, int64_t B, cudaStream_t s);

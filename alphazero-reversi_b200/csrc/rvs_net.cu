@@ -34,6 +34,7 @@ struct NetState {
     float *v1w = nullptr, *v1b = nullptr;    // fc1 TRANSPOSED [64][256], [256]
     float *w0f = nullptr, *b0f = nullptr;    // first conv for the bit-plane kernel: [27][C] f32, [C]
     uint64_t* bits = nullptr;                // [B][3] own / opponent / legal bit planes (K3 output)
+    __nv_bfloat16* x0 = nullptr;             // [tile][y][board][x][64] bf16 input planes (3 used) for the tcgen05 first layer
     float *v2w = nullptr, *v2b = nullptr;    // fc2 [256], [1]
     // activations
     __nv_bfloat16 *a = nullptr, *b = nullptr, *c = nullptr;  // [tile][y][board][x][C] (act_row)
@@ -323,6 +324,29 @@ __global__ void __launch_bounds__(256) conv0_bits_kernel(const uint64_t* __restr
     }
 }
 
+// bit planes -> bf16 input tiles [tile][y][board][x][64] (channels 0..2 used) for the tensor-core first
+// layer: one thread per pixel row, 128 B = 4 x 256-bit... written as 8 x uint4
+__global__ void __launch_bounds__(256) planes_tiles_kernel(const uint64_t* __restrict__ bits, int64_t B, int64_t n_tiles,
+                                                            uint4* __restrict__ out) {
+    const int64_t total = n_tiles * 128;
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < total; r += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t tile = r >> 7;
+        const int row = (int)(r & 127), y = row >> 4, b = (row >> 3) & 1, x = row & 7;
+        const int64_t board = tile * 2 + b;
+        uint32_t c01 = 0, c2 = 0;
+        if (board < B) {
+            const int sq = y * 8 + x;
+            const uint32_t one = 0x3F80u;
+            c01 = (((bits[board * 3] >> sq) & 1) ? one : 0u) | ((((bits[board * 3 + 1] >> sq) & 1) ? one : 0u) << 16);
+            c2 = ((bits[board * 3 + 2] >> sq) & 1) ? one : 0u;
+        }
+        uint4* o = out + r * 8;
+        o[0] = make_uint4(c01, c2, 0u, 0u);
+#pragma unroll
+        for (int i = 1; i < 8; ++i) o[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
 // K3 for the engine: (own, opponent, legal) bit planes of the selected leaves, consumed by the
 // fused first convolution; slots that need no evaluation are zeroed.
 __global__ void __launch_bounds__(256) encode_leaves_kernel(EngineView ev, int k, uint64_t* __restrict__ out) {
@@ -385,7 +409,11 @@ int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s) {
     if (B > n->max_batch) return fail(-7, "network batch %lld exceeds capacity %lld", (long long)B, (long long)n->max_batch);
     if (B == 0) return 0;
     int rc;
-    {  // network.py:97, fused with the leaf encoding
+    if (!n->force_direct && n->conv0.tc.valid) {  // first layer on the tensor cores: planes -> bf16 tiles -> tcgen05
+        const int64_t tiles = (B + 1) / 2;
+        RVS_LAUNCH(planes_tiles_kernel, grid_for(tiles * 128, 256), 256, 0, s, n->bits, B, tiles, (uint4*)n->x0);
+        if ((rc = conv_tc_launch(n->conv0.tc, n->x0, nullptr, n->a, n->conv0.bias, B, s))) return rc;
+    } else {  // network.py:97, fused with the leaf encoding (CUDA cores)
         const int tiles = (int)((B + 1) / 2);
         if (n->C == 64) RVS_LAUNCH(conv0_bits_kernel<64>, tiles, 256, 0, s, n->bits, B, n->w0f, n->b0f, n->a);
         else if (n->C == 128) RVS_LAUNCH(conv0_bits_kernel<128>, tiles, 256, 0, s, n->bits, B, n->w0f, n->b0f, n->a);
@@ -424,8 +452,10 @@ int net_create(rvs_engine* h) {
     const size_t B = (size_t)((n->max_batch + 1) / 2) * 2;  // whole tiles of two boards
     int rc = 0;
     n->tower = new ConvLayer[2 * blocks];
-    if ((rc = nalloc(n, &n->conv0.w, (size_t)9 * C * 16)) || (rc = nalloc(n, &n->conv0.bias, (size_t)C))) return rc;
-    n->conv0.cin = 16; n->conv0.cout = C;
+    if ((rc = nalloc(n, &n->conv0.w, (size_t)9 * C * 64)) || (rc = nalloc(n, &n->conv0.bias, (size_t)C)) ||
+        (rc = nalloc(n, &n->x0, B * 64 * 64)))
+        return rc;
+    n->conv0.cin = 64; n->conv0.cout = C;
     // one contiguous slab for the tower weights so that a single TMA descriptor family covers it
     for (int i = 0; i < 2 * blocks; ++i) {
         ConvLayer& L = n->tower[i];
@@ -459,6 +489,7 @@ void rvs_net_destroy(rvs::NetState* n) {
     for (int i = 0; i < n->n_allocs; ++i) cudaFree(n->allocs[i]);
     if (n->flat) cudaFree(n->flat);
     for (int i = 0; i < 2 * n->blocks; ++i) conv_tc_destroy(n->tower[i].tc);
+    conv_tc_destroy(n->conv0.tc);
     delete[] n->tower;
     delete n;
 }
@@ -503,7 +534,7 @@ int rvs_engine_load_weights(rvs_engine* h, const float* flat, int64_t n_floats, 
     {
         const float* w = take((int64_t)C * 27);
         const float *g = take(C), *b = take(C), *m = take(C), *v = take(C);
-        RVS_LAUNCH(fold_conv3x3_kernel, 64, 256, 0, s, w, g, b, m, v, C, 3, 16, n->conv0.w, n->conv0.bias);
+        RVS_LAUNCH(fold_conv3x3_kernel, 64, 256, 0, s, w, g, b, m, v, C, 3, 64, n->conv0.w, n->conv0.bias);
         RVS_LAUNCH(fold_conv0_kernel, 16, 256, 0, s, w, g, b, m, v, C, n->w0f, n->b0f);
     }
     for (int i = 0; i < 2 * blocks; ++i) {
@@ -529,6 +560,9 @@ int rvs_engine_load_weights(rvs_engine* h, const float* flat, int64_t n_floats, 
     }
     for (int i = 0; i < 2 * blocks; ++i) {
         if ((rc = conv_tc_plan(n->tower[i].tc, n->tower[i].w, C, n->max_batch))) return rc;
+    }
+    if (C == 128 && !(getenv("RVS_CONV_1SM") && atoi(getenv("RVS_CONV_1SM")) != 0)) {
+        if ((rc = conv_tc_plan(n->conv0.tc, n->conv0.w, C, n->max_batch, 64))) return rc;
     }
     RVS_CUDA(cudaStreamSynchronize(s));
     n->loaded = true;
