@@ -373,6 +373,15 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     } while (!done);
 }
 
+// HEAD variant (last tower layer): the policy / value 1x1 convolutions + BN + ReLU
+// (network.py:104-105, 111-112) are three dot products over the output row the epilogue already
+// holds in registers, so the 67 MB activation write and its re-read by the head kernel disappear;
+// weights travel in the kernel parameter space (constant cache, warp-uniform reads).
+struct HeadW {
+    float w[3][128];
+    float b[4];
+};
+
 template <int C, int CIN>
 struct Cfg2 {
     static constexpr int KC = CIN / 64;
@@ -385,11 +394,12 @@ struct Cfg2 {
     static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 };
 
-template <int C, int CIN>
+template <int C, int CIN, bool HEAD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap w_map,
                    const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
-                   const float* __restrict__ bias, int n_tiles) {
+                   const float* __restrict__ bias, int n_tiles, const __grid_constant__ HeadW head,
+                   float* __restrict__ feat) {
     using K = Cfg2<C, CIN>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -490,6 +500,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
             const bool live = tile < n_tiles;
             // residual row prefetched into registers BEFORE waiting for the accumulator: its HBM/L2
             // latency hides behind the MMAs of this tile instead of extending the epilogue
+            float hd0 = 0.f, hd1 = 0.f, hd2 = 0.f;
             uint32_t res[C / 2];  // C bf16 = C/2 words, as C/16 256-bit loads
             if (residual && live) {
 #pragma unroll
@@ -516,6 +527,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
 #pragma unroll
                     for (int c16 = 0; c16 < 4; ++c16) {  // 16 couts = one 32-byte sector of bf16
                         uint32_t o[8];
+                        (void)o;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int col = c16 * 16 + 2 * i;
@@ -524,11 +536,26 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
                             const float f0 = __uint_as_float(v[col]) + sbias[h * 64 + col] + t.x;
                             const float f1 = __uint_as_float(v[col + 1]) + sbias[h * 64 + col + 1] + t.y;
                             const __nv_bfloat162 ob = __floats2bfloat162_rn(fmaxf(f0, 0.f), fmaxf(f1, 0.f));
-                            o[i] = *reinterpret_cast<const uint32_t*>(&ob);
+                            if (HEAD) {  // the heads see the same bf16-rounded activations as the unfused path
+                                const float2 a = __bfloat1622float2(ob);
+                                const int cc = h * 64 + col;
+                                hd0 = fmaf(a.x, head.w[0][cc], fmaf(a.y, head.w[0][cc + 1], hd0));
+                                hd1 = fmaf(a.x, head.w[1][cc], fmaf(a.y, head.w[1][cc + 1], hd1));
+                                hd2 = fmaf(a.x, head.w[2][cc], fmaf(a.y, head.w[2][cc + 1], hd2));
+                            } else {
+                                o[i] = *reinterpret_cast<const uint32_t*>(&ob);
+                            }
                         }
-                        stg256(out + off + h * 64 + c16 * 16, o);
+                        if (!HEAD) stg256(out + off + h * 64 + c16 * 16, o);
                     }
                 }
+            }
+            if (HEAD && live) {  // feat[board][plane*64 + px], plane 0/1 policy, 2 value
+                const int y = row >> 4, b = (row >> 3) & 1, x = row & 7;
+                float* fp = feat + ((size_t)tile * 2 + b) * 192 + y * 8 + x;
+                fp[0] = fmaxf(hd0 + head.b[0], 0.f);
+                fp[64] = fmaxf(hd1 + head.b[1], 0.f);
+                fp[128] = fmaxf(hd2 + head.b[2], 0.f);
             }
         }
     }
@@ -543,7 +570,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
 
 template <typename Kern>
 int launch_pdl(Kern kern, int grid, int smem, cudaStream_t s, const CUtensorMap& a_map, const CUtensorMap& w_map,
-               const __nv_bfloat16* residual, __nv_bfloat16* out, const float* bias, int n_tiles) {
+               const __nv_bfloat16* residual, __nv_bfloat16* out, const float* bias, int n_tiles, const HeadW& head,
+               float* feat) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
@@ -554,7 +582,7 @@ int launch_pdl(Kern kern, int grid, int smem, cudaStream_t s, const CUtensorMap&
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    RVS_CUDA(cudaLaunchKernelEx(&cfg, kern, a_map, w_map, residual, out, bias, n_tiles));
+    RVS_CUDA(cudaLaunchKernelEx(&cfg, kern, a_map, w_map, residual, out, bias, n_tiles, head, feat));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
@@ -608,9 +636,20 @@ int conv_tc_plan(ConvTcPlan& plan, const __nv_bfloat16* w, int C, int64_t max_ba
 }
 
 int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
-                   const float* bias, int64_t B, cudaStream_t s) {
+                   const float* bias, int64_t B, cudaStream_t s, const float* head_host, float* feat) {
     if (!plan.valid || !plan.impl) return fail(-8, "tcgen05 convolution: no plan");
     Impl* im = static_cast<Impl*>(plan.impl);
+    static HeadW zero_head = {};
+    static HeadW cur_head = {};
+    const HeadW* hw = &zero_head;
+    if (feat && head_host && im->two_sm) {  // head_host: [3][C] folded 1x1 weights followed by 3 biases (host memory)
+        for (int j = 0; j < 3; ++j)
+            for (int c = 0; c < 128; ++c) cur_head.w[j][c] = c < plan.C ? head_host[j * plan.C + c] : 0.f;
+        for (int j = 0; j < 3; ++j) cur_head.b[j] = head_host[3 * plan.C + j];
+        hw = &cur_head;
+    } else {
+        feat = nullptr;
+    }
     int slot = -1;
     for (int i = 0; i < im->n_act; ++i)
         if (im->act_ptr[i] == in) slot = i;
@@ -628,16 +667,26 @@ int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_b
         if (pairs > kNumSMs / 2) pairs = kNumSMs / 2;
         if (C == 64) {
             static bool attr = false;
-            if (!attr) { RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<64, 64>::SMEM)); attr = true; }
-            return launch_pdl(conv3x3_tc2_kernel<64, 64>, 2 * pairs, Cfg2<64, 64>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles);
+            if (!attr) {
+                RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<64, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<64, 64>::SMEM));
+                RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<64, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<64, 64>::SMEM));
+                attr = true;
+            }
+            if (feat) return launch_pdl(conv3x3_tc2_kernel<64, 64, true>, 2 * pairs, Cfg2<64, 64>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles, *hw, feat);
+            return launch_pdl(conv3x3_tc2_kernel<64, 64, false>, 2 * pairs, Cfg2<64, 64>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles, *hw, feat);
         } else if (im->cin == 64) {  // first layer of a 128-filter tower: 64 (3 used) -> 128
             static bool attr = false;
-            if (!attr) { RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<128, 64>::SMEM)); attr = true; }
-            return launch_pdl(conv3x3_tc2_kernel<128, 64>, 2 * pairs, Cfg2<128, 64>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles);
+            if (!attr) { RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<128, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<128, 64>::SMEM)); attr = true; }
+            return launch_pdl(conv3x3_tc2_kernel<128, 64, false>, 2 * pairs, Cfg2<128, 64>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles, *hw, nullptr);
         } else {
             static bool attr = false;
-            if (!attr) { RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<128, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<128, 128>::SMEM)); attr = true; }
-            return launch_pdl(conv3x3_tc2_kernel<128, 128>, 2 * pairs, Cfg2<128, 128>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles);
+            if (!attr) {
+                RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<128, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<128, 128>::SMEM));
+                RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<128, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<128, 128>::SMEM));
+                attr = true;
+            }
+            if (feat) return launch_pdl(conv3x3_tc2_kernel<128, 128, true>, 2 * pairs, Cfg2<128, 128>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles, *hw, feat);
+            return launch_pdl(conv3x3_tc2_kernel<128, 128, false>, 2 * pairs, Cfg2<128, 128>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles, *hw, feat);
         }
         return 0;
     }
@@ -662,4 +711,10 @@ void conv_tc_destroy(ConvTcPlan& plan) {
     plan.valid = false;
 }
 
+}  // namespace rvs
+
+namespace rvs {
+bool conv_tc_can_fuse_head(const ConvTcPlan& plan) {
+    return plan.valid && plan.impl && static_cast<Impl*>(plan.impl)->two_sm && static_cast<Impl*>(plan.impl)->cin == plan.C;
+}
 }  // namespace rvs

@@ -39,6 +39,8 @@ struct NetState {
     // activations
     __nv_bfloat16 *a = nullptr, *b = nullptr, *c = nullptr;  // [tile][y][board][x][C] (act_row)
     float *probs = nullptr, *logits = nullptr, *values = nullptr;          // [B][65], [B][65], [B]
+    float* feat = nullptr;                   // [B][192] head planes written by the fused last-layer epilogue
+    float head_host[3 * 256 + 4];            // host copy of the folded 1x1 head weights [3][C] + 3 biases
     float* flat = nullptr;  // staging of the raw state_dict
     bool loaded = false;
     bool force_direct = false;  // RVS_NET_DIRECT=1: run the tower on the CUDA-core kernel (debug)
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(256) conv3x3_direct_kernel(const __nv_bfloat16
 // addresses, each weight reused for the 8 boards; (3) one warp per board: softmax over the 65
 // logits (no legal-move masking: mcts.py:596 applies the plain softmax), value_fc2 + tanh.
 constexpr int kHB = 8;
-__global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restrict__ x, int C, int64_t B,
+__global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ feat_in, int C, int64_t B,
                                                      const float* __restrict__ pw, const float* __restrict__ pb,
                                                      const float* __restrict__ pfwT, const float* __restrict__ pfb,
                                                      const float* __restrict__ vw, const float* __restrict__ vb,
@@ -176,9 +178,15 @@ __global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restr
     __shared__ float lg[kHB][68];
     const int t = threadIdx.x;
     const int64_t board0 = (int64_t)blockIdx.x * kHB;
+    if (feat_in) {  // (1') the last tower layer already produced the three head planes (fused epilogue)
+        for (int i = t; i < kHB * 192; i += 256) {
+            const int bi = i / 192;
+            feat[bi][i - bi * 192] = board0 + bi < B ? feat_in[(size_t)(board0 + bi) * 192 + (i - bi * 192)] : 0.f;
+        }
+    }
     for (int i = t; i < 3 * C; i += 256) w1x1[i] = i < 2 * C ? pw[i] : vw[i - 2 * C];
     __syncthreads();
-    for (int p = t; p < kHB * 64; p += 256) {  // (1) 1x1 convs
+    for (int p = t; p < kHB * 64 && !feat_in; p += 256) {  // (1) 1x1 convs
         const int bi = p >> 6, px = p & 63;
         const int64_t board = board0 + bi;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f;
@@ -420,6 +428,7 @@ int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s) {
         else RVS_LAUNCH(conv0_bits_kernel<256>, tiles, 256, 0, s, n->bits, B, n->w0f, n->b0f, n->a);
     }
     __nv_bfloat16 *x = n->a, *t = n->b, *y = n->c;
+    bool fused_head = false;
     for (int i = 0; i < n->blocks; ++i) {  // ResBlock (network.py:23-28)
         const ConvLayer& c1 = n->tower[2 * i];
         const ConvLayer& c2 = n->tower[2 * i + 1];
@@ -428,12 +437,14 @@ int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s) {
             if ((rc = launch_direct(c2, t, x, y, B, 1, s))) return rc;
         } else {
             if ((rc = conv_tc_launch(c1.tc, x, nullptr, t, c1.bias, B, s))) return rc;
-            if ((rc = conv_tc_launch(c2.tc, t, x, y, c2.bias, B, s))) return rc;
-            h->launches += 0;
+            if (i == n->blocks - 1 && conv_tc_can_fuse_head(c2.tc)) {  // last layer: heads' 1x1 convs in the epilogue
+                if ((rc = conv_tc_launch(c2.tc, t, x, y, c2.bias, B, s, n->head_host, n->feat))) return rc;
+                fused_head = true;
+            } else if ((rc = conv_tc_launch(c2.tc, t, x, y, c2.bias, B, s))) return rc;
         }
         __nv_bfloat16* tmp = x; x = y; y = tmp;
     }
-    RVS_LAUNCH(heads_kernel, (int)((B + kHB - 1) / kHB), 256, 0, s, x, n->C, B, n->pw, n->pb, n->pfw, n->pfb, n->vw, n->vb, n->v1w, n->v1b,
+    RVS_LAUNCH(heads_kernel, (int)((B + kHB - 1) / kHB), 256, 0, s, x, fused_head ? n->feat : (const float*)nullptr, n->C, B, n->pw, n->pb, n->pfw, n->pfb, n->vw, n->vb, n->v1w, n->v1b,
                n->v2w, n->v2b, want_logits ? n->logits : nullptr, n->probs, n->values);
     return 0;
 }
@@ -467,7 +478,7 @@ int net_create(rvs_engine* h) {
         (rc = nalloc(n, &n->v1w, 256 * 64)) || (rc = nalloc(n, &n->v1b, 256)) || (rc = nalloc(n, &n->v2w, 256)) ||
         (rc = nalloc(n, &n->v2b, 1)) || (rc = nalloc(n, &n->bits, B * 3)) || (rc = nalloc(n, &n->w0f, (size_t)27 * C)) || (rc = nalloc(n, &n->b0f, (size_t)C)) || (rc = nalloc(n, &n->a, B * 64 * C)) ||
         (rc = nalloc(n, &n->b, B * 64 * C)) || (rc = nalloc(n, &n->c, B * 64 * C)) || (rc = nalloc(n, &n->probs, B * 65)) ||
-        (rc = nalloc(n, &n->logits, B * 65)) || (rc = nalloc(n, &n->values, B)))
+        (rc = nalloc(n, &n->logits, B * 65)) || (rc = nalloc(n, &n->values, B)) || (rc = nalloc(n, &n->feat, B * 192)))
         return rc;
     return 0;
 }
@@ -565,6 +576,11 @@ int rvs_engine_load_weights(rvs_engine* h, const float* flat, int64_t n_floats, 
         if ((rc = conv_tc_plan(n->conv0.tc, n->conv0.w, C, n->max_batch, 64))) return rc;
     }
     RVS_CUDA(cudaStreamSynchronize(s));
+    // host copy of the folded 1x1 head weights for the fused last-layer epilogue (kernel parameter)
+    RVS_CUDA(cudaMemcpy(n->head_host, n->pw, (size_t)2 * C * 4, cudaMemcpyDeviceToHost));
+    RVS_CUDA(cudaMemcpy(n->head_host + 2 * C, n->vw, (size_t)C * 4, cudaMemcpyDeviceToHost));
+    RVS_CUDA(cudaMemcpy(n->head_host + 3 * C, n->pb, 8, cudaMemcpyDeviceToHost));
+    RVS_CUDA(cudaMemcpy(n->head_host + 3 * C + 2, n->vb, 4, cudaMemcpyDeviceToHost));
     n->loaded = true;
     return 0;
 }
