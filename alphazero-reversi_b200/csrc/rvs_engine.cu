@@ -2,6 +2,8 @@
 // the engine C ABI.  One warp per game everywhere; grids are G/4 CTAs of 128 threads.
 #include "rvs_engine.cuh"
 
+#include <stdlib.h>
+
 #include <new>
 
 namespace rvs {
@@ -298,14 +300,16 @@ __global__ void __launch_bounds__(128) play_kernel(EngineView ev, float temperat
 
 // Finished game of slot g, by its warp: z back-fill (self_play.py:117-126), samples to the ring,
 // recycle or park the slot.
-__device__ __forceinline__ void finalize_game(const EngineView& ev, int g, int lane, int recycle) {
+// `lane` counts inside the owning group of `width` lanes (a whole warp, or 8 lanes in the 4-games-per-warp kernels)
+__device__ __forceinline__ void finalize_game(const EngineView& ev, int g, int lane, int recycle, unsigned mask = kFull,
+                                              int width = 32) {
     if (!ev.finished[g]) return;
     const int n = ev.ply[g] < 64 ? ev.ply[g] : 64;
     const int w = (ev.flags[g] & F_WIN_MASK) >> F_WIN_SHIFT;
-    __syncwarp();
+    __syncwarp(mask);
     unsigned long long at = 0;
     if (lane == 0) at = atomicAdd(ev.ring_count, (unsigned long long)n);
-    at = __shfl_sync(kFull, at, 0);
+    at = __shfl_sync(mask, at, 0, width);
     int stored = 0;
     for (int p = 0; p < n; ++p) {
         const unsigned long long dst = at + p;
@@ -316,7 +320,7 @@ __device__ __forceinline__ void finalize_game(const EngineView& ev, int g, int l
             ev.r_black[dst] = ev.s_black[o]; ev.r_white[dst] = ev.s_white[o]; ev.r_side[dst] = (uint8_t)s;
             ev.r_z[dst] = (int8_t)(w == 0 ? 0 : (s == w ? 1 : -1));
         }
-        for (int i = lane; i < 65; i += 32) ev.r_pi[dst * 65 + i] = ev.s_pi[o * 65 + i];
+        for (int i = lane; i < 65; i += width) ev.r_pi[dst * 65 + i] = ev.s_pi[o * 65 + i];
         ++stored;
     }
     if (lane == 0) {
@@ -332,7 +336,7 @@ __device__ __forceinline__ void finalize_game(const EngineView& ev, int g, int l
             ev.live[g] = 0;
         }
     }
-    __syncwarp();
+    __syncwarp(mask);
 }
 
 __global__ void __launch_bounds__(kBlock) finalize_kernel(EngineView ev, int recycle) {
@@ -375,6 +379,162 @@ __global__ void __launch_bounds__(kBlock, 7) selfplay_k1_kernel(EngineView ev, i
         if (lane == 0) play_game<RULES>(ev, g, temperature);
         __syncwarp();
         finalize_game(ev, g, lane, recycle);
+    }
+}
+
+// ---- wave 1, four games per warp (rvs_tree8.cuh) ---------------------------------------------
+constexpr int kBlock8 = 32;          // one warp per CTA: the finest grain for the block scheduler
+constexpr int kGamesPerBlock8 = kBlock8 / 8;
+
+__device__ __forceinline__ void flush_stats8(const EngineView& ev, const TreeCtx8& cx, bool act) {
+    if (act && cx.g.lane == 0) {
+        atomicAdd(&ev.stats[ST_SIMS], (unsigned long long)cx.sims);
+        atomicAdd(&ev.stats[ST_EVALS], (unsigned long long)cx.evals);
+        atomicAdd(&ev.stats[ST_STEPS], (unsigned long long)cx.steps);
+        atomicAdd(&ev.stats[ST_BYTES], (unsigned long long)cx.bytes);
+        atomicAdd(&ev.stats[ST_NODES], (unsigned long long)cx.created);
+        if (cx.overflow) atomicAdd(&ev.stats[ST_OVERFLOW], 1ULL);
+    }
+}
+
+template <int RULES>
+__device__ __forceinline__ TreeCtx8 make_ctx8(const EngineView& ev, int g, const Grp& grp) {
+    return TreeCtx8{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, 1, ev.c_puct, 0, 0, 0, 0, 0, 0,
+                    make_dir<RULES>(grp.lane), grp};
+}
+
+__device__ __forceinline__ void init_root8(TreeCtx8& cx, int side, bool act) {  // mcts.py:334-341
+    if (act && cx.g.lane == 0) {
+        cx.hot[0] = make_int4(0, 0, 0, 0);
+        cx.cold[0] = make_int4(__float_as_int(1.0f), -1, (255 << 8) | (side << 16), 0);
+    }
+    cx.n_nodes = 1;
+    __syncwarp();
+}
+
+// finalize_game() for the 8-lane groups of a converged warp
+__device__ __forceinline__ void finalize_game8(const EngineView& ev, int g, int lane, int recycle, bool act) {
+    const bool fin = act && ev.finished[g];
+    const int n = fin ? (ev.ply[g] < 64 ? ev.ply[g] : 64) : 0;
+    const int w = fin ? (ev.flags[g] & F_WIN_MASK) >> F_WIN_SHIFT : 0;
+    __syncwarp();
+    unsigned long long at = 0;
+    if (fin && lane == 0) at = atomicAdd(ev.ring_count, (unsigned long long)n);
+    at = __shfl_sync(kFull, at, 0, 8);
+    int stored = 0;
+    for (int p = 0; p < n; ++p) {
+        const unsigned long long dst = at + p;
+        if (dst >= (unsigned long long)ev.ring_cap) break;
+        const size_t o = (size_t)g * 64 + p;
+        if (lane == 0) {
+            const int s = ev.s_side[o];
+            ev.r_black[dst] = ev.s_black[o]; ev.r_white[dst] = ev.s_white[o]; ev.r_side[dst] = (uint8_t)s;
+            ev.r_z[dst] = (int8_t)(w == 0 ? 0 : (s == w ? 1 : -1));
+        }
+        for (int i = lane; i < 65; i += 8) ev.r_pi[dst * 65 + i] = ev.s_pi[o * 65 + i];
+        ++stored;
+    }
+    if (fin && lane == 0) {
+        atomicAdd(&ev.stats[ST_FINISHED], 1ULL);
+        atomicAdd(&ev.stats[ST_SAMPLES], (unsigned long long)stored);
+        if (stored < n) atomicAdd(&ev.stats[ST_DROPPED], (unsigned long long)(n - stored));
+        ev.finished[g] = 0;
+        if (recycle) {
+            ev.black[g] = kStartBlack; ev.white[g] = kStartWhite; ev.side[g] = 1; ev.flags[g] = 0;
+            ev.ply[g] = 0;
+            ev.game_id[g] += (uint64_t)ev.G;
+        } else {
+            ev.live[g] = 0;
+        }
+    }
+    __syncwarp();
+}
+
+// Slots ordered by game phase (disc count; parked / finished slots last): the four games that share
+// a warp then have rollouts of similar length, so the groups of a warp stay converged.
+__global__ void __launch_bounds__(1024) phase_order_kernel(EngineView ev) {
+    __shared__ int hist[66];
+    __shared__ int start[66];
+    for (int i = threadIdx.x; i < 66; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int g = threadIdx.x; g < ev.G; g += blockDim.x) {
+        const int key = (ev.live[g] && !(ev.flags[g] & F_OVER)) ? popc64(ev.black[g] | ev.white[g]) : 65;
+        atomicAdd(&hist[key], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int a = 0;
+        for (int k = 0; k < 66; ++k) { start[k] = a; a += hist[k]; }
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < ev.G; g += blockDim.x) {
+        const int key = (ev.live[g] && !(ev.flags[g] & F_OVER)) ? popc64(ev.black[g] | ev.white[g]) : 65;
+        ev.order[atomicAdd(&start[key], 1)] = g;
+    }
+}
+
+// MCTS.search, batch_size 1, built-in evaluator: search_k1_kernel with an 8-lane group per game.
+// The warp stays converged (rvs_tree8.cuh); groups without a game are predicated off.
+template <int RULES, int EVAL>
+__global__ void __launch_bounds__(kBlock8, 16) search_k1g_kernel(EngineView ev, int S) {
+    __shared__ uint8_t lut[256 * 8];
+    __shared__ int spath[kGamesPerBlock8][kMaxPath];
+    lut_init(lut, threadIdx.x, kBlock8);
+    __syncthreads();
+    const int slot = blockIdx.x * kGamesPerBlock8 + (threadIdx.x >> 3);
+    const bool act = slot < ev.G;
+    const int g = act ? ev.order[slot] : 0;
+    const Grp grp = make_grp(threadIdx.x & 31, lut, spath[threadIdx.x >> 3]);
+    TreeCtx8 cx = make_ctx8<RULES>(ev, g, grp);
+    const Board root{ev.black[g], ev.white[g], ev.side[g], ev.flags[g]};
+    const uint64_t game_id = ev.game_id[g];
+    const uint64_t search_id = (uint64_t)ev.ply[g];
+    init_root8(cx, root.side, act);
+    const CoopBoard root_c = coop_load(cx.dir, root);
+    for (int sim = 0; sim < S; ++sim) {
+        const uint64_t st = EVAL == RVS_EVAL_ROLLOUT ? stream_seed(ev.seed, game_id, (search_id << 16) | (uint64_t)sim) : 0ULL;
+        simulate_one8<EVAL>(cx, root_c, st, act);
+    }
+    if (act && grp.lane == 0) ev.n_nodes[g] = cx.n_nodes;
+    flush_stats8(ev, cx, act);
+}
+
+// selfplay_k1_kernel with an 8-lane group per game (persistent, work-conserving)
+template <int RULES, int EVAL>
+__global__ void __launch_bounds__(kBlock8, 16) selfplay_k1g_kernel(EngineView ev, int S, float temperature,
+                                                                   unsigned long long budget, int recycle) {
+    __shared__ uint8_t lut[256 * 8];
+    __shared__ int spath[kGamesPerBlock8][kMaxPath];
+    lut_init(lut, threadIdx.x, kBlock8);
+    __syncthreads();
+    const int slot = blockIdx.x * kGamesPerBlock8 + (threadIdx.x >> 3);
+    bool alive = slot < ev.G;
+    const int g = alive ? ev.order[slot] : 0;
+    const Grp grp = make_grp(threadIdx.x & 31, lut, spath[threadIdx.x >> 3]);
+    while (true) {
+        alive = alive && ev.live[g];
+        const Board root{ev.black[g], ev.white[g], ev.side[g], ev.flags[g]};
+        alive = alive && !is_over(root);
+        unsigned long long t = 0;
+        if (alive && grp.lane == 0) t = atomicAdd(ev.ply_counter, 1ULL);
+        t = __shfl_sync(kFull, t, 0, 8);
+        alive = alive && t < budget;
+        if (!__any_sync(kFull, alive)) break;
+        TreeCtx8 cx = make_ctx8<RULES>(ev, g, grp);
+        const uint64_t game_id = ev.game_id[g];
+        const uint64_t search_id = (uint64_t)ev.ply[g];
+        init_root8(cx, root.side, alive);
+        const CoopBoard root_c = coop_load(cx.dir, root);
+        for (int sim = 0; sim < S; ++sim) {
+            const uint64_t st = EVAL == RVS_EVAL_ROLLOUT ? stream_seed(ev.seed, game_id, (search_id << 16) | (uint64_t)sim) : 0ULL;
+            simulate_one8<EVAL>(cx, root_c, st, alive);
+        }
+        if (alive && grp.lane == 0) ev.n_nodes[g] = cx.n_nodes;
+        flush_stats8(ev, cx, alive);
+        __syncwarp();
+        if (alive && grp.lane == 0) play_game<RULES>(ev, g, temperature);
+        __syncwarp();
+        finalize_game8(ev, g, grp.lane, recycle, alive);
     }
 }
 
@@ -457,6 +617,11 @@ int io_stage(rvs_engine* h, size_t bytes, void** out) {
 
 inline int games_grid(int G) { return (G + kWarpsPerBlock - 1) / kWarpsPerBlock; }
 
+inline bool warp_per_game() {
+    static const bool v = getenv("RVS_K1_WARP") && atoi(getenv("RVS_K1_WARP")) != 0;
+    return v;
+}
+
 #define RVS_ENGINE_LAUNCH(h, ...)          \
     do {                                   \
         RVS_LAUNCH(__VA_ARGS__);           \
@@ -501,7 +666,7 @@ int rvs_engine_create(const rvs_engine_config* cfg, rvs_engine** out) {
     if ((rc = dalloc(h, &v.black, G)) || (rc = dalloc(h, &v.white, G)) || (rc = dalloc(h, &v.side, G)) ||
         (rc = dalloc(h, &v.flags, G)) || (rc = dalloc(h, &v.game_id, G)) || (rc = dalloc(h, &v.ply, G)) ||
         (rc = dalloc(h, &v.live, G)) || (rc = dalloc(h, &v.finished, G)) || (rc = dalloc(h, &v.hot, GN)) ||
-        (rc = dalloc(h, &v.cold, GN)) || (rc = dalloc(h, &v.n_nodes, G)) || (rc = dalloc(h, &v.w_node, GK)) ||
+        (rc = dalloc(h, &v.cold, GN)) || (rc = dalloc(h, &v.n_nodes, G)) || (rc = dalloc(h, &v.order, G)) || (rc = dalloc(h, &v.w_node, GK)) ||
         (rc = dalloc(h, &v.w_plen, GK)) || (rc = dalloc(h, &v.w_path, GK * kMaxPath)) || (rc = dalloc(h, &v.w_black, GK)) ||
         (rc = dalloc(h, &v.w_white, GK)) || (rc = dalloc(h, &v.w_sf, GK)) || (rc = dalloc(h, &v.w_lm, GK)) ||
         (rc = dalloc(h, &v.w_val, GK)) || (rc = dalloc(h, &v.s_black, G * 64)) || (rc = dalloc(h, &v.s_white, G * 64)) ||
@@ -601,10 +766,19 @@ int rvs_engine_search(rvs_engine* h, int32_t num_sims, int32_t wave, void* strea
     const bool strict = h->cfg.rules == RVS_RULES_STRICT;
     if (wave == 1 && (h->cfg.evaluator == RVS_EVAL_E0 || h->cfg.evaluator == RVS_EVAL_ROLLOUT)) {
         const bool e0 = h->cfg.evaluator == RVS_EVAL_E0;
-        if (strict && e0) RVS_ENGINE_LAUNCH(h, (search_k1_kernel<RULES_STRICT, RVS_EVAL_E0>), grid, kBlock, 0, s, h->v, num_sims);
-        else if (strict) RVS_ENGINE_LAUNCH(h, (search_k1_kernel<RULES_STRICT, RVS_EVAL_ROLLOUT>), grid, kBlock, 0, s, h->v, num_sims);
-        else if (e0) RVS_ENGINE_LAUNCH(h, (search_k1_kernel<RULES_REF, RVS_EVAL_E0>), grid, kBlock, 0, s, h->v, num_sims);
-        else RVS_ENGINE_LAUNCH(h, (search_k1_kernel<RULES_REF, RVS_EVAL_ROLLOUT>), grid, kBlock, 0, s, h->v, num_sims);
+        if (warp_per_game()) {  // RVS_K1_WARP=1: the one-warp-per-game kernels (kept for A/B measurements)
+            if (strict && e0) RVS_ENGINE_LAUNCH(h, (search_k1_kernel<RULES_STRICT, RVS_EVAL_E0>), grid, kBlock, 0, s, h->v, num_sims);
+            else if (strict) RVS_ENGINE_LAUNCH(h, (search_k1_kernel<RULES_STRICT, RVS_EVAL_ROLLOUT>), grid, kBlock, 0, s, h->v, num_sims);
+            else if (e0) RVS_ENGINE_LAUNCH(h, (search_k1_kernel<RULES_REF, RVS_EVAL_E0>), grid, kBlock, 0, s, h->v, num_sims);
+            else RVS_ENGINE_LAUNCH(h, (search_k1_kernel<RULES_REF, RVS_EVAL_ROLLOUT>), grid, kBlock, 0, s, h->v, num_sims);
+        } else {
+            const int grid8 = (h->v.G + kGamesPerBlock8 - 1) / kGamesPerBlock8;
+            RVS_ENGINE_LAUNCH(h, phase_order_kernel, 1, 1024, 0, s, h->v);
+            if (strict && e0) RVS_ENGINE_LAUNCH(h, (search_k1g_kernel<RULES_STRICT, RVS_EVAL_E0>), grid8, kBlock8, 0, s, h->v, num_sims);
+            else if (strict) RVS_ENGINE_LAUNCH(h, (search_k1g_kernel<RULES_STRICT, RVS_EVAL_ROLLOUT>), grid8, kBlock8, 0, s, h->v, num_sims);
+            else if (e0) RVS_ENGINE_LAUNCH(h, (search_k1g_kernel<RULES_REF, RVS_EVAL_E0>), grid8, kBlock8, 0, s, h->v, num_sims);
+            else RVS_ENGINE_LAUNCH(h, (search_k1g_kernel<RULES_REF, RVS_EVAL_ROLLOUT>), grid8, kBlock8, 0, s, h->v, num_sims);
+        }
         h->searching = false;
         return 0;
     }
@@ -739,10 +913,19 @@ int rvs_engine_selfplay(rvs_engine* h, int32_t num_sims, float temperature, int6
     const int grid = games_grid(h->v.G);
     const bool strict = h->cfg.rules == RVS_RULES_STRICT, e0 = h->cfg.evaluator == RVS_EVAL_E0;
     const unsigned long long budget = (unsigned long long)plies;
-    if (strict && e0) RVS_ENGINE_LAUNCH(h, (selfplay_k1_kernel<RULES_STRICT, RVS_EVAL_E0>), grid, kBlock, 0, s, h->v, num_sims, temperature, budget, recycle);
-    else if (strict) RVS_ENGINE_LAUNCH(h, (selfplay_k1_kernel<RULES_STRICT, RVS_EVAL_ROLLOUT>), grid, kBlock, 0, s, h->v, num_sims, temperature, budget, recycle);
-    else if (e0) RVS_ENGINE_LAUNCH(h, (selfplay_k1_kernel<RULES_REF, RVS_EVAL_E0>), grid, kBlock, 0, s, h->v, num_sims, temperature, budget, recycle);
-    else RVS_ENGINE_LAUNCH(h, (selfplay_k1_kernel<RULES_REF, RVS_EVAL_ROLLOUT>), grid, kBlock, 0, s, h->v, num_sims, temperature, budget, recycle);
+    if (warp_per_game()) {
+        if (strict && e0) RVS_ENGINE_LAUNCH(h, (selfplay_k1_kernel<RULES_STRICT, RVS_EVAL_E0>), grid, kBlock, 0, s, h->v, num_sims, temperature, budget, recycle);
+        else if (strict) RVS_ENGINE_LAUNCH(h, (selfplay_k1_kernel<RULES_STRICT, RVS_EVAL_ROLLOUT>), grid, kBlock, 0, s, h->v, num_sims, temperature, budget, recycle);
+        else if (e0) RVS_ENGINE_LAUNCH(h, (selfplay_k1_kernel<RULES_REF, RVS_EVAL_E0>), grid, kBlock, 0, s, h->v, num_sims, temperature, budget, recycle);
+        else RVS_ENGINE_LAUNCH(h, (selfplay_k1_kernel<RULES_REF, RVS_EVAL_ROLLOUT>), grid, kBlock, 0, s, h->v, num_sims, temperature, budget, recycle);
+    } else {
+        const int grid8 = (h->v.G + kGamesPerBlock8 - 1) / kGamesPerBlock8;
+        RVS_ENGINE_LAUNCH(h, phase_order_kernel, 1, 1024, 0, s, h->v);
+        if (strict && e0) RVS_ENGINE_LAUNCH(h, (selfplay_k1g_kernel<RULES_STRICT, RVS_EVAL_E0>), grid8, kBlock8, 0, s, h->v, num_sims, temperature, budget, recycle);
+        else if (strict) RVS_ENGINE_LAUNCH(h, (selfplay_k1g_kernel<RULES_STRICT, RVS_EVAL_ROLLOUT>), grid8, kBlock8, 0, s, h->v, num_sims, temperature, budget, recycle);
+        else if (e0) RVS_ENGINE_LAUNCH(h, (selfplay_k1g_kernel<RULES_REF, RVS_EVAL_E0>), grid8, kBlock8, 0, s, h->v, num_sims, temperature, budget, recycle);
+        else RVS_ENGINE_LAUNCH(h, (selfplay_k1g_kernel<RULES_REF, RVS_EVAL_ROLLOUT>), grid8, kBlock8, 0, s, h->v, num_sims, temperature, budget, recycle);
+    }
     h->searching = false;
     return 0;
 }

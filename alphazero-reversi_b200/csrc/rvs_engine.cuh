@@ -3,6 +3,7 @@
 #pragma once
 #include "rvs_common.cuh"
 #include "rvs_tree.cuh"
+#include "rvs_tree8.cuh"
 
 namespace rvs {
 
@@ -20,6 +21,7 @@ struct EngineView {
     uint64_t* game_id; int* ply; uint8_t* live; uint8_t* finished;
     // trees
     int4* hot; int4* cold; int* n_nodes;
+    int* order;  // slots sorted by game phase (disc count): the four games of a warp have similar rollout lengths
     // wave scratch [G*kmax]
     int* w_node; int* w_plen; int* w_path; uint64_t* w_black; uint64_t* w_white; uint16_t* w_sf;
     uint64_t* w_lm; float* w_val;
