@@ -291,20 +291,22 @@ RVS_HD uint64_t sh2(const DirLane& L, uint64_t x) { return x << L.s2; }
 
 RVS_HD uint64_t to_dom(uint64_t x, bool neg) { return neg ? brev64(x) : x; }
 
-// contribution of one direction to Board.get_valid_moves; Pd/Od in the lane's working domain,
-// result in the normal domain
-RVS_HD uint64_t legal_part(const DirLane& L, uint64_t Pd, uint64_t Od) {
+// contribution of one direction to Board.get_valid_moves; Pd/Od and the result in the lane's
+// working domain
+RVS_HD uint64_t legal_raw(const DirLane& L, uint64_t Pd, uint64_t Od) {
     const uint64_t E = ~(Pd | Od), Om = Od & L.gm;
     uint64_t c = sh1(L, Pd) & Om;
     c |= sh1(L, c) & Om;
     const uint64_t Om2 = Om & sh1(L, Om);
     c |= sh2(L, c) & Om2;
     c |= sh2(L, c) & Om2;
-    return to_dom(sh1(L, c) & E, L.neg);
+    return sh1(L, c) & E;
 }
+// same, result in the normal domain
+RVS_HD uint64_t legal_part(const DirLane& L, uint64_t Pd, uint64_t Od) { return to_dom(legal_raw(L, Pd, Od), L.neg); }
 
-// contribution of one direction to the flip scan for the move bit `mvd` (working domain)
-RVS_HD uint64_t flip_part(const DirLane& L, uint64_t Pd, uint64_t Od, uint64_t mvd) {
+// contribution of one direction to the flip scan for the move bit `mvd` (all in the working domain)
+RVS_HD uint64_t flip_raw(const DirLane& L, uint64_t Pd, uint64_t Od, uint64_t mvd) {
     const uint64_t Om = Od & L.fm, Pm = Pd & L.fm;
     uint64_t x = sh1(L, mvd) & Om;
     x |= sh1(L, x) & Om;
@@ -312,7 +314,10 @@ RVS_HD uint64_t flip_part(const DirLane& L, uint64_t Pd, uint64_t Od, uint64_t m
     x |= sh2(L, x) & Om2;
     x |= sh2(L, x) & Om2;
     const uint64_t end = sh1(L, x) & ~x & Pm;
-    return to_dom(end ? x : 0ULL, L.neg);
+    return end ? x : 0ULL;
+}
+RVS_HD uint64_t flip_part(const DirLane& L, uint64_t Pd, uint64_t Od, uint64_t mvd) {
+    return to_dom(flip_raw(L, Pd, Od, mvd), L.neg);
 }
 
 #if defined(__CUDACC__)

@@ -382,11 +382,11 @@ __global__ void __launch_bounds__(kBlock, 7) selfplay_k1_kernel(EngineView ev, i
     }
 }
 
-// ---- wave 1, four games per warp (rvs_tree8.cuh) ---------------------------------------------
-constexpr int kBlock8 = 32;          // one warp per CTA: the finest grain for the block scheduler
-constexpr int kGamesPerBlock8 = kBlock8 / 8;
+// ---- wave 1, several games per warp (rvs_treeg.cuh) -------------------------------------------
+constexpr int kBlockG = 32;  // one warp per CTA: the finest grain for the block scheduler
 
-__device__ __forceinline__ void flush_stats8(const EngineView& ev, const TreeCtx8& cx, bool act) {
+template <int LPG>
+__device__ __forceinline__ void flush_stats_g(const EngineView& ev, const TreeCtxG<LPG>& cx, bool act) {
     if (act && cx.g.lane == 0) {
         atomicAdd(&ev.stats[ST_SIMS], (unsigned long long)cx.sims);
         atomicAdd(&ev.stats[ST_EVALS], (unsigned long long)cx.evals);
@@ -397,13 +397,13 @@ __device__ __forceinline__ void flush_stats8(const EngineView& ev, const TreeCtx
     }
 }
 
-template <int RULES>
-__device__ __forceinline__ TreeCtx8 make_ctx8(const EngineView& ev, int g, const Grp& grp) {
-    return TreeCtx8{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, 1, ev.c_puct, 0, 0, 0, 0, 0, 0,
-                    make_dir<RULES>(grp.lane), grp};
+template <int LPG>
+__device__ __forceinline__ TreeCtxG<LPG> make_ctx_g(const EngineView& ev, int g, const Grp<LPG>& grp) {
+    return TreeCtxG<LPG>{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, 1, ev.c_puct, 0, 0, 0, 0, 0, 0, grp};
 }
 
-__device__ __forceinline__ void init_root8(TreeCtx8& cx, int side, bool act) {  // mcts.py:334-341
+template <int LPG>
+__device__ __forceinline__ void init_root_g(TreeCtxG<LPG>& cx, int side, bool act) {  // mcts.py:334-341
     if (act && cx.g.lane == 0) {
         cx.hot[0] = make_int4(0, 0, 0, 0);
         cx.cold[0] = make_int4(__float_as_int(1.0f), -1, (255 << 8) | (side << 16), 0);
@@ -412,15 +412,16 @@ __device__ __forceinline__ void init_root8(TreeCtx8& cx, int side, bool act) {  
     __syncwarp();
 }
 
-// finalize_game() for the 8-lane groups of a converged warp
-__device__ __forceinline__ void finalize_game8(const EngineView& ev, int g, int lane, int recycle, bool act) {
+// finalize_game() for the LPG-lane groups of a converged warp
+template <int LPG>
+__device__ __forceinline__ void finalize_game_g(const EngineView& ev, int g, int lane, int recycle, bool act) {
     const bool fin = act && ev.finished[g];
     const int n = fin ? (ev.ply[g] < 64 ? ev.ply[g] : 64) : 0;
     const int w = fin ? (ev.flags[g] & F_WIN_MASK) >> F_WIN_SHIFT : 0;
     __syncwarp();
     unsigned long long at = 0;
     if (fin && lane == 0) at = atomicAdd(ev.ring_count, (unsigned long long)n);
-    at = __shfl_sync(kFull, at, 0, 8);
+    at = __shfl_sync(kFull, at, 0, LPG);
     int stored = 0;
     for (int p = 0; p < n; ++p) {
         const unsigned long long dst = at + p;
@@ -431,7 +432,7 @@ __device__ __forceinline__ void finalize_game8(const EngineView& ev, int g, int 
             ev.r_black[dst] = ev.s_black[o]; ev.r_white[dst] = ev.s_white[o]; ev.r_side[dst] = (uint8_t)s;
             ev.r_z[dst] = (int8_t)(w == 0 ? 0 : (s == w ? 1 : -1));
         }
-        for (int i = lane; i < 65; i += 8) ev.r_pi[dst * 65 + i] = ev.s_pi[o * 65 + i];
+        for (int i = lane; i < 65; i += LPG) ev.r_pi[dst * 65 + i] = ev.s_pi[o * 65 + i];
         ++stored;
     }
     if (fin && lane == 0) {
@@ -473,68 +474,84 @@ __global__ void __launch_bounds__(1024) phase_order_kernel(EngineView ev) {
     }
 }
 
-// MCTS.search, batch_size 1, built-in evaluator: search_k1_kernel with an 8-lane group per game.
-// The warp stays converged (rvs_tree8.cuh); groups without a game are predicated off.
-template <int RULES, int EVAL>
-__global__ void __launch_bounds__(kBlock8, 16) search_k1g_kernel(EngineView ev, int S) {
+// MCTS.search, batch_size 1, built-in evaluator: search_k1_kernel with an LPG-lane group per game.
+// The warp stays converged (rvs_treeg.cuh); groups without a game are predicated off.  A group
+// owns the slots gidx, gidx + n_groups, ... (phase order), so any G runs on a resident grid.
+constexpr int kMaxWarpsG = kNumSMs * 16;  // 16 one-warp CTAs per SM (__launch_bounds__(32, 16): <= 128 registers)
+
+template <int RULES, int EVAL, int LPG>
+__global__ void __launch_bounds__(kBlockG, 16) search_k1g_kernel(EngineView ev, int S) {
+    constexpr int GPB = kBlockG / LPG;
     __shared__ uint8_t lut[256 * 8];
-    __shared__ int spath[kGamesPerBlock8][kMaxPath];
-    lut_init(lut, threadIdx.x, kBlock8);
+    __shared__ int spath[GPB][kMaxPath];
+    lut_init(lut, threadIdx.x, kBlockG);
     __syncthreads();
-    const int slot = blockIdx.x * kGamesPerBlock8 + (threadIdx.x >> 3);
-    const bool act = slot < ev.G;
-    const int g = act ? ev.order[slot] : 0;
-    const Grp grp = make_grp(threadIdx.x & 31, lut, spath[threadIdx.x >> 3]);
-    TreeCtx8 cx = make_ctx8<RULES>(ev, g, grp);
-    const Board root{ev.black[g], ev.white[g], ev.side[g], ev.flags[g]};
-    const uint64_t game_id = ev.game_id[g];
-    const uint64_t search_id = (uint64_t)ev.ply[g];
-    init_root8(cx, root.side, act);
-    const CoopBoard root_c = coop_load(cx.dir, root);
-    for (int sim = 0; sim < S; ++sim) {
-        const uint64_t st = EVAL == RVS_EVAL_ROLLOUT ? stream_seed(ev.seed, game_id, (search_id << 16) | (uint64_t)sim) : 0ULL;
-        simulate_one8<EVAL>(cx, root_c, st, act);
+    const int n_groups = gridDim.x * GPB;
+    const Grp<LPG> grp = make_grp<RULES, LPG>(threadIdx.x & 31, lut, spath[threadIdx.x / LPG]);
+    for (int slot = blockIdx.x * GPB + (int)threadIdx.x / LPG; __any_sync(kFull, slot < ev.G); slot += n_groups) {
+        const bool act = slot < ev.G;
+        const int g = act ? ev.order[slot] : 0;
+        TreeCtxG<LPG> cx = make_ctx_g(ev, g, grp);
+        const Board root{ev.black[g], ev.white[g], ev.side[g], ev.flags[g]};
+        const uint64_t game_id = ev.game_id[g];
+        const uint64_t search_id = (uint64_t)ev.ply[g];
+        init_root_g(cx, root.side, act);
+        const GBoard root_g = gboard_load(root);
+        for (int sim = 0; sim < S; ++sim) {
+            const uint64_t st = EVAL == RVS_EVAL_ROLLOUT ? stream_seed(ev.seed, game_id, (search_id << 16) | (uint64_t)sim) : 0ULL;
+            simulate_one_g<EVAL>(cx, root_g, st, act);
+        }
+        if (act && grp.lane == 0) ev.n_nodes[g] = cx.n_nodes;
+        flush_stats_g(ev, cx, act);
     }
-    if (act && grp.lane == 0) ev.n_nodes[g] = cx.n_nodes;
-    flush_stats8(ev, cx, act);
 }
 
-// selfplay_k1_kernel with an 8-lane group per game (persistent, work-conserving)
-template <int RULES, int EVAL>
-__global__ void __launch_bounds__(kBlock8, 16) selfplay_k1g_kernel(EngineView ev, int S, float temperature,
+// selfplay_k1_kernel with an LPG-lane group per game (persistent, work-conserving): every group
+// keeps playing plies of its slots, round-robin, until the launch-wide budget of game-plies is used up
+template <int RULES, int EVAL, int LPG>
+__global__ void __launch_bounds__(kBlockG, 16) selfplay_k1g_kernel(EngineView ev, int S, float temperature,
                                                                    unsigned long long budget, int recycle) {
+    constexpr int GPB = kBlockG / LPG;
     __shared__ uint8_t lut[256 * 8];
-    __shared__ int spath[kGamesPerBlock8][kMaxPath];
-    lut_init(lut, threadIdx.x, kBlock8);
+    __shared__ int spath[GPB][kMaxPath];
+    lut_init(lut, threadIdx.x, kBlockG);
     __syncthreads();
-    const int slot = blockIdx.x * kGamesPerBlock8 + (threadIdx.x >> 3);
-    bool alive = slot < ev.G;
-    const int g = alive ? ev.order[slot] : 0;
-    const Grp grp = make_grp(threadIdx.x & 31, lut, spath[threadIdx.x >> 3]);
+    const int n_groups = gridDim.x * GPB;
+    const int slot0 = blockIdx.x * GPB + (int)threadIdx.x / LPG;
+    const int n_mine = slot0 < ev.G ? (ev.G - slot0 + n_groups - 1) / n_groups : 0;  // slots of this group
+    const Grp<LPG> grp = make_grp<RULES, LPG>(threadIdx.x & 31, lut, spath[threadIdx.x / LPG]);
+    bool quit = n_mine == 0;
+    int k = 0, idle = 0;  // current slot of the round-robin; consecutive slots found parked / finished
     while (true) {
-        alive = alive && ev.live[g];
+        if (!__any_sync(kFull, !quit)) break;
+        const int g = quit ? 0 : ev.order[slot0 + k * n_groups];
+        bool alive = !quit && ev.live[g];
         const Board root{ev.black[g], ev.white[g], ev.side[g], ev.flags[g]};
         alive = alive && !is_over(root);
         unsigned long long t = 0;
         if (alive && grp.lane == 0) t = atomicAdd(ev.ply_counter, 1ULL);
-        t = __shfl_sync(kFull, t, 0, 8);
-        alive = alive && t < budget;
-        if (!__any_sync(kFull, alive)) break;
-        TreeCtx8 cx = make_ctx8<RULES>(ev, g, grp);
+        t = __shfl_sync(kFull, t, 0, LPG);
+        if (alive && t >= budget) { alive = false; quit = true; }
+        TreeCtxG<LPG> cx = make_ctx_g(ev, g, grp);
         const uint64_t game_id = ev.game_id[g];
         const uint64_t search_id = (uint64_t)ev.ply[g];
-        init_root8(cx, root.side, alive);
-        const CoopBoard root_c = coop_load(cx.dir, root);
-        for (int sim = 0; sim < S; ++sim) {
-            const uint64_t st = EVAL == RVS_EVAL_ROLLOUT ? stream_seed(ev.seed, game_id, (search_id << 16) | (uint64_t)sim) : 0ULL;
-            simulate_one8<EVAL>(cx, root_c, st, alive);
+        init_root_g(cx, root.side, alive);
+        const GBoard root_g = gboard_load(root);
+        if (__any_sync(kFull, alive)) {
+            for (int sim = 0; sim < S; ++sim) {
+                const uint64_t st = EVAL == RVS_EVAL_ROLLOUT ? stream_seed(ev.seed, game_id, (search_id << 16) | (uint64_t)sim) : 0ULL;
+                simulate_one_g<EVAL>(cx, root_g, st, alive);
+            }
         }
         if (alive && grp.lane == 0) ev.n_nodes[g] = cx.n_nodes;
-        flush_stats8(ev, cx, alive);
+        flush_stats_g(ev, cx, alive);
         __syncwarp();
         if (alive && grp.lane == 0) play_game<RULES>(ev, g, temperature);
         __syncwarp();
-        finalize_game8(ev, g, grp.lane, recycle, alive);
+        finalize_game_g<LPG>(ev, g, grp.lane, recycle, alive);
+        idle = alive ? 0 : idle + 1;
+        if (idle >= n_mine) quit = true;  // every slot of this group is parked or over
+        k = k + 1 < n_mine ? k + 1 : 0;
     }
 }
 
@@ -616,6 +633,16 @@ int io_stage(rvs_engine* h, size_t bytes, void** out) {
 }
 
 inline int games_grid(int G) { return (G + kWarpsPerBlock - 1) / kWarpsPerBlock; }
+
+// lanes per game of the wave-1 kernels (rvs_treeg.cuh): 4 by default, RVS_K1_LPG=8|2 for A/B measurements
+inline int lanes_per_game(int G) {
+    static const int forced = getenv("RVS_K1_LPG") ? atoi(getenv("RVS_K1_LPG")) : 0;
+    if (forced) return forced;
+    // measured on B200: with few games the kernel is bound by the latency of one ply's
+    // dependency chain, so more lanes per game (shorter per-lane chains, more warps) win; with many
+    // games it is issue bound and fewer lanes per game (fewer instructions per game-ply) win
+    return G <= 6144 ? 8 : 4;  // 16384 games: 3.6e8 / 4.9e8 / 4.0e8 sims/s with 8 / 4 / 2 lanes per game
+}
 
 inline bool warp_per_game() {
     static const bool v = getenv("RVS_K1_WARP") && atoi(getenv("RVS_K1_WARP")) != 0;
@@ -772,12 +799,21 @@ int rvs_engine_search(rvs_engine* h, int32_t num_sims, int32_t wave, void* strea
             else if (e0) RVS_ENGINE_LAUNCH(h, (search_k1_kernel<RULES_REF, RVS_EVAL_E0>), grid, kBlock, 0, s, h->v, num_sims);
             else RVS_ENGINE_LAUNCH(h, (search_k1_kernel<RULES_REF, RVS_EVAL_ROLLOUT>), grid, kBlock, 0, s, h->v, num_sims);
         } else {
-            const int grid8 = (h->v.G + kGamesPerBlock8 - 1) / kGamesPerBlock8;
             RVS_ENGINE_LAUNCH(h, phase_order_kernel, 1, 1024, 0, s, h->v);
-            if (strict && e0) RVS_ENGINE_LAUNCH(h, (search_k1g_kernel<RULES_STRICT, RVS_EVAL_E0>), grid8, kBlock8, 0, s, h->v, num_sims);
-            else if (strict) RVS_ENGINE_LAUNCH(h, (search_k1g_kernel<RULES_STRICT, RVS_EVAL_ROLLOUT>), grid8, kBlock8, 0, s, h->v, num_sims);
-            else if (e0) RVS_ENGINE_LAUNCH(h, (search_k1g_kernel<RULES_REF, RVS_EVAL_E0>), grid8, kBlock8, 0, s, h->v, num_sims);
-            else RVS_ENGINE_LAUNCH(h, (search_k1g_kernel<RULES_REF, RVS_EVAL_ROLLOUT>), grid8, kBlock8, 0, s, h->v, num_sims);
+            const int lpg = lanes_per_game(h->v.G);
+#define RVS_SEARCH_G(LPG)                                                                                                         \
+    do {                                                                                                                          \
+        const int need = (h->v.G * LPG + kBlockG - 1) / kBlockG;                                                                  \
+        const int gridg = need < kMaxWarpsG ? need : kMaxWarpsG;                                                                  \
+        if (strict && e0) RVS_ENGINE_LAUNCH(h, (search_k1g_kernel<RULES_STRICT, RVS_EVAL_E0, LPG>), gridg, kBlockG, 0, s, h->v, num_sims); \
+        else if (strict) RVS_ENGINE_LAUNCH(h, (search_k1g_kernel<RULES_STRICT, RVS_EVAL_ROLLOUT, LPG>), gridg, kBlockG, 0, s, h->v, num_sims); \
+        else if (e0) RVS_ENGINE_LAUNCH(h, (search_k1g_kernel<RULES_REF, RVS_EVAL_E0, LPG>), gridg, kBlockG, 0, s, h->v, num_sims); \
+        else RVS_ENGINE_LAUNCH(h, (search_k1g_kernel<RULES_REF, RVS_EVAL_ROLLOUT, LPG>), gridg, kBlockG, 0, s, h->v, num_sims);  \
+    } while (0)
+            if (lpg == 8) RVS_SEARCH_G(8);
+            else if (lpg == 2) RVS_SEARCH_G(2);
+            else RVS_SEARCH_G(4);
+#undef RVS_SEARCH_G
         }
         h->searching = false;
         return 0;
@@ -919,12 +955,21 @@ int rvs_engine_selfplay(rvs_engine* h, int32_t num_sims, float temperature, int6
         else if (e0) RVS_ENGINE_LAUNCH(h, (selfplay_k1_kernel<RULES_REF, RVS_EVAL_E0>), grid, kBlock, 0, s, h->v, num_sims, temperature, budget, recycle);
         else RVS_ENGINE_LAUNCH(h, (selfplay_k1_kernel<RULES_REF, RVS_EVAL_ROLLOUT>), grid, kBlock, 0, s, h->v, num_sims, temperature, budget, recycle);
     } else {
-        const int grid8 = (h->v.G + kGamesPerBlock8 - 1) / kGamesPerBlock8;
         RVS_ENGINE_LAUNCH(h, phase_order_kernel, 1, 1024, 0, s, h->v);
-        if (strict && e0) RVS_ENGINE_LAUNCH(h, (selfplay_k1g_kernel<RULES_STRICT, RVS_EVAL_E0>), grid8, kBlock8, 0, s, h->v, num_sims, temperature, budget, recycle);
-        else if (strict) RVS_ENGINE_LAUNCH(h, (selfplay_k1g_kernel<RULES_STRICT, RVS_EVAL_ROLLOUT>), grid8, kBlock8, 0, s, h->v, num_sims, temperature, budget, recycle);
-        else if (e0) RVS_ENGINE_LAUNCH(h, (selfplay_k1g_kernel<RULES_REF, RVS_EVAL_E0>), grid8, kBlock8, 0, s, h->v, num_sims, temperature, budget, recycle);
-        else RVS_ENGINE_LAUNCH(h, (selfplay_k1g_kernel<RULES_REF, RVS_EVAL_ROLLOUT>), grid8, kBlock8, 0, s, h->v, num_sims, temperature, budget, recycle);
+        const int lpg = lanes_per_game(h->v.G);
+#define RVS_SELFPLAY_G(LPG)                                                                                                       \
+    do {                                                                                                                          \
+        const int need = (h->v.G * LPG + kBlockG - 1) / kBlockG;                                                                  \
+        const int gridg = need < kMaxWarpsG ? need : kMaxWarpsG;                                                                  \
+        if (strict && e0) RVS_ENGINE_LAUNCH(h, (selfplay_k1g_kernel<RULES_STRICT, RVS_EVAL_E0, LPG>), gridg, kBlockG, 0, s, h->v, num_sims, temperature, budget, recycle); \
+        else if (strict) RVS_ENGINE_LAUNCH(h, (selfplay_k1g_kernel<RULES_STRICT, RVS_EVAL_ROLLOUT, LPG>), gridg, kBlockG, 0, s, h->v, num_sims, temperature, budget, recycle); \
+        else if (e0) RVS_ENGINE_LAUNCH(h, (selfplay_k1g_kernel<RULES_REF, RVS_EVAL_E0, LPG>), gridg, kBlockG, 0, s, h->v, num_sims, temperature, budget, recycle); \
+        else RVS_ENGINE_LAUNCH(h, (selfplay_k1g_kernel<RULES_REF, RVS_EVAL_ROLLOUT, LPG>), gridg, kBlockG, 0, s, h->v, num_sims, temperature, budget, recycle); \
+    } while (0)
+        if (lpg == 8) RVS_SELFPLAY_G(8);
+        else if (lpg == 2) RVS_SELFPLAY_G(2);
+        else RVS_SELFPLAY_G(4);
+#undef RVS_SELFPLAY_G
     }
     h->searching = false;
     return 0;

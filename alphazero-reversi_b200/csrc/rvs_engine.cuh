@@ -3,7 +3,7 @@
 #pragma once
 #include "rvs_common.cuh"
 #include "rvs_tree.cuh"
-#include "rvs_tree8.cuh"
+#include "rvs_treeg.cuh"
 
 namespace rvs {
 

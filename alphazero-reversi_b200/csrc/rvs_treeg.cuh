@@ -1,0 +1,460 @@
+// rvs_treeg.cuh -- K2 for wave 1 (MCTS(batch_size=1)) with SEVERAL games per warp.
+//
+// Profiling the warp-per-game kernel (profiles/ncu_selfplay_r1.txt) showed ~95 % of its warp
+// instructions in the rollout, whose direction-sliced board ops use only 8 distinct lanes
+// (lane & 7 = direction): the other 24 lanes repeat the same work.  Here a game is owned by a
+// GROUP of LPG lanes (8, 4 or 2); every lane evaluates 8/LPG directions of the flip / move
+// generation scans (independent dependency chains = ILP inside the thread) and one warp
+// instruction advances 32/LPG independent games.  With LPG = 4 a lane owns the direction pair
+// (+s, -s): the same shift amount, once on the normal and once on the bit-reversed board.
+//
+// The warp stays CONVERGED: every loop runs while ANY of its groups still has work and a group
+// that is done is predicated off.  That is what lets the group reductions be plain full-mask
+// SHFL.BFLY butterflies.  (Per-group member masks do not work: REDUX writes one uniform register
+// per warp, so nvcc serialises a masked __reduce_*_sync over the distinct masks with MATCH.ANY
+// loops -- measured 1.8x SLOWER than one warp per game.)
+//
+// Semantics are those of rvs_tree.cuh (same citations: mcts.py:84-114 score, :409-444 traverse,
+// :544-623 process, :625-640 backup); only the work distribution differs:
+//   * children are scanned LPG per step (first chunk / lowest lane keeps ties = first-max rule),
+//   * the path lives in shared memory (64 ints per game) instead of one node per lane,
+//   * expansion: lane l creates the children whose squares lie in its 8/LPG board rows,
+//   * the k-th legal square of a rollout ply is found by the lane whose rows hold it, through a
+//     256 x 8 select-in-byte table in shared memory, and broadcast with one ballot + one shuffle.
+#pragma once
+#include "rvs_tree.cuh"
+
+namespace rvs {
+
+template <int LPG>
+struct Grp {
+    static constexpr int ND = 8 / LPG;    // directions per lane
+    static constexpr int RPL = 8 / LPG;   // board rows per lane
+    int sh;              // first lane of the group inside the warp
+    int lane;            // 0..LPG-1 inside the group
+    uint64_t below;      // squares of the rows owned by lower lanes
+    uint32_t lut;        // shared-window address: lut[byte * 8 + j] = position of the j-th set bit of byte
+    uint32_t path;       // shared-window address: int[kMaxPath] nodes of the current path
+                         // (32-bit shared addresses: a generic pointer costs an S2R + LEA per access)
+    DirLane d[ND];       // this lane's directions; d[j].neg == (j & 1) when ND >= 2
+};
+
+__device__ __forceinline__ void lut_init(uint8_t* lut, int tid, int nthreads) {
+    for (int e = tid; e < 256 * 8; e += nthreads) {
+        unsigned b = (unsigned)(e >> 3);
+        int j = e & 7, pos = 0;
+        for (int i = 0; i < 8; ++i)
+            if ((b >> i) & 1u) {
+                if (j == 0) { pos = i; break; }
+                --j;
+            }
+        lut[e] = (uint8_t)pos;
+    }
+}
+
+template <int RULES, int LPG>
+__device__ __forceinline__ Grp<LPG> make_grp(int lane32, const uint8_t* lut, int* path) {
+    Grp<LPG> g;
+    g.sh = lane32 & ~(LPG - 1);
+    g.lane = lane32 & (LPG - 1);
+    g.below = Grp<LPG>::RPL * g.lane == 0 ? 0ULL : ((1ULL << (8 * Grp<LPG>::RPL * g.lane)) - 1ULL);
+    g.lut = (uint32_t)__cvta_generic_to_shared(lut);
+    g.path = (uint32_t)__cvta_generic_to_shared(path);
+#pragma unroll
+    for (int j = 0; j < Grp<LPG>::ND; ++j) g.d[j] = make_dir<RULES>(g.lane * Grp<LPG>::ND + j);
+    return g;
+}
+
+__device__ __forceinline__ unsigned lds_u8(uint32_t a) {
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds_s32(uint32_t a) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_s32(uint32_t a, int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// ---- butterflies over the LPG lanes of a group; the whole warp must be converged ---------------
+template <int LPG>
+__device__ __forceinline__ uint64_t grp_or64(uint64_t x) {
+    unsigned lo = (unsigned)x, hi = (unsigned)(x >> 32);
+#pragma unroll
+    for (int o = 1; o < LPG; o <<= 1) {
+        lo |= __shfl_xor_sync(kFull, lo, o);
+        hi |= __shfl_xor_sync(kFull, hi, o);
+    }
+    return ((uint64_t)hi << 32) | lo;
+}
+template <int LPG>
+__device__ __forceinline__ unsigned grp_max(unsigned x) {
+#pragma unroll
+    for (int o = 1; o < LPG; o <<= 1) {
+        const unsigned y = __shfl_xor_sync(kFull, x, o);
+        x = x > y ? x : y;
+    }
+    return x;
+}
+template <int LPG>
+__device__ __forceinline__ int4 grp_shfl4(const int4& v, int src) {
+    return make_int4(__shfl_sync(kFull, v.x, src, LPG), __shfl_sync(kFull, v.y, src, LPG), __shfl_sync(kFull, v.z, src, LPG),
+                     __shfl_sync(kFull, v.w, src, LPG));
+}
+
+// the rows of a group-uniform mask that this lane owns, as the low 8*RPL bits of a word (RPL <= 4)
+template <int LPG>
+__device__ __forceinline__ unsigned grp_slice(const Grp<LPG>& g, uint64_t m) {
+    constexpr int RPL = Grp<LPG>::RPL;
+    if constexpr (RPL == 4) {
+        return g.lane == 0 ? (unsigned)m : (unsigned)(m >> 32);
+    } else {
+        constexpr int per_word = 4 / RPL;  // slices per 32-bit word
+        const unsigned w = g.lane < per_word ? (unsigned)m : (unsigned)(m >> 32);
+        return (w >> ((g.lane & (per_word - 1)) * 8 * RPL)) & ((1u << (8 * RPL)) - 1u);
+    }
+}
+
+// k-th (0-based) set bit of a group-uniform mask with more than k bits
+template <int LPG>
+__device__ __forceinline__ int grp_nth_set_bit(const Grp<LPG>& g, uint64_t m, int k) {
+    constexpr int RPL = Grp<LPG>::RPL;
+    unsigned slice = grp_slice(g, m);
+    int j = k - popc64(m & g.below);
+    const bool hit = (unsigned)j < (unsigned)__popc(slice);
+    int row = 0;
+#pragma unroll
+    for (int r = 0; r + 1 < RPL; ++r) {  // walk to the row of the slice that holds bit j
+        const int n = __popc(slice & 0xFFu);
+        const bool next = j >= n && row == r;
+        j = next ? j - n : j;
+        slice = next ? slice >> 8 : slice;
+        row = next ? r + 1 : row;
+    }
+    const int pos = (g.lane * RPL + row) * 8 + (int)lds_u8(g.lut + (slice & 0xFFu) * 8 + (j & 7));
+    const unsigned bal = __ballot_sync(kFull, hit) >> g.sh;
+    return __shfl_sync(kFull, pos, (__ffs(bal) - 1) & (LPG - 1), LPG);
+}
+
+// A position held by a group: side to move / opponent in the normal [0] and the bit-reversed [1]
+// domain (popcounts are domain independent)
+struct GBoard {
+    uint64_t P[2], O[2];
+    int side;   // 1 BLACK, 2 WHITE
+    int flags;  // F_OVER | winner | F_PASSED like Board::flags
+};
+
+__device__ __forceinline__ GBoard gboard_load(const Board& b) {
+    const bool blk = b.side == 1;
+    const uint64_t P = blk ? b.black : b.white, O = blk ? b.white : b.black;
+    return GBoard{{P, brev64(P)}, {O, brev64(O)}, b.side, b.flags};
+}
+
+template <int LPG>
+__device__ __forceinline__ bool dir_neg(const Grp<LPG>& g, int j) {
+    return Grp<LPG>::ND >= 2 ? (j & 1) != 0 : g.d[0].neg;  // compile-time unless a lane owns a single direction
+}
+
+// Board.get_valid_moves for side P against O (both domains given), group-uniform result
+template <int LPG>
+__device__ __forceinline__ uint64_t grp_legal(const Grp<LPG>& g, const uint64_t (&P)[2], const uint64_t (&O)[2]) {
+    if constexpr (Grp<LPG>::ND == 1) {  // one direction per lane: its domain is a run-time property of the lane
+        const bool neg = g.d[0].neg;
+        return grp_or64<LPG>(to_dom(legal_raw(g.d[0], neg ? P[1] : P[0], neg ? O[1] : O[0]), neg));
+    }
+    uint64_t xn = 0, xr = 0;
+#pragma unroll
+    for (int j = 0; j < Grp<LPG>::ND; ++j) {
+        if (dir_neg(g, j)) xr |= legal_raw(g.d[j], P[1], O[1]);
+        else xn |= legal_raw(g.d[j], P[0], O[0]);
+    }
+    return grp_or64<LPG>(xn | brev64(xr));
+}
+
+struct MoveOut {
+    uint64_t P[2], O[2];  // mover / opponent after the flips (roles not swapped yet)
+    uint64_t lm_opp;      // legal mask of the opponent
+};
+
+// flips of move idx by the side to move + the opponent's reply mask (board.py:181-240)
+template <int LPG>
+__device__ __forceinline__ MoveOut grp_flip(const Grp<LPG>& g, const GBoard& c, int idx) {
+    const uint64_t mvn = 1ULL << idx, mvr = 1ULL << (63 - idx);
+    uint64_t fn = 0, fr = 0;
+    if constexpr (Grp<LPG>::ND == 1) {
+        const bool neg = g.d[0].neg;
+        fn = to_dom(flip_raw(g.d[0], neg ? c.P[1] : c.P[0], neg ? c.O[1] : c.O[0], neg ? mvr : mvn), neg);
+    } else {
+#pragma unroll
+        for (int j = 0; j < Grp<LPG>::ND; ++j) {
+            if (dir_neg(g, j)) fr |= flip_raw(g.d[j], c.P[1], c.O[1], mvr);
+            else fn |= flip_raw(g.d[j], c.P[0], c.O[0], mvn);
+        }
+        fn |= brev64(fr);
+    }
+    const uint64_t f = grp_or64<LPG>(fn);
+    const uint64_t fb = brev64(f);
+    MoveOut m;
+    m.P[0] = c.P[0] ^ (mvn | f); m.P[1] = c.P[1] ^ (mvr | fb);
+    m.O[0] = c.O[0] ^ f;         m.O[1] = c.O[1] ^ fb;
+    m.lm_opp = grp_legal(g, m.O, m.P);
+    return m;
+}
+
+__device__ __forceinline__ int over_flags(const GBoard& c, uint64_t P, uint64_t O) {  // board.py:246-249, 363-373
+    const int np = popc64(P), no = popc64(O);
+    const int nb = c.side == 1 ? np : no, nw = c.side == 1 ? no : np;
+    const int w = nb > nw ? 1 : (nw > nb ? 2 : 0);
+    return F_PASSED | F_OVER | (w << F_WIN_SHIFT);
+}
+
+// apply_move() by a group (board.py:181-251).  Groups with act == false keep their position, get 0.
+template <int LPG>
+__device__ __forceinline__ uint64_t grp_apply_move(const Grp<LPG>& g, GBoard& c, int idx, bool act) {
+    const MoveOut m = grp_flip(g, c, act ? idx : 0);
+    uint64_t lm = m.lm_opp;
+    const bool pass = act && lm == 0;
+    if (__any_sync(kFull, pass)) {  // rare, warp-uniform branch: auto-pass (board.py:242-249)
+        const uint64_t lm2 = grp_legal(g, m.P, m.O);
+        if (pass) {
+            c.P[0] = m.P[0]; c.P[1] = m.P[1]; c.O[0] = m.O[0]; c.O[1] = m.O[1];
+            c.flags = lm2 == 0 ? over_flags(c, m.P[0], m.O[0]) : (int)F_PASSED;
+            lm = lm2;
+        }
+    }
+    if (act && !pass) {
+        c.P[0] = m.O[0]; c.P[1] = m.O[1]; c.O[0] = m.P[0]; c.O[1] = m.P[1];
+        c.side = 3 - c.side;
+        c.flags = 0;
+    }
+    return act ? lm : 0ULL;
+}
+
+// random_playout() of one position per group.  A group whose game has ended keeps executing the
+// loop body on a dead position (cheaper than predicating every state update); its result was
+// captured when the game ended.  Returns the winner (0 draw, 1 black, 2 white); plies are counted
+// into `plies`.  lm == 0 on entry means "no rollout for this group".
+template <int LPG>
+__device__ __forceinline__ int grp_random_playout(const Grp<LPG>& g, GBoard c, uint64_t lm, uint64_t stream, int& plies) {
+    uint32_t rs = roll_init(stream);
+    bool done = lm == 0;
+    int winner = 0;
+    plies = 0;
+    if (done) lm = 1;  // a dead group plays square 0 over and over; nothing of it is read
+    while (!__all_sync(kFull, done)) {
+        const int n = popc64(lm);
+        const int k = roll_pick(roll_next(rs), n);
+        const int idx = grp_nth_set_bit(g, lm, k) & 63;
+        const MoveOut m = grp_flip(g, c, idx);
+        plies += done ? 0 : 1;
+        lm = m.lm_opp;
+        const bool pass = !done && lm == 0;
+        // default: the opponent moves next
+        c.P[0] = m.O[0]; c.P[1] = m.O[1]; c.O[0] = m.P[0]; c.O[1] = m.P[1];
+        c.side = 3 - c.side;
+        if (__any_sync(kFull, pass)) {  // rare: auto-pass or game over (board.py:242-249)
+            const uint64_t lm2 = grp_legal(g, m.P, m.O);
+            if (pass) {
+                c.side = 3 - c.side;  // the mover keeps the turn
+                c.P[0] = m.P[0]; c.P[1] = m.P[1]; c.O[0] = m.O[0]; c.O[1] = m.O[1];
+                lm = lm2;
+                if (lm2 == 0) {
+                    winner = (over_flags(c, m.P[0], m.O[0]) & F_WIN_MASK) >> F_WIN_SHIFT;
+                    done = true;
+                }
+            }
+        }
+        if (done) lm = 1;  // keep the dead group's ply well defined
+    }
+    return winner;
+}
+
+// per-group view of one game's tree + running counters (TreeCtx of rvs_tree.cuh, LPG lanes wide)
+template <int LPG>
+struct TreeCtxG {
+    int4* hot;
+    int4* cold;
+    int cap;
+    int n_nodes;
+    float c_puct;
+    int overflow;
+    unsigned steps, sims, evals, bytes, created;
+    Grp<LPG> g;
+};
+
+// MCTS._backpropagate_path (mcts.py:625-640): lane l owns path nodes l, l+LPG, ...
+template <int LPG>
+__device__ __forceinline__ void backup_path_g(TreeCtxG<LPG>& cx, int plen, float v, bool act) {
+    const int n_upd = act ? plen : 0;
+    for (int d = cx.g.lane; d < n_upd; d += LPG) {
+        const int n = lds_s32(cx.g.path + 4 * d);
+        int4 h = cx.hot[n];
+        const float sv = ((plen - 1 - d) & 1) ? -v : v;
+        h.x += 1;
+        h.y = __float_as_int(__fadd_rn(__int_as_float(h.y), sv));
+        int vl = h.z & kVLMask;
+        if (vl > 0) --vl;
+        h.z = (h.z & ~(kVLMask | kCacheValid)) | vl;
+        cx.hot[n] = h;
+    }
+    cx.bytes += 32u * (unsigned)n_upd;
+    __syncwarp();
+}
+
+// MCTS._traverse (mcts.py:409-444); the path is left in cx.g.path[0..plen)
+template <int LPG>
+__device__ __forceinline__ int select_one_g(TreeCtxG<LPG>& cx, GBoard& b, int& plen, int& leaf_vlf, bool act) {
+    const Grp<LPG>& g = cx.g;
+    int node = 0;
+    plen = 1;
+    int4 h = make_int4(0, 0, 0, 0), c = make_int4(0, 0, 0, 0);
+    if (act) {
+        if (g.lane == 0) sts_s32(g.path, 0);
+        h = cx.hot[0];
+        c = cx.cold[0];
+        cx.bytes += 32;
+    }
+    const unsigned key_floor = ordered_key(-INFINITY);
+    bool going = act;
+    while (true) {
+        const int nchild = c.z & 0xFF;
+        going = going && nchild != 0 && !(h.z & kTerminal);
+        if (!__any_sync(kFull, going)) break;
+        if (going) {
+            h.z += 1;  // node.virtual_loss += 1 (mcts.py:416)
+            if (g.lane == 0) reinterpret_cast<int*>(&cx.hot[node])[2] = h.z;
+            cx.bytes += 32u * (unsigned)nchild;
+        }
+        const float sq = __fsqrt_rn((float)h.x);
+        const int fc = c.y;
+        const int nscan = going ? nchild : 0;
+        unsigned best_key = key_floor;
+        int best_i = -1;
+        int4 bh = h, bc = c;
+        for (int base = 0; __any_sync(kFull, base < nscan); base += LPG) {
+            const int i = base + g.lane;
+            int4 ch = make_int4(0, 0, 0, 0), cc = make_int4(0, 0, 0, 0);
+            unsigned key = 0;
+            if (i < nscan) {
+                ch = cx.hot[fc + i];
+                cc = cx.cold[fc + i];
+                float score;
+                if (ch.x == 0) {
+                    score = INFINITY;  // mcts.py:96-97
+                } else if (ch.z & kCacheValid) {
+                    score = __int_as_float(ch.w);  // mcts.py:99-100
+                } else {
+                    score = score_child(ch.x, __int_as_float(ch.y), ch.z & kVLMask, __int_as_float(cc.x),
+                                        (cc.z >> 16) & 3, cx.c_puct, sq);
+                    ch.w = __float_as_int(score);
+                    ch.z |= kCacheValid;
+                    reinterpret_cast<int2*>(&cx.hot[fc + i])[1] = make_int2(ch.z, ch.w);
+                }
+                key = (score == score) ? ordered_key(score) : 0u;
+            }
+            const unsigned mx = grp_max<LPG>(key);
+            const unsigned bal = __ballot_sync(kFull, key == mx) >> g.sh;  // never empty inside the group: mx is one of its keys
+            const int src = (__ffs(bal) - 1) & (LPG - 1);
+            const int4 nh = grp_shfl4<LPG>(ch, src), nc = grp_shfl4<LPG>(cc, src);
+            if (mx > best_key) {  // strict: an earlier chunk keeps ties (mcts.py:425)
+                best_key = mx;
+                best_i = base + src;
+                bh = nh;
+                bc = nc;
+            }
+        }
+        if (going && best_i < 0) { cx.overflow |= 2; going = false; }
+        grp_apply_move(g, b, (bc.z >> 8) & 0x3F, going);  // game.make_move(*next_move) (mcts.py:439)
+        if (going) {
+            ++cx.steps;
+            node = fc + best_i;
+            h = bh;
+            c = bc;
+            if (plen < kMaxPath) {
+                if (g.lane == 0) sts_s32(g.path + 4 * plen, node);
+                ++plen;
+            } else {
+                cx.overflow |= 4;
+                going = false;
+            }
+        }
+    }
+    leaf_vlf = h.z;
+    __syncwarp();
+    return node;
+}
+
+// node.expand (mcts.py:141-161, 605-618) with the uniform prior of the built-in evaluators:
+// lane l creates the children whose squares lie in its rows; child index = rank of the square
+template <int LPG>
+__device__ __forceinline__ void expand_node_g(TreeCtxG<LPG>& cx, int node, uint64_t lm, float prior, bool act) {
+    const Grp<LPG>& g = cx.g;
+    if (act) {
+        int4 c = cx.cold[node];
+        const int nc = popc64(lm);
+        if ((c.z & 0xFF) != 0) {
+            // 'if action not in self.children' (mcts.py:154): already expanded, nothing to add
+        } else if (cx.n_nodes + nc > cx.cap) {
+            cx.overflow |= 1;
+        } else {
+            const int fc = cx.n_nodes;
+            const int turn = 3 - ((c.z >> 16) & 3);  // mcts.py:618
+            unsigned slice = grp_slice(g, lm);
+            int i = fc + popc64(lm & g.below);
+            while (slice) {
+                const int sq = g.lane * 8 * Grp<LPG>::RPL + (__ffs(slice) - 1);
+                slice &= slice - 1;
+                cx.hot[i] = make_int4(0, 0, 0, 0);
+                cx.cold[i] = make_int4(__float_as_int(prior), -1, (sq << 8) | (turn << 16), 0);
+                ++i;
+            }
+            if (g.lane == 0) {
+                c.y = fc;
+                c.z = (c.z & ~0xFF) | nc;
+                cx.cold[node] = c;
+            }
+            cx.n_nodes += nc;
+            cx.created += (unsigned)nc;
+            cx.bytes += 32u * (unsigned)nc;
+        }
+    }
+    __syncwarp();
+}
+
+// one simulation per group (select -> evaluate -> expand -> backup), same results as simulate_one()
+template <int EVAL, int LPG>
+__device__ __forceinline__ void simulate_one_g(TreeCtxG<LPG>& cx, const GBoard& root, uint64_t stream_for_sim, bool act) {
+    GBoard b = root;
+    int plen, vlf;
+    const int node = select_one_g(cx, b, plen, vlf, act);
+    if (act) ++cx.sims;
+    const bool term = act && (vlf & kTerminal);          // mcts.py:364-366: back its stored value up
+    const uint64_t lm = grp_legal(cx.g, b.P, b.O);
+    const bool dead = act && !term && lm == 0;           // mcts.py:567-579: flag terminal, ABSOLUTE value
+    const bool eval = act && !term && lm != 0;
+    float v = 0.0f;
+    if (EVAL == RVS_EVAL_E0) {
+        v = __fdiv_rn((float)(popc64(b.P[0]) - popc64(b.O[0])), 64.0f);
+    } else {
+        int plies;
+        const int w = grp_random_playout(cx.g, b, eval ? lm : 0ULL, stream_for_sim, plies);
+        if (eval) cx.steps += (unsigned)plies;
+        v = w == 0 ? 0.0f : (w == b.side ? 1.0f : -1.0f);
+    }
+    if (eval) ++cx.evals;
+    if (term) v = term_value_of(vlf);
+    if (dead) {
+        const int w = (b.flags & F_WIN_MASK) >> F_WIN_SHIFT;
+        const int code = !(b.flags & F_OVER) ? 0 : (w == 1 ? 1 : (w == 2 ? 2 : 0));
+        if (cx.g.lane == 0) {
+            int* z = &reinterpret_cast<int*>(&cx.hot[node])[2];
+            *z = (*z & ~(3 << kTermShift)) | kTerminal | (code << kTermShift);
+        }
+        v = code == 1 ? 1.0f : (code == 2 ? -1.0f : 0.0f);
+    }
+    expand_node_g(cx, node, lm, 1.0f / 65.0f, eval);  // ends with __syncwarp(): the flag above is visible
+    backup_path_g(cx, plen, v, act);
+}
+
+}  // namespace rvs

@@ -252,6 +252,28 @@ def run_ours(args):
     torch.cuda.synchronize()
     po_ms = g0.elapsed_time(g1)
 
+    # ---- side metric: the same workload with 16384 concurrent games (4 games' worth of latency hiding per
+    # scheduler more than the headline): shows how far the 4096-game figure is from the issue-bound rate
+    big = None
+    if not args.no_big:
+        GB = 16384
+        engb = az.Engine(GB, N_SIMS, 1, evaluator=az.EVAL_ROLLOUT, c_puct=1.0, seed=4000 + rank, device=local,
+                         sample_capacity=80 * GB)
+        engb.set_positions(np.tile(pb0, GB // N_GAMES), np.tile(pw0, GB // N_GAMES), np.tile(ps0, GB // N_GAMES), stream=stream)
+        engb.selfplay(N_SIMS, plies=GB * 2, temperature=1.0, recycle=True, stream=stream)
+        torch.cuda.synchronize()
+        b0s = engb.stats()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        engb.selfplay(N_SIMS, plies=GB * 6, temperature=1.0, recycle=True, stream=stream)
+        h1.record()
+        torch.cuda.synchronize()
+        b1s = engb.stats()
+        bms = h0.elapsed_time(h1)
+        big = {"games": GB, "sims_per_sec": (b1s["sims"] - b0s["sims"]) / (bms * 1e-3),
+               "board_steps_per_sec": (b1s["board_steps"] - b0s["board_steps"]) / (bms * 1e-3), "ms": bms}
+        engb.close()
+
     # ---- config-3 side metric: ResNet 5x128 (default_config.json) NN-evaluated self-play ------
     nn = None
     if not args.no_nn:
@@ -336,13 +358,15 @@ def run_ours(args):
             "gpu_launches": int(launches_all),
             "samples_gathered_rank0": gathered,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": traffic, "peak_source": which, "kernel": ("selfplay_k1_kernel<REF,ROLLOUT>" if persistent else
-                                    ("search_k1_kernel<REF,ROLLOUT>" if wave == 1 else "search_fused_kernel<REF,ROLLOUT>")),
+                         "traffic": traffic, "peak_source": which, "kernel": ("selfplay_k1g_kernel<REF,ROLLOUT,8>" if persistent else
+                                    ("search_k1g_kernel<REF,ROLLOUT,8>" if wave == 1 else "search_fused_kernel<REF,ROLLOUT>")),
                          "steps_per_launch": ppl if persistent else 1,
                          "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms * len(ks) / ms,
                          "note": "latency/issue-bound integer kernel: rollouts are register resident; see DESIGN.md"},
             "clocks": clocks,
         }
+        if big is not None:
+            out["games_16384"] = big
         if nn is not None:
             pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1412.9) \
                 if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1400.0
@@ -465,6 +489,7 @@ def main():
     ap.add_argument("--lockstep", action="store_true", help="wave 1 through search+play launches per ply")
     ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per launch of the search kernel")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-big", action="store_true", help="skip the 16384-game side measurement")
     ap.add_argument("--no-nn", action="store_true", help="skip the config-3 (ResNet) side measurement")
     args = ap.parse_args()
     if args.impl == "reference":
