@@ -6,7 +6,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "librvs_b200.so")
 
-MEM_DEVICE, MEM_HOST = 0, 1
+MEM_DEVICE, MEM_HOST, MEM_HOST_ASYNC = 0, 1, 2
 RULES_REF, RULES_STRICT = 0, 1
 PLANES_F32_NCHW, PLANES_BF16_NHWC = 0, 1
 EVAL_E0, EVAL_ROLLOUT, EVAL_EXTERNAL, EVAL_NN = 0, 1, 2, 3

@@ -751,7 +751,7 @@ int rvs_engine_set_positions(rvs_engine* h, const uint64_t* black, const uint64_
     cudaStream_t s = (cudaStream_t)stream;
     const uint64_t *db = black, *dw = white;
     const uint8_t* ds = side;
-    if (mem == RVS_MEM_HOST) {
+    if (mem == RVS_MEM_HOST || mem == RVS_MEM_HOST_ASYNC) {
         void* st = nullptr;
         const size_t nb = (size_t)n * 8;
         if ((rc = io_stage(h, 2 * nb + n, &st))) return rc;
@@ -911,11 +911,12 @@ int rvs_engine_root_visits(rvs_engine* h, int32_t* out, int32_t n, int mem, void
     if (!out || n < 0 || n > h->v.G) return fail(-1, "rvs_engine_root_visits: bad arguments");
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    int32_t* d = mem == RVS_MEM_HOST ? h->visits : out;
+    const bool host = mem == RVS_MEM_HOST || mem == RVS_MEM_HOST_ASYNC;
+    int32_t* d = host ? h->visits : out;
     RVS_ENGINE_LAUNCH(h, root_visits_kernel, games_grid(n), kBlock, 0, s, h->v, d, n);
-    if (mem == RVS_MEM_HOST) {
+    if (host) {
         RVS_CUDA(cudaMemcpyAsync(out, d, (size_t)n * 65 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-        RVS_CUDA(cudaStreamSynchronize(s));
+        if (mem == RVS_MEM_HOST) RVS_CUDA(cudaStreamSynchronize(s));
     }
     return 0;
 }

@@ -31,6 +31,11 @@ extern "C" {
 
 #define RVS_MEM_DEVICE 0
 #define RVS_MEM_HOST 1
+/* host pointers in PINNED memory, copies only enqueued on `stream`: the call returns without
+ * synchronising, so several engine handles can be pipelined on several streams; the caller
+ * synchronises the stream before reading outputs / reusing inputs (accepted by
+ * rvs_engine_set_positions and rvs_engine_root_visits; everywhere else it means RVS_MEM_HOST) */
+#define RVS_MEM_HOST_ASYNC 2
 
 #define RVS_RULES_REF 0    /* bug-compatible with src/game/board.py (graded) */
 #define RVS_RULES_STRICT 1 /* true Othello */
