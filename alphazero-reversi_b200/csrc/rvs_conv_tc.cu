@@ -568,6 +568,187 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
     }
 }
 
+
+// =============================================================================================
+// 256-filter variant (BASELINE config 4: 20 blocks x 256 filters): the 1.18 MB of one layer's
+// weights cannot stay resident, so they STREAM through the same mbarrier ring as the activations.
+// A CTA pair computes D[256 px, 256 couts]; a stage is one (dx, 64-channel chunk): the CTA's
+// activation box (20 KB) + its half (128 couts) of the three vertical taps' weight tiles
+// (3 x 16 KB), consumed by 12 MMAs of M256 x N256 x K16 (128 tensor cycles each: 8 KB of operands
+// per CTA per MMA = 64 B/cycle of shared memory, below the 128 B/cycle port).  Two 256-column
+// accumulators fill the 512 TMEM columns, so the epilogue of tile i still overlaps the MMAs of
+// tile i+1.  L2 -> SM traffic is 68 KB per 1536 tensor cycles per SM (44 B/cycle, at the measured
+// ~42 B/cycle/SM L2 ceiling): this layer shape is L2-bandwidth bound, not tensor bound.
+// =============================================================================================
+struct Cfg2S {
+    static constexpr int C = 256;
+    static constexpr int KC = C / 64;
+    static constexpr int NH = C / 2;                  // weight rows (couts) held by each CTA
+    static constexpr int W_TILE = NH * 128;           // 16 KB: one (tap, kc) weight tile per CTA
+    static constexpr int STAGE = kABytes + 3 * W_TILE;  // 68 KB
+    static constexpr int STAGES = 3;
+    static constexpr int TMEM_COLS = 2 * C;           // 512: the whole tensor memory
+    static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 1280 /*barriers, bias*/;
+    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv3x3_tc2s_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap w_map,
+                    const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
+                    const float* __restrict__ bias, int n_tiles) {
+    using K = Cfg2S;
+    constexpr int C = K::C;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
+    unsigned char* tail = gen + K::STAGES * K::STAGE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 192);
+    float* sbias = reinterpret_cast<float*>(tail + 256);  // [256]
+    const uint32_t bar0 = smem_u32(bars);
+    auto FULL = [&](int s) { return bar0 + 8u * s; };                              // leader
+    auto EMPTY = [&](int s) { return bar0 + 8u * (K::STAGES + s); };               // both CTAs (multicast commit)
+    auto ACC_FULL = [&](int a) { return bar0 + 8u * (2 * K::STAGES + a); };        // both CTAs
+    auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (2 * K::STAGES + 2 + a); };   // leader, 8 arrivals
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int n_iters = (n_tiles + 2 * n_pairs - 1) / (2 * n_pairs);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < K::STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(ACC_FULL(a), 1); mbar_init(ACC_EMPTY(a), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < C; i += kThreads) sbias[i] = bias[i];
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(K::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) pdl_launch_dependents();
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer (both CTAs): own activation tile + own half of the weights =====
+            pdl_wait();
+            int stage = 0, phase = 0;
+            for (int it = 0; it < n_iters; ++it) {
+                const int tile = (it * n_pairs + pair) * 2 + (int)rank;  // may be >= n_tiles: TMA zero-fills
+                for (int dx = 0; dx < 3; ++dx)
+                    for (int kc = 0; kc < K::KC; ++kc) {
+                        mbar_wait_cluster(EMPTY(stage), phase ^ 1);
+                        if (rank == 0) mbar_expect_tx(FULL(stage), 2 * K::STAGE);
+                        const uint32_t st = base + stage * K::STAGE;
+                        tma2_load_5d(&a_map, FULL(stage), st, kc * 64, dx - 1, 0, -1, tile);
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy)
+                            tma2_load_2d(&w_map, FULL(stage), st + kABytes + dy * K::W_TILE, kc * 64, (dy * 3 + dx) * C + (int)rank * K::NH);
+                        if (++stage == K::STAGES) { stage = 0; phase ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {  // ===== MMA issuer (leader only) =====
+            int stage = 0, phase = 0;
+            for (int it = 0; it < n_iters; ++it) {
+                const int acc = it & 1;
+                mbar_wait_cluster(ACC_EMPTY(acc), ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(acc * C);
+                uint32_t accum = 0;
+                for (int s12 = 0; s12 < 3 * K::KC; ++s12) {
+                    mbar_wait_cluster(FULL(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a0 = base + stage * K::STAGE;
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        const uint32_t wt = a0 + kABytes + dy * K::W_TILE;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            tc2_mma(d, make_desc(a0 + dy * 2048 + k * 32), make_desc(wt + k * 32), K::IDESC, accum);
+                            accum = 1;
+                        }
+                    }
+                    tc2_commit_mc(EMPTY(stage));
+                    if (++stage == K::STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc2_commit_mc(ACC_FULL(acc));
+            }
+        }
+    } else {  // ===== epilogue (both CTAs, own tile): 4 chunks of 64 couts, residual chunk h+1 in flight during chunk h =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        pdl_wait();
+        for (int it = 0; it < n_iters; ++it) {
+            const int acc = it & 1;
+            const int tile = (it * n_pairs + pair) * 2 + (int)rank;
+            const size_t off = ((size_t)tile * kTileRows + row) * C;
+            const bool live = tile < n_tiles;
+            const bool has_res = residual != nullptr && live;
+            uint32_t res[2][32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) res[0][i] = 0u;
+            if (has_res) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ldg256(residual + off + i * 16, res[0] + i * 8);
+            }
+            mbar_wait_cluster(ACC_FULL(acc), (it >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                if (h < 3) {
+                    if (has_res) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) ldg256(residual + off + (h + 1) * 64 + i * 16, res[(h + 1) & 1] + i * 8);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) res[(h + 1) & 1][i] = 0u;
+                    }
+                }
+                uint32_t v[64];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C + h * 64);
+                tc_ld32(taddr, v);
+                tc_ld32(taddr + 32, v + 32);
+                tc_wait_ld();
+                if (h == 3) {  // all TMEM reads of this accumulator are done
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(ACC_EMPTY(acc));
+                }
+                if (live) {
+#pragma unroll
+                    for (int c16 = 0; c16 < 4; ++c16) {
+                        uint32_t o[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int col = c16 * 16 + 2 * i;
+                            const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&res[h & 1][c16 * 8 + i]);
+                            const float2 t = __bfloat1622float2(r2);
+                            const float f0 = __uint_as_float(v[col]) + sbias[h * 64 + col] + t.x;
+                            const float f1 = __uint_as_float(v[col + 1]) + sbias[h * 64 + col + 1] + t.y;
+                            const __nv_bfloat162 ob = __floats2bfloat162_rn(fmaxf(f0, 0.f), fmaxf(f1, 0.f));
+                            o[i] = *reinterpret_cast<const uint32_t*>(&ob);
+                        }
+                        stg256(out + off + h * 64 + c16 * 16, o);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(K::TMEM_COLS));
+    }
+}
+
 template <typename Kern>
 int launch_pdl(Kern kern, int grid, int smem, cudaStream_t s, const CUtensorMap& a_map, const CUtensorMap& w_map,
                const __nv_bfloat16* residual, __nv_bfloat16* out, const float* bias, int n_tiles, const HeadW& head,
@@ -583,6 +764,28 @@ int launch_pdl(Kern kern, int grid, int smem, cudaStream_t s, const CUtensorMap&
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     RVS_CUDA(cudaLaunchKernelEx(&cfg, kern, a_map, w_map, residual, out, bias, n_tiles, head, feat));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+int launch_pdl_s(int grid, cudaStream_t s, const CUtensorMap& a_map, const CUtensorMap& w_map, const __nv_bfloat16* residual,
+                 __nv_bfloat16* out, const float* bias, int n_tiles) {
+    static bool attr = false;
+    if (!attr) {
+        RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2S::SMEM));
+        attr = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg2S::SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    RVS_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2s_kernel, a_map, w_map, residual, out, bias, n_tiles));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
@@ -609,7 +812,8 @@ int conv_tc_plan(ConvTcPlan& plan, const __nv_bfloat16* w, int C, int64_t max_ba
     plan.C = C;
     plan.max_batch = max_batch;
     if (cin <= 0) cin = C;
-    if (!((C == 64 && cin == 64) || (C == 128 && (cin == 128 || cin == 64)))) return 0;  // 256 filters: resident weights do not fit; direct path
+    if (!((C == 64 && cin == 64) || (C == 128 && (cin == 128 || cin == 64)) || (C == 256 && cin == 256))) return 0;
+    if (C == 256 && getenv("RVS_CONV_1SM") && atoi(getenv("RVS_CONV_1SM")) != 0) return 0;  // 256 filters exist as the 2-CTA streamed kernel only
     EncodeFn enc = get_encode();
     if (!enc) return fail(-9, "cuTensorMapEncodeTiled entry point not available");
     Impl* im = plan.impl ? static_cast<Impl*>(plan.impl) : new Impl();
@@ -665,6 +869,7 @@ int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_b
     if (im->two_sm) {  // CTA pairs: grid = 2 x pairs, at most one CTA per SM
         int pairs = (n_tiles + 1) / 2;
         if (pairs > kNumSMs / 2) pairs = kNumSMs / 2;
+        if (C == 256) return launch_pdl_s(2 * pairs, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles);
         if (C == 64) {
             static bool attr = false;
             if (!attr) {
@@ -715,6 +920,6 @@ void conv_tc_destroy(ConvTcPlan& plan) {
 
 namespace rvs {
 bool conv_tc_can_fuse_head(const ConvTcPlan& plan) {
-    return plan.valid && plan.impl && static_cast<Impl*>(plan.impl)->two_sm && static_cast<Impl*>(plan.impl)->cin == plan.C;
+    return plan.valid && plan.impl && plan.C <= 128 && static_cast<Impl*>(plan.impl)->two_sm && static_cast<Impl*>(plan.impl)->cin == plan.C;
 }
 }  // namespace rvs

@@ -11,6 +11,8 @@
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "rvs_conv_tc.cuh"
 
 namespace rvs {
@@ -44,8 +46,7 @@ struct NetState {
     float* flat = nullptr;  // staging of the raw state_dict
     bool loaded = false;
     bool force_direct = false;  // RVS_NET_DIRECT=1: run the tower on the CUDA-core kernel (debug)
-    void* allocs[64];
-    int n_allocs = 0;
+    std::vector<void*> allocs;  // 2 per tower layer: 80 for the 20-block network
 };
 
 namespace {
@@ -56,7 +57,7 @@ int nalloc(NetState* n, T** p, size_t count) {
     cudaError_t e = cudaMalloc(&q, count * sizeof(T) > 0 ? count * sizeof(T) : 16);
     if (e != cudaSuccess) return fail(-100 - (int)e, "cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
     cudaMemset(q, 0, count * sizeof(T));
-    n->allocs[n->n_allocs++] = q;
+    n->allocs.push_back(q);
     *p = (T*)q;
     return 0;
 }
@@ -497,7 +498,7 @@ using namespace rvs;
 
 void rvs_net_destroy(rvs::NetState* n) {
     if (!n) return;
-    for (int i = 0; i < n->n_allocs; ++i) cudaFree(n->allocs[i]);
+    for (void* q : n->allocs) cudaFree(q);
     if (n->flat) cudaFree(n->flat);
     for (int i = 0; i < 2 * n->blocks; ++i) conv_tc_destroy(n->tower[i].tc);
     conv_tc_destroy(n->conv0.tc);

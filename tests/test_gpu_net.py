@@ -162,7 +162,8 @@ def test_mcts_and_selfplay_with_rvs_network(az):
     assert data["states"].shape[1:] == (3, 8, 8) and np.allclose(data["action_probs"].sum(axis=1), 1.0, atol=1e-5)
 
 
-@pytest.mark.parametrize("nb,nf,n", [(1, 64, 2), (1, 128, 2), (1, 64, 1500), (1, 128, 1501), (2, 128, 37), (5, 128, 512)])
+@pytest.mark.parametrize("nb,nf,n", [(1, 64, 2), (1, 128, 2), (1, 64, 1500), (1, 128, 1501), (2, 128, 37), (5, 128, 512),
+                                     (1, 256, 2), (1, 256, 1501), (2, 256, 37), (3, 256, 600)])
 def test_tcgen05_tower_matches_direct_kernel(az, nb, nf, n):
     """the tensor-core implicit GEMM (TMA + tcgen05 + TMEM) against the CUDA-core direct kernel on
     the same bf16 weights/activations: only the f32 summation order differs"""
