@@ -102,6 +102,11 @@ __global__ void __launch_bounds__(kBlock) search_fused_kernel(EngineView ev, int
         select_wave(cx, root, ws, k);
         eval_wave<RULES, EVAL>(ev, cx, ws, k, game_id, search_id, start, lane_steps);
         process_wave(cx, ws, k, [](int, int) { return 1.0f / 65.0f; });
+        if (start == 0 && ev.noise_eps > 0.0f) {
+            __syncwarp();
+            if (cx.lane == 0) root_noise_apply(ev, g, game_id, search_id);
+            __syncwarp();
+        }
     }
     if (cx.lane == 0) ev.n_nodes[g] = cx.n_nodes;
     flush_stats(ev, cx, lane_steps);
@@ -122,6 +127,11 @@ __global__ void __launch_bounds__(kBlock, 7) search_k1_kernel(EngineView ev, int
     for (int sim = 0; sim < S; ++sim) {
         const uint64_t st = EVAL == RVS_EVAL_ROLLOUT ? stream_seed(ev.seed, game_id, (search_id << 16) | (uint64_t)sim) : 0ULL;
         simulate_one<EVAL>(cx, root_c, st);
+        if (sim == 0 && ev.noise_eps > 0.0f) {
+            __syncwarp();
+            if (cx.lane == 0) root_noise_apply(ev, g, game_id, search_id);
+            __syncwarp();
+        }
     }
     if (cx.lane == 0) ev.n_nodes[g] = cx.n_nodes;
     flush_stats(ev, cx, 0);
@@ -157,7 +167,7 @@ __global__ void __launch_bounds__(kBlock) select_kernel(EngineView ev, int k) {
 // MCTS._process_batch with caller-supplied softmax outputs (mcts.py:596-623).
 // probs [G*k,65], values [G*k], slot = g*k + j.
 __global__ void __launch_bounds__(kBlock) process_probs_kernel(EngineView ev, int k, const float* __restrict__ probs,
-                                                                const float* __restrict__ values) {
+                                                                const float* __restrict__ values, int first_wave) {
     const int g = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (g >= ev.G) return;
     TreeCtx cx{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, ev.n_nodes[g], ev.c_puct, (int)(threadIdx.x & 31), 0, 0, 0, 0, 0, 0, DirLane{}};
@@ -166,6 +176,11 @@ __global__ void __launch_bounds__(kBlock) process_probs_kernel(EngineView ev, in
     for (int j = cx.lane; j < k; j += 32) ws.val[j] = values[slot0 + j];
     __syncwarp();
     process_wave(cx, ws, k, [&](int j, int sq) { return probs[(slot0 + j) * 65 + sq]; });
+    if (first_wave && ev.noise_eps > 0.0f) {
+        __syncwarp();
+        if (cx.lane == 0) root_noise_apply(ev, g, ev.game_id[g], (uint64_t)ev.ply[g]);
+        __syncwarp();
+    }
     if (cx.lane == 0) ev.n_nodes[g] = cx.n_nodes;
     flush_stats(ev, cx, 0);
 }
@@ -372,6 +387,11 @@ __global__ void __launch_bounds__(kBlock, 7) selfplay_k1_kernel(EngineView ev, i
         for (int sim = 0; sim < S; ++sim) {
             const uint64_t st = EVAL == RVS_EVAL_ROLLOUT ? stream_seed(ev.seed, game_id, (search_id << 16) | (uint64_t)sim) : 0ULL;
             simulate_one<EVAL>(cx, root_c, st);
+            if (sim == 0 && ev.noise_eps > 0.0f) {
+                __syncwarp();
+                if (lane == 0) root_noise_apply(ev, g, game_id, search_id);
+                __syncwarp();
+            }
         }
         if (lane == 0) ev.n_nodes[g] = cx.n_nodes;
         flush_stats(ev, cx, 0);
@@ -500,6 +520,10 @@ __global__ void __launch_bounds__(kBlockG, 16) search_k1g_kernel(EngineView ev, 
         for (int sim = 0; sim < S; ++sim) {
             const uint64_t st = EVAL == RVS_EVAL_ROLLOUT ? stream_seed(ev.seed, game_id, (search_id << 16) | (uint64_t)sim) : 0ULL;
             simulate_one_g<EVAL>(cx, root_g, st, act);
+            if (sim == 0 && ev.noise_eps > 0.0f) {
+                if (act && grp.lane == 0) root_noise_apply(ev, g, game_id, search_id);
+                __syncwarp();
+            }
         }
         if (act && grp.lane == 0) ev.n_nodes[g] = cx.n_nodes;
         flush_stats_g(ev, cx, act);
@@ -541,6 +565,10 @@ __global__ void __launch_bounds__(kBlockG, 16) selfplay_k1g_kernel(EngineView ev
             for (int sim = 0; sim < S; ++sim) {
                 const uint64_t st = EVAL == RVS_EVAL_ROLLOUT ? stream_seed(ev.seed, game_id, (search_id << 16) | (uint64_t)sim) : 0ULL;
                 simulate_one_g<EVAL>(cx, root_g, st, alive);
+                if (sim == 0 && ev.noise_eps > 0.0f) {
+                    if (alive && grp.lane == 0) root_noise_apply(ev, g, game_id, search_id);
+                    __syncwarp();
+                }
             }
         }
         if (alive && grp.lane == 0) ev.n_nodes[g] = cx.n_nodes;
@@ -636,7 +664,8 @@ inline int games_grid(int G) { return (G + kWarpsPerBlock - 1) / kWarpsPerBlock;
 
 // lanes per game of the wave-1 kernels (rvs_treeg.cuh): 4 by default, RVS_K1_LPG=8|2 for A/B measurements
 inline int lanes_per_game(int G) {
-    static const int forced = getenv("RVS_K1_LPG") ? atoi(getenv("RVS_K1_LPG")) : 0;
+    const char* e = getenv("RVS_K1_LPG");  // read per call: tests switch it inside one process
+    const int forced = e ? atoi(e) : 0;
     if (forced) return forced;
     // measured on B200: with few games the kernel is bound by the latency of one ply's
     // dependency chain, so more lanes per game (shorter per-lane chains, more warps) win; with many
@@ -686,6 +715,8 @@ int rvs_engine_create(const rvs_engine_config* cfg, rvs_engine** out) {
     v.kmax = cfg->max_wave;
     v.cap = cfg->nodes_per_game > 0 ? cfg->nodes_per_game : 2 + 34 * cfg->max_sims;
     v.c_puct = cfg->c_puct;
+    v.noise_eps = 0.0f;
+    v.noise_alpha = 0.0;
     v.seed = cfg->seed;
     v.ring_cap = cfg->sample_capacity > 0 ? cfg->sample_capacity : (int64_t)64 * v.G;
     const size_t G = v.G, GK = G * v.kmax, GN = G * (size_t)v.cap;
@@ -842,6 +873,7 @@ int rvs_engine_begin_search(rvs_engine* h, void* stream) {
     RVS_ENGINE_LAUNCH(h, begin_search_kernel, games_grid(h->v.G), kBlock, 0, (cudaStream_t)stream, h->v);
     h->searching = true;
     h->cur_k = 0;
+    h->waves_done = 0;
     return 0;
 }
 
@@ -900,7 +932,8 @@ int rvs_engine_process(rvs_engine* h, const float* probs, const float* values, i
         dp = h->ext_probs;
         dv = h->ext_values;
     }
-    RVS_ENGINE_LAUNCH(h, process_probs_kernel, games_grid(h->v.G), kBlock, 0, s, h->v, h->cur_k, dp, dv);
+    RVS_ENGINE_LAUNCH(h, process_probs_kernel, games_grid(h->v.G), kBlock, 0, s, h->v, h->cur_k, dp, dv, h->waves_done == 0 ? 1 : 0);
+    h->waves_done++;
     h->cur_k = 0;
     return 0;
 }
@@ -1007,6 +1040,16 @@ int rvs_engine_drain_samples(rvs_engine* h, float* states, float* pi, float* z, 
         RVS_CUDA(cudaMemcpyAsync(z, dz, bz, cudaMemcpyDeviceToHost, s));
         RVS_CUDA(cudaStreamSynchronize(s));
     }
+    return 0;
+}
+
+int rvs_engine_set_root_noise(rvs_engine* h, double alpha, float epsilon) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!(epsilon >= 0.0f && epsilon <= 1.0f)) return fail(-1, "rvs_engine_set_root_noise: epsilon %g outside [0,1]", (double)epsilon);
+    if (epsilon > 0.0f && !(alpha >= 1e-3 && alpha <= 1e3)) return fail(-1, "rvs_engine_set_root_noise: alpha %g outside [1e-3,1e3]", alpha);
+    h->v.noise_alpha = alpha;
+    h->v.noise_eps = epsilon;
     return 0;
 }
 

@@ -4,6 +4,7 @@
 #include "rvs_common.cuh"
 #include "rvs_tree.cuh"
 #include "rvs_treeg.cuh"
+#include "rvs_noise.cuh"
 
 namespace rvs {
 
@@ -15,6 +16,8 @@ struct NetState;  // rvs_net.cu
 struct EngineView {
     int G, cap, kmax;
     float c_puct;
+    float noise_eps;     // Dirichlet root noise (rvs_noise.cuh); 0 = off
+    double noise_alpha;
     uint64_t seed;
     // game state per slot
     uint64_t* black; uint64_t* white; uint8_t* side; uint8_t* flags;
@@ -35,6 +38,21 @@ struct EngineView {
     unsigned long long* stats;  // [ST_COUNT]
 };
 
+// Dirichlet noise into the priors of the root's children (rvs_noise.cuh), by ONE thread, right
+// after the expansion of the root; children still have N == 0, so no cached score is stale
+static __device__ __noinline__ void root_noise_apply(const EngineView& ev, int g, uint64_t game_id, uint64_t search_id) {
+    int4* cold = ev.cold + (size_t)g * ev.cap;
+    const int4 c = cold[0];
+    const int nc = c.z & 0xFF, fc = c.y;
+    if (nc == 0 || nc > 64) return;
+    float eta[64];
+    noise_dirichlet(ev.noise_alpha, nc, stream_seed(ev.seed, game_id, 0xD1000000ULL + search_id), eta);
+    for (int i = 0; i < nc; ++i) {
+        float* P = reinterpret_cast<float*>(&cold[fc + i]);
+        *P = noise_mix(*P, eta[i], ev.noise_eps);
+    }
+}
+
 __device__ __forceinline__ WaveScratch scratch_of(const EngineView& ev, int g) {
     const size_t o = (size_t)g * ev.kmax;
     return WaveScratch{ev.w_node + o, ev.w_plen + o, ev.w_path + o * kMaxPath, ev.w_black + o, ev.w_white + o,
@@ -47,6 +65,7 @@ struct rvs_engine {
     rvs_engine_config cfg;
     rvs::EngineView v;
     int cur_k = 0;          // wave size of the last select (external path)
+    int waves_done = 0;     // waves processed since begin_search (root noise goes in after the first)
     bool searching = false;
     float* ext_probs = nullptr;   // staging for host-side probs/values/planes of the external path
     float* ext_values = nullptr;

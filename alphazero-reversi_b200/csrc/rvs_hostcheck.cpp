@@ -1,7 +1,10 @@
 // rvs_hostcheck.cpp -- TEST ARTEFACT: compiles the kernels' bit formulas (rvs_board.cuh)
 // with g++ so the CPU-only test tier can compare them with the oracle before any GPU time
 // is spent.  Never loaded by the product package.
+#include <math.h>
+
 #include "rvs_board.cuh"
+#include "rvs_noise.cuh"
 
 using namespace rvs;
 
@@ -47,4 +50,9 @@ uint64_t hc_flips_sliced(uint64_t P, uint64_t O, int idx, int rules) {
 }
 int hc_nth_set_bit(uint64_t m, int k) { return nth_set_bit(m, k); }
 uint64_t hc_stream_seed(uint64_t s, uint64_t a, uint64_t b) { return stream_seed(s, a, b); }
+// Dirichlet root noise (rvs_noise.cuh): the product's formulas against the oracle's restatement
+double hc_det_log(double x) { return det_log(x); }
+double hc_det_exp(double x) { return det_exp(x); }
+void hc_dirichlet(double alpha, int k, uint64_t stream, float* eta) { noise_dirichlet(alpha, k, stream, eta); }
+float hc_noise_mix(float p, float eta, float eps) { return noise_mix(p, eta, eps); }
 }

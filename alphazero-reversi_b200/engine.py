@@ -127,6 +127,12 @@ class Engine:
         n = cnt.value
         return st[:n], pi[:n], z[:n]
 
+    def set_root_noise(self, alpha, epsilon):
+        """Dirichlet(alpha) noise mixed into the root priors with weight epsilon by every following
+        search (engine feature: the reference configures it, src/config.py:25-26, but never applies
+        it); epsilon = 0 switches it off"""
+        L.check(L.lib().rvs_engine_set_root_noise(self._h, float(alpha), float(epsilon)))
+
     def stats(self, stream=None):
         st = L.EngineStats()
         L.check(L.lib().rvs_engine_stats_get(self._h, C.byref(st), self._s(stream)))

@@ -184,6 +184,13 @@ int rvs_engine_selfplay(rvs_engine *h, int32_t num_sims, float temperature, int6
 int rvs_engine_drain_samples(rvs_engine *h, float *states, float *pi, float *z, int64_t capacity,
                              int64_t *out_count, int mem, void *stream);
 
+/* Dirichlet noise on the root priors: P' = (1-eps) P + eps Dir(alpha), mixed in right after the root
+ * is expanded by every following search (BASELINE config 4).  The reference only CONFIGURES this
+ * (dirichlet_alpha / dirichlet_epsilon, src/config.py:25-26, src/self_play/self_play.py:18-47) and
+ * never applies it, so it is off by default (epsilon = 0) and the sampling algorithm is this engine's
+ * own (csrc/rvs_noise.cuh), restated by the oracle. */
+int rvs_engine_set_root_noise(rvs_engine *h, double alpha, float epsilon);
+
 int rvs_engine_stats_get(rvs_engine *h, rvs_engine_stats *out, void *stream);
 
 /* ---- K4: network -------------------------------------------------------------------- */

@@ -225,6 +225,92 @@ void orc_random_playouts(int64_t n, uint64_t seed, int rules, uint64_t *black,
     }
 }
 
+
+/* ---------------- Dirichlet root noise (new-engine feature, no reference behaviour) ----------------
+ * The reference threads dirichlet_alpha / dirichlet_epsilon through its config (src/config.py:25-26,
+ * src/self_play/self_play.py:18-47) and never uses them.  This restates the ENGINE's
+ * specification (alphazero-reversi_b200/csrc/rvs_noise.cuh header comment), written independently:
+ * fixed-polynomial log / exp, every step one IEEE f64 operation (this file is built with
+ * -ffp-contract=off), so the CUDA path can be compared bit for bit. */
+static double g_noise_alpha = 0.0;
+static float g_noise_eps = 0.0f;
+void orc_set_root_noise(double alpha, float eps) { g_noise_alpha = alpha; g_noise_eps = eps; }
+
+static double o_log(double x) {
+    uint64_t u; memcpy(&u, &x, 8);
+    int e = (int)((u >> 52) & 0x7FF) - 1023;
+    u = (u & 0x000FFFFFFFFFFFFFULL) | 0x3FF0000000000000ULL;
+    double m; memcpy(&m, &u, 8);
+    if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
+    double s = (m - 1.0) / (m + 1.0);
+    double s2 = s * s;
+    static const double k[12] = {1.0 / 23.0, 1.0 / 21.0, 1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0,
+                                 1.0 / 11.0, 1.0 / 9.0, 1.0 / 7.0, 1.0 / 5.0, 1.0 / 3.0, 1.0};
+    double p = k[0];
+    for (int i = 1; i < 12; i++) { p = p * s2; p = p + k[i]; }
+    double lm = (2.0 * s) * p;
+    return (double)e * 0.6931471805599453 + lm;
+}
+static double o_exp(double x) {
+    if (!(x > -690.0)) return 0.0;
+    double kf = floor(x * 1.4426950408889634 + 0.5);
+    double r = x - kf * 0.6931471805599453;
+    static const double c[14] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0,
+                                 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0,
+                                 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0};
+    double p = c[0];
+    for (int i = 1; i < 14; i++) { p = p * r; p = p + c[i]; }
+    uint64_t sb = (uint64_t)((int)kf + 1023) << 52;
+    double sc; memcpy(&sc, &sb, 8);
+    return p * sc;
+}
+static double o_unif(uint64_t *s) { return (double)((rng_next(s) >> 11) + 1ULL) * (1.0 / 9007199254740992.0); }
+static double o_normal(uint64_t *s) {
+    for (;;) {
+        double v1 = 2.0 * o_unif(s) - 1.0;
+        double v2 = 2.0 * o_unif(s) - 1.0;
+        double q = v1 * v1 + v2 * v2;
+        if (q >= 1.0 || q == 0.0) continue;
+        return v1 * sqrt((-2.0 * o_log(q)) / q);
+    }
+}
+static double o_log_gamma_dev(double a, uint64_t *s) {
+    double a1 = a < 1.0 ? a + 1.0 : a;
+    double d = a1 + (-1.0 / 3.0);
+    double c = 1.0 / sqrt(9.0 * d);
+    double lg;
+    for (;;) {
+        double z = o_normal(s);
+        double t = 1.0 + c * z;
+        if (t <= 0.0) continue;
+        double v = (t * t) * t;
+        double lu = o_log(o_unif(s));
+        double lv = o_log(v);
+        double zz = z * z;
+        double rhs = 0.5 * zz;
+        rhs = rhs + d;
+        double dv = d * v;
+        rhs = rhs - dv;
+        double dl = d * lv;
+        rhs = rhs + dl;
+        if (lu < rhs) { lg = o_log(d) + lv; break; }
+    }
+    if (a < 1.0) lg = lg + o_log(o_unif(s)) / a;
+    return lg;
+}
+/* eta[k] ~ Dirichlet(alpha), exported for the tests */
+void orc_dirichlet(double alpha, int k, uint64_t stream, float *eta) {
+    double lg[64];
+    uint64_t s = stream;
+    double mx = -1e300;
+    for (int i = 0; i < k; i++) { lg[i] = o_log_gamma_dev(alpha, &s); if (lg[i] > mx) mx = lg[i]; }
+    double sum = 0.0;
+    for (int i = 0; i < k; i++) { lg[i] = o_exp(lg[i] - mx); sum = sum + lg[i]; }
+    for (int i = 0; i < k; i++) eta[i] = (float)(lg[i] / sum);
+}
+double orc_det_log(double x) { return o_log(x); }
+double orc_det_exp(double x) { return o_exp(x); }
+
 /* ---------------- MCTS (src/mcts/mcts.py) ---------------- */
 typedef struct {
     int32_t N;          /* visit_count      mcts.py:57 */
@@ -426,6 +512,17 @@ int orc_mcts_search(const orc_board *root, int num_sims, int wave, float c_puct,
                 x->nchild = nc;
             }
             backprop(&t, L->path, L->plen, values[i]);
+        }
+        if (start == 0 && g_noise_eps > 0.0f && t.nodes[0].nchild > 0 && t.nodes[0].nchild <= 64) {
+            /* engine feature: mix Dirichlet noise into the root priors right after the root expansion */
+            float eta[64];
+            int fc = t.nodes[0].first_child, nc = t.nodes[0].nchild;
+            orc_dirichlet(g_noise_alpha, nc, orc_stream_seed(seed, game_id, 0xD1000000ULL + search_id), eta);
+            for (int c = 0; c < nc; c++) {
+                float keep = (1.0f + (-g_noise_eps)) * t.nodes[fc + c].P;
+                float add = g_noise_eps * eta[c];
+                t.nodes[fc + c].P = keep + add;
+            }
         }
     }
 

@@ -63,6 +63,13 @@ int orc_mcts_search(const orc_board *root, int num_sims, int wave, float c_puct,
                     uint64_t game_id, uint64_t search_id, int32_t *visits, int32_t *root_n,
                     float *root_w, int64_t *n_evals);
 
+/* Dirichlet noise on the root priors (engine feature, see rvs_oracle.c): applied by every following
+ * orc_mcts_search / orc_self_play_game right after the root expansion; eps == 0 switches it off */
+void orc_set_root_noise(double alpha, float eps);
+void orc_dirichlet(double alpha, int k, uint64_t stream, float *eta);
+double orc_det_log(double x);
+double orc_det_exp(double x);
+
 /* bench helper: orc_mcts_search over n roots on the calling thread */
 int orc_search_batch(const uint64_t *black, const uint64_t *white, const uint8_t *side, int n,
                      int num_sims, int wave, float c_puct, int rules, int evaluator, uint64_t seed,

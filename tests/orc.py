@@ -52,6 +52,14 @@ def lib():
         u64, i32, i64, u8p = C.c_uint64, C.c_int, C.c_int64, C.POINTER(C.c_uint8)
         L.orc_legal.restype = u64
         L.orc_legal.argtypes = [u64, u64, i32]
+        L.orc_set_root_noise.restype = None
+        L.orc_set_root_noise.argtypes = [C.c_double, C.c_float]
+        L.orc_dirichlet.restype = None
+        L.orc_dirichlet.argtypes = [C.c_double, i32, u64, C.POINTER(C.c_float)]
+        L.orc_det_log.restype = C.c_double
+        L.orc_det_log.argtypes = [C.c_double]
+        L.orc_det_exp.restype = C.c_double
+        L.orc_det_exp.argtypes = [C.c_double]
         L.orc_flips.restype = u64
         L.orc_flips.argtypes = [u64, u64, i32, i32]
         L.orc_apply.restype = i32
@@ -154,6 +162,11 @@ def mcts_search(pos, num_sims, wave, c_puct=1.0, rules=RULES_REF, evaluator=EVAL
     if rc < 0:
         raise RuntimeError(f"orc_mcts_search failed rc={rc}")
     return np.array(vis[:], dtype=np.int32), rn.value, np.float32(rw.value), ne.value
+
+
+def set_root_noise(alpha, eps):
+    """engine feature restated by the oracle: Dirichlet noise on the root priors (0 = off)"""
+    lib().orc_set_root_noise(float(alpha), float(eps))
 
 
 def action_probs(visits, temperature):

@@ -19,7 +19,7 @@ def hc():
     out = os.path.join(orc.ROOT, "build")
     os.makedirs(out, exist_ok=True)
     so = os.path.join(out, "rvs_hostcheck.so")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so,
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-o", so,
                            os.path.join(CSRC, "rvs_hostcheck.cpp")])
     L = C.CDLL(so)
     L.hc_legal.restype = C.c_uint64
@@ -37,6 +37,13 @@ def hc():
     L.hc_nth_set_bit.argtypes = [C.c_uint64, C.c_int]
     L.hc_stream_seed.restype = C.c_uint64
     L.hc_stream_seed.argtypes = [C.c_uint64] * 3
+    L.hc_det_log.restype = C.c_double
+    L.hc_det_log.argtypes = [C.c_double]
+    L.hc_det_exp.restype = C.c_double
+    L.hc_det_exp.argtypes = [C.c_double]
+    L.hc_dirichlet.argtypes = [C.c_double, C.c_int, C.c_uint64, C.POINTER(C.c_float)]
+    L.hc_noise_mix.restype = C.c_float
+    L.hc_noise_mix.argtypes = [C.c_float] * 3
     return L
 
 
@@ -133,3 +140,49 @@ def test_nth_set_bit(hc):
         bits = [i for i in range(64) if (m >> i) & 1]
         k = rr.randrange(len(bits))
         assert hc.hc_nth_set_bit(m, k) == bits[k]
+
+
+# ---- Dirichlet root noise (csrc/rvs_noise.cuh): product formulas vs the oracle's restatement ----
+def test_det_log_exp_match_oracle_and_libm(hc):
+    import math
+    L = orc.lib()
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([rng.uniform(1e-300, 1.0, 2000), rng.uniform(1.0, 1e6, 500), 10.0 ** rng.uniform(-300, 300, 500),
+                         [1.0, 2.0, 0.5, math.sqrt(2.0), 1.4142135623730951, 2.0 ** -53]])
+    for x in xs:
+        a, b = hc.hc_det_log(float(x)), L.orc_det_log(float(x))
+        assert a == b, x                                   # bit exact between the two implementations
+        assert abs(a - math.log(x)) <= 4e-16 * max(1.0, abs(math.log(x))) + 1e-15, (x, a, math.log(x))
+    for x in np.concatenate([-rng.uniform(0, 700, 3000), [0.0, -1e-300, -689.9, -690.0, -800.0]]):
+        a, b = hc.hc_det_exp(float(x)), L.orc_det_exp(float(x))
+        assert a == b, x
+        ref = math.exp(x) if x > -690.0 else 0.0
+        assert abs(a - ref) <= 2e-13 * ref + 1e-300, (x, a, ref)  # single-constant ln2 reduction: ~1e-16 * |k|
+
+
+@pytest.mark.parametrize("alpha", [0.03, 0.3, 1.0, 2.5])
+def test_dirichlet_matches_oracle_and_distribution(hc, alpha):
+    L = orc.lib()
+    k = 10
+    n = 3000
+    a = np.zeros(k, dtype=np.float32)
+    b = np.zeros(k, dtype=np.float32)
+    acc = np.zeros((n, k))
+    for i in range(n):
+        st = L.orc_stream_seed(99, i, 0xD1000000 + 7)
+        hc.hc_dirichlet(alpha, k, st, a.ctypes.data_as(C.POINTER(C.c_float)))
+        L.orc_dirichlet(alpha, k, st, b.ctypes.data_as(C.POINTER(C.c_float)))
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), i
+        acc[i] = a
+    assert np.allclose(acc.sum(axis=1), 1.0, atol=1e-5) and (acc >= 0).all()
+    # Dirichlet(alpha) moments: E = 1/k, Var = (k-1) / (k^2 (k alpha + 1))
+    var = (k - 1) / (k * k * (k * alpha + 1))
+    se = np.sqrt(var / n)
+    assert np.abs(acc.mean(axis=0) - 1.0 / k).max() < 5 * se
+    assert abs(acc.var(axis=0).mean() - var) < 0.15 * var
+    # ragged sizes incl. a single child
+    for kk in (1, 2, 33, 64):
+        aa = np.zeros(kk, dtype=np.float32); bb = np.zeros(kk, dtype=np.float32)
+        hc.hc_dirichlet(alpha, kk, 12345, aa.ctypes.data_as(C.POINTER(C.c_float)))
+        L.orc_dirichlet(alpha, kk, 12345, bb.ctypes.data_as(C.POINTER(C.c_float)))
+        assert np.array_equal(aa, bb) and abs(float(aa.sum()) - 1.0) < 1e-5

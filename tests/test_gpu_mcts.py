@@ -163,6 +163,57 @@ def test_batched_search_vs_oracle(az, evaluator, S, K):
     assert st["evals"] == tot_evals
 
 
+@pytest.mark.parametrize("evaluator,S,K,alpha,eps,lpg", [(0, 100, 1, 0.03, 0.25, 8), (0, 100, 1, 0.3, 0.25, 4), (1, 100, 1, 0.03, 0.25, 2),
+                                                         (0, 128, 64, 0.03, 0.25, 0), (1, 150, 8, 1.0, 0.5, 0), (0, 200, 16, 2.5, 1.0, 0)])
+def test_root_dirichlet_noise_vs_oracle(az, evaluator, S, K, alpha, eps, lpg):
+    """engine feature (BASELINE config 4): Dirichlet noise mixed into the root priors after the root
+    expansion; the oracle restates the sampler, visit counts must stay bit exact.  Covers the
+    several-games-per-warp wave-1 kernels (lanes per game forced through RVS_K1_LPG), the fused wave
+    kernel, and -- with an E0 evaluator driven from the host -- the external select/process path."""
+    import os
+    n = 192
+    bl, wh, sd = _random_roots(n, 500 + S + K)
+    if lpg:
+        os.environ["RVS_K1_LPG"] = str(lpg)
+    orc.set_root_noise(alpha, eps)
+    try:
+        eng = az.Engine(n, S, K, evaluator=evaluator, seed=777)
+        eng.set_root_noise(alpha, eps)
+        eng.set_positions(bl, wh, sd)
+        eng.search(S, K)
+        v = eng.root_visits()
+        assert eng.stats()["overflow"] == 0
+        changed = 0
+        for g in range(n):
+            pos = (int(bl[g]), int(wh[g]), int(sd[g]))
+            ov, *_ = orc.mcts_search(pos, S, K, evaluator=evaluator, seed=777, game_id=g, search_id=0)
+            assert np.array_equal(v[g], ov), (g, hex(pos[0]), hex(pos[1]), pos[2])
+        eng.close()
+        if evaluator == 0:  # same searches through select / leaf_planes / process (the path NN evaluators use)
+            m = 48
+            ext = az.Engine(m, S, K, evaluator=az.EVAL_EXTERNAL, seed=777)
+            ext.set_root_noise(alpha, eps)
+            ext.set_positions(bl[:m], wh[:m], sd[:m])
+
+            def ev(pos):
+                p = np.full((len(pos), 65), np.float32(1.0) / np.float32(65.0), dtype=np.float32)
+                val = np.array([np.float32(bin(o).count("1") - bin(q).count("1")) / np.float32(64) for o, q, _ in pos], dtype=np.float32)
+                return p, val
+            _run_external(az, ext, S, K, ev)
+            assert np.array_equal(ext.root_visits(), v[:m])
+            ext.close()
+        # the noise really changes searches (otherwise this test proves nothing)
+        orc.set_root_noise(0.0, 0.0)
+        for g in range(n):
+            ov0, *_ = orc.mcts_search((int(bl[g]), int(wh[g]), int(sd[g])), S, K, evaluator=evaluator, seed=777, game_id=g)
+            changed += int(not np.array_equal(ov0, v[g]))
+        if K <= 16:  # with the reference's wave of 64 the first waves all follow +inf scores: priors cannot matter yet
+            assert changed > n // 4, changed
+    finally:
+        orc.set_root_noise(0.0, 0.0)
+        os.environ.pop("RVS_K1_LPG", None)
+
+
 def test_strict_rules_search_vs_oracle(az):
     n, S, K = 64, 120, 4
     bl, wh, sd = _random_roots(n, 9)
