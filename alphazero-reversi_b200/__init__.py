@@ -12,6 +12,8 @@ from .engine import Engine
 from .game import Board, ReversiGame
 from .mcts import MCTS, UniformDiscDiff, UniformRollout
 from .self_play import SelfPlay
+from . import replay
+from .replay import PackedSamples
 
 
 def __getattr__(name):  # torch-dependent members are imported lazily
@@ -23,4 +25,4 @@ def __getattr__(name):  # torch-dependent members are imported lazily
 
 __all__ = ["Board", "ReversiGame", "MCTS", "SelfPlay", "Engine", "board_ops", "UniformDiscDiff",
            "UniformRollout", "RvsError", "RULES_REF", "RULES_STRICT", "EVAL_E0", "EVAL_ROLLOUT",
-           "EVAL_EXTERNAL", "EVAL_NN"]
+           "EVAL_EXTERNAL", "EVAL_NN", "replay", "PackedSamples"]

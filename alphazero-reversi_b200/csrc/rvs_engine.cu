@@ -1043,6 +1043,31 @@ int rvs_engine_drain_samples(rvs_engine* h, float* states, float* pi, float* z, 
     return 0;
 }
 
+int rvs_engine_drain_packed(rvs_engine* h, uint64_t* black, uint64_t* white, uint8_t* side, int8_t* z, float* pi,
+                            int64_t capacity, int64_t* out_count, int mem, void* stream) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (!out_count) return fail(-1, "rvs_engine_drain_packed: null out_count");
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long cnt = 0;
+    RVS_CUDA(cudaMemcpyAsync(&cnt, h->v.ring_count, 8, cudaMemcpyDeviceToHost, s));
+    RVS_CUDA(cudaStreamSynchronize(s));
+    const int64_t n = (int64_t)cnt < h->v.ring_cap ? (int64_t)cnt : h->v.ring_cap;
+    *out_count = n;
+    if (n == 0) return 0;
+    if (!black || !white || !side || !z || !pi) return fail(-1, "rvs_engine_drain_packed: null output");
+    if (capacity < n) return fail(-4, "rvs_engine_drain_packed: capacity %lld < %lld samples pending", (long long)capacity, (long long)n);
+    const cudaMemcpyKind kind = mem == RVS_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    RVS_CUDA(cudaMemcpyAsync(black, h->v.r_black, (size_t)n * 8, kind, s));
+    RVS_CUDA(cudaMemcpyAsync(white, h->v.r_white, (size_t)n * 8, kind, s));
+    RVS_CUDA(cudaMemcpyAsync(side, h->v.r_side, (size_t)n, kind, s));
+    RVS_CUDA(cudaMemcpyAsync(z, h->v.r_z, (size_t)n, kind, s));
+    RVS_CUDA(cudaMemcpyAsync(pi, h->v.r_pi, (size_t)n * 65 * sizeof(float), kind, s));
+    RVS_CUDA(cudaMemsetAsync(h->v.ring_count, 0, 8, s));
+    if (mem != RVS_MEM_DEVICE) RVS_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
 int rvs_engine_set_root_noise(rvs_engine* h, double alpha, float epsilon) {
     int rc = check_handle(h);
     if (rc) return rc;

@@ -59,3 +59,34 @@ def gather_samples(states: torch.Tensor, pi: torch.Tensor, z: torch.Tensor, dst:
     parts = [bufs[r][:counts[r]] for r in range(world)]
     allr = torch.cat(parts, dim=0)
     return allr[:, :192].reshape(-1, 3, 8, 8), allr[:, 192:257].contiguous(), allr[:, 257].contiguous()
+
+
+def gather_packed(s, dst: int = 0):
+    """replay.PackedSamples (torch, on this rank's device) from every rank -> concatenated on `dst`
+    (None elsewhere).  One 280-byte row per sample (black, white, side, z, pi) instead of the 1032 bytes
+    of the trainer format: 3.7x less NVLink traffic; planes are re-derived on `dst` by the K3 kernel."""
+    from .replay import PackedSamples
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return s
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = s.side.device
+    n = torch.tensor([len(s)], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    mx = max(max(counts), 1)
+    row = torch.zeros((mx, 70), dtype=torch.int32, device=dev)  # 2+2 words of boards, 1 word side|z, 65 words of pi bits
+    k = len(s)
+    if k:
+        row[:k, 0:2] = s.black.view(torch.int32).reshape(k, 2)
+        row[:k, 2:4] = s.white.view(torch.int32).reshape(k, 2)
+        row[:k, 4] = s.side.to(torch.int32) | ((s.z.to(torch.int32) & 0xFF) << 8)
+        row[:k, 5:70] = s.pi.view(torch.int32)
+    bufs = [torch.empty_like(row) for _ in range(world)] if rank == dst else None
+    dist.gather(row, bufs, dst=dst)
+    if rank != dst:
+        return None
+    allr = torch.cat([bufs[r][:counts[r]] for r in range(world)], dim=0).contiguous()
+    zz = ((allr[:, 4] >> 8) & 0xFF).to(torch.uint8).view(torch.int8)
+    return PackedSamples(allr[:, 0:2].contiguous().view(torch.int64).reshape(-1), allr[:, 2:4].contiguous().view(torch.int64).reshape(-1),
+                         (allr[:, 4] & 0xFF).to(torch.uint8), zz, allr[:, 5:70].contiguous().view(torch.float32))

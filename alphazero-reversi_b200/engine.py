@@ -127,6 +127,28 @@ class Engine:
         n = cnt.value
         return st[:n], pi[:n], z[:n]
 
+    def drain_packed(self, capacity=None, device=None, stream=None):
+        """completed-game samples as the engine keeps them (replay.PackedSamples: black, white, side,
+        z int8, pi f32[65]; 277 B per sample) -- numpy on the host, or torch tensors on `device`"""
+        from .replay import PackedSamples
+        cap = capacity if capacity is not None else self.sample_capacity
+        cnt = C.c_int64(0)
+        if device is None:
+            bl = np.empty(cap, dtype=np.uint64); wh = np.empty(cap, dtype=np.uint64)
+            sd = np.empty(cap, dtype=np.uint8); z = np.empty(cap, dtype=np.int8)
+            pi = np.empty((cap, 65), dtype=np.float32)
+            mem = L.MEM_HOST
+        else:
+            import torch
+            bl = torch.empty(cap, dtype=torch.int64, device=device); wh = torch.empty(cap, dtype=torch.int64, device=device)
+            sd = torch.empty(cap, dtype=torch.uint8, device=device); z = torch.empty(cap, dtype=torch.int8, device=device)
+            pi = torch.empty((cap, 65), dtype=torch.float32, device=device)
+            mem = L.MEM_DEVICE
+        L.check(L.lib().rvs_engine_drain_packed(self._h, L.ptr(bl)[0], L.ptr(wh)[0], L.ptr(sd)[0], L.ptr(z)[0], L.ptr(pi)[0], cap,
+                                                C.byref(cnt), mem, self._s(stream)))
+        n = cnt.value
+        return PackedSamples(bl[:n], wh[:n], sd[:n], z[:n], pi[:n])
+
     def set_root_noise(self, alpha, epsilon):
         """Dirichlet(alpha) noise mixed into the root priors with weight epsilon by every following
         search (engine feature: the reference configures it, src/config.py:25-26, but never applies

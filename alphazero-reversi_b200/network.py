@@ -111,5 +111,17 @@ class RvsNetwork:
     def from_state_dict(cls, sd) -> "RvsNetwork":
         return cls(*pack_state_dict(sd))
 
+    @classmethod
+    def from_checkpoint(cls, path: str) -> "RvsNetwork":
+        """a reference checkpoint file: `checkpoint_XXXX.pth` (dict with 'model_state_dict',
+        pipeline.py:463-480) or `best_model.pth` (bare state_dict, pipeline.py:482-485), with or
+        without the `_script_module.` duplicates of a TorchScript-compiled model (mcts.py:459-479)"""
+        obj = torch.load(path, map_location="cpu", weights_only=False)
+        if isinstance(obj, dict) and "model_state_dict" in obj:
+            obj = obj["model_state_dict"]
+        if hasattr(obj, "state_dict"):
+            obj = obj.state_dict()
+        return cls(*pack_state_dict(obj))
+
     def attach(self, engine) -> None:
         engine.load_weights(self.flat)

@@ -21,6 +21,7 @@ from . import _lib as L
 from .engine import Engine
 from .game import ReversiGame
 from .mcts import MCTS
+from .replay import to_reference_games
 
 
 class SelfPlay:
@@ -78,18 +79,25 @@ class SelfPlay:
                      net_filters=getattr(self.model, "net_filters", 0))
         if hasattr(self.model, "attach"):
             self.model.attach(eng)
+        if self.args.get("apply_dirichlet_noise", False):
+            # engine feature: the reference accepts dirichlet_alpha / dirichlet_epsilon and never applies
+            # them (self_play.py:18-47), so the noise needs this explicit switch
+            eng.set_root_noise(self.args.get("dirichlet_alpha", 0.3), self.args.get("dirichlet_epsilon", 0.25))
+        persistent = K == 1 and self._builtin in (L.EVAL_E0, L.EVAL_ROLLOUT)
         games: List[Dict] = []
         collected = 0
         while len(games) < num_games:
-            eng.search(S, K)
-            eng.play(T, recycle=True)  # finished slots restart at once; surplus games are discarded
+            if persistent:  # one work-conserving launch plays 8 plies of every slot (rvs_engine_selfplay)
+                eng.selfplay(S, plies=8 * slots, temperature=T, recycle=True)
+            else:
+                eng.search(S, K)
+                eng.play(T, recycle=True)  # finished slots restart at once; surplus games are discarded
             st = eng.stats()
             if st["overflow"] or st["stalled"] or st["samples_dropped"]:
                 raise L.RvsError(f"engine error counters non-zero: {st}")
             if st["games_finished"] > collected:
                 collected = st["games_finished"]
-                states, pi, z = eng.drain_samples()
-                games.extend(_split_games(states, pi, z))
+                games.extend(to_reference_games(eng.drain_packed()))
         eng.close()
         return games[:num_games]
 
@@ -126,22 +134,3 @@ class SelfPlay:
         return {"states": np.array(all_states, dtype=np.float32),
                 "action_probs": np.array(all_probs, dtype=np.float32),
                 "values": np.array(all_values, dtype=np.float32).reshape(-1, 1)}
-
-
-def _split_games(states, pi, z) -> List[Dict]:
-    """the ring stores each finished game's plies contiguously, ply 0 first: split on start positions"""
-    states = np.asarray(states)
-    pi = np.asarray(pi)
-    z = np.asarray(z)
-    games, cur = [], None
-    for i in range(len(states)):
-        s = states[i]
-        is_start = s[0].sum() == 2 and s[1].sum() == 2
-        if is_start or cur is None:
-            cur = {"states": [], "action_probs": [], "current_players": [], "values": []}
-            games.append(cur)
-        cur["states"].append(s)
-        cur["action_probs"].append(pi[i].astype(np.float64))
-        cur["values"].append(float(z[i]))
-        cur["current_players"].append(0)  # side to move is implicit in the canonical planes
-    return games

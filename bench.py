@@ -321,16 +321,46 @@ def run_ours(args):
               "tflops": batch_evals * flops_per_eval / (nn_ms * 1e-3) / 1e12, "flops_per_eval": flops_per_eval}
         eng3.close()
 
+    # ---- config-4 side metric: ResNet 20x256, 16384 concurrent games, Dirichlet root noise; a bounded slice
+    # (32 of the 800 simulations of one ply) -- a full ply is 13.1 M network evaluations (~27 s)
+    nn4 = None
+    if not args.no_nn and not args.no_big:
+        torch.manual_seed(42)
+        net4 = az.AlphaZeroNetwork(8, 20, 256).eval()
+        rn4 = az.RvsNetwork.from_module(net4)
+        G4, S4 = 16384, 32
+        eng4 = az.Engine(G4, S4, 1, evaluator=az.EVAL_NN, c_puct=1.0, seed=5000 + rank, device=local, net_blocks=20, net_filters=256)
+        rn4.attach(eng4)
+        eng4.set_root_noise(0.03, 0.25)  # src/config.py:25-26
+        eng4.set_positions(np.tile(pb0, G4 // N_GAMES), np.tile(pw0, G4 // N_GAMES), np.tile(ps0, G4 // N_GAMES), stream=stream)
+        eng4.search(4, 1, stream=stream)
+        torch.cuda.synchronize()
+        q0s = eng4.stats()
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        eng4.search(S4, 1, stream=stream)
+        q1.record()
+        torch.cuda.synchronize()
+        q1s = eng4.stats()
+        qms = q0.elapsed_time(q1)
+        f4 = 2 * (64 * 27 * 256 + 2 * 20 * 64 * 9 * 256 * 256 + 64 * 256 * 2 + 128 * 65 + 64 * 256 + 64 * 256 + 256)
+        nn4 = {"sims_per_sec": (q1s["sims"] - q0s["sims"]) / (qms * 1e-3), "network_evals_per_sec": G4 * S4 / (qms * 1e-3),
+               "tflops": G4 * S4 * f4 / (qms * 1e-3) / 1e12, "flops_per_eval": f4, "ms": qms,
+               "config": "configs[3]: ResNet 20x256, 16384 concurrent games, Dirichlet(0.03, 0.25) root noise, bf16, wave 1; "
+                         f"timed slice = {S4} of the 800 simulations of one ply"}
+        eng4.close()
+        del net4, rn4
+
     # ---- config 5: replay samples of the timed self-play gathered to rank 0 (outside the timing) --
     gathered = None
-    st_, pi_, z_ = eng.drain_samples(device=dev)
+    pk_ = eng.drain_packed(device=dev)  # packed rows (280 B) travel over NVLink; planes are re-derived on rank 0
     if dist is not None:
         from alphazero_reversi_b200 import dist as azd
-        cap = min(int(st_.shape[0]), 8192)
-        res = azd.gather_samples(st_[:cap].contiguous(), pi_[:cap].contiguous(), z_[:cap].contiguous(), dst=0)
-        gathered = None if res is None else int(res[0].shape[0])
+        cap = min(len(pk_), 65536)
+        res = azd.gather_packed(az.PackedSamples(pk_.black[:cap], pk_.white[:cap], pk_.side[:cap], pk_.z[:cap], pk_.pi[:cap]), dst=0)
+        gathered = None if res is None else int(res.states().shape[0])
     else:
-        gathered = int(st_.shape[0])
+        gathered = len(pk_)
 
     # ---- reductions over ranks --------------------------------------------------------------
     vals = torch.tensor([ms, e2e_ms, kernel_ms], dtype=torch.float64, device=dev)
@@ -350,7 +380,7 @@ def run_ours(args):
         traffic = args.traffic  # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
         tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
         if traffic is None and persistent and os.path.exists(tpath):
-            traffic = json.load(open(tpath))["selfplay_k1_kernel"]["dram_bytes_per_step"] * min(ppl, args.steps)
+            traffic = json.load(open(tpath))["selfplay_k1g_kernel"]["dram_bytes_per_step"] * min(ppl, args.steps)
         out = {
             "metric": METRIC, "value": sims / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3) + args.presteps, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -387,6 +417,10 @@ def run_ours(args):
                               "frac": nn["tflops"] / pk, "note": "whole search step incl. tree kernels; rank 0"}
             nn["config"] = "configs[2]: ResNet 5x128 self-play, 100 sims/move, 4096 games, bf16, random-init weights, wave 1"
             out["nn"] = nn
+            if nn4 is not None:
+                nn4["roofline"] = {"bound": "tensor", "achieved": nn4["tflops"], "peak": pk, "unit": "TFLOP/s", "frac": nn4["tflops"] / pk,
+                                   "note": "whole search slice incl. tree kernels; rank 0"}
+                out["nn_20x256"] = nn4
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(wave, threads=os.cpu_count() or 1, budget_s=12.0)
         print(json.dumps(out))

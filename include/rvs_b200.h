@@ -184,6 +184,14 @@ int rvs_engine_selfplay(rvs_engine *h, int32_t num_sims, float temperature, int6
 int rvs_engine_drain_samples(rvs_engine *h, float *states, float *pi, float *z, int64_t capacity,
                              int64_t *out_count, int mem, void *stream);
 
+/* The same samples PACKED, as the engine keeps them (277 B instead of 1032 B per sample): position
+ * before the move as black / white bitboards + side to move (the reference's game_data
+ * 'current_players', self_play.py:91), z (self_play.py:117-126) as int8 and pi [65] f32.  The
+ * canonical planes are a pure function of (black, white, side): rvs_encode_planes.  This is the
+ * replay-file / NCCL-gather format (alphazero-reversi_b200/replay.py). */
+int rvs_engine_drain_packed(rvs_engine *h, uint64_t *black, uint64_t *white, uint8_t *side, int8_t *z,
+                            float *pi, int64_t capacity, int64_t *out_count, int mem, void *stream);
+
 /* Dirichlet noise on the root priors: P' = (1-eps) P + eps Dir(alpha), mixed in right after the root
  * is expanded by every following search (BASELINE config 4).  The reference only CONFIGURES this
  * (dirichlet_alpha / dirichlet_epsilon, src/config.py:25-26, src/self_play/self_play.py:18-47) and

@@ -37,9 +37,28 @@ def _worker(rank, world, port, q):
     pi = torch.full((n, 65), 1.0 / 65)
     z = torch.arange(n, dtype=torch.float32) + 100 * rank
     out = azd.gather_samples(st, pi, z, dst=0)
+    # packed samples (replay.PackedSamples): bit patterns incl. the sign bit of the boards and z = -1
+    gp = torch.Generator().manual_seed(5 + rank)
+    pk = az.PackedSamples(torch.randint(-2**63, 2**63 - 1, (n,), generator=gp, dtype=torch.int64),
+                          torch.randint(-2**63, 2**63 - 1, (n,), generator=gp, dtype=torch.int64),
+                          torch.randint(1, 3, (n,), generator=gp).to(torch.uint8),
+                          (torch.randint(0, 3, (n,), generator=gp) - 1).to(torch.int8), torch.rand((n, 65), generator=gp))
+    gk = azd.gather_packed(pk, dst=0)
+    packed_ok = None
+    if gk is not None:
+        parts = []
+        for r in range(world):
+            g2 = torch.Generator().manual_seed(5 + r)
+            m = 3 + 2 * r
+            parts.append((torch.randint(-2**63, 2**63 - 1, (m,), generator=g2, dtype=torch.int64),
+                          torch.randint(-2**63, 2**63 - 1, (m,), generator=g2, dtype=torch.int64),
+                          torch.randint(1, 3, (m,), generator=g2).to(torch.uint8),
+                          (torch.randint(0, 3, (m,), generator=g2) - 1).to(torch.int8), torch.rand((m, 65), generator=g2)))
+        exp = [torch.cat([p[i] for p in parts]) for i in range(5)]
+        packed_ok = all(torch.equal(a, b) for a, b in zip((gk.black, gk.white, gk.side, gk.z, gk.pi), exp))
     first, count = azd.shard_range(65536 + 1, rank, world)
     q.put((rank, ok_w, None if out is None else (out[0].shape[0], out[0][:, 0, 0, 0].tolist(), out[2].tolist()),
-           first, count, azd.rank_seed(7, rank)))
+           first, count, azd.rank_seed(7, rank), packed_ok))
     dist.destroy_process_group()
 
 
@@ -55,7 +74,8 @@ def test_two_rank_gloo_broadcast_and_gather():
     for p in ps:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, w0, g0, f0, c0, s0), (r1, w1, g1, f1, c1, s1) = res
+    (r0, w0, g0, f0, c0, s0, p0), (r1, w1, g1, f1, c1, s1, p1) = res
+    assert p0 is True and p1 is None      # packed gather: bit-identical rows on rank 0 only
     assert w0 and w1                      # broadcast delivered identical weights
     assert g1 is None and g0[0] == 8      # 3 + 5 samples gathered on rank 0 only
     assert g0[1] == [1.0] * 3 + [2.0] * 5

@@ -1,0 +1,75 @@
+"""GPU tier: packed samples against the trainer-format drain, the reference's game dicts (golden
+games of the live reference SelfPlay) through the K3 encode kernel, and the trainer-ingest batches
+(SURVEY.md 8(f) N1/N2)."""
+import numpy as np
+import pytest
+import torch
+
+from test_replay_cpu import _golden_games
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def az():
+    import alphazero_reversi_b200 as m
+    return m
+
+
+def test_packed_drain_equals_trainer_format_drain(az):
+    outs = []
+    for packed in (False, True):
+        eng = az.Engine(64, 30, 1, evaluator=az.EVAL_ROLLOUT, seed=11)
+        eng.selfplay(30, plies=64 * 70, temperature=1.0, recycle=False)
+        outs.append(eng.drain_packed() if packed else eng.drain_samples())
+        assert eng.stats()["games_finished"] == 64
+        eng.close()
+    (st, pi, z), pk = outs
+    assert len(pk) == len(z) > 64 * 50
+    # the ring order depends on which game finishes first; compare as multisets keyed by the full row
+    a = np.concatenate([st.reshape(len(z), -1), pi, z.reshape(-1, 1)], axis=1)
+    b = np.concatenate([np.asarray(pk.states()).reshape(len(z), -1), pk.pi, pk.z.astype(np.float32).reshape(-1, 1)], axis=1)
+    assert np.array_equal(a[np.lexsort(a.T[::-1])], b[np.lexsort(b.T[::-1])])
+    assert set(np.unique(pk.side)) == {1, 2}
+
+
+def test_reference_game_dicts_round_trip_through_k3(az):
+    games = _golden_games()
+    s = az.replay.from_reference_games(games)
+    back = az.replay.to_reference_games(s)
+    assert len(back) == len(games)
+    for g, h in zip(games, back):
+        assert h["current_players"] == g["current_players"] and h["values"] == g["values"]
+        assert np.array_equal(np.array(h["states"]), np.array(g["states"]))   # planes incl. the legal-move plane
+        assert np.array_equal(np.array(h["action_probs"]).astype(np.float32), np.array(g["action_probs"]).astype(np.float32))
+    dev = s.to("cuda:0")
+    td = az.replay.to_training_data(dev)
+    assert td["states"].is_cuda and td["states"].shape == (180, 3, 8, 8) and td["value_targets"].shape == (180, 1)
+    assert np.array_equal(td["states"].cpu().numpy(), np.array([x for g in games for x in g["states"]]))
+
+
+def test_training_batches_feed_a_torch_step(az):
+    s = az.replay.from_reference_games(_golden_games()).to("cuda:0")
+    torch.manual_seed(0)
+    net = az.AlphaZeroNetwork(8, 1, 64).cuda().train()
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-3)
+    seen = 0
+    g = torch.Generator(device="cuda:0").manual_seed(1)
+    for states, labels, zt in az.replay.training_batches(s, 64, shuffle=True, generator=g):
+        assert states.is_cuda and labels.dtype == torch.int64 and states.shape[1:] == (3, 8, 8)
+        logits, v = net.predict(states)
+        loss = torch.nn.functional.cross_entropy(logits, labels) + torch.nn.functional.mse_loss(v, zt)   # pipeline.py:306-327
+        opt.zero_grad(); loss.backward(); opt.step()
+        seen += states.shape[0]
+    assert seen == 180 and torch.isfinite(loss)
+
+
+def test_selfplay_mirror_reports_players_and_noise_switch(az):
+    sp = az.SelfPlay(az.UniformRollout(seed=3), {"num_simulations": 20, "batch_size": 1, "temperature": 1.0, "num_parallel_games": 16,
+                                                 "apply_dirichlet_noise": True, "dirichlet_alpha": 0.3, "dirichlet_epsilon": 0.25})
+    games = sp.generate_games(20)
+    assert len(games) == 20
+    for gd in games:
+        assert set(gd) == {"states", "action_probs", "current_players", "values"}
+        assert gd["current_players"][0] == 1 and set(gd["current_players"]) <= {1, 2}
+        assert len(gd["states"]) == len(gd["values"]) == len(gd["current_players"]) >= 50
