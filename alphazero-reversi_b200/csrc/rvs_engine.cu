@@ -503,7 +503,7 @@ template <int RULES, int EVAL, int LPG>
 __global__ void __launch_bounds__(kBlockG, 16) search_k1g_kernel(EngineView ev, int S) {
     constexpr int GPB = kBlockG / LPG;
     __shared__ uint8_t lut[256 * 8];
-    __shared__ int spath[GPB][kMaxPath];
+    __shared__ int spath[GPB][kMaxPath + 1];
     lut_init(lut, threadIdx.x, kBlockG);
     __syncthreads();
     const int n_groups = gridDim.x * GPB;
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(kBlockG, 16) search_k1g_kernel(EngineView ev, 
         const uint64_t game_id = ev.game_id[g];
         const uint64_t search_id = (uint64_t)ev.ply[g];
         init_root_g(cx, root.side, act);
-        const GBoard root_g = gboard_load(root);
+        const GBoard root_g = gboard_load(grp, root);
         for (int sim = 0; sim < S; ++sim) {
             const uint64_t st = EVAL == RVS_EVAL_ROLLOUT ? stream_seed(ev.seed, game_id, (search_id << 16) | (uint64_t)sim) : 0ULL;
             simulate_one_g<EVAL>(cx, root_g, st, act);
@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(kBlockG, 16) selfplay_k1g_kernel(EngineView ev
                                                                    unsigned long long budget, int recycle) {
     constexpr int GPB = kBlockG / LPG;
     __shared__ uint8_t lut[256 * 8];
-    __shared__ int spath[GPB][kMaxPath];
+    __shared__ int spath[GPB][kMaxPath + 1];
     lut_init(lut, threadIdx.x, kBlockG);
     __syncthreads();
     const int n_groups = gridDim.x * GPB;
@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(kBlockG, 16) selfplay_k1g_kernel(EngineView ev
         const uint64_t game_id = ev.game_id[g];
         const uint64_t search_id = (uint64_t)ev.ply[g];
         init_root_g(cx, root.side, alive);
-        const GBoard root_g = gboard_load(root);
+        const GBoard root_g = gboard_load(grp, root);
         if (__any_sync(kFull, alive)) {
             for (int sim = 0; sim < S; ++sim) {
                 const uint64_t st = EVAL == RVS_EVAL_ROLLOUT ? stream_seed(ev.seed, game_id, (search_id << 16) | (uint64_t)sim) : 0ULL;

@@ -34,7 +34,8 @@ struct Grp {
     int lane;            // 0..LPG-1 inside the group
     uint64_t below;      // squares of the rows owned by lower lanes
     uint32_t lut;        // shared-window address: lut[byte * 8 + j] = position of the j-th set bit of byte
-    uint32_t path;       // shared-window address: int[kMaxPath] nodes of the current path
+    uint32_t path;       // shared-window address: int[kMaxPath + 1] nodes of the current path; the extra word
+                         // is the group's broadcast slot (grp_nth_set_bit)
                          // (32-bit shared addresses: a generic pointer costs an S2R + LEA per access)
     DirLane d[ND];       // this lane's directions; d[j].neg == (j & 1) when ND >= 2
 };
@@ -88,6 +89,22 @@ __device__ __forceinline__ uint64_t grp_or64(uint64_t x) {
     }
     return ((uint64_t)hi << 32) | lo;
 }
+// LPG == 8 only (one direction per lane, lanes 2a / 2a+1 own +s / -s): OR over the group of partial
+// masks that every lane holds in ITS OWN domain (normal for even lanes, bit-reversed for odd ones);
+// the result is again in the lane's own domain.  Partners of the first step are in opposite domains
+// (one unconditional brev), partners of the later steps in the same one.
+__device__ __forceinline__ uint64_t grp_or64_own8(uint64_t x) {
+    unsigned lo = (unsigned)x, hi = (unsigned)(x >> 32);
+    const unsigned plo = __shfl_xor_sync(kFull, lo, 1), phi = __shfl_xor_sync(kFull, hi, 1);
+    lo |= __brev(phi);  // brev64(partner): halves swap
+    hi |= __brev(plo);
+#pragma unroll
+    for (int o = 2; o < 8; o <<= 1) {
+        lo |= __shfl_xor_sync(kFull, lo, o);
+        hi |= __shfl_xor_sync(kFull, hi, o);
+    }
+    return ((uint64_t)hi << 32) | lo;
+}
 template <int LPG>
 __device__ __forceinline__ unsigned grp_max(unsigned x) {
 #pragma unroll
@@ -133,21 +150,29 @@ __device__ __forceinline__ int grp_nth_set_bit(const Grp<LPG>& g, uint64_t m, in
         row = next ? r + 1 : row;
     }
     const int pos = (g.lane * RPL + row) * 8 + (int)lds_u8(g.lut + (slice & 0xFFu) * 8 + (j & 7));
-    const unsigned bal = __ballot_sync(kFull, hit) >> g.sh;
-    return __shfl_sync(kFull, pos, (__ffs(bal) - 1) & (LPG - 1), LPG);
+    // exactly one lane of the group holds the bit: it posts the square in the group's shared slot
+    // (STS -> LDS is ~45 cycles shorter than ballot + find-first-set + SHFL on the critical path)
+    if (hit) sts_s32(g.path + 4 * kMaxPath, pos);
+    __syncwarp();
+    const int sq = lds_s32(g.path + 4 * kMaxPath);
+    __syncwarp();
+    return sq;
 }
 
 // A position held by a group: side to move / opponent in the normal [0] and the bit-reversed [1]
-// domain (popcounts are domain independent)
+// domain (popcounts are domain independent).  With one direction per lane (LPG == 8) only [0] is
+// used and holds the boards in the lane's OWN domain.
 struct GBoard {
     uint64_t P[2], O[2];
     int side;   // 1 BLACK, 2 WHITE
     int flags;  // F_OVER | winner | F_PASSED like Board::flags
 };
 
-__device__ __forceinline__ GBoard gboard_load(const Board& b) {
+template <int LPG>
+__device__ __forceinline__ GBoard gboard_load(const Grp<LPG>& g, const Board& b) {
     const bool blk = b.side == 1;
     const uint64_t P = blk ? b.black : b.white, O = blk ? b.white : b.black;
+    if constexpr (Grp<LPG>::ND == 1) return GBoard{{to_dom(P, g.d[0].neg), 0ULL}, {to_dom(O, g.d[0].neg), 0ULL}, b.side, b.flags};
     return GBoard{{P, brev64(P)}, {O, brev64(O)}, b.side, b.flags};
 }
 
@@ -159,10 +184,8 @@ __device__ __forceinline__ bool dir_neg(const Grp<LPG>& g, int j) {
 // Board.get_valid_moves for side P against O (both domains given), group-uniform result
 template <int LPG>
 __device__ __forceinline__ uint64_t grp_legal(const Grp<LPG>& g, const uint64_t (&P)[2], const uint64_t (&O)[2]) {
-    if constexpr (Grp<LPG>::ND == 1) {  // one direction per lane: its domain is a run-time property of the lane
-        const bool neg = g.d[0].neg;
-        return grp_or64<LPG>(to_dom(legal_raw(g.d[0], neg ? P[1] : P[0], neg ? O[1] : O[0]), neg));
-    }
+    if constexpr (Grp<LPG>::ND == 1)  // boards and partial masks in the lane's own domain, result normalised once
+        return to_dom(grp_or64_own8(legal_raw(g.d[0], P[0], O[0])), g.d[0].neg);
     uint64_t xn = 0, xr = 0;
 #pragma unroll
     for (int j = 0; j < Grp<LPG>::ND; ++j) {
@@ -180,24 +203,25 @@ struct MoveOut {
 // flips of move idx by the side to move + the opponent's reply mask (board.py:181-240)
 template <int LPG>
 __device__ __forceinline__ MoveOut grp_flip(const Grp<LPG>& g, const GBoard& c, int idx) {
-    const uint64_t mvn = 1ULL << idx, mvr = 1ULL << (63 - idx);
-    uint64_t fn = 0, fr = 0;
-    if constexpr (Grp<LPG>::ND == 1) {
-        const bool neg = g.d[0].neg;
-        fn = to_dom(flip_raw(g.d[0], neg ? c.P[1] : c.P[0], neg ? c.O[1] : c.O[0], neg ? mvr : mvn), neg);
+    MoveOut m;
+    if constexpr (Grp<LPG>::ND == 1) {  // everything in the lane's own domain
+        const uint64_t mv = 1ULL << (g.d[0].neg ? 63 - idx : idx);
+        const uint64_t f = grp_or64_own8(flip_raw(g.d[0], c.P[0], c.O[0], mv));
+        m.P[0] = c.P[0] ^ (mv | f); m.P[1] = 0ULL;
+        m.O[0] = c.O[0] ^ f;        m.O[1] = 0ULL;
     } else {
+        const uint64_t mvn = 1ULL << idx, mvr = 1ULL << (63 - idx);
+        uint64_t fn = 0, fr = 0;
 #pragma unroll
         for (int j = 0; j < Grp<LPG>::ND; ++j) {
             if (dir_neg(g, j)) fr |= flip_raw(g.d[j], c.P[1], c.O[1], mvr);
             else fn |= flip_raw(g.d[j], c.P[0], c.O[0], mvn);
         }
-        fn |= brev64(fr);
+        const uint64_t f = grp_or64<LPG>(fn | brev64(fr));
+        const uint64_t fb = brev64(f);
+        m.P[0] = c.P[0] ^ (mvn | f); m.P[1] = c.P[1] ^ (mvr | fb);
+        m.O[0] = c.O[0] ^ f;         m.O[1] = c.O[1] ^ fb;
     }
-    const uint64_t f = grp_or64<LPG>(fn);
-    const uint64_t fb = brev64(f);
-    MoveOut m;
-    m.P[0] = c.P[0] ^ (mvn | f); m.P[1] = c.P[1] ^ (mvr | fb);
-    m.O[0] = c.O[0] ^ f;         m.O[1] = c.O[1] ^ fb;
     m.lm_opp = grp_legal(g, m.O, m.P);
     return m;
 }
@@ -242,7 +266,8 @@ __device__ __forceinline__ int grp_random_playout(const Grp<LPG>& g, GBoard c, u
     int winner = 0;
     plies = 0;
     if (done) lm = 1;  // a dead group plays square 0 over and over; nothing of it is read
-    while (!__all_sync(kFull, done)) {
+    bool all_done = __all_sync(kFull, done);
+    while (!all_done) {  // one vote per ply on the common path: `done` only changes inside the pass branch
         const int n = popc64(lm);
         const int k = roll_pick(roll_next(rs), n);
         const int idx = grp_nth_set_bit(g, lm, k) & 63;
@@ -264,8 +289,9 @@ __device__ __forceinline__ int grp_random_playout(const Grp<LPG>& g, GBoard c, u
                     done = true;
                 }
             }
+            if (done) lm = 1;  // keep the dead group's ply well defined
+            all_done = __all_sync(kFull, done);
         }
-        if (done) lm = 1;  // keep the dead group's ply well defined
     }
     return winner;
 }
