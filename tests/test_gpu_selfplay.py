@@ -126,3 +126,62 @@ def test_persistent_selfplay_budget_and_recycling(az):
     assert st["games_finished"] >= n            # ~60 plies per game: every slot recycled at least once
     states, pi, z = eng.drain_samples()
     assert len(states) == st["samples"] and np.allclose(pi.sum(axis=1), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("lpg,n", [(8, 5), (4, 13), (2, 37), (4, 1)])
+def test_group_kernels_ragged_sizes_and_lane_counts(az, lpg, n):
+    """the several-games-per-warp wave-1 kernels (rvs_treeg.cuh) with 8 / 4 / 2 lanes per game and game
+    counts that leave groups of the last warp empty: persistent self-play samples == oracle"""
+    import os
+    os.environ["RVS_K1_LPG"] = str(lpg)
+    try:
+        S, T = 40, 1.0
+        eng = az.Engine(n, S, 1, evaluator=az.EVAL_ROLLOUT, seed=77)
+        eng.selfplay(S, plies=n * 64, temperature=T, recycle=False)
+        st = eng.stats()
+        assert st["overflow"] == 0 and st["games_finished"] == n
+        pk = eng.drain_packed()
+        got = {}
+        i = 0
+        while i < len(pk):
+            j = i + 1
+            while j < len(pk) and not (int(pk.black[j]) == orc.START[0] and int(pk.white[j]) == orc.START[1]):
+                j += 1
+            got[(pk.black[i:j].tobytes(), pk.white[i:j].tobytes(), pk.side[i:j].tobytes())] = (pk.pi[i:j], pk.z[i:j])
+            i = j
+        for g in range(n):
+            samples, win = orc.self_play_game(S, 1, evaluator=1, seed=77, game_id=g, temperature=T)
+            key = (np.array([s.black for s in samples], dtype=np.uint64).tobytes(), np.array([s.white for s in samples], dtype=np.uint64).tobytes(),
+                   np.array([s.side for s in samples], dtype=np.uint8).tobytes())
+            assert key in got, g
+            gpi, gz = got[key]
+            assert np.array_equal(gpi, np.array([orc.action_probs(np.array(s.visits[:]), T).astype(np.float32) for s in samples]))
+            assert np.array_equal(gz, np.array([s.z for s in samples], dtype=np.int8))
+        eng.close()
+    finally:
+        os.environ.pop("RVS_K1_LPG", None)
+
+
+def test_more_games_than_resident_groups(az):
+    """12 000 games x 8 lanes = 3000 warps > the 2368 resident one-warp CTAs: groups own several slots
+    (search: one after the other; persistent self-play: round-robin).  Visit counts of a strided sample of
+    games equal the oracle's, and a budgeted self-play launch spends exactly its budget."""
+    import os
+    os.environ["RVS_K1_LPG"] = "8"
+    try:
+        n, S = 12000, 24
+        eng = az.Engine(n, S, 1, evaluator=az.EVAL_ROLLOUT, seed=5)
+        eng.search(S, 1)
+        v = eng.root_visits()
+        st = eng.stats()
+        assert st["overflow"] == 0 and st["sims"] == n * S
+        for g in list(range(0, n, 397)) + [n - 1, 9471, 9472, 9473]:
+            ov, *_ = orc.mcts_search(orc.START, S, 1, evaluator=1, seed=5, game_id=g, search_id=0)
+            assert np.array_equal(v[g], ov), g
+        s0 = eng.stats()
+        eng.selfplay(S, plies=3 * n + 5, temperature=1.0, recycle=True)
+        s1 = eng.stats()
+        assert s1["sims"] - s0["sims"] == (3 * n + 5) * S and s1["overflow"] == 0 and s1["stalled"] == 0
+        eng.close()
+    finally:
+        os.environ.pop("RVS_K1_LPG", None)
