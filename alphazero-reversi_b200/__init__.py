@@ -13,6 +13,7 @@ from .game import Board, ReversiGame
 from .mcts import MCTS, UniformDiscDiff, UniformRollout
 from .self_play import SelfPlay
 from . import replay
+from .arena import Arena, ELOPlayer, ELORatingSystem
 from .replay import PackedSamples
 
 
@@ -25,4 +26,4 @@ def __getattr__(name):  # torch-dependent members are imported lazily
 
 __all__ = ["Board", "ReversiGame", "MCTS", "SelfPlay", "Engine", "board_ops", "UniformDiscDiff",
            "UniformRollout", "RvsError", "RULES_REF", "RULES_STRICT", "EVAL_E0", "EVAL_ROLLOUT",
-           "EVAL_EXTERNAL", "EVAL_NN", "replay", "PackedSamples"]
+           "EVAL_EXTERNAL", "EVAL_NN", "replay", "PackedSamples", "Arena", "ELOPlayer", "ELORatingSystem"]
