@@ -28,7 +28,7 @@ class EngineConfig(C.Structure):
 
 class EngineStats(C.Structure):
     _fields_ = [(k, C.c_int64) for k in ("sims", "evals", "board_steps", "nodes", "games_finished",
-                                          "samples", "launches", "overflow", "tree_bytes", "samples_dropped", "stalled")]
+                                          "samples", "launches", "overflow", "tree_bytes", "samples_dropped", "stalled", "nn_evals")]
 
 
 # every symbol include/rvs_b200.h declares: name -> (restype, argtypes)

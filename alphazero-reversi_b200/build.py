@@ -16,7 +16,7 @@ OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(PKG, "librvs_b200.so")
 SOURCES = ["rvs_board.cu", "rvs_engine.cu", "rvs_net.cu", "rvs_conv_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17"] + os.environ.get("RVS_EXTRA_NVCC", "").split() + [
          "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-diag-suppress", "550"]
 
 

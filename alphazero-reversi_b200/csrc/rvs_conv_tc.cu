@@ -398,9 +398,12 @@ template <int C, int CIN, bool HEAD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap w_map,
                    const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
-                   const float* __restrict__ bias, int n_tiles, const __grid_constant__ HeadW head,
-                   float* __restrict__ feat) {
+                   const float* __restrict__ bias, int n_tiles_arg, const __grid_constant__ HeadW head,
+                   float* __restrict__ feat, const int* __restrict__ n_boards_dev) {
     using K = Cfg2<C, CIN>;
+    // compacted leaf batches: the number of boards is only known on the device (written at least two
+    // kernels upstream, so it is visible even when this launch overlaps its predecessor's tail)
+    const int n_tiles = n_boards_dev ? (*n_boards_dev + 1) >> 1 : n_tiles_arg;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -595,8 +598,9 @@ struct Cfg2S {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv3x3_tc2s_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap w_map,
                     const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
-                    const float* __restrict__ bias, int n_tiles) {
+                    const float* __restrict__ bias, int n_tiles_arg, const int* __restrict__ n_boards_dev) {
     using K = Cfg2S;
+    const int n_tiles = n_boards_dev ? (*n_boards_dev + 1) >> 1 : n_tiles_arg;
     constexpr int C = K::C;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -752,7 +756,7 @@ conv3x3_tc2s_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_cons
 template <typename Kern>
 int launch_pdl(Kern kern, int grid, int smem, cudaStream_t s, const CUtensorMap& a_map, const CUtensorMap& w_map,
                const __nv_bfloat16* residual, __nv_bfloat16* out, const float* bias, int n_tiles, const HeadW& head,
-               float* feat) {
+               float* feat, const int* n_dev) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
@@ -763,13 +767,13 @@ int launch_pdl(Kern kern, int grid, int smem, cudaStream_t s, const CUtensorMap&
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    RVS_CUDA(cudaLaunchKernelEx(&cfg, kern, a_map, w_map, residual, out, bias, n_tiles, head, feat));
+    RVS_CUDA(cudaLaunchKernelEx(&cfg, kern, a_map, w_map, residual, out, bias, n_tiles, head, feat, n_dev));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
 
 int launch_pdl_s(int grid, cudaStream_t s, const CUtensorMap& a_map, const CUtensorMap& w_map, const __nv_bfloat16* residual,
-                 __nv_bfloat16* out, const float* bias, int n_tiles) {
+                 __nv_bfloat16* out, const float* bias, int n_tiles, const int* n_dev) {
     static bool attr = false;
     if (!attr) {
         RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2S::SMEM));
@@ -785,7 +789,7 @@ int launch_pdl_s(int grid, cudaStream_t s, const CUtensorMap& a_map, const CUten
     attrs[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = 1;
-    RVS_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2s_kernel, a_map, w_map, residual, out, bias, n_tiles));
+    RVS_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2s_kernel, a_map, w_map, residual, out, bias, n_tiles, n_dev));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
@@ -840,7 +844,7 @@ int conv_tc_plan(ConvTcPlan& plan, const __nv_bfloat16* w, int C, int64_t max_ba
 }
 
 int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
-                   const float* bias, int64_t B, cudaStream_t s, const float* head_host, float* feat) {
+                   const float* bias, int64_t B, cudaStream_t s, const float* head_host, float* feat, const int* n_dev) {
     if (!plan.valid || !plan.impl) return fail(-8, "tcgen05 convolution: no plan");
     Impl* im = static_cast<Impl*>(plan.impl);
     static HeadW zero_head = {};
@@ -869,7 +873,7 @@ int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_b
     if (im->two_sm) {  // CTA pairs: grid = 2 x pairs, at most one CTA per SM
         int pairs = (n_tiles + 1) / 2;
         if (pairs > kNumSMs / 2) pairs = kNumSMs / 2;
-        if (C == 256) return launch_pdl_s(2 * pairs, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles);
+        if (C == 256) return launch_pdl_s(2 * pairs, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles, n_dev);
         if (C == 64) {
             static bool attr = false;
             if (!attr) {
@@ -877,12 +881,12 @@ int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_b
                 RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<64, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<64, 64>::SMEM));
                 attr = true;
             }
-            if (feat) return launch_pdl(conv3x3_tc2_kernel<64, 64, true>, 2 * pairs, Cfg2<64, 64>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles, *hw, feat);
-            return launch_pdl(conv3x3_tc2_kernel<64, 64, false>, 2 * pairs, Cfg2<64, 64>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles, *hw, feat);
+            if (feat) return launch_pdl(conv3x3_tc2_kernel<64, 64, true>, 2 * pairs, Cfg2<64, 64>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles, *hw, feat, n_dev);
+            return launch_pdl(conv3x3_tc2_kernel<64, 64, false>, 2 * pairs, Cfg2<64, 64>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles, *hw, feat, n_dev);
         } else if (im->cin == 64) {  // first layer of a 128-filter tower: 64 (3 used) -> 128
             static bool attr = false;
             if (!attr) { RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<128, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<128, 64>::SMEM)); attr = true; }
-            return launch_pdl(conv3x3_tc2_kernel<128, 64, false>, 2 * pairs, Cfg2<128, 64>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles, *hw, nullptr);
+            return launch_pdl(conv3x3_tc2_kernel<128, 64, false>, 2 * pairs, Cfg2<128, 64>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles, *hw, nullptr, n_dev);
         } else {
             static bool attr = false;
             if (!attr) {
@@ -890,8 +894,8 @@ int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_b
                 RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<128, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<128, 128>::SMEM));
                 attr = true;
             }
-            if (feat) return launch_pdl(conv3x3_tc2_kernel<128, 128, true>, 2 * pairs, Cfg2<128, 128>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles, *hw, feat);
-            return launch_pdl(conv3x3_tc2_kernel<128, 128, false>, 2 * pairs, Cfg2<128, 128>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles, *hw, feat);
+            if (feat) return launch_pdl(conv3x3_tc2_kernel<128, 128, true>, 2 * pairs, Cfg2<128, 128>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles, *hw, feat, n_dev);
+            return launch_pdl(conv3x3_tc2_kernel<128, 128, false>, 2 * pairs, Cfg2<128, 128>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles, *hw, feat, n_dev);
         }
         return 0;
     }

@@ -24,8 +24,11 @@ int conv_tc_plan(ConvTcPlan& plan, const __nv_bfloat16* w, int C, int64_t max_ba
 // out = relu(conv3x3(in) + bias [+ residual]) on B boards, NHWC bf16
 // head_host / feat (optional, 2-CTA kernel only): fuse the policy/value 1x1 convolutions into the epilogue:
 // head_host = host copy of [3][C] folded weights + 3 biases, feat = device [B][192] f32 output; `out` is then unused
+// n_dev (optional, 2-CTA kernels only): device int with the actual number of boards (<= B, which then only sizes
+// the grid): compacted leaf batches whose size never visits the host
 int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
-                   const float* bias, int64_t B, cudaStream_t s, const float* head_host = nullptr, float* feat = nullptr);
+                   const float* bias, int64_t B, cudaStream_t s, const float* head_host = nullptr, float* feat = nullptr,
+                   const int* n_dev = nullptr);
 bool conv_tc_can_fuse_head(const ConvTcPlan& plan);
 void conv_tc_destroy(ConvTcPlan& plan);
 

@@ -166,16 +166,28 @@ __global__ void __launch_bounds__(kBlock) select_kernel(EngineView ev, int k) {
 
 // MCTS._process_batch with caller-supplied softmax outputs (mcts.py:596-623).
 // probs [G*k,65], values [G*k], slot = g*k + j.
+// `inv` (optional): slot -> row of probs / values (compacted batch of rvs_net.cu); -1 = no evaluation,
+// <= -2 = same row as slot -2-inv of this game's wave
 __global__ void __launch_bounds__(kBlock) process_probs_kernel(EngineView ev, int k, const float* __restrict__ probs,
-                                                                const float* __restrict__ values, int first_wave) {
+                                                                const float* __restrict__ values, int first_wave,
+                                                                const int* __restrict__ inv) {
     const int g = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (g >= ev.G) return;
     TreeCtx cx{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, ev.n_nodes[g], ev.c_puct, (int)(threadIdx.x & 31), 0, 0, 0, 0, 0, 0, DirLane{}};
     const WaveScratch ws = scratch_of(ev, g);
     const size_t slot0 = (size_t)g * k;
-    for (int j = cx.lane; j < k; j += 32) ws.val[j] = values[slot0 + j];
+    auto row_of = [&](int j) -> long long {
+        if (!inv) return (long long)(slot0 + j);
+        int c = inv[slot0 + j];
+        if (c <= -2) c = inv[slot0 + (-2 - c)];
+        return (long long)c;
+    };
+    for (int j = cx.lane; j < k; j += 32) {
+        const long long r = row_of(j);
+        ws.val[j] = r >= 0 ? values[r] : 0.0f;
+    }
     __syncwarp();
-    process_wave(cx, ws, k, [&](int j, int sq) { return probs[(slot0 + j) * 65 + sq]; });
+    process_wave(cx, ws, k, [&](int j, int sq) { return probs[row_of(j) * 65 + sq]; });
     if (first_wave && ev.noise_eps > 0.0f) {
         __syncwarp();
         if (cx.lane == 0) root_noise_apply(ev, g, ev.game_id[g], (uint64_t)ev.ply[g]);
@@ -932,7 +944,7 @@ int rvs_engine_process(rvs_engine* h, const float* probs, const float* values, i
         dp = h->ext_probs;
         dv = h->ext_values;
     }
-    RVS_ENGINE_LAUNCH(h, process_probs_kernel, games_grid(h->v.G), kBlock, 0, s, h->v, h->cur_k, dp, dv, h->waves_done == 0 ? 1 : 0);
+    RVS_ENGINE_LAUNCH(h, process_probs_kernel, games_grid(h->v.G), kBlock, 0, s, h->v, h->cur_k, dp, dv, h->waves_done == 0 ? 1 : 0, (const int*)nullptr);
     h->waves_done++;
     h->cur_k = 0;
     return 0;
@@ -1099,7 +1111,18 @@ int rvs_engine_stats_get(rvs_engine* h, rvs_engine_stats* out, void* stream) {
     out->overflow = (int64_t)st[ST_OVERFLOW];
     out->samples_dropped = (int64_t)st[ST_DROPPED];
     out->stalled = (int64_t)st[ST_STALLED];
+    out->nn_evals = (int64_t)st[ST_NNEVALS];
     return 0;
 }
 
 }  // extern "C"
+
+int rvs_engine_process_mapped(rvs_engine* h, const float* probs, const float* values, const int* inv, cudaStream_t s) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (h->cur_k == 0) return fail(-1, "rvs_engine_process: no selected wave");
+    RVS_ENGINE_LAUNCH(h, process_probs_kernel, games_grid(h->v.G), kBlock, 0, s, h->v, h->cur_k, probs, values, h->waves_done == 0 ? 1 : 0, inv);
+    h->waves_done++;
+    h->cur_k = 0;
+    return 0;
+}

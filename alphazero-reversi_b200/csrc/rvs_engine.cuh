@@ -8,7 +8,7 @@
 
 namespace rvs {
 
-enum : int { ST_SIMS = 0, ST_EVALS, ST_STEPS, ST_FINISHED, ST_SAMPLES, ST_OVERFLOW, ST_DROPPED, ST_STALLED, ST_BYTES, ST_NODES, ST_COUNT };
+enum : int { ST_SIMS = 0, ST_EVALS, ST_STEPS, ST_FINISHED, ST_SAMPLES, ST_OVERFLOW, ST_DROPPED, ST_STALLED, ST_BYTES, ST_NODES, ST_NNEVALS, ST_COUNT };
 
 struct NetState;  // rvs_net.cu
 
@@ -83,4 +83,6 @@ struct rvs_engine {
 
 // K4 hooks implemented in rvs_net.cu
 int rvs_net_search(rvs_engine* h, int32_t num_sims, int32_t wave, cudaStream_t s);
+// rvs_engine_process with device probs / values addressed through the compaction map of rvs_net.cu
+int rvs_engine_process_mapped(rvs_engine* h, const float* probs, const float* values, const int* inv, cudaStream_t s);
 void rvs_net_destroy(rvs::NetState* n);

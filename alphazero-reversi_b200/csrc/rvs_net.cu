@@ -36,6 +36,8 @@ struct NetState {
     float *v1w = nullptr, *v1b = nullptr;    // fc1 TRANSPOSED [64][256], [256]
     float *w0f = nullptr, *b0f = nullptr;    // first conv for the bit-plane kernel: [27][C] f32, [C]
     uint64_t* bits = nullptr;                // [B][3] own / opponent / legal bit planes (K3 output)
+    int* n_valid = nullptr;                  // [1] boards in the compacted leaf batch of the current wave
+    int* inv = nullptr;                      // [B] wave slot -> row of the compacted batch (-1: none, <= -2: same as slot -2-inv of its game)
     __nv_bfloat16* x0 = nullptr;             // [tile][y][board][x][64] bf16 input planes (3 used) for the tcgen05 first layer
     float *v2w = nullptr, *v2b = nullptr;    // fc2 [256], [1]
     // activations
@@ -172,7 +174,13 @@ __global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restr
                                                      const float* __restrict__ v1wT, const float* __restrict__ v1b,
                                                      const float* __restrict__ v2w, const float* __restrict__ v2b,
                                                      float* __restrict__ logits, float* __restrict__ probs,
-                                                     float* __restrict__ values) {
+                                                     float* __restrict__ values, const int* __restrict__ n_dev,
+                                                     unsigned long long* __restrict__ nn_evals) {
+    if (n_dev) {
+        B = *n_dev;
+        if (nn_evals && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(nn_evals, (unsigned long long)B);
+        if ((int64_t)blockIdx.x * kHB >= B) return;
+    }
     __shared__ float w1x1[3 * 256];        // [3][C] (C <= 256)
     __shared__ float feat[kHB][192];       // [0,128): policy planes channel-major (ch*64+px); [128,192): value plane
     __shared__ float hid[kHB][256];
@@ -291,8 +299,12 @@ __global__ void fold_conv0_kernel(const float* __restrict__ w, const float* __re
 template <int C>
 __global__ void __launch_bounds__(256) conv0_bits_kernel(const uint64_t* __restrict__ bits /*[B][3]*/, int64_t B,
                                                           const float* __restrict__ wf, const float* __restrict__ bias,
-                                                          __nv_bfloat16* __restrict__ out) {
+                                                          __nv_bfloat16* __restrict__ out, const int* __restrict__ n_dev) {
     constexpr int PER = C / 32;  // couts per lane: 2, 4 or 8
+    if (n_dev) {
+        B = *n_dev;
+        if ((int64_t)blockIdx.x * 2 >= B) return;
+    }
     __shared__ __align__(16) float sw[27 * C];
     for (int i = threadIdx.x; i < 27 * C; i += 256) sw[i] = wf[i];
     __syncthreads();
@@ -336,7 +348,11 @@ __global__ void __launch_bounds__(256) conv0_bits_kernel(const uint64_t* __restr
 // bit planes -> bf16 input tiles [tile][y][board][x][64] (channels 0..2 used) for the tensor-core first
 // layer: one thread per pixel row, 128 B = 4 x 256-bit... written as 8 x uint4
 __global__ void __launch_bounds__(256) planes_tiles_kernel(const uint64_t* __restrict__ bits, int64_t B, int64_t n_tiles,
-                                                            uint4* __restrict__ out) {
+                                                            uint4* __restrict__ out, const int* __restrict__ n_dev) {
+    if (n_dev) {
+        B = *n_dev;
+        n_tiles = (B + 1) >> 1;
+    }
     const int64_t total = n_tiles * 128;
     for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < total; r += (int64_t)gridDim.x * blockDim.x) {
         const int64_t tile = r >> 7;
@@ -371,6 +387,38 @@ __global__ void __launch_bounds__(256) encode_leaves_kernel(EngineView ev, int k
             O = blk ? ev.w_white[o] : ev.w_black[o];
         }
         out[slot * 3] = P; out[slot * 3 + 1] = O; out[slot * 3 + 2] = lm;
+    }
+}
+
+// K3 with compaction: only leaves that need a network evaluation enter the batch, and the leaves of
+// one game's wave that sit on the SAME node are evaluated once (the reference's wave sends most of its
+// simulations down one path, SURVEY.md 0.3, and evaluates every copy: mcts.py:586-597).  Rows are
+// appended with one atomic per unique leaf; their order is arbitrary, which cannot change any result
+// because the network treats boards independently.
+__global__ void __launch_bounds__(256) encode_compact_kernel(EngineView ev, int k, uint64_t* __restrict__ out,
+                                                              int* __restrict__ inv, int* __restrict__ n_valid) {
+    const int64_t total = (int64_t)ev.G * k;
+    for (int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; slot < total; slot += (int64_t)gridDim.x * blockDim.x) {
+        const int g = (int)(slot / k), j = (int)(slot - (int64_t)g * k);
+        const size_t o = (size_t)g * ev.kmax + j;
+        const int node = ev.w_node[o];
+        const uint64_t lm = node < 0 ? 0ULL : ev.w_lm[o];
+        int code = -1;
+        if (lm) {
+            int rep = -1;
+            for (int q = 0; q < j; ++q)
+                if (ev.w_node[(size_t)g * ev.kmax + q] == node) { rep = q; break; }
+            if (rep >= 0) {
+                code = -2 - rep;
+            } else {
+                code = atomicAdd(n_valid, 1);
+                const bool blk = (ev.w_sf[o] & 0xFF) == 1;
+                out[(size_t)code * 3] = blk ? ev.w_black[o] : ev.w_white[o];
+                out[(size_t)code * 3 + 1] = blk ? ev.w_white[o] : ev.w_black[o];
+                out[(size_t)code * 3 + 2] = lm;
+            }
+        }
+        inv[slot] = code;
     }
 }
 
@@ -412,7 +460,7 @@ int launch_direct(const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat
 }  // namespace
 
 // forward pass on B boards whose bit planes are already in n->bits; results in n->probs/logits/values
-int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s) {
+int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s, const int* n_dev = nullptr) {
     NetState* n = h->net;
     if (!n || !n->loaded) return fail(-7, "network weights not loaded: call rvs_engine_load_weights first");
     if (B > n->max_batch) return fail(-7, "network batch %lld exceeds capacity %lld", (long long)B, (long long)n->max_batch);
@@ -420,13 +468,13 @@ int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s) {
     int rc;
     if (!n->force_direct && n->conv0.tc.valid) {  // first layer on the tensor cores: planes -> bf16 tiles -> tcgen05
         const int64_t tiles = (B + 1) / 2;
-        RVS_LAUNCH(planes_tiles_kernel, grid_for(tiles * 128, 256), 256, 0, s, n->bits, B, tiles, (uint4*)n->x0);
-        if ((rc = conv_tc_launch(n->conv0.tc, n->x0, nullptr, n->a, n->conv0.bias, B, s))) return rc;
+        RVS_LAUNCH(planes_tiles_kernel, grid_for(tiles * 128, 256), 256, 0, s, n->bits, B, tiles, (uint4*)n->x0, n_dev);
+        if ((rc = conv_tc_launch(n->conv0.tc, n->x0, nullptr, n->a, n->conv0.bias, B, s, nullptr, nullptr, n_dev))) return rc;
     } else {  // network.py:97, fused with the leaf encoding (CUDA cores)
         const int tiles = (int)((B + 1) / 2);
-        if (n->C == 64) RVS_LAUNCH(conv0_bits_kernel<64>, tiles, 256, 0, s, n->bits, B, n->w0f, n->b0f, n->a);
-        else if (n->C == 128) RVS_LAUNCH(conv0_bits_kernel<128>, tiles, 256, 0, s, n->bits, B, n->w0f, n->b0f, n->a);
-        else RVS_LAUNCH(conv0_bits_kernel<256>, tiles, 256, 0, s, n->bits, B, n->w0f, n->b0f, n->a);
+        if (n->C == 64) RVS_LAUNCH(conv0_bits_kernel<64>, tiles, 256, 0, s, n->bits, B, n->w0f, n->b0f, n->a, n_dev);
+        else if (n->C == 128) RVS_LAUNCH(conv0_bits_kernel<128>, tiles, 256, 0, s, n->bits, B, n->w0f, n->b0f, n->a, n_dev);
+        else RVS_LAUNCH(conv0_bits_kernel<256>, tiles, 256, 0, s, n->bits, B, n->w0f, n->b0f, n->a, n_dev);
     }
     __nv_bfloat16 *x = n->a, *t = n->b, *y = n->c;
     bool fused_head = false;
@@ -437,16 +485,16 @@ int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s) {
             if ((rc = launch_direct(c1, x, nullptr, t, B, 1, s))) return rc;
             if ((rc = launch_direct(c2, t, x, y, B, 1, s))) return rc;
         } else {
-            if ((rc = conv_tc_launch(c1.tc, x, nullptr, t, c1.bias, B, s))) return rc;
+            if ((rc = conv_tc_launch(c1.tc, x, nullptr, t, c1.bias, B, s, nullptr, nullptr, n_dev))) return rc;
             if (i == n->blocks - 1 && conv_tc_can_fuse_head(c2.tc)) {  // last layer: heads' 1x1 convs in the epilogue
-                if ((rc = conv_tc_launch(c2.tc, t, x, y, c2.bias, B, s, n->head_host, n->feat))) return rc;
+                if ((rc = conv_tc_launch(c2.tc, t, x, y, c2.bias, B, s, n->head_host, n->feat, n_dev))) return rc;
                 fused_head = true;
-            } else if ((rc = conv_tc_launch(c2.tc, t, x, y, c2.bias, B, s))) return rc;
+            } else if ((rc = conv_tc_launch(c2.tc, t, x, y, c2.bias, B, s, nullptr, nullptr, n_dev))) return rc;
         }
         __nv_bfloat16* tmp = x; x = y; y = tmp;
     }
     RVS_LAUNCH(heads_kernel, (int)((B + kHB - 1) / kHB), 256, 0, s, x, fused_head ? n->feat : (const float*)nullptr, n->C, B, n->pw, n->pb, n->pfw, n->pfb, n->vw, n->vb, n->v1w, n->v1b,
-               n->v2w, n->v2b, want_logits ? n->logits : nullptr, n->probs, n->values);
+               n->v2w, n->v2b, want_logits ? n->logits : nullptr, n->probs, n->values, n_dev, n_dev ? h->v.stats + ST_NNEVALS : nullptr);
     return 0;
 }
 
@@ -477,7 +525,7 @@ int net_create(rvs_engine* h) {
     if ((rc = nalloc(n, &n->pw, (size_t)2 * C)) || (rc = nalloc(n, &n->pb, 2)) || (rc = nalloc(n, &n->pfw, 65 * 128)) ||
         (rc = nalloc(n, &n->pfb, 65)) || (rc = nalloc(n, &n->vw, (size_t)C)) || (rc = nalloc(n, &n->vb, 1)) ||
         (rc = nalloc(n, &n->v1w, 256 * 64)) || (rc = nalloc(n, &n->v1b, 256)) || (rc = nalloc(n, &n->v2w, 256)) ||
-        (rc = nalloc(n, &n->v2b, 1)) || (rc = nalloc(n, &n->bits, B * 3)) || (rc = nalloc(n, &n->w0f, (size_t)27 * C)) || (rc = nalloc(n, &n->b0f, (size_t)C)) || (rc = nalloc(n, &n->a, B * 64 * C)) ||
+        (rc = nalloc(n, &n->v2b, 1)) || (rc = nalloc(n, &n->bits, B * 3)) || (rc = nalloc(n, &n->n_valid, 1)) || (rc = nalloc(n, &n->inv, B)) || (rc = nalloc(n, &n->w0f, (size_t)27 * C)) || (rc = nalloc(n, &n->b0f, (size_t)C)) || (rc = nalloc(n, &n->a, B * 64 * C)) ||
         (rc = nalloc(n, &n->b, B * 64 * C)) || (rc = nalloc(n, &n->c, B * 64 * C)) || (rc = nalloc(n, &n->probs, B * 65)) ||
         (rc = nalloc(n, &n->logits, B * 65)) || (rc = nalloc(n, &n->values, B)) || (rc = nalloc(n, &n->feat, B * 192)))
         return rc;
@@ -516,11 +564,12 @@ int rvs_net_search(rvs_engine* h, int32_t num_sims, int32_t wave, cudaStream_t s
     for (int start = 0; start < num_sims; start += wave) {
         const int k = num_sims - start < wave ? num_sims - start : wave;
         if ((rc = rvs_engine_select(h, k, s))) return rc;
-        const int64_t B = (int64_t)h->v.G * k;
-        RVS_LAUNCH(encode_leaves_kernel, grid_for(B, 256), 256, 0, s, h->v, k, h->net->bits);
+        const int64_t B = (int64_t)h->v.G * k;  // capacity; the batch itself is compacted on the device
+        RVS_CUDA(cudaMemsetAsync(h->net->n_valid, 0, sizeof(int), s));
+        RVS_LAUNCH(encode_compact_kernel, grid_for(B, 256), 256, 0, s, h->v, k, h->net->bits, h->net->inv, h->net->n_valid);
         h->launches++;
-        if ((rc = net_forward(h, B, false, s))) return rc;
-        if ((rc = rvs_engine_process(h, h->net->probs, h->net->values, RVS_MEM_DEVICE, s))) return rc;
+        if ((rc = net_forward(h, B, false, s, h->net->n_valid))) return rc;
+        if ((rc = rvs_engine_process_mapped(h, h->net->probs, h->net->values, h->net->inv, s))) return rc;
     }
     h->searching = false;
     return 0;

@@ -314,11 +314,33 @@ def run_ours(args):
         nn_ms = n0.elapsed_time(n1)
         t1s = eng3.stats()
         flops_per_eval = 2 * (64 * 27 * 128 + 2 * 5 * 64 * 9 * 128 * 128 + 64 * 128 * 2 + 128 * 65 + 64 * 128 + 64 * 256 + 256)
-        batch_evals = nn_steps * N_SIMS * N_GAMES  # the tower runs on every slot of every wave
+        batch_evals = t1s["nn_evals"] - t0s["nn_evals"]  # boards run through the network (compacted leaf batches)
         nn = {"sims_per_sec": (t1s["sims"] - t0s["sims"]) / (nn_ms * 1e-3),
               "consumed_evals_per_sec": (t1s["evals"] - t0s["evals"]) / (nn_ms * 1e-3),
               "network_evals_per_sec": batch_evals / (nn_ms * 1e-3), "ms_per_step": nn_ms / nn_steps,
               "tflops": batch_evals * flops_per_eval / (nn_ms * 1e-3) / 1e12, "flops_per_eval": flops_per_eval}
+        # the reference's own default: MCTS(batch_size=64) -- most simulations of a wave share one leaf
+        # (SURVEY.md 0.3), which the engine evaluates once per wave
+        eng3.close()
+        eng3 = az.Engine(N_GAMES, N_SIMS, 64, evaluator=az.EVAL_NN, c_puct=1.0, seed=3500 + rank, device=local,
+                         net_blocks=5, net_filters=128)
+        rn.attach(eng3)
+        eng3.set_positions(pb0, pw0, ps0, stream=stream)
+        eng3.search(N_SIMS, 64, stream=stream); eng3.play(1.0, recycle=True, stream=stream)
+        torch.cuda.synchronize()
+        u0 = eng3.stats()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        for _ in range(5):
+            eng3.search(N_SIMS, 64, stream=stream); eng3.play(1.0, recycle=True, stream=stream)
+        m1.record()
+        torch.cuda.synchronize()
+        u1 = eng3.stats()
+        wms = m0.elapsed_time(m1)
+        nn["wave64"] = {"sims_per_sec": (u1["sims"] - u0["sims"]) / (wms * 1e-3),
+                        "network_evals_per_sec": (u1["nn_evals"] - u0["nn_evals"]) / (wms * 1e-3),
+                        "consumed_evals_per_sec": (u1["evals"] - u0["evals"]) / (wms * 1e-3), "ms_per_step": wms / 5,
+                        "config": "same network and games with the reference's default MCTS(batch_size=64) wave semantics"}
         eng3.close()
 
     # ---- config-4 side metric: ResNet 20x256, 16384 concurrent games, Dirichlet root noise; a bounded slice
@@ -344,8 +366,9 @@ def run_ours(args):
         q1s = eng4.stats()
         qms = q0.elapsed_time(q1)
         f4 = 2 * (64 * 27 * 256 + 2 * 20 * 64 * 9 * 256 * 256 + 64 * 256 * 2 + 128 * 65 + 64 * 256 + 64 * 256 + 256)
-        nn4 = {"sims_per_sec": (q1s["sims"] - q0s["sims"]) / (qms * 1e-3), "network_evals_per_sec": G4 * S4 / (qms * 1e-3),
-               "tflops": G4 * S4 * f4 / (qms * 1e-3) / 1e12, "flops_per_eval": f4, "ms": qms,
+        e4 = q1s["nn_evals"] - q0s["nn_evals"]
+        nn4 = {"sims_per_sec": (q1s["sims"] - q0s["sims"]) / (qms * 1e-3), "network_evals_per_sec": e4 / (qms * 1e-3),
+               "tflops": e4 * f4 / (qms * 1e-3) / 1e12, "flops_per_eval": f4, "ms": qms,
                "config": "configs[3]: ResNet 20x256, 16384 concurrent games, Dirichlet(0.03, 0.25) root noise, bf16, wave 1; "
                          f"timed slice = {S4} of the 800 simulations of one ply"}
         eng4.close()

@@ -127,6 +127,7 @@ typedef struct rvs_engine_stats {
     int64_t tree_bytes;  /* algorithmic HBM bytes of the tree kernels: 32 B per node row touched */
     int64_t samples_dropped; /* samples lost because the ring was full (drain more often) */
     int64_t stalled;     /* slots parked after an illegal move choice (num_sims <= wave hazard) */
+    int64_t nn_evals;    /* RVS_EVAL_NN: boards actually run through the network (terminal / duplicate leaves of a wave are compacted away) */
 } rvs_engine_stats;
 
 int rvs_engine_create(const rvs_engine_config *cfg, rvs_engine **out);
