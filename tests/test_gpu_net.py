@@ -109,7 +109,9 @@ def test_nn_search_consistency(az):
     rb = np.array([r[0] for r in roots], dtype=np.uint64)
     rw = np.array([r[1] for r in roots], dtype=np.uint64)
     rs = np.array([r[2] for r in roots], dtype=np.uint8)
-    for K in (1, 8):
+    import os
+    for K, graph in ((1, "0"), (8, "0"), (1, "1"), (32, "0")):
+        os.environ["RVS_NET_GRAPH"] = graph  # "1": waves 2.. replay a captured CUDA graph
         eng = az.Engine(g, S, K, evaluator=az.EVAL_NN, net_blocks=nb, net_filters=nf)
         rn.attach(eng)
         eng.set_positions(rb, rw, rs)
@@ -141,6 +143,7 @@ def test_nn_search_consistency(az):
         assert np.array_equal(v_nn.sum(axis=1), v_ext.sum(axis=1))
         eng.close()
         ext.close()
+    os.environ.pop("RVS_NET_GRAPH", None)
 
 
 def test_mcts_and_selfplay_with_rvs_network(az):
