@@ -61,6 +61,7 @@ PROTOTYPES = {
     "rvs_engine_drain_packed": (C.c_int, [V, V, V, V, V, V, C.c_int64, C.POINTER(C.c_int64), C.c_int, V]),
     "rvs_engine_stats_get": (C.c_int, [V, C.POINTER(EngineStats), V]),
     "rvs_engine_set_root_noise": (C.c_int, [V, C.c_double, C.c_float]),
+    "rvs_engine_set_lanes_per_game": (C.c_int, [V, C.c_int32]),
     "rvs_engine_load_weights": (C.c_int, [V, V, C.c_int64, C.c_int, V]),
     "rvs_engine_predict": (C.c_int, [V, V, V, V, C.c_int64, V, V, C.c_int, V]),
 }

@@ -675,7 +675,9 @@ int io_stage(rvs_engine* h, size_t bytes, void** out) {
 inline int games_grid(int G) { return (G + kWarpsPerBlock - 1) / kWarpsPerBlock; }
 
 // lanes per game of the wave-1 kernels (rvs_treeg.cuh): 4 by default, RVS_K1_LPG=8|2 for A/B measurements
-inline int lanes_per_game(int G) {
+inline int lanes_per_game(const rvs_engine* h) {
+    const int G = h->v.G;
+    if (h->lanes_per_game) return h->lanes_per_game;  // rvs_engine_set_lanes_per_game
     const char* e = getenv("RVS_K1_LPG");  // read per call: tests switch it inside one process
     const int forced = e ? atoi(e) : 0;
     if (forced) return forced;
@@ -843,7 +845,7 @@ int rvs_engine_search(rvs_engine* h, int32_t num_sims, int32_t wave, void* strea
             else RVS_ENGINE_LAUNCH(h, (search_k1_kernel<RULES_REF, RVS_EVAL_ROLLOUT>), grid, kBlock, 0, s, h->v, num_sims);
         } else {
             RVS_ENGINE_LAUNCH(h, phase_order_kernel, 1, 1024, 0, s, h->v);
-            const int lpg = lanes_per_game(h->v.G);
+            const int lpg = lanes_per_game(h);
 #define RVS_SEARCH_G(LPG)                                                                                                         \
     do {                                                                                                                          \
         const int need = (h->v.G * LPG + kBlockG - 1) / kBlockG;                                                                  \
@@ -1002,7 +1004,7 @@ int rvs_engine_selfplay(rvs_engine* h, int32_t num_sims, float temperature, int6
         else RVS_ENGINE_LAUNCH(h, (selfplay_k1_kernel<RULES_REF, RVS_EVAL_ROLLOUT>), grid, kBlock, 0, s, h->v, num_sims, temperature, budget, recycle);
     } else {
         RVS_ENGINE_LAUNCH(h, phase_order_kernel, 1, 1024, 0, s, h->v);
-        const int lpg = lanes_per_game(h->v.G);
+        const int lpg = lanes_per_game(h);
 #define RVS_SELFPLAY_G(LPG)                                                                                                       \
     do {                                                                                                                          \
         const int need = (h->v.G * LPG + kBlockG - 1) / kBlockG;                                                                  \
@@ -1077,6 +1079,14 @@ int rvs_engine_drain_packed(rvs_engine* h, uint64_t* black, uint64_t* white, uin
     RVS_CUDA(cudaMemcpyAsync(pi, h->v.r_pi, (size_t)n * 65 * sizeof(float), kind, s));
     RVS_CUDA(cudaMemsetAsync(h->v.ring_count, 0, 8, s));
     if (mem != RVS_MEM_DEVICE) RVS_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int rvs_engine_set_lanes_per_game(rvs_engine* h, int32_t lanes) {
+    int rc = check_handle(h);
+    if (rc) return rc;
+    if (lanes != 0 && lanes != 2 && lanes != 4 && lanes != 8) return fail(-1, "rvs_engine_set_lanes_per_game: %d not in {0, 2, 4, 8}", lanes);
+    h->lanes_per_game = lanes;
     return 0;
 }
 

@@ -65,6 +65,7 @@ struct rvs_engine {
     rvs_engine_config cfg;
     rvs::EngineView v;
     int cur_k = 0;          // wave size of the last select (external path)
+    int lanes_per_game = 0; // wave-1 kernels: 0 = choose by the number of games (rvs_engine_set_lanes_per_game)
     int waves_done = 0;     // waves processed since begin_search (root noise goes in after the first)
     bool searching = false;
     float* ext_probs = nullptr;   // staging for host-side probs/values/planes of the external path

@@ -155,6 +155,10 @@ class Engine:
         it); epsilon = 0 switches it off"""
         L.check(L.lib().rvs_engine_set_root_noise(self._h, float(alpha), float(epsilon)))
 
+    def set_lanes_per_game(self, lanes):
+        """wave-1 kernels: lanes of a warp per game (8 / 4 / 2, 0 = automatic); never changes results"""
+        L.check(L.lib().rvs_engine_set_lanes_per_game(self._h, int(lanes)))
+
     def stats(self, stream=None):
         st = L.EngineStats()
         L.check(L.lib().rvs_engine_stats_get(self._h, C.byref(st), self._s(stream)))

@@ -224,6 +224,8 @@ def run_ours(args):
     hvs = [torch.empty((N_GAMES, 65), dtype=torch.int32).pin_memory() for _ in range(depth)]
     engs = [az.Engine(N_GAMES, N_SIMS, max(wave, 64), evaluator=az.EVAL_ROLLOUT, c_puct=1.0, seed=2000 + rank, device=local)
             for _ in range(depth)]
+    for e in engs:  # depth x 4096 games are in flight: the many-games setting of the wave-1 kernels
+        e.set_lanes_per_game(4 if depth >= 3 else 0)
     MH = az._lib.MEM_HOST_ASYNC
 
     def e2e_step(i):
@@ -559,7 +561,7 @@ def main():
     ap.add_argument("--lockstep", action="store_true", help="wave 1 through search+play launches per ply")
     ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per launch of the search kernel")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-depth", type=int, default=4, help="engine handles pipelined in the e2e leg")
+    ap.add_argument("--e2e-depth", type=int, default=8, help="engine handles pipelined in the e2e leg")
     ap.add_argument("--no-big", action="store_true", help="skip the 16384-game side measurement")
     ap.add_argument("--no-nn", action="store_true", help="skip the config-3 (ResNet) side measurement")
     args = ap.parse_args()

@@ -200,6 +200,12 @@ int rvs_engine_drain_packed(rvs_engine *h, uint64_t *black, uint64_t *white, uin
  * own (csrc/rvs_noise.cuh), restated by the oracle. */
 int rvs_engine_set_root_noise(rvs_engine *h, double alpha, float epsilon);
 
+/* Tuning knob of the wave-1 kernels (rvs_engine_search / rvs_engine_selfplay with a built-in evaluator):
+ * lanes of a warp that cooperate on one game, 8 / 4 / 2 (0 = automatic: 8 up to 6144 games per handle,
+ * else 4).  Results never depend on it.  Worth setting to 4 when several handles are pipelined on one
+ * GPU, i.e. when far more games are in flight than one handle holds. */
+int rvs_engine_set_lanes_per_game(rvs_engine *h, int32_t lanes);
+
 int rvs_engine_stats_get(rvs_engine *h, rvs_engine_stats *out, void *stream);
 
 /* ---- K4: network -------------------------------------------------------------------- */
