@@ -448,7 +448,7 @@ def run_ours(args):
                 out["nn_20x256"] = nn4
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(wave, threads=os.cpu_count() or 1, budget_s=12.0)
-        print(json.dumps(out))
+        _emit(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
 
@@ -535,7 +535,7 @@ def run_reference(args):
     v = args.steps * n * N_SIMS / dt
     sample = (f"{args.steps} steps x {n} mid-game roots x {N_SIMS} sims (wave {args.wave}), C oracle port of the "
               f"reference path, {threads} host threads")
-    print(json.dumps({
+    _emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64+f32", "data": "synthetic",
@@ -548,7 +548,20 @@ def run_reference(args):
     }))
 
 
+def _emit(line):
+    """the ONE JSON line goes to the process's original stdout"""
+    os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    # libraries write to stdout too (NCCL prints its version banner there): keep fd 1 for the JSON line only
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
