@@ -214,6 +214,26 @@ def test_root_dirichlet_noise_vs_oracle(az, evaluator, S, K, alpha, eps, lpg):
         os.environ.pop("RVS_K1_LPG", None)
 
 
+@pytest.mark.parametrize("rules,c_puct,lpg,evaluator", [(1, 0.7, 8, 1), (1, 2.5, 4, 0), (1, 1.0, 2, 1), (0, 0.7, 4, 1), (0, 2.5, 2, 0), (0, 1.5, 8, 1)])
+def test_wave1_group_kernels_rules_and_cpuct_vs_oracle(az, rules, c_puct, lpg, evaluator):
+    """the several-games-per-warp wave-1 search kernels under both rule sets, several exploration
+    constants and every lanes-per-game setting: visit counts equal the oracle's"""
+    n, S = 96, 120
+    bl, wh, sd = _random_roots(n, 31 + lpg + rules)
+    eng = az.Engine(n, S, 1, evaluator=evaluator, rules=rules, c_puct=c_puct, seed=2024)
+    eng.set_lanes_per_game(lpg)
+    eng.set_positions(bl, wh, sd)
+    eng.search(S, 1)
+    v = eng.root_visits()
+    st = eng.stats()
+    assert st["overflow"] == 0 and st["sims"] == n * S
+    for g in range(n):
+        ov, *_ = orc.mcts_search((int(bl[g]), int(wh[g]), int(sd[g])), S, 1, c_puct=c_puct, rules=rules, evaluator=evaluator,
+                                 seed=2024, game_id=g)
+        assert np.array_equal(v[g], ov), (g, hex(int(bl[g])), hex(int(wh[g])), int(sd[g]))
+    eng.close()
+
+
 def test_strict_rules_search_vs_oracle(az):
     n, S, K = 64, 120, 4
     bl, wh, sd = _random_roots(n, 9)
