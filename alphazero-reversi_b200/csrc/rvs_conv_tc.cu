@@ -390,6 +390,9 @@ struct Cfg2 {
     static constexpr int W_TILES = 9 * KC;
     static constexpr int STAGES = (C == 128 && CIN == 128) ? 4 : 6;  // 128->128: 144 KB weights + 4 x 20 KB = 224 KB
     static constexpr int TMEM_COLS = 2 * C;                 // two accumulators of C fp32 columns
+    // K = 16 steps per 64-channel chunk.  The 64 -> 128 instantiation is the network's FIRST layer: only
+    // channels 0..2 of its input tiles are non-zero, so the steps over channels 16..63 would multiply zeros
+    static constexpr int KSTEPS = (C == 128 && CIN == 64) ? 1 : 4;
     static constexpr int SMEM = W_TILES * W_TILE + STAGES * kABytes + 1024 /*align*/ + 1280 /*barriers, bias*/;
     static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 };
@@ -481,7 +484,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
                         for (int dy = 0; dy < 3; ++dy) {
                             const uint32_t wt = w_s + ((dy * 3 + dx) * K::KC + kc) * K::W_TILE;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
+                            for (int k = 0; k < K::KSTEPS; ++k) {
                                 tc2_mma(d, make_desc(a0 + dy * 2048 + k * 32), make_desc(wt + k * 32), K::IDESC, accum);
                                 accum = 1;
                             }

@@ -330,7 +330,7 @@ __device__ __forceinline__ void backup_path_g(TreeCtxG<LPG>& cx, int plen, float
 
 // MCTS._traverse (mcts.py:409-444); the path is left in cx.g.path[0..plen)
 template <int LPG>
-__device__ __forceinline__ int select_one_g(TreeCtxG<LPG>& cx, GBoard& b, int& plen, int& leaf_vlf, bool act) {
+__device__ __forceinline__ int select_one_g(TreeCtxG<LPG>& cx, GBoard& b, int& plen, int& leaf_vlf, uint64_t& leaf_lm, bool act) {
     const Grp<LPG>& g = cx.g;
     int node = 0;
     plen = 1;
@@ -343,6 +343,8 @@ __device__ __forceinline__ int select_one_g(TreeCtxG<LPG>& cx, GBoard& b, int& p
     }
     const unsigned key_floor = ordered_key(-INFINITY);
     bool going = act;
+    bool have_lm = false;  // the last applied move already produced the leaf's legal mask
+    leaf_lm = 0;
     while (true) {
         const int nchild = c.z & 0xFF;
         going = going && nchild != 0 && !(h.z & kTerminal);
@@ -391,8 +393,10 @@ __device__ __forceinline__ int select_one_g(TreeCtxG<LPG>& cx, GBoard& b, int& p
             }
         }
         if (going && best_i < 0) { cx.overflow |= 2; going = false; }
-        grp_apply_move(g, b, (bc.z >> 8) & 0x3F, going);  // game.make_move(*next_move) (mcts.py:439)
+        const uint64_t lm_next = grp_apply_move(g, b, (bc.z >> 8) & 0x3F, going);  // game.make_move(*next_move) (mcts.py:439)
         if (going) {
+            leaf_lm = lm_next;
+            have_lm = true;
             ++cx.steps;
             node = fc + best_i;
             h = bh;
@@ -405,6 +409,10 @@ __device__ __forceinline__ int select_one_g(TreeCtxG<LPG>& cx, GBoard& b, int& p
                 going = false;
             }
         }
+    }
+    if (__any_sync(kFull, act && !have_lm)) {  // the root itself is the leaf (first simulation of a search)
+        const uint64_t lm0 = grp_legal(g, b.P, b.O);
+        if (!have_lm) leaf_lm = lm0;
     }
     leaf_vlf = h.z;
     __syncwarp();
@@ -453,10 +461,10 @@ template <int EVAL, int LPG>
 __device__ __forceinline__ void simulate_one_g(TreeCtxG<LPG>& cx, const GBoard& root, uint64_t stream_for_sim, bool act) {
     GBoard b = root;
     int plen, vlf;
-    const int node = select_one_g(cx, b, plen, vlf, act);
+    uint64_t lm;  // legal mask of the leaf position
+    const int node = select_one_g(cx, b, plen, vlf, lm, act);
     if (act) ++cx.sims;
     const bool term = act && (vlf & kTerminal);          // mcts.py:364-366: back its stored value up
-    const uint64_t lm = grp_legal(cx.g, b.P, b.O);
     const bool dead = act && !term && lm == 0;           // mcts.py:567-579: flag terminal, ABSOLUTE value
     const bool eval = act && !term && lm != 0;
     float v = 0.0f;
