@@ -516,10 +516,11 @@ __global__ void __launch_bounds__(kBlockG, 16) search_k1g_kernel(EngineView ev, 
     constexpr int GPB = kBlockG / LPG;
     __shared__ uint8_t lut[256 * 8];
     __shared__ int spath[GPB][kMaxPath + 1];
+    __shared__ __align__(16) unsigned sgather[GPB][48];  // 3 x 64-byte exchange buffers per group (8-lane groups)
     lut_init(lut, threadIdx.x, kBlockG);
     __syncthreads();
     const int n_groups = gridDim.x * GPB;
-    const Grp<LPG> grp = make_grp<RULES, LPG>(threadIdx.x & 31, lut, spath[threadIdx.x / LPG]);
+    const Grp<LPG> grp = make_grp<RULES, LPG>(threadIdx.x & 31, lut, spath[threadIdx.x / LPG], LPG == 8 ? sgather[threadIdx.x / LPG] : nullptr);
     for (int slot = blockIdx.x * GPB + (int)threadIdx.x / LPG; __any_sync(kFull, slot < ev.G); slot += n_groups) {
         const bool act = slot < ev.G;
         const int g = act ? ev.order[slot] : 0;
@@ -550,12 +551,13 @@ __global__ void __launch_bounds__(kBlockG, 16) selfplay_k1g_kernel(EngineView ev
     constexpr int GPB = kBlockG / LPG;
     __shared__ uint8_t lut[256 * 8];
     __shared__ int spath[GPB][kMaxPath + 1];
+    __shared__ __align__(16) unsigned sgather[GPB][48];  // 3 x 64-byte exchange buffers per group (8-lane groups)
     lut_init(lut, threadIdx.x, kBlockG);
     __syncthreads();
     const int n_groups = gridDim.x * GPB;
     const int slot0 = blockIdx.x * GPB + (int)threadIdx.x / LPG;
     const int n_mine = slot0 < ev.G ? (ev.G - slot0 + n_groups - 1) / n_groups : 0;  // slots of this group
-    const Grp<LPG> grp = make_grp<RULES, LPG>(threadIdx.x & 31, lut, spath[threadIdx.x / LPG]);
+    const Grp<LPG> grp = make_grp<RULES, LPG>(threadIdx.x & 31, lut, spath[threadIdx.x / LPG], LPG == 8 ? sgather[threadIdx.x / LPG] : nullptr);
     bool quit = n_mine == 0;
     int k = 0, idle = 0;  // current slot of the round-robin; consecutive slots found parked / finished
     while (true) {
