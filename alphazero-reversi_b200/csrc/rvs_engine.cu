@@ -992,8 +992,18 @@ int rvs_engine_selfplay(rvs_engine* h, int32_t num_sims, float temperature, int6
     if (rc) return rc;
     if (num_sims < 1 || num_sims > h->cfg.max_sims) return fail(-1, "rvs_engine_selfplay: num_sims %d outside [1,%d]", num_sims, h->cfg.max_sims);
     if (plies < 0 || temperature < 0.0f) return fail(-1, "rvs_engine_selfplay: bad arguments");
+    if (h->cfg.evaluator == RVS_EVAL_NN) {
+        // the network evaluates all leaves of a wave in one batch, so NN self-play advances in lockstep:
+        // ceil(plies / n_games) rounds of (search with wave 1, play); all launches stay on `stream`
+        const int64_t rounds = (plies + h->v.G - 1) / h->v.G;
+        for (int64_t r = 0; r < rounds; ++r) {
+            if ((rc = rvs_engine_search(h, num_sims, 1, stream))) return rc;
+            if ((rc = rvs_engine_play(h, temperature, recycle, nullptr, RVS_MEM_DEVICE, stream))) return rc;
+        }
+        return 0;
+    }
     if (h->cfg.evaluator != RVS_EVAL_E0 && h->cfg.evaluator != RVS_EVAL_ROLLOUT)
-        return fail(-1, "rvs_engine_selfplay: needs a built-in in-kernel evaluator (E0 or ROLLOUT); use search+play for NN");
+        return fail(-1, "rvs_engine_selfplay: the external evaluator is driven by the caller (begin_search / select / process + play)");
     cudaStream_t s = (cudaStream_t)stream;
     RVS_CUDA(cudaMemsetAsync(h->v.ply_counter, 0, 8, s));
     const int grid = games_grid(h->v.G);

@@ -83,7 +83,7 @@ class SelfPlay:
             # engine feature: the reference accepts dirichlet_alpha / dirichlet_epsilon and never applies
             # them (self_play.py:18-47), so the noise needs this explicit switch
             eng.set_root_noise(self.args.get("dirichlet_alpha", 0.3), self.args.get("dirichlet_epsilon", 0.25))
-        persistent = K == 1 and self._builtin in (L.EVAL_E0, L.EVAL_ROLLOUT)
+        persistent = K == 1 and self._builtin in (L.EVAL_E0, L.EVAL_ROLLOUT, L.EVAL_NN)
         games: List[Dict] = []
         collected = 0
         while len(games) < num_games:

@@ -175,7 +175,8 @@ int rvs_engine_play(rvs_engine *h, float temperature, int recycle, uint8_t *out_
  * built-in evaluator): ONE launch in which every slot keeps playing plies -- search, move choice,
  * sample record, make_move, game end, recycling -- until `plies` game-plies have been played in
  * total.  Work conserving: slots do not wait for each other between plies.  Per-game results are
- * identical to repeating rvs_engine_search(num_sims, 1) + rvs_engine_play. */
+ * identical to repeating rvs_engine_search(num_sims, 1) + rvs_engine_play.  With RVS_EVAL_NN the network
+ * evaluates a whole wave in one batch, so the call runs ceil(plies / n_games) lockstep rounds of exactly that. */
 int rvs_engine_selfplay(rvs_engine *h, int32_t num_sims, float temperature, int64_t plies,
                         int recycle, void *stream);
 

@@ -161,7 +161,7 @@ def test_mcts_and_selfplay_with_rvs_network(az):
     b = np.array([c32[k] for k in sorted(c32)], dtype=np.float64)
     assert np.abs(a - b).sum() <= 20, (counts, c32)
     sp = az.SelfPlay(rn, {"num_simulations": 16, "batch_size": 1, "temperature": 1.0, "num_parallel_games": 32})
-    data = sp.generate_training_data(40)
+    data = sp.generate_training_data(40)   # rvs_engine_selfplay with the NN evaluator (lockstep rounds)
     assert data["states"].shape[1:] == (3, 8, 8) and np.allclose(data["action_probs"].sum(axis=1), 1.0, atol=1e-5)
 
 
