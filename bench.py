@@ -430,7 +430,9 @@ def run_ours(args):
                                     ("search_k1g_kernel<REF,ROLLOUT,8>" if wave == 1 else "search_fused_kernel<REF,ROLLOUT>")),
                          "steps_per_launch": ppl if persistent else 1,
                          "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms * len(ks) / ms,
-                         "note": "latency/issue-bound integer kernel: rollouts are register resident; see DESIGN.md"},
+                         "note": "not HBM bound: rollouts are register resident (0 B); at 4096 games the kernel is bound by the "
+                                 "latency of one rollout ply's dependency chain (1.7 warps per scheduler), see DESIGN.md K2",
+                         "issue": issue_evidence()},
             "clocks": clocks,
         }
         if big is not None:
@@ -451,6 +453,23 @@ def run_ours(args):
         _emit(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def issue_evidence():
+    """instruction-side figures of the dominant kernel from the committed ncu capture (profiles/)"""
+    import re
+    path = os.path.join(ROOT, "profiles", "ncu_selfplay_k1g_r1.txt")
+    if not os.path.exists(path):
+        return None
+    t = open(path).read()
+
+    def grab(pat):
+        m = re.search(pat, t)
+        return float(m.group(1)) if m else None
+    return {"warp_inst_per_sim": grab(r"warp instructions per unit:\s+([\d.]+)"),
+            "issue_active_pct": grab(r"smsp__issue_active\S*\s+([\d.]+)"),
+            "warps_eligible_per_cycle": grab(r"smsp__warps_eligible\S*\s+([\d.]+)"),
+            "source": "profiles/ncu_selfplay_k1g_r1.txt"}
 
 
 def algorithmic_bytes(d):
