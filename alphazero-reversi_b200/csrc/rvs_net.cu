@@ -373,10 +373,11 @@ __global__ void __launch_bounds__(256) planes_tiles_kernel(const uint64_t* __res
             c01 = (((bits[board * 3] >> sq) & 1) ? one : 0u) | ((((bits[board * 3 + 1] >> sq) & 1) ? one : 0u) << 16);
             c2 = ((bits[board * 3 + 2] >> sq) & 1) ? one : 0u;
         }
+        // only channels 0..15 (the first 32 bytes of the 128-byte row) are ever read by the first layer's single
+        // K = 16 step (Cfg2::KSTEPS); the rest of the buffer stays at its initial zero
         uint4* o = out + r * 8;
         o[0] = make_uint4(c01, c2, 0u, 0u);
-#pragma unroll
-        for (int i = 1; i < 8; ++i) o[i] = make_uint4(0u, 0u, 0u, 0u);
+        o[1] = make_uint4(0u, 0u, 0u, 0u);
     }
 }
 
