@@ -686,7 +686,8 @@ inline int lanes_per_game(const rvs_engine* h) {
     // measured on B200: with few games the kernel is bound by the latency of one ply's
     // dependency chain, so more lanes per game (shorter per-lane chains, more warps) win; with many
     // games it is issue bound and fewer lanes per game (fewer instructions per game-ply) win
-    return G <= 6144 ? 8 : 4;  // 16384 games: 3.6e8 / 4.9e8 / 4.0e8 sims/s with 8 / 4 / 2 lanes per game
+    // 16384 games: 3.6e8 / 4.9e8 / 4.0e8 sims/s with 8 / 4 / 2 lanes per game; 32768: - / 4.5e8 / 4.9e8; 65536: - / 4.8e8 / 5.6e8
+    return G <= 6144 ? 8 : (G <= 24576 ? 4 : 2);
 }
 
 inline bool warp_per_game() {

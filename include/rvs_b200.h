@@ -203,7 +203,7 @@ int rvs_engine_set_root_noise(rvs_engine *h, double alpha, float epsilon);
 
 /* Tuning knob of the wave-1 kernels (rvs_engine_search / rvs_engine_selfplay with a built-in evaluator):
  * lanes of a warp that cooperate on one game, 8 / 4 / 2 (0 = automatic: 8 up to 6144 games per handle,
- * else 4).  Results never depend on it.  Worth setting to 4 when several handles are pipelined on one
+ * 4 up to 24576, else 2).  Results never depend on it.  Worth setting to 4 when several handles are pipelined on one
  * GPU, i.e. when far more games are in flight than one handle holds. */
 int rvs_engine_set_lanes_per_game(rvs_engine *h, int32_t lanes);
 
