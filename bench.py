@@ -225,7 +225,7 @@ def run_ours(args):
     engs = [az.Engine(N_GAMES, N_SIMS, max(wave, 64), evaluator=az.EVAL_ROLLOUT, c_puct=1.0, seed=2000 + rank, device=local)
             for _ in range(depth)]
     for e in engs:  # depth x 4096 games are in flight: the many-games setting of the wave-1 kernels
-        e.set_lanes_per_game(4 if depth >= 3 else 0)
+        e.set_lanes_per_game(args.e2e_lanes if args.e2e_lanes else (4 if depth >= 3 else 0))
     MH = az._lib.MEM_HOST_ASYNC
 
     def e2e_step(i):
@@ -594,6 +594,7 @@ def main():
     ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per launch of the search kernel")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-depth", type=int, default=8, help="engine handles pipelined in the e2e leg")
+    ap.add_argument("--e2e-lanes", type=int, default=0, help="lanes per game of the e2e engines (0: 4 when pipelined)")
     ap.add_argument("--no-big", action="store_true", help="skip the 16384-game side measurement")
     ap.add_argument("--no-nn", action="store_true", help="skip the config-3 (ResNet) side measurement")
     args = ap.parse_args()
