@@ -353,7 +353,8 @@ def run_ours(args):
         net4 = az.AlphaZeroNetwork(8, 20, 256).eval()
         rn4 = az.RvsNetwork.from_module(net4)
         G4, S4 = 16384, 32
-        eng4 = az.Engine(G4, S4, 1, evaluator=az.EVAL_NN, c_puct=1.0, seed=5000 + rank, device=local, net_blocks=20, net_filters=256)
+        # node pools sized for the full 800 simulations per move (14 GB of tree rows), the timed slice runs 32 of them
+        eng4 = az.Engine(G4, 800, 1, evaluator=az.EVAL_NN, c_puct=1.0, seed=5000 + rank, device=local, net_blocks=20, net_filters=256)
         rn4.attach(eng4)
         eng4.set_root_noise(0.03, 0.25)  # src/config.py:25-26
         eng4.set_positions(np.tile(pb0, G4 // N_GAMES), np.tile(pw0, G4 // N_GAMES), np.tile(ps0, G4 // N_GAMES), stream=stream)
