@@ -271,3 +271,32 @@ def test_mcts_mirror_class(az, golden):
     ci = [i for i, (kd, pi_, S, K) in enumerate(g["cases"]) if KINDS[kd] == "T1" and pi_ == 0 and S == 100 and K == 8][0]
     assert {k: v for k, v in c3.items()} == {divmod(i, 8): int(n) for i, n in enumerate(g["visits"][ci][:64])
                                               if (i // 8, i % 8) in c3}
+
+
+def test_full_size_search_properties(az):
+    """BASELINE configs[1] at full size: 4096 concurrent games x 100 simulations (wave 1, rollout evaluator)
+    from random reachable roots.  Size-independent properties for every game (root N = 100, child visits =
+    sims that left the root, visits only on legal squares, counters consistent) and the oracle on a strided
+    sample of games."""
+    n, S = 4096, 100
+    bl, wh, sd = _random_roots(n, 4242)
+    eng = az.Engine(n, S, 1, evaluator=az.EVAL_ROLLOUT, seed=31337)
+    eng.set_positions(bl, wh, sd)
+    eng.search(S, 1)
+    v = eng.root_visits()
+    st = eng.stats()
+    assert st["overflow"] == 0 and st["sims"] == n * S and st["stalled"] == 0
+    lm = az.board_ops.legal_masks(bl, wh, sd)
+    total = v.sum(axis=1)
+    for g in range(n):
+        legal = [(int(lm[g]) >> q) & 1 for q in range(64)]
+        assert all(v[g][q] == 0 for q in range(64) if not legal[q]) and v[g][64] == 0
+        if int(lm[g]) == 0:
+            assert total[g] == 0              # finished game / no move: every simulation stops at the root
+        else:
+            assert total[g] == S - 1          # the first simulation expands the root, the other 99 descend
+    assert st["evals"] <= n * S and st["nodes"] > 0 and st["tree_bytes"] > 0
+    for g in range(0, n, 127):
+        ov, *_ = orc.mcts_search((int(bl[g]), int(wh[g]), int(sd[g])), S, 1, evaluator=1, seed=31337, game_id=g)
+        assert np.array_equal(v[g], ov), g
+    eng.close()
