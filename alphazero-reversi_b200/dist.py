@@ -90,3 +90,55 @@ def gather_packed(s, dst: int = 0):
     zz = ((allr[:, 4] >> 8) & 0xFF).to(torch.uint8).view(torch.int8)
     return PackedSamples(allr[:, 0:2].contiguous().view(torch.int64).reshape(-1), allr[:, 2:4].contiguous().view(torch.int64).reshape(-1),
                          (allr[:, 4] & 0xFF).to(torch.uint8), zz, allr[:, 5:70].contiguous().view(torch.float32))
+
+
+def sharded_self_play(model, args: dict, total_games: int, dst: int = 0, slots_per_rank: int = 4096):
+    """BASELINE config 5: `total_games` self-play games sharded over the ranks of the default process group
+    (one process per GPU).  Rank `dst` is the trainer rank: its weights are broadcast first (NCCL), every rank
+    then plays its contiguous block of games with its own RNG streams, trees and sample ring -- no collective
+    inside the search loop -- and the packed samples are gathered on `dst`.
+
+    model: RvsNetwork (weights taken from rank `dst`) or a built-in evaluator object (UniformRollout, ...).
+    args:  the reference's SelfPlay args (`num_simulations`, `c_puct`, `temperature`, `batch_size`, `seed`, and the
+           opt-in `apply_dirichlet_noise` / `dirichlet_alpha` / `dirichlet_epsilon`).
+    Returns replay.PackedSamples on rank `dst` (every finished game of every rank, whole games only), None elsewhere.
+    """
+    from . import _lib as L
+    from .engine import Engine
+    from .replay import PackedSamples
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    dev = torch.device("cuda", torch.cuda.current_device())
+    _, count = shard_range(total_games, rank, world)
+    S = args.get("num_simulations", 800)
+    K = max(1, args.get("batch_size", 1))
+    T = args.get("temperature", 1.0)
+    ev = model.evaluator
+    slots = max(1, min(slots_per_rank, count))
+    eng = Engine(slots, S, K, evaluator=ev, c_puct=args.get("c_puct", 1.0), seed=rank_seed(args.get("seed", 0), rank),
+                 device=dev.index, sample_capacity=64 * slots * 3, net_blocks=getattr(model, "net_blocks", 0),
+                 net_filters=getattr(model, "net_filters", 0))
+    if ev == L.EVAL_NN:
+        flat = model.flat.to(dev) if rank == dst else torch.empty_like(model.flat, device=dev)
+        broadcast_weights(flat, src=dst)
+        eng.load_weights(flat)
+    if args.get("apply_dirichlet_noise", False):
+        eng.set_root_noise(args.get("dirichlet_alpha", 0.3), args.get("dirichlet_epsilon", 0.25))
+    parts = []
+    persistent = K == 1 and ev in (L.EVAL_E0, L.EVAL_ROLLOUT, L.EVAL_NN)
+    finished = 0
+    while finished < count:
+        if persistent:
+            eng.selfplay(S, plies=8 * slots, temperature=T, recycle=True)
+        else:
+            eng.search(S, K)
+            eng.play(T, recycle=True)
+        st = eng.stats()
+        if st["overflow"] or st["stalled"] or st["samples_dropped"]:
+            raise L.RvsError(f"engine error counters non-zero: {st}")
+        if st["games_finished"] > finished:
+            finished = st["games_finished"]
+            parts.append(eng.drain_packed(device=dev))
+    eng.close()
+    mine = PackedSamples(*(torch.cat([getattr(p_, f) for p_ in parts]) for f in ("black", "white", "side", "z", "pi")))
+    return gather_packed(mine, dst=dst) if world > 1 else mine

@@ -73,3 +73,15 @@ def test_selfplay_mirror_reports_players_and_noise_switch(az):
         assert set(gd) == {"states", "action_probs", "current_players", "values"}
         assert gd["current_players"][0] == 1 and set(gd["current_players"]) <= {1, 2}
         assert len(gd["states"]) == len(gd["values"]) == len(gd["current_players"]) >= 50
+
+
+def test_sharded_self_play_single_rank(az):
+    """dist.sharded_self_play without a process group = one shard (the N > 1 path runs under torchrun:
+    tools/run_sharded_selfplay.py, verified on 2 x B200 with NCCL broadcast + packed gather)"""
+    from alphazero_reversi_b200 import dist as azd
+    res = azd.sharded_self_play(az.UniformRollout(seed=2), {"num_simulations": 20, "batch_size": 1, "temperature": 1.0, "seed": 5}, 70,
+                                slots_per_rank=32)
+    starts = int(((res.black == 0x0000000810000000) & (res.white == 0x0000001008000000) & (res.side == 1)).sum())
+    assert starts >= 70 and len(res) >= 70 * 50 and res.pi.is_cuda
+    games = az.replay.to_reference_games(res)
+    assert len(games) == starts and all(len(g["states"]) >= 50 for g in games)
