@@ -129,7 +129,7 @@ def sharded_self_play(model, args: dict, total_games: int, dst: int = 0, slots_p
     finished = 0
     while finished < count:
         if persistent:
-            eng.selfplay(S, plies=8 * slots, temperature=T, recycle=True)
+            eng.selfplay(S, plies=16 * slots, temperature=T, recycle=True)
         else:
             eng.search(S, K)
             eng.play(T, recycle=True)

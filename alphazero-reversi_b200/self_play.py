@@ -88,7 +88,7 @@ class SelfPlay:
         collected = 0
         while len(games) < num_games:
             if persistent:  # one work-conserving launch plays 8 plies of every slot (rvs_engine_selfplay)
-                eng.selfplay(S, plies=8 * slots, temperature=T, recycle=True)
+                eng.selfplay(S, plies=16 * slots, temperature=T, recycle=True)
             else:
                 eng.search(S, K)
                 eng.play(T, recycle=True)  # finished slots restart at once; surplus games are discarded

@@ -589,7 +589,7 @@ def main():
     ap.add_argument("--presteps", type=int, default=5, help="untimed plies that spread games over all phases")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--wave", type=int, default=1, help="MCTS batch_size per game (reference default 64)")
-    ap.add_argument("--steps-per-launch", type=int, default=10,
+    ap.add_argument("--steps-per-launch", type=int, default=50,
                     help="persistent self-play: steps (x4096 game-plies) per launch")
     ap.add_argument("--lockstep", action="store_true", help="wave 1 through search+play launches per ply")
     ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per launch of the search kernel")
