@@ -584,7 +584,7 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=600)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--presteps", type=int, default=5, help="untimed plies that spread games over all phases")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
