@@ -85,3 +85,35 @@ def test_sharded_self_play_single_rank(az):
     assert starts >= 70 and len(res) >= 70 * 50 and res.pi.is_cuda
     games = az.replay.to_reference_games(res)
     assert len(games) == starts and all(len(g["states"]) >= 50 for g in games)
+
+
+def test_selfplay_train_reload_cycle(az):
+    """one iteration of the reference pipeline (pipeline.py:114-150) with the engine on the self-play side:
+    NN self-play -> packed samples on the device -> the trainer's batches -> optimiser steps -> the updated
+    weights back into the SAME engine handle -> its predictions follow the trained torch module"""
+    torch.manual_seed(7)
+    net = az.AlphaZeroNetwork(8, 2, 64).cuda()
+    eng = az.Engine(64, 16, 1, evaluator=az.EVAL_NN, seed=3, net_blocks=2, net_filters=64)
+    az.RvsNetwork.from_module(net.eval()).attach(eng)
+    eng.selfplay(16, plies=64 * 64, temperature=1.0, recycle=False)
+    assert eng.stats()["games_finished"] == 64 and eng.stats()["nn_evals"] > 0
+    samples = eng.drain_packed(device="cuda:0")
+    assert len(samples) >= 64 * 50
+    bl = np.array([0x0000000810000000], dtype=np.uint64); wh = np.array([0x0000001008000000], dtype=np.uint64); sd = np.ones(1, np.uint8)
+    lg0, v0 = eng.predict(bl, wh, sd)
+    net.train()
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-3, weight_decay=1e-4)       # pipeline.py:60-75
+    for states, labels, zt in az.replay.training_batches(samples, 256, shuffle=True):
+        logits, v = net.predict(states)
+        loss = torch.nn.functional.cross_entropy(logits, labels) + torch.nn.functional.mse_loss(v, zt)
+        opt.zero_grad(); loss.backward(); opt.step()
+    net.eval()
+    az.RvsNetwork.from_module(net).attach(eng)                                   # broadcast_weights + load in the multi-GPU case
+    lg1, v1 = eng.predict(bl, wh, sd)
+    with torch.no_grad():
+        tl, tv = net(torch.from_numpy(az.board_ops.encode_planes(bl, wh, sd)).cuda())
+    assert np.abs(lg1 - lg0).max() > 1e-3                                        # the engine really runs the new weights
+    assert np.abs(lg1 - tl.cpu().numpy()).max() < 0.05 * max(1.0, float(tl.abs().max())) and abs(float(v1[0]) - float(tv[0])) < 0.05
+    eng.selfplay(16, plies=64 * 8, temperature=1.0, recycle=True)                # and keeps playing
+    assert eng.stats()["overflow"] == 0
+    eng.close()
