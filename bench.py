@@ -44,7 +44,7 @@ UNIT = "sims/s"
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
-        return float(json.load(open(p))["hbm_gbs"]), "measured"
+        return float(json.load(open(p))["hbm_gbs"]), "of measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "of fallback (B200_PROFILING.md)"
 
@@ -441,15 +441,17 @@ def run_ours(args):
         if nn is not None:
             try:
                 pk = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+                pk_src = "of measured (MEASURED_PEAKS.json bf16_tflops_sustained: kernels timed inside a long step)"
             except Exception:
                 pk = 1590.0  # B200_PROFILING.md fallback (burst figure; the sustained one is about 15 % lower)
+                pk_src = "of fallback (B200_PROFILING.md)"
             nn["roofline"] = {"bound": "tensor", "achieved": nn["tflops"], "peak": pk, "unit": "TFLOP/s",
-                              "frac": nn["tflops"] / pk, "note": "whole search step incl. tree kernels; rank 0"}
+                              "frac": nn["tflops"] / pk, "peak_source": pk_src, "note": "whole search step incl. tree kernels; rank 0"}
             nn["config"] = "configs[2]: ResNet 5x128 self-play, 100 sims/move, 4096 games, bf16, random-init weights, wave 1"
             out["nn"] = nn
             if nn4 is not None:
                 nn4["roofline"] = {"bound": "tensor", "achieved": nn4["tflops"], "peak": pk, "unit": "TFLOP/s", "frac": nn4["tflops"] / pk,
-                                   "note": "whole search slice incl. tree kernels; rank 0"}
+                                   "peak_source": pk_src, "note": "whole search slice incl. tree kernels; rank 0"}
                 out["nn_20x256"] = nn4
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(wave, threads=os.cpu_count() or 1, budget_s=12.0)
