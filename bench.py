@@ -265,6 +265,12 @@ def run_ours(args):
     torch.cuda.synchronize()
     po_ms = g0.elapsed_time(g1)
 
+    # ---- config-0 side metric: perft(8) from the start position under the reference's rules (391 210 leaves)
+    az.board_ops.perft(6)
+    tp0 = time.perf_counter()
+    perft_nodes = az.board_ops.perft(8)
+    perft_ms = (time.perf_counter() - tp0) * 1e3
+
     # ---- side metric: the same workload with 16384 concurrent games (4 games' worth of latency hiding per
     # scheduler more than the headline): shows how far the 4096-game figure is from the issue-bound rate
     big = None
@@ -436,6 +442,7 @@ def run_ours(args):
                          "issue": issue_evidence()},
             "clocks": clocks,
         }
+        out["perft8"] = {"leaves": int(perft_nodes), "ms": perft_ms, "expected": 391210}
         if big is not None:
             out["games_16384"] = big
         if nn is not None:
@@ -518,8 +525,11 @@ def cpu_baseline(wave, threads, budget_s):
         steps += st
         rounds += 1
     dt = time.perf_counter() - t0
+    tq = time.perf_counter()
+    p8 = orc.perft(8)
+    p8_ms = (time.perf_counter() - tq) * 1e3
     return {"value": sims / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "board_steps_per_sec": steps / dt,
+            "board_steps_per_sec": steps / dt, "perft8_ms_one_thread": p8_ms, "perft8_leaves": int(p8),
             "sample": f"{rounds} x {n} mid-game roots x {N_SIMS} sims (wave {wave}), C oracle (oracle/rvs_oracle.c), "
                       f"{threads} host threads, {dt:.1f} s"}
 
