@@ -381,24 +381,6 @@ __global__ void __launch_bounds__(256) planes_tiles_kernel(const uint64_t* __res
     }
 }
 
-// K3 for the engine: (own, opponent, legal) bit planes of the selected leaves, consumed by the
-// fused first convolution; slots that need no evaluation are zeroed.
-__global__ void __launch_bounds__(256) encode_leaves_kernel(EngineView ev, int k, uint64_t* __restrict__ out) {
-    const int64_t total = (int64_t)ev.G * k;
-    for (int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; slot < total; slot += (int64_t)gridDim.x * blockDim.x) {
-        const int g = (int)(slot / k), j = (int)(slot - (int64_t)g * k);
-        const size_t o = (size_t)g * ev.kmax + j;
-        const uint64_t lm = ev.w_node[o] < 0 ? 0ULL : ev.w_lm[o];
-        uint64_t P = 0, O = 0;
-        if (lm) {
-            const bool blk = (ev.w_sf[o] & 0xFF) == 1;
-            P = blk ? ev.w_black[o] : ev.w_white[o];
-            O = blk ? ev.w_white[o] : ev.w_black[o];
-        }
-        out[slot * 3] = P; out[slot * 3 + 1] = O; out[slot * 3 + 2] = lm;
-    }
-}
-
 // K3 with compaction: only leaves that need a network evaluation enter the batch, and the leaves of
 // one game's wave that sit on the SAME node are evaluated once (the reference's wave sends most of its
 // simulations down one path, SURVEY.md 0.3, and evaluates every copy: mcts.py:586-597).  Rows are
