@@ -300,3 +300,23 @@ def test_full_size_search_properties(az):
         ov, *_ = orc.mcts_search((int(bl[g]), int(wh[g]), int(sd[g])), S, 1, evaluator=1, seed=31337, game_id=g)
         assert np.array_equal(v[g], ov), g
     eng.close()
+
+
+@pytest.mark.parametrize("lpg,evaluator", [(8, 1), (4, 0), (2, 1)])
+def test_wave1_800_simulations_vs_oracle(az, lpg, evaluator):
+    """config-4 depth of search (800 simulations per move, wave 1): deep trees, multi-chunk child scans,
+    node pools of 2 + 34 * 800 rows"""
+    n, S = 24, 800
+    bl, wh, sd = _random_roots(n, 808 + lpg)
+    bl[0], wh[0], sd[0] = orc.START
+    eng = az.Engine(n, S, 1, evaluator=evaluator, seed=55)
+    eng.set_lanes_per_game(lpg)
+    eng.set_positions(bl, wh, sd)
+    eng.search(S, 1)
+    v = eng.root_visits()
+    st = eng.stats()
+    assert st["overflow"] == 0 and st["sims"] == n * S
+    for g in range(n):
+        ov, *_ = orc.mcts_search((int(bl[g]), int(wh[g]), int(sd[g])), S, 1, evaluator=evaluator, seed=55, game_id=g)
+        assert np.array_equal(v[g], ov), g
+    eng.close()
