@@ -19,13 +19,17 @@ rank = dist.get_rank() if world > 1 else 0
 games = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 sims = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 kind = sys.argv[3] if len(sys.argv) > 3 else "rollout"
+nb = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+nf = int(sys.argv[5]) if len(sys.argv) > 5 else 64
+slots = int(sys.argv[6]) if len(sys.argv) > 6 else 4096
 if kind == "nn":
     torch.manual_seed(42 + rank)        # ranks start from DIFFERENT weights: the broadcast must make them equal
-    model = az.RvsNetwork.from_module(az.AlphaZeroNetwork(8, 2, 64).eval())
+    model = az.RvsNetwork.from_module(az.AlphaZeroNetwork(8, nb, nf).eval())
 else:
     model = az.UniformRollout(seed=9)
 t0 = time.perf_counter()
-res = azd.sharded_self_play(model, {"num_simulations": sims, "batch_size": 1, "temperature": 1.0, "seed": 123}, games)
+res = azd.sharded_self_play(model, {"num_simulations": sims, "batch_size": 1, "temperature": 1.0, "seed": 123}, games,
+                            slots_per_rank=slots)
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
 if rank == 0:
@@ -36,7 +40,8 @@ if rank == 0:
     assert torch.allclose(res.pi.sum(dim=1), torch.ones(n, device=res.pi.device), atol=1e-5)
     td = az.replay.to_training_data(res)
     assert td["states"].shape == (n, 3, 8, 8)
-    print(f"sharded self-play ok: world {world}, {starts} games, {n} samples gathered on rank 0 in {dt:.2f} s ({kind})")
+    print(f"sharded self-play ok: world {world}, {starts} games, {n} samples gathered on rank 0 in {dt:.2f} s ({kind} {nb}x{nf}, {sims} sims/move, "
+          f"{slots} slots per rank) = {n * sims / dt / 1e6:.1f} M sims/s incl. engine setup, weight broadcast and gather")
 else:
     assert res is None
 if world > 1:
