@@ -112,31 +112,6 @@ __global__ void __launch_bounds__(kBlock) search_fused_kernel(EngineView ev, int
     flush_stats(ev, cx, lane_steps);
 }
 
-// MCTS.search with batch_size == 1 and a built-in evaluator: every simulation is register
-// resident (path one node per lane, position in the warp's CoopBoard), no wave scratch.
-template <int RULES, int EVAL>
-__global__ void __launch_bounds__(kBlock, 7) search_k1_kernel(EngineView ev, int S) {
-    const int g = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (g >= ev.G) return;
-    TreeCtx cx{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, 1, ev.c_puct, (int)(threadIdx.x & 31), 0, 0, 0, 0, 0, 0, make_dir<RULES>(threadIdx.x & 7)};
-    const Board root{ev.black[g], ev.white[g], ev.side[g], ev.flags[g]};
-    const uint64_t game_id = ev.game_id[g];
-    const uint64_t search_id = (uint64_t)ev.ply[g];
-    init_root(cx, root.side);
-    const CoopBoard root_c = coop_load(cx.dir, root);
-    for (int sim = 0; sim < S; ++sim) {
-        const uint64_t st = EVAL == RVS_EVAL_ROLLOUT ? stream_seed(ev.seed, game_id, (search_id << 16) | (uint64_t)sim) : 0ULL;
-        simulate_one<EVAL>(cx, root_c, st);
-        if (sim == 0 && ev.noise_eps > 0.0f) {
-            __syncwarp();
-            if (cx.lane == 0) root_noise_apply(ev, g, game_id, search_id);
-            __syncwarp();
-        }
-    }
-    if (cx.lane == 0) ev.n_nodes[g] = cx.n_nodes;
-    flush_stats(ev, cx, 0);
-}
-
 __global__ void __launch_bounds__(kBlock) begin_search_kernel(EngineView ev) {
     const int g = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (g >= ev.G) return;
@@ -372,48 +347,6 @@ __global__ void __launch_bounds__(kBlock) finalize_kernel(EngineView ev, int rec
     finalize_game(ev, g, threadIdx.x & 31, recycle);
 }
 
-// Persistent self-play (SelfPlay.generate_games, self_play.py:66-131, with MCTS batch_size 1):
-// every warp keeps playing plies of its slot -- search (S register-resident simulations), move
-// choice + sample record, make_move, game end + recycling -- until the launch-wide budget of
-// game-plies is used up.  Games desynchronise freely, so the launch is work-conserving: no warp
-// waits at a per-ply barrier for the slowest (early-game, long-rollout) positions.
-template <int RULES, int EVAL>
-__global__ void __launch_bounds__(kBlock, 7) selfplay_k1_kernel(EngineView ev, int S, float temperature,
-                                                               unsigned long long budget, int recycle) {
-    const int g = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (g >= ev.G) return;
-    const int lane = threadIdx.x & 31;
-    while (true) {
-        if (!ev.live[g]) break;
-        const Board root{ev.black[g], ev.white[g], ev.side[g], ev.flags[g]};
-        if (is_over(root)) break;
-        unsigned long long t = 0;
-        if (lane == 0) t = atomicAdd(ev.ply_counter, 1ULL);
-        t = __shfl_sync(kFull, t, 0);
-        if (t >= budget) break;
-        TreeCtx cx{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, 1, ev.c_puct, lane, 0, 0, 0, 0, 0, 0, make_dir<RULES>(lane & 7)};
-        const uint64_t game_id = ev.game_id[g];
-        const uint64_t search_id = (uint64_t)ev.ply[g];
-        init_root(cx, root.side);
-        const CoopBoard root_c = coop_load(cx.dir, root);
-        for (int sim = 0; sim < S; ++sim) {
-            const uint64_t st = EVAL == RVS_EVAL_ROLLOUT ? stream_seed(ev.seed, game_id, (search_id << 16) | (uint64_t)sim) : 0ULL;
-            simulate_one<EVAL>(cx, root_c, st);
-            if (sim == 0 && ev.noise_eps > 0.0f) {
-                __syncwarp();
-                if (lane == 0) root_noise_apply(ev, g, game_id, search_id);
-                __syncwarp();
-            }
-        }
-        if (lane == 0) ev.n_nodes[g] = cx.n_nodes;
-        flush_stats(ev, cx, 0);
-        __syncwarp();
-        if (lane == 0) play_game<RULES>(ev, g, temperature);
-        __syncwarp();
-        finalize_game(ev, g, lane, recycle);
-    }
-}
-
 // ---- wave 1, several games per warp (rvs_treeg.cuh) -------------------------------------------
 constexpr int kBlockG = 32;  // one warp per CTA: the finest grain for the block scheduler
 
@@ -506,7 +439,8 @@ __global__ void __launch_bounds__(1024) phase_order_kernel(EngineView ev) {
     }
 }
 
-// MCTS.search, batch_size 1, built-in evaluator: search_k1_kernel with an LPG-lane group per game.
+// MCTS.search with batch_size 1 and a built-in evaluator, an LPG-lane group per game: every simulation stays
+// in registers / shared memory (path, position, rollout) except for the tree rows.
 // The warp stays converged (rvs_treeg.cuh); groups without a game are predicated off.  A group
 // owns the slots gidx, gidx + n_groups, ... (phase order), so any G runs on a resident grid.
 constexpr int kMaxWarpsG = kNumSMs * 16;  // 16 one-warp CTAs per SM (__launch_bounds__(32, 16): <= 128 registers)
@@ -543,7 +477,8 @@ __global__ void __launch_bounds__(kBlockG, 16) search_k1g_kernel(EngineView ev, 
     }
 }
 
-// selfplay_k1_kernel with an LPG-lane group per game (persistent, work-conserving): every group
+// Persistent self-play (SelfPlay.generate_games, self_play.py:66-131, with MCTS batch_size 1), an LPG-lane
+// group per game, work-conserving: every group
 // keeps playing plies of its slots, round-robin, until the launch-wide budget of game-plies is used up
 template <int RULES, int EVAL, int LPG>
 __global__ void __launch_bounds__(kBlockG, 16) selfplay_k1g_kernel(EngineView ev, int S, float temperature,
@@ -690,10 +625,6 @@ inline int lanes_per_game(const rvs_engine* h) {
     return G <= 6144 ? 8 : (G <= 24576 ? 4 : 2);
 }
 
-inline bool warp_per_game() {
-    static const bool v = getenv("RVS_K1_WARP") && atoi(getenv("RVS_K1_WARP")) != 0;
-    return v;
-}
 
 #define RVS_ENGINE_LAUNCH(h, ...)          \
     do {                                   \
@@ -841,12 +772,7 @@ int rvs_engine_search(rvs_engine* h, int32_t num_sims, int32_t wave, void* strea
     const bool strict = h->cfg.rules == RVS_RULES_STRICT;
     if (wave == 1 && (h->cfg.evaluator == RVS_EVAL_E0 || h->cfg.evaluator == RVS_EVAL_ROLLOUT)) {
         const bool e0 = h->cfg.evaluator == RVS_EVAL_E0;
-        if (warp_per_game()) {  // RVS_K1_WARP=1: the one-warp-per-game kernels (kept for A/B measurements)
-            if (strict && e0) RVS_ENGINE_LAUNCH(h, (search_k1_kernel<RULES_STRICT, RVS_EVAL_E0>), grid, kBlock, 0, s, h->v, num_sims);
-            else if (strict) RVS_ENGINE_LAUNCH(h, (search_k1_kernel<RULES_STRICT, RVS_EVAL_ROLLOUT>), grid, kBlock, 0, s, h->v, num_sims);
-            else if (e0) RVS_ENGINE_LAUNCH(h, (search_k1_kernel<RULES_REF, RVS_EVAL_E0>), grid, kBlock, 0, s, h->v, num_sims);
-            else RVS_ENGINE_LAUNCH(h, (search_k1_kernel<RULES_REF, RVS_EVAL_ROLLOUT>), grid, kBlock, 0, s, h->v, num_sims);
-        } else {
+        {
             RVS_ENGINE_LAUNCH(h, phase_order_kernel, 1, 1024, 0, s, h->v);
             const int lpg = lanes_per_game(h);
 #define RVS_SEARCH_G(LPG)                                                                                                         \
@@ -1007,15 +933,9 @@ int rvs_engine_selfplay(rvs_engine* h, int32_t num_sims, float temperature, int6
         return fail(-1, "rvs_engine_selfplay: the external evaluator is driven by the caller (begin_search / select / process + play)");
     cudaStream_t s = (cudaStream_t)stream;
     RVS_CUDA(cudaMemsetAsync(h->v.ply_counter, 0, 8, s));
-    const int grid = games_grid(h->v.G);
     const bool strict = h->cfg.rules == RVS_RULES_STRICT, e0 = h->cfg.evaluator == RVS_EVAL_E0;
     const unsigned long long budget = (unsigned long long)plies;
-    if (warp_per_game()) {
-        if (strict && e0) RVS_ENGINE_LAUNCH(h, (selfplay_k1_kernel<RULES_STRICT, RVS_EVAL_E0>), grid, kBlock, 0, s, h->v, num_sims, temperature, budget, recycle);
-        else if (strict) RVS_ENGINE_LAUNCH(h, (selfplay_k1_kernel<RULES_STRICT, RVS_EVAL_ROLLOUT>), grid, kBlock, 0, s, h->v, num_sims, temperature, budget, recycle);
-        else if (e0) RVS_ENGINE_LAUNCH(h, (selfplay_k1_kernel<RULES_REF, RVS_EVAL_E0>), grid, kBlock, 0, s, h->v, num_sims, temperature, budget, recycle);
-        else RVS_ENGINE_LAUNCH(h, (selfplay_k1_kernel<RULES_REF, RVS_EVAL_ROLLOUT>), grid, kBlock, 0, s, h->v, num_sims, temperature, budget, recycle);
-    } else {
+    {
         RVS_ENGINE_LAUNCH(h, phase_order_kernel, 1, 1024, 0, s, h->v);
         const int lpg = lanes_per_game(h);
 #define RVS_SELFPLAY_G(LPG)                                                                                                       \

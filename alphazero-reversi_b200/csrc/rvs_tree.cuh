@@ -251,40 +251,6 @@ __device__ __forceinline__ void mark_terminal_and_backup(TreeCtx& cx, int node, 
     backup_path(cx, p0, p1, plen, code == 1 ? 1.0f : (code == 2 ? -1.0f : 0.0f));
 }
 
-// One whole simulation with wave size 1 (MCTS(batch_size=1): select -> evaluate -> expand ->
-// backup), entirely in registers: the path lives one node per lane, the leaf position stays in
-// the warp's CoopBoard and the rollout continues from it.  Identical results to
-// select_wave/eval/process_wave with k == 1.
-template <int EVAL>
-__device__ __forceinline__ void simulate_one(TreeCtx& cx, const CoopBoard& root_c, uint64_t stream_for_sim) {
-    CoopBoard b = root_c;
-    int p0, p1, plen, vlf;
-    const int node = select_one(cx, b, p0, p1, plen, vlf);
-    ++cx.sims;
-    if (vlf & kTerminal) {  // mcts.py:364-366
-        backup_path(cx, p0, p1, plen, term_value_of(vlf));
-        return;
-    }
-    const uint64_t lm = coop_legal(cx.dir, b);
-    if (lm == 0) {
-        mark_terminal_and_backup(cx, node, b.flags, p0, p1, plen);
-        return;
-    }
-    float v;
-    if (EVAL == RVS_EVAL_E0) {
-        v = __fdiv_rn((float)(popc64(b.Pd) - popc64(b.Od)), 64.0f);
-    } else {
-        const int leaf_side = b.side;
-        CoopBoard r = b;
-        cx.steps += (unsigned)coop_random_playout(cx.dir, r, lm, stream_for_sim, cx.lane);
-        const int w = (r.flags & F_WIN_MASK) >> F_WIN_SHIFT;
-        v = (!(r.flags & F_OVER) || w == 0) ? 0.0f : (w == leaf_side ? 1.0f : -1.0f);
-    }
-    ++cx.evals;
-    expand_node(cx, node, lm, [](int) { return 1.0f / 65.0f; });
-    backup_path(cx, p0, p1, plen, v);
-}
-
 // MCTS._process_batch (mcts.py:544-623) for one game's wave.  ws.lm / ws.val must be filled
 // for every slot with node >= 0.  Pass 1 marks and backs up terminal leaves (ABSOLUTE value,
 // mcts.py:567-579), pass 2 expands and backs up the evaluated ones, both in slot order.
