@@ -63,7 +63,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -435,7 +435,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": traffic, "peak_source": which, "kernel": ("selfplay_k1g_kernel<REF,ROLLOUT,8>" if persistent else
                                     ("search_k1g_kernel<REF,ROLLOUT,8>" if wave == 1 else "search_fused_kernel<REF,ROLLOUT>")),
-                         "steps_per_launch": ppl if persistent else 1,
+                         "steps_per_launch": min(ppl, args.steps) if persistent else 1,
                          "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms * len(ks) / ms,
                          "note": "not HBM bound: rollouts are register resident (0 B); at 4096 games the kernel is bound by the "
                                  "latency of one rollout ply's dependency chain (1.7 warps per scheduler), see DESIGN.md K2",
