@@ -477,6 +477,16 @@ __global__ void __launch_bounds__(kBlockG, 16) search_k1g_kernel(EngineView ev, 
     }
 }
 
+// move choice + sample record + make_move + game end of one ply, out of line so that its registers (f64 pi
+// arithmetic) do not weigh on the allocation of the simulation loop
+template <int RULES, int LPG>
+__device__ __noinline__ void end_of_ply(const EngineView& ev, int g, int lane, float temperature, int recycle, bool alive) {
+    __syncwarp();
+    if (alive && lane == 0) play_game<RULES>(ev, g, temperature);
+    __syncwarp();
+    finalize_game_g<LPG>(ev, g, lane, recycle, alive);
+}
+
 // Persistent self-play (SelfPlay.generate_games, self_play.py:66-131, with MCTS batch_size 1), an LPG-lane
 // group per game, work-conserving: every group
 // keeps playing plies of its slots, round-robin, until the launch-wide budget of game-plies is used up
@@ -522,10 +532,7 @@ __global__ void __launch_bounds__(kBlockG, 16) selfplay_k1g_kernel(EngineView ev
         }
         if (alive && grp.lane == 0) ev.n_nodes[g] = cx.n_nodes;
         flush_stats_g(ev, cx, alive);
-        __syncwarp();
-        if (alive && grp.lane == 0) play_game<RULES>(ev, g, temperature);
-        __syncwarp();
-        finalize_game_g<LPG>(ev, g, grp.lane, recycle, alive);
+        end_of_ply<RULES, LPG>(ev, g, grp.lane, temperature, recycle, alive);
         idle = alive ? 0 : idle + 1;
         if (idle >= n_mine) quit = true;  // every slot of this group is parked or over
         k = k + 1 < n_mine ? k + 1 : 0;
