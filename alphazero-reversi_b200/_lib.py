@@ -10,6 +10,8 @@ MEM_DEVICE, MEM_HOST, MEM_HOST_ASYNC = 0, 1, 2
 RULES_REF, RULES_STRICT = 0, 1
 PLANES_F32_NCHW, PLANES_BF16_NHWC = 0, 1
 EVAL_E0, EVAL_ROLLOUT, EVAL_EXTERNAL, EVAL_NN = 0, 1, 2, 3
+MODE_REF, MODE_FAST = 0, 1
+OPT_LANES_PER_GAME, OPT_NET_GRAPH, OPT_SEARCH_MODE, OPT_GAME_LIMIT, OPT_NET_MAX_CTAS, OPT_NET_PIPELINE = 1, 2, 3, 4, 5, 6
 FLAG_OVER, FLAG_WINNER_SHIFT, FLAG_WINNER_MASK, FLAG_PASSED = 1, 1, 6, 8
 
 u64p = C.POINTER(C.c_uint64)
@@ -28,7 +30,8 @@ class EngineConfig(C.Structure):
 
 class EngineStats(C.Structure):
     _fields_ = [(k, C.c_int64) for k in ("sims", "evals", "board_steps", "nodes", "games_finished",
-                                          "samples", "launches", "overflow", "tree_bytes", "samples_dropped", "stalled", "nn_evals")]
+                                          "samples", "launches", "overflow", "tree_bytes", "samples_dropped", "stalled", "nn_evals",
+                                          "bad_positions")]
 
 
 # every symbol include/rvs_b200.h declares: name -> (restype, argtypes)
@@ -59,6 +62,9 @@ PROTOTYPES = {
     "rvs_engine_selfplay": (C.c_int, [V, C.c_int32, C.c_float, C.c_int64, C.c_int, V]),
     "rvs_engine_drain_samples": (C.c_int, [V, V, V, V, C.c_int64, C.POINTER(C.c_int64), C.c_int, V]),
     "rvs_engine_drain_packed": (C.c_int, [V, V, V, V, V, V, C.c_int64, C.POINTER(C.c_int64), C.c_int, V]),
+    "rvs_engine_drain_packed_async": (C.c_int, [V, V, V, V, V, V, C.c_int64, V, V]),
+    "rvs_engine_set_option": (C.c_int, [V, C.c_int32, C.c_int64]),
+    "rvs_engine_predict_probs": (C.c_int, [V, V, V, V, C.c_int64, V, V, C.c_int, V]),
     "rvs_engine_stats_get": (C.c_int, [V, C.POINTER(EngineStats), V]),
     "rvs_engine_set_root_noise": (C.c_int, [V, C.c_double, C.c_float]),
     "rvs_engine_set_lanes_per_game": (C.c_int, [V, C.c_int32]),
@@ -94,16 +100,26 @@ def check(rc):
         raise RvsError(f"librvs_b200 error {rc}: {lib().rvs_last_error().decode(errors='replace')}")
 
 
-def ptr(x):
-    """(pointer, mem kind, keep-alive) of a numpy array or a torch tensor; None -> NULL"""
+_TORCH_NAMES = {"uint64": ("int64", "uint64"), "uint8": ("uint8",), "int8": ("int8",), "int32": ("int32",),
+                "float32": ("float32",), "int64": ("int64",)}
+
+
+def ptr(x, dtype=None):
+    """(pointer, mem kind) of a numpy array or a torch tensor; None -> (None, None).
+    `dtype` (numpy dtype name) is what the C side will read: a mismatch raises instead of being
+    reinterpreted silently (torch has no uint64 arithmetic, so int64 tensors stand in for uint64)."""
     if x is None:
         return None, None
     if hasattr(x, "data_ptr"):  # torch tensor
         if not x.is_contiguous():
             raise ValueError("tensor must be contiguous")
+        if dtype is not None and str(x.dtype).replace("torch.", "") not in _TORCH_NAMES[dtype]:
+            raise TypeError(f"expected a {dtype} tensor, got {x.dtype}")
         return x.data_ptr(), (MEM_DEVICE if x.is_cuda else MEM_HOST)
     if not x.flags["C_CONTIGUOUS"]:
         raise ValueError("array must be C-contiguous")
+    if dtype is not None and x.dtype.name != dtype:
+        raise TypeError(f"expected a {dtype} array, got {x.dtype.name}")
     return x.ctypes.data, MEM_HOST
 
 
@@ -114,10 +130,20 @@ def mem_of(*xs):
     return kinds.pop()
 
 
-def current_stream():
-    """torch's current CUDA stream handle when torch is loaded, else the default stream"""
+def current_stream(device=None):
+    """torch's current CUDA stream handle ON `device` when torch is loaded, else the default stream"""
     import sys
     t = sys.modules.get("torch")
     if t is not None and t.cuda.is_available():
-        return t.cuda.current_stream().cuda_stream
+        return t.cuda.current_stream(device).cuda_stream
     return None
+
+
+def current_device():
+    """the CUDA device new engines are created on: torch's current device when torch is loaded (a torchrun
+    rank that called torch.cuda.set_device(local_rank) gets ITS GPU), else device 0"""
+    import sys
+    t = sys.modules.get("torch")
+    if t is not None and t.cuda.is_available():
+        return t.cuda.current_device()
+    return 0

@@ -89,6 +89,17 @@ class ELORatingSystem:
         return elo
 
 
+def _cuda_index(device):
+    """'cuda' / 'cuda:1' / torch.device / int -> CUDA device index for the engines (None = the current device)"""
+    if device is None or isinstance(device, int):
+        return device
+    idx = getattr(device, "index", None)
+    if idx is not None:
+        return idx
+    d = str(device)
+    return int(d.split(":", 1)[1]) if ":" in d else None
+
+
 class ELOPlayer:
     """player_id + model (None = uniform-random mover) + MCTS parameters (arena.py:137-197)"""
 
@@ -104,7 +115,7 @@ class ELOPlayer:
                 model.to(device)
             self.mcts = MCTS(model=model, c_puct=self.mcts_params.get("c_puct", 1.0),
                              num_simulations=self.mcts_params.get("num_simulations", 800),
-                             batch_size=self.mcts_params.get("batch_size", 64))
+                             batch_size=self.mcts_params.get("batch_size", 64), device=_cuda_index(device))
 
     def get_move(self, game: ReversiGame) -> Tuple[int, int]:
         if self.model is None:
@@ -173,7 +184,8 @@ class Arena:
                 S = pl.mcts_params.get("num_simulations", 800)
                 K = max(1, pl.mcts_params.get("batch_size", 64))
                 eng = Engine(cap, S, K, evaluator=pl.model.evaluator, c_puct=pl.mcts_params.get("c_puct", 1.0),
-                             seed=getattr(pl.model, "seed", 0) + 7919 * pi, net_blocks=getattr(pl.model, "net_blocks", 0),
+                             seed=getattr(pl.model, "seed", 0) + 7919 * pi, device=_cuda_index(pl.device),
+                             net_blocks=getattr(pl.model, "net_blocks", 0),
                              net_filters=getattr(pl.model, "net_filters", 0))
                 if hasattr(pl.model, "attach"):
                     pl.model.attach(eng)

@@ -20,8 +20,16 @@ def _like(x, shape, np_dtype, torch_dtype_name):
     return np.empty(shape, dtype=np_dtype)
 
 
-def _p(x):
-    return L.ptr(x)[0]
+def _p(x, dtype=None):
+    return L.ptr(x, dtype)[0]
+
+
+def _u64(x):
+    return L.ptr(x, "uint64")[0]
+
+
+def _u8(x):
+    return L.ptr(x, "uint8")[0]
 
 
 def legal_masks(black, white, side, rules=L.RULES_REF, stream=None):
@@ -29,7 +37,7 @@ def legal_masks(black, white, side, rules=L.RULES_REF, stream=None):
     n = len(black)
     out = _like(black, (n,), np.uint64, "int64")
     mem = L.mem_of(black, white, side, out)
-    L.check(L.lib().rvs_legal_masks(_p(black), _p(white), _p(side), _p(out), n, rules, mem,
+    L.check(L.lib().rvs_legal_masks(_u64(black), _u64(white), _u8(side), _u64(out), n, rules, mem,
                                     stream if stream is not None else L.current_stream()))
     return out
 
@@ -39,7 +47,7 @@ def flip_masks(black, white, side, move, rules=L.RULES_REF, stream=None):
     n = len(black)
     out = _like(black, (n,), np.uint64, "int64")
     mem = L.mem_of(black, white, side, move, out)
-    L.check(L.lib().rvs_flip_masks(_p(black), _p(white), _p(side), _p(move), _p(out), n, rules, mem,
+    L.check(L.lib().rvs_flip_masks(_u64(black), _u64(white), _u8(side), _u8(move), _u64(out), n, rules, mem,
                                    stream if stream is not None else L.current_stream()))
     return out
 
@@ -50,7 +58,7 @@ def apply_moves(black, white, side, flags, move, rules=L.RULES_REF, want_legal=T
     ok = _like(black, (n,), np.uint8, "uint8")
     nl = _like(black, (n,), np.uint64, "int64") if want_legal else None
     mem = L.mem_of(black, white, side, flags, move, ok)
-    L.check(L.lib().rvs_apply_moves(_p(black), _p(white), _p(side), _p(flags), _p(move), _p(ok), _p(nl), n,
+    L.check(L.lib().rvs_apply_moves(_u64(black), _u64(white), _u8(side), _u8(flags), _u8(move), _u8(ok), _u64(nl), n,
                                     rules, mem, stream if stream is not None else L.current_stream()))
     return ok, nl
 
@@ -97,6 +105,6 @@ def encode_planes(black, white, side, layout=L.PLANES_F32_NCHW, rules=L.RULES_RE
     else:
         out = _like(black, (n, 8, 8, 16), np.uint16, "bfloat16")
     mem = L.mem_of(black, white, side, out)
-    L.check(L.lib().rvs_encode_planes(_p(black), _p(white), _p(side), _p(out), n, layout, rules, mem,
+    L.check(L.lib().rvs_encode_planes(_u64(black), _u64(white), _u8(side), _p(out), n, layout, rules, mem,
                                       stream if stream is not None else L.current_stream()))
     return out

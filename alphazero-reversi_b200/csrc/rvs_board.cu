@@ -259,6 +259,7 @@ int64_t rvs_launch_count(void) { return g_launches.load(); }
 
 int rvs_legal_masks(const uint64_t* black, const uint64_t* white, const uint8_t* side, uint64_t* out_mask,
                     int64_t n, int rules, int mem, void* stream) {
+    RVS_NORMALISE_MEM(mem);
     if (n < 0 || (n > 0 && (!black || !white || !side || !out_mask))) return fail(-1, "rvs_legal_masks: bad arguments");
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
@@ -285,6 +286,7 @@ int rvs_legal_masks(const uint64_t* black, const uint64_t* white, const uint8_t*
 
 int rvs_flip_masks(const uint64_t* black, const uint64_t* white, const uint8_t* side, const uint8_t* move,
                    uint64_t* out_flip, int64_t n, int rules, int mem, void* stream) {
+    RVS_NORMALISE_MEM(mem);
     if (n < 0 || (n > 0 && (!black || !white || !side || !move || !out_flip))) return fail(-1, "rvs_flip_masks: bad arguments");
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
@@ -312,6 +314,7 @@ int rvs_flip_masks(const uint64_t* black, const uint64_t* white, const uint8_t* 
 
 int rvs_apply_moves(uint64_t* black, uint64_t* white, uint8_t* side, uint8_t* flags, const uint8_t* move,
                     uint8_t* ok, uint64_t* out_next_legal, int64_t n, int rules, int mem, void* stream) {
+    RVS_NORMALISE_MEM(mem);
     if (n < 0 || (n > 0 && (!black || !white || !side || !flags || !move))) return fail(-1, "rvs_apply_moves: bad arguments");
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
@@ -343,6 +346,7 @@ int rvs_apply_moves(uint64_t* black, uint64_t* white, uint8_t* side, uint8_t* fl
 int rvs_random_playouts(int64_t n_games, uint64_t seed, uint64_t first_game, int rules, uint64_t* out_black,
                         uint64_t* out_white, uint8_t* out_winner, uint8_t* out_plies, int64_t* out_total_plies,
                         int mem, void* stream) {
+    RVS_NORMALISE_MEM(mem);
     if (n_games < 0) return fail(-1, "rvs_random_playouts: bad arguments");
     if (out_total_plies) *out_total_plies = 0;
     if (n_games == 0) return 0;
@@ -439,6 +443,7 @@ int rvs_perft(uint64_t black, uint64_t white, int side, int depth, int rules, ui
 
 int rvs_encode_planes(const uint64_t* black, const uint64_t* white, const uint8_t* side, void* out, int64_t n,
                       int layout, int rules, int mem, void* stream) {
+    RVS_NORMALISE_MEM(mem);
     if (n < 0 || (n > 0 && (!black || !white || !side || !out))) return fail(-1, "rvs_encode_planes: bad arguments");
     if (layout != RVS_PLANES_F32_NCHW && layout != RVS_PLANES_BF16_NHWC) return fail(-1, "rvs_encode_planes: bad layout");
     if (n == 0) return 0;

@@ -43,6 +43,14 @@ inline int fail(int code, const char* fmt, ...) {
         RVS_CUDA(cudaGetLastError());                                                        \
     } while (0)
 
+// RVS_MEM_HOST_ASYNC is only honoured by rvs_engine_set_positions / rvs_engine_root_visits; everywhere else it
+// is RVS_MEM_HOST (staged copies under the staging lock, outputs complete on return)
+#define RVS_NORMALISE_MEM(mem)                                                                   \
+    do {                                                                                         \
+        if ((mem) == RVS_MEM_HOST_ASYNC) (mem) = RVS_MEM_HOST;                                   \
+        if ((mem) != RVS_MEM_DEVICE && (mem) != RVS_MEM_HOST) return ::rvs::fail(-1, "bad mem %d", (int)(mem)); \
+    } while (0)
+
 inline int grid_for(int64_t n, int block, int ctas_per_sm = 8) {
     int64_t need = (n + block - 1) / block;
     int64_t cap = (int64_t)kNumSMs * ctas_per_sm;

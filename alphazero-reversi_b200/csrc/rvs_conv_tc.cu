@@ -2,21 +2,21 @@
 // implicit GEMM on the 5th-generation tensor cores: TMA -> shared memory -> tcgen05.mma -> TMEM ->
 // tcgen05.ld epilogue.  sm_100a only.
 //
-// GEMM view per CTA:  D[128 pixels, 64 couts] += A_tap[128 pixels, cin] * W_tap[64 couts, cin]^T
-//   M = 128 = one "tile" = two boards, rows ordered (y, board, x): with this order a vertical tap
-//       shift dy is a shift by 16 rows = 2048 B, i.e. a whole number of 1024-byte swizzle atoms.
-//   N = 64 couts per CTA (C/64 CTAs share a pixel tile); its 9 x C/64 weight tiles (8 KB each) are
-//       loaded ONCE and stay resident in shared memory for the whole persistent CTA.
-//   K = 9 taps x cin, consumed as 3 (dx) x C/64 stages; each stage is ONE TMA box of the
+// GEMM view per CTA PAIR (cta_group::2):  D[256 pixels, C couts] += A_tap[256 pixels, cin] * W_tap[C couts, cin]^T
+//   M = 2 x 128: each CTA supplies one "tile" = two boards, rows ordered (y, board, x): with this order a
+//       vertical tap shift dy is a shift by 16 rows = 2048 B, i.e. a whole number of 1024-byte swizzle atoms.
+//   N = C couts; each CTA holds HALF of the weight rows (resident for C <= 128, streamed for C = 256).
+//   K = 9 taps x cin, consumed as 3 (dx) x cin/64 stages; each stage is ONE TMA box of the
 //       activations: 10 rows of y (halo -1..8) x 2 boards x 8 x (shifted by dx) x 64 channels,
 //       out-of-bounds rows/columns zero-filled by the TMA unit = the convolution's zero padding.
 //       The three vertical taps of that dx reuse the same box at row offsets 0 / 16 / 32.
 // Activations live in HBM in the same tiled order [tile][y][board][x][c] (rvs_conv_tc.cuh:
 // act_row), so accumulator row r of a tile is simply row r of the output tile.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2-5 = epilogue (TMEM lane quarter = warp_id % 4).  Two 64-column accumulators in TMEM
-// ping-pong so that the epilogue of tile i overlaps the MMAs of tile i+1.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (leader CTA only),
+// warps 2-5 = epilogue (TMEM lane quarter = warp_id % 4).  Two accumulators in TMEM ping-pong so that the
+// epilogue of tile i overlaps the MMAs of tile i+1.  (The first-generation 1-CTA kernel -- N = 64 per CTA,
+// tensor pipe at 31 % of its throughput, profiles/superseded/ncu_conv_tc1_r1.txt -- was removed in round 2.)
 #include "rvs_conv_tc.cuh"
 
 #include <cuda.h>
@@ -29,15 +29,11 @@ namespace rvs {
 namespace {
 
 constexpr int kTileRows = 128;              // pixels per tile (2 boards)
-constexpr int kNT = 64;                     // couts per CTA
 constexpr int kABytes = 10 * 2 * 8 * 128;   // one activation stage: 160 rows x 128 B
-constexpr int kWBytes = kNT * 128;          // one weight tile: 64 rows x 128 B
 constexpr int kThreads = 192;
 
 struct Impl {
-    CUtensorMap w_map;
-    CUtensorMap w_map2;   // box of C/2 weight rows for the 2-CTA kernel
-    bool two_sm = true;
+    CUtensorMap w_map2;   // box of C/2 weight rows (one CTA's half of a tap)
     int cin = 0;
     const void* act_ptr[4] = {nullptr, nullptr, nullptr, nullptr};
     CUtensorMap act_map[4];
@@ -69,48 +65,8 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
-                                            int c3, int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, one elected thread
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -143,162 +99,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16
-// [10,13)=1, A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kNT >> 3) << 17) | ((uint32_t)(kTileRows >> 4) << 24);
-
-template <int C>
-struct Cfg {
-    static constexpr int KC = C / 64;                      // 64-channel k chunks
-    static constexpr int NSPLIT = C / kNT;                 // CTAs sharing one pixel tile
-    static constexpr int W_TILES = 9 * KC;
-    static constexpr int STAGES = C == 64 ? 4 : 3;
-    static constexpr int SMEM = W_TILES * kWBytes + STAGES * kABytes + 1024 /*align*/ + 512 /*barriers, bias*/;
-};
-
-template <int C>
-__global__ void __launch_bounds__(kThreads, 1) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap a_map,
-                                                                  const __grid_constant__ CUtensorMap w_map,
-                                                                  const __nv_bfloat16* __restrict__ residual,
-                                                                  __nv_bfloat16* __restrict__ out,
-                                                                  const float* __restrict__ bias, int n_tiles) {
-    using K = Cfg<C>;
-    extern __shared__ unsigned char smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-B alignment
-    unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t w_s = base;
-    const uint32_t a_s = base + K::W_TILES * kWBytes;
-    unsigned char* tail = gen + K::W_TILES * kWBytes + K::STAGES * kABytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);   // full[S], empty[S], wfull, acc_full[2], acc_empty[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 128);
-    float* sbias = reinterpret_cast<float*>(tail + 192);  // [64]
-    const uint32_t bar0 = smem_u32(bars);
-    auto FULL = [&](int s) { return bar0 + 8u * s; };
-    auto EMPTY = [&](int s) { return bar0 + 8u * (K::STAGES + s); };
-    const uint32_t WFULL = bar0 + 8u * (2 * K::STAGES);
-    auto ACC_FULL = [&](int a) { return bar0 + 8u * (2 * K::STAGES + 1 + a); };
-    auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (2 * K::STAGES + 3 + a); };
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_split = blockIdx.x % K::NSPLIT;
-    const int tile0 = blockIdx.x / K::NSPLIT;
-    const int tile_step = gridDim.x / K::NSPLIT;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < K::STAGES; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); }
-        mbar_init(WFULL, 1);
-        for (int a = 0; a < 2; ++a) { mbar_init(ACC_FULL(a), 1); mbar_init(ACC_EMPTY(a), 4); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (threadIdx.x < kNT) sbias[threadIdx.x] = bias[n_split * kNT + threadIdx.x];
-    if (warp == 1) {  // TMEM: 2 accumulators x 64 fp32 columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        if (lane == 0) {  // ===== TMA producer =====
-            mbar_expect_tx(WFULL, K::W_TILES * kWBytes);
-            for (int tap = 0; tap < 9; ++tap)
-                for (int kc = 0; kc < K::KC; ++kc)
-                    tma_load_2d(&w_map, WFULL, w_s + (tap * K::KC + kc) * kWBytes, kc * 64, tap * C + n_split * kNT);
-            int stage = 0, phase = 0;
-            for (int tile = tile0; tile < n_tiles; tile += tile_step) {
-                for (int dx = 0; dx < 3; ++dx)
-                    for (int kc = 0; kc < K::KC; ++kc) {
-                        mbar_wait(EMPTY(stage), phase ^ 1);
-                        mbar_expect_tx(FULL(stage), kABytes);
-                        tma_load_5d(&a_map, FULL(stage), a_s + stage * kABytes, kc * 64, dx - 1, 0, -1, tile);
-                        if (++stage == K::STAGES) { stage = 0; phase ^= 1; }
-                    }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {  // ===== MMA issuer =====
-            mbar_wait(WFULL, 0);
-            int stage = 0, phase = 0, it = 0;
-            for (int tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
-                const int acc = it & 1;
-                mbar_wait(ACC_EMPTY(acc), ((it >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d = tmem_base + (uint32_t)(acc * kNT);
-                uint32_t accum = 0;
-                for (int dx = 0; dx < 3; ++dx)
-                    for (int kc = 0; kc < K::KC; ++kc) {
-                        mbar_wait(FULL(stage), phase);
-                        tc_fence_after();
-                        const uint32_t a0 = a_s + stage * kABytes;
-#pragma unroll
-                        for (int dy = 0; dy < 3; ++dy) {
-                            const uint32_t wt = w_s + ((dy * 3 + dx) * K::KC + kc) * kWBytes;
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {  // 4 x (K = 16 bf16 = 32 B) inside the 128-B swizzle atom
-                                tc_mma(d, make_desc(a0 + dy * 2048 + k * 32), make_desc(wt + k * 32), kIdesc, accum);
-                                accum = 1;
-                            }
-                        }
-                        tc_commit(EMPTY(stage));  // the stage is free once these MMAs have read it
-                        if (++stage == K::STAGES) { stage = 0; phase ^= 1; }
-                    }
-                tc_commit(ACC_FULL(acc));
-            }
-        }
-    } else {  // ===== epilogue: TMEM -> registers -> (+bias, +residual, ReLU) -> bf16 -> HBM =====
-        const int q = warp & 3;             // TMEM lane quarter this warp may access
-        const int row = q * 32 + lane;      // accumulator row = output row inside the tile
-        int it = 0;
-        for (int tile = tile0; tile < n_tiles; tile += tile_step, ++it) {
-            const int acc = it & 1;
-            mbar_wait(ACC_FULL(acc), (it >> 1) & 1);
-            tc_fence_after();
-            uint32_t v[64];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kNT);
-            tc_ld32(taddr, v);
-            tc_ld32(taddr + 32, v + 32);
-            tc_wait_ld();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(ACC_EMPTY(acc));  // accumulator may be overwritten now
-            const size_t off = ((size_t)tile * kTileRows + row) * C + (size_t)n_split * kNT;
-            uint4* optr = reinterpret_cast<uint4*>(out + off);
-            const uint4* rptr = residual ? reinterpret_cast<const uint4*>(residual + off) : nullptr;
-#pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) {
-                float f[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[c8 * 8 + i]) + sbias[c8 * 8 + i];
-                if (rptr) {
-                    const uint4 r = rptr[c8];
-                    const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float2 t = __bfloat1622float2(r2[i]);
-                        f[2 * i] += t.x;
-                        f[2 * i + 1] += t.y;
-                    }
-                }
-                uint4 o;
-                __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) o2[i] = __floats2bfloat162_rn(fmaxf(f[2 * i], 0.f), fmaxf(f[2 * i + 1], 0.f));
-                optr[c8] = o;
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128));
-    }
-}
-
+// [10,13)=1, A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)  -> Cfg2::IDESC / Cfg2S::IDESC
 
 // =============================================================================================
-// 2-CTA variant (cta_group::2).  Profiling the 1-CTA kernel showed the tensor pipe busy 73 % of
+// CTA pairs (cta_group::2).  Profiling a 1-CTA kernel showed the tensor pipe busy 73 % of
 // the time at only 31 % of its throughput: with N = 64 every MMA streams 4 KB of A + 2 KB of B
 // from shared memory for 32 cycles of math (192 B/cycle > the 128 B/cycle SMEM port).  Here a CTA
 // pair computes D[256 px, C couts]: each CTA supplies its own 128-pixel tile (A) and HALF of the
@@ -377,10 +181,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
 // (network.py:104-105, 111-112) are three dot products over the output row the epilogue already
 // holds in registers, so the 67 MB activation write and its re-read by the head kernel disappear;
 // weights travel in the kernel parameter space (constant cache, warp-uniform reads).
-struct HeadW {
-    float w[3][128];
-    float b[4];
-};
+using HeadW = ConvHeadW;  // rvs_conv_tc.cuh
 
 template <int C, int CIN>
 struct Cfg2 {
@@ -777,11 +578,6 @@ int launch_pdl(Kern kern, int grid, int smem, cudaStream_t s, const CUtensorMap&
 
 int launch_pdl_s(int grid, cudaStream_t s, const CUtensorMap& a_map, const CUtensorMap& w_map, const __nv_bfloat16* residual,
                  __nv_bfloat16* out, const float* bias, int n_tiles, const int* n_dev) {
-    static bool attr = false;
-    if (!attr) {
-        RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2S::SMEM));
-        attr = true;
-    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
@@ -819,48 +615,47 @@ int conv_tc_plan(ConvTcPlan& plan, const __nv_bfloat16* w, int C, int64_t max_ba
     plan.C = C;
     plan.max_batch = max_batch;
     if (cin <= 0) cin = C;
-    if (!((C == 64 && cin == 64) || (C == 128 && (cin == 128 || cin == 64)) || (C == 256 && cin == 256))) return 0;
-    if (C == 256 && getenv("RVS_CONV_1SM") && atoi(getenv("RVS_CONV_1SM")) != 0) return 0;  // 256 filters exist as the 2-CTA streamed kernel only
+    if (!((C == 64 && cin == 64) || (C == 128 && (cin == 128 || cin == 64)) || (C == 256 && cin == 256)))
+        return fail(-8, "tcgen05 convolution: unsupported shape %d -> %d", cin, C);
     EncodeFn enc = get_encode();
     if (!enc) return fail(-9, "cuTensorMapEncodeTiled entry point not available");
     Impl* im = plan.impl ? static_cast<Impl*>(plan.impl) : new Impl();
     plan.impl = im;
     im->n_act = 0;
     im->cin = cin;
-    // weights [9*C rows (tap, cout)][cin] bf16, box = 64 cin x 64 couts
+    // weights [9*C rows (tap, cout)][cin] bf16, box = 64 cin x C/2 couts (the CTA's half of one tap)
     const cuuint64_t dims[2] = {(cuuint64_t)cin, (cuuint64_t)9 * C};
     const cuuint64_t strides[1] = {(cuuint64_t)cin * 2};
-    const cuuint32_t box[2] = {64, kNT};
     const cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&im->w_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(w), dims, strides, box, es,
+    const cuuint32_t box2[2] = {64, (cuuint32_t)(C / 2)};
+    CUresult r = enc(&im->w_map2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(w), dims, strides, box2, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(-9, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
-    const cuuint32_t box2[2] = {64, (cuuint32_t)(C / 2)};
-    r = enc(&im->w_map2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(w), dims, strides, box2, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(-9, "cuTensorMapEncodeTiled(weights, 2-CTA) failed: %d", (int)r);
-    im->two_sm = !(getenv("RVS_CONV_1SM") && atoi(getenv("RVS_CONV_1SM")) != 0);
+    // opt in to > 48 KB of dynamic shared memory on THIS device (function attributes are per device, and a
+    // process may hold engines on several GPUs, so this is done per plan rather than once per process)
+    if (C == 256) {
+        RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2S::SMEM));
+    } else if (C == 64) {
+        RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<64, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<64, 64>::SMEM));
+        RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<64, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<64, 64>::SMEM));
+    } else if (cin == 64) {
+        RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<128, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<128, 64>::SMEM));
+    } else {
+        RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<128, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<128, 128>::SMEM));
+        RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<128, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<128, 128>::SMEM));
+    }
     plan.valid = true;
     return 0;
 }
 
 int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
-                   const float* bias, int64_t B, cudaStream_t s, const float* head_host, float* feat, const int* n_dev) {
+                   const float* bias, int64_t B, cudaStream_t s, const ConvHeadW* head, float* feat, const int* n_dev,
+                   int max_ctas) {
     if (!plan.valid || !plan.impl) return fail(-8, "tcgen05 convolution: no plan");
     Impl* im = static_cast<Impl*>(plan.impl);
-    static HeadW zero_head = {};
-    static HeadW cur_head = {};
-    const HeadW* hw = &zero_head;
-    if (feat && head_host && im->two_sm) {  // head_host: [3][C] folded 1x1 weights followed by 3 biases (host memory)
-        for (int j = 0; j < 3; ++j)
-            for (int c = 0; c < 128; ++c) cur_head.w[j][c] = c < plan.C ? head_host[j * plan.C + c] : 0.f;
-        for (int j = 0; j < 3; ++j) cur_head.b[j] = head_host[3 * plan.C + j];
-        hw = &cur_head;
-    } else {
-        feat = nullptr;
-    }
+    static const ConvHeadW zero_head = {};
+    if (!(feat && head)) { feat = nullptr; head = &zero_head; }
     int slot = -1;
     for (int i = 0; i < im->n_act; ++i)
         if (im->act_ptr[i] == in) slot = i;
@@ -873,48 +668,21 @@ int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_b
     }
     const int n_tiles = (int)((B + 1) / 2);
     const int C = plan.C;
-    if (im->two_sm) {  // CTA pairs: grid = 2 x pairs, at most one CTA per SM
-        int pairs = (n_tiles + 1) / 2;
-        if (pairs > kNumSMs / 2) pairs = kNumSMs / 2;
-        if (C == 256) return launch_pdl_s(2 * pairs, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles, n_dev);
-        if (C == 64) {
-            static bool attr = false;
-            if (!attr) {
-                RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<64, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<64, 64>::SMEM));
-                RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<64, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<64, 64>::SMEM));
-                attr = true;
-            }
-            if (feat) return launch_pdl(conv3x3_tc2_kernel<64, 64, true>, 2 * pairs, Cfg2<64, 64>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles, *hw, feat, n_dev);
-            return launch_pdl(conv3x3_tc2_kernel<64, 64, false>, 2 * pairs, Cfg2<64, 64>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles, *hw, feat, n_dev);
-        } else if (im->cin == 64) {  // first layer of a 128-filter tower: 64 (3 used) -> 128
-            static bool attr = false;
-            if (!attr) { RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<128, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<128, 64>::SMEM)); attr = true; }
-            return launch_pdl(conv3x3_tc2_kernel<128, 64, false>, 2 * pairs, Cfg2<128, 64>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles, *hw, nullptr, n_dev);
-        } else {
-            static bool attr = false;
-            if (!attr) {
-                RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<128, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<128, 128>::SMEM));
-                RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<128, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<128, 128>::SMEM));
-                attr = true;
-            }
-            if (feat) return launch_pdl(conv3x3_tc2_kernel<128, 128, true>, 2 * pairs, Cfg2<128, 128>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles, *hw, feat, n_dev);
-            return launch_pdl(conv3x3_tc2_kernel<128, 128, false>, 2 * pairs, Cfg2<128, 128>::SMEM, s, im->act_map[slot], im->w_map2, residual, out, bias, n_tiles, *hw, feat, n_dev);
-        }
-        return 0;
-    }
-    if (im->cin != C) return fail(-8, "1-CTA tcgen05 convolution supports cin == cout only");
-    const int nsplit = C / kNT;
-    int ctas = n_tiles * nsplit < kNumSMs ? n_tiles * nsplit : (kNumSMs / nsplit) * nsplit;
+    // CTA pairs: grid = 2 x pairs, at most one CTA per SM (max_ctas < 148 leaves SMs to concurrent tree kernels)
+    int cap = (max_ctas > 0 && max_ctas < kNumSMs ? max_ctas : kNumSMs) / 2;
+    if (cap < 1) cap = 1;
+    int pairs = (n_tiles + 1) / 2;
+    if (pairs > cap) pairs = cap;
+    const CUtensorMap& am = im->act_map[slot];
+    if (C == 256) return launch_pdl_s(2 * pairs, s, am, im->w_map2, residual, out, bias, n_tiles, n_dev);
     if (C == 64) {
-        static bool attr = false;
-        if (!attr) { RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<64>::SMEM)); attr = true; }
-        RVS_LAUNCH(conv3x3_tc_kernel<64>, ctas, kThreads, Cfg<64>::SMEM, s, im->act_map[slot], im->w_map, residual, out, bias, n_tiles);
-    } else {
-        static bool attr = false;
-        if (!attr) { RVS_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<128>::SMEM)); attr = true; }
-        RVS_LAUNCH(conv3x3_tc_kernel<128>, ctas, kThreads, Cfg<128>::SMEM, s, im->act_map[slot], im->w_map, residual, out, bias, n_tiles);
+        if (feat) return launch_pdl(conv3x3_tc2_kernel<64, 64, true>, 2 * pairs, Cfg2<64, 64>::SMEM, s, am, im->w_map2, residual, out, bias, n_tiles, *head, feat, n_dev);
+        return launch_pdl(conv3x3_tc2_kernel<64, 64, false>, 2 * pairs, Cfg2<64, 64>::SMEM, s, am, im->w_map2, residual, out, bias, n_tiles, *head, feat, n_dev);
     }
-    return 0;
+    if (im->cin == 64)  // first layer of a 128-filter tower: 64 (3 used) -> 128
+        return launch_pdl(conv3x3_tc2_kernel<128, 64, false>, 2 * pairs, Cfg2<128, 64>::SMEM, s, am, im->w_map2, residual, out, bias, n_tiles, *head, nullptr, n_dev);
+    if (feat) return launch_pdl(conv3x3_tc2_kernel<128, 128, true>, 2 * pairs, Cfg2<128, 128>::SMEM, s, am, im->w_map2, residual, out, bias, n_tiles, *head, feat, n_dev);
+    return launch_pdl(conv3x3_tc2_kernel<128, 128, false>, 2 * pairs, Cfg2<128, 128>::SMEM, s, am, im->w_map2, residual, out, bias, n_tiles, *head, feat, n_dev);
 }
 
 void conv_tc_destroy(ConvTcPlan& plan) {
@@ -923,10 +691,8 @@ void conv_tc_destroy(ConvTcPlan& plan) {
     plan.valid = false;
 }
 
-}  // namespace rvs
-
-namespace rvs {
 bool conv_tc_can_fuse_head(const ConvTcPlan& plan) {
-    return plan.valid && plan.impl && plan.C <= 128 && static_cast<Impl*>(plan.impl)->two_sm && static_cast<Impl*>(plan.impl)->cin == plan.C;
+    return plan.valid && plan.impl && plan.C <= 128 && static_cast<Impl*>(plan.impl)->cin == plan.C;
 }
+
 }  // namespace rvs

@@ -19,16 +19,25 @@ struct ConvTcPlan {
     void* impl = nullptr;
 };
 
+// folded policy / value 1x1 convolutions (network.py:104-105, 111-112) for the fused last-layer epilogue:
+// rows 0,1 = policy planes, row 2 = value plane, padded to 128 channels; b = the three folded BN biases.
+// Passed to the kernel BY VALUE (kernel parameter space), owned per network (never shared between handles).
+struct ConvHeadW {
+    float w[3][128];
+    float b[4];
+};
+
 // builds the TMA descriptors for one layer's folded weights [9][C][cin] bf16 (cin = C by default)
 int conv_tc_plan(ConvTcPlan& plan, const __nv_bfloat16* w, int C, int64_t max_batch, int cin = 0);
 // out = relu(conv3x3(in) + bias [+ residual]) on B boards, NHWC bf16
-// head_host / feat (optional, 2-CTA kernel only): fuse the policy/value 1x1 convolutions into the epilogue:
-// head_host = host copy of [3][C] folded weights + 3 biases, feat = device [B][192] f32 output; `out` is then unused
-// n_dev (optional, 2-CTA kernels only): device int with the actual number of boards (<= B, which then only sizes
-// the grid): compacted leaf batches whose size never visits the host
+// head / feat (optional): fuse the policy/value 1x1 convolutions into the epilogue: feat = device [B][192] f32
+// output; `out` is then unused
+// n_dev (optional): device int with the actual number of boards (<= B, which then only sizes the grid):
+// compacted leaf batches whose size never visits the host
+// max_ctas (optional): cap of the persistent grid (default: all 148 SMs)
 int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
-                   const float* bias, int64_t B, cudaStream_t s, const float* head_host = nullptr, float* feat = nullptr,
-                   const int* n_dev = nullptr);
+                   const float* bias, int64_t B, cudaStream_t s, const ConvHeadW* head = nullptr, float* feat = nullptr,
+                   const int* n_dev = nullptr, int max_ctas = 0);
 bool conv_tc_can_fuse_head(const ConvTcPlan& plan);
 void conv_tc_destroy(ConvTcPlan& plan);
 

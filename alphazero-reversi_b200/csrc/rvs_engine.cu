@@ -330,7 +330,7 @@ __device__ __forceinline__ void finalize_game(const EngineView& ev, int g, int l
         atomicAdd(&ev.stats[ST_SAMPLES], (unsigned long long)stored);
         if (stored < n) atomicAdd(&ev.stats[ST_DROPPED], (unsigned long long)(n - stored));
         ev.finished[g] = 0;
-        if (recycle) {
+        if (recycle && (ev.game_limit == 0 || ev.game_id[g] + (uint64_t)ev.G < ev.game_limit)) {
             ev.black[g] = kStartBlack; ev.white[g] = kStartWhite; ev.side[g] = 1; ev.flags[g] = 0;
             ev.ply[g] = 0;
             ev.game_id[g] += (uint64_t)ev.G;
@@ -405,7 +405,7 @@ __device__ __forceinline__ void finalize_game_g(const EngineView& ev, int g, int
         atomicAdd(&ev.stats[ST_SAMPLES], (unsigned long long)stored);
         if (stored < n) atomicAdd(&ev.stats[ST_DROPPED], (unsigned long long)(n - stored));
         ev.finished[g] = 0;
-        if (recycle) {
+        if (recycle && (ev.game_limit == 0 || ev.game_id[g] + (uint64_t)ev.G < ev.game_limit)) {
             ev.black[g] = kStartBlack; ev.white[g] = kStartWhite; ev.side[g] = 1; ev.flags[g] = 0;
             ev.ply[g] = 0;
             ev.game_id[g] += (uint64_t)ev.G;
@@ -560,21 +560,72 @@ __global__ void __launch_bounds__(256) drain_kernel(EngineView ev, int64_t n, fl
         pi[t] = ev.r_pi[t];
 }
 
+// rvs_engine_drain_packed_async: min(ring_count, capacity) oldest samples -> caller buffers, count read on the device
+__global__ void __launch_bounds__(256) drain_packed_kernel(EngineView ev, int64_t capacity, uint64_t* __restrict__ black,
+                                                            uint64_t* __restrict__ white, uint8_t* __restrict__ side,
+                                                            int8_t* __restrict__ z, float* __restrict__ pi) {
+    unsigned long long cnt = *ev.ring_count;
+    if (cnt > (unsigned long long)ev.ring_cap) cnt = (unsigned long long)ev.ring_cap;
+    const int64_t n = (int64_t)cnt < capacity ? (int64_t)cnt : capacity;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n * 65; t += stride) {
+        pi[t] = ev.r_pi[t];
+        if (t < n) { black[t] = ev.r_black[t]; white[t] = ev.r_white[t]; side[t] = ev.r_side[t]; z[t] = ev.r_z[t]; }
+    }
+}
+// ... then the samples beyond `capacity` (rare: the caller sizes its buffers for a generation) move to the front of
+// the ring, chunk by chunk through one CTA so that overlapping ranges are safe, and the count is published
+__global__ void __launch_bounds__(1024) drain_commit_kernel(EngineView ev, int64_t capacity, int64_t* __restrict__ out_count) {
+    unsigned long long cnt = *ev.ring_count;
+    if (cnt > (unsigned long long)ev.ring_cap) cnt = (unsigned long long)ev.ring_cap;
+    const int64_t n = (int64_t)cnt < capacity ? (int64_t)cnt : capacity;
+    const int64_t rest = (int64_t)cnt - n;
+    for (int64_t base = 0; base < rest; base += blockDim.x) {  // forward move in chunks: dst < src, chunk-synchronous
+        const int64_t i = base + threadIdx.x;
+        uint64_t b = 0, w = 0; uint8_t sd = 0; int8_t zz = 0;
+        if (i < rest) { b = ev.r_black[n + i]; w = ev.r_white[n + i]; sd = ev.r_side[n + i]; zz = ev.r_z[n + i]; }
+        __syncthreads();
+        if (i < rest) { ev.r_black[i] = b; ev.r_white[i] = w; ev.r_side[i] = sd; ev.r_z[i] = zz; }
+        __syncthreads();
+    }
+    for (int64_t base = 0; base < rest * 65; base += blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        float v = 0.f;
+        if (i < rest * 65) v = ev.r_pi[n * 65 + i];
+        __syncthreads();
+        if (i < rest * 65) ev.r_pi[i] = v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        *ev.ring_count = (unsigned long long)rest;
+        *out_count = n;
+        __threadfence_system();
+    }
+}
+
 __global__ void reset_games_kernel(EngineView ev) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= ev.G) return;
     ev.black[g] = kStartBlack; ev.white[g] = kStartWhite; ev.side[g] = 1; ev.flags[g] = 0;
-    ev.game_id[g] = (uint64_t)g; ev.ply[g] = 0; ev.live[g] = 1; ev.finished[g] = 0; ev.n_nodes[g] = 0;
+    ev.game_id[g] = (uint64_t)g; ev.ply[g] = 0; ev.finished[g] = 0; ev.n_nodes[g] = 0;
+    ev.live[g] = (ev.game_limit == 0 || (uint64_t)g < ev.game_limit) ? 1 : 0;
 }
 
 // positions handed in by the caller: derive game_over / winner the way Board would have when the
 // game ended (neither side can move), so that root terminal handling matches mcts.py:567-575.
 template <int RULES>
 __global__ void set_positions_kernel(EngineView ev, const uint64_t* __restrict__ black, const uint64_t* __restrict__ white,
-                                     const uint8_t* __restrict__ side, int n) {
+                                     const uint8_t* __restrict__ side, int n, uint64_t epoch) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
     Board b{black[g], white[g], side[g], 0};
+    ev.game_id[g] = (uint64_t)g + epoch * (uint64_t)ev.G;
+    if ((b.side != 1 && b.side != 2) || (b.black & b.white)) {  // not a position: park the slot, count it
+        ev.black[g] = kStartBlack; ev.white[g] = kStartWhite; ev.side[g] = 1; ev.flags[g] = 0;
+        ev.ply[g] = 0; ev.live[g] = 0; ev.finished[g] = 0; ev.n_nodes[g] = 0;
+        atomicAdd(&ev.stats[ST_BADPOS], 1ULL);
+        return;
+    }
     if (board_legal<RULES>(b) == 0) {
         Board o = b; o.side = (uint8_t)(3 - b.side);
         if (board_legal<RULES>(o) == 0) {
@@ -618,13 +669,10 @@ int io_stage(rvs_engine* h, size_t bytes, void** out) {
 
 inline int games_grid(int G) { return (G + kWarpsPerBlock - 1) / kWarpsPerBlock; }
 
-// lanes per game of the wave-1 kernels (rvs_treeg.cuh): 4 by default, RVS_K1_LPG=8|2 for A/B measurements
+// lanes per game of the wave-1 kernels (rvs_treeg.cuh)
 inline int lanes_per_game(const rvs_engine* h) {
     const int G = h->v.G;
     if (h->lanes_per_game) return h->lanes_per_game;  // rvs_engine_set_lanes_per_game
-    const char* e = getenv("RVS_K1_LPG");  // read per call: tests switch it inside one process
-    const int forced = e ? atoi(e) : 0;
-    if (forced) return forced;
     // measured on B200: with few games the kernel is bound by the latency of one ply's
     // dependency chain, so more lanes per game (shorter per-lane chains, more warps) win; with many
     // games it is issue bound and fewer lanes per game (fewer instructions per game-ply) win
@@ -638,12 +686,6 @@ inline int lanes_per_game(const rvs_engine* h) {
         RVS_LAUNCH(__VA_ARGS__);           \
         (h)->launches++;                   \
     } while (0)
-
-int check_handle(rvs_engine* h) {
-    if (!h) return fail(-1, "null engine handle");
-    RVS_CUDA(cudaSetDevice(h->cfg.device));
-    return 0;
-}
 
 }  // namespace
 
@@ -661,7 +703,8 @@ int rvs_engine_create(const rvs_engine_config* cfg, rvs_engine** out) {
     if (e != cudaSuccess || ndev == 0)
         return fail(-2, "rvs_engine_create: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(-1, "rvs_engine_create: bad device %d", cfg->device);
-    RVS_CUDA(cudaSetDevice(cfg->device));
+    DeviceGuard dg;
+    if (int rc0 = dg.enter(cfg->device)) return rc0;
     rvs_engine* h = new (std::nothrow) rvs_engine();
     if (!h) return fail(-3, "out of host memory");
     h->cfg = *cfg;
@@ -673,6 +716,7 @@ int rvs_engine_create(const rvs_engine_config* cfg, rvs_engine** out) {
     v.noise_eps = 0.0f;
     v.noise_alpha = 0.0;
     v.seed = cfg->seed;
+    v.game_limit = 0;
     v.ring_cap = cfg->sample_capacity > 0 ? cfg->sample_capacity : (int64_t)64 * v.G;
     const size_t G = v.G, GK = G * v.kmax, GN = G * (size_t)v.cap;
     int rc = 0;
@@ -691,6 +735,11 @@ int rvs_engine_create(const rvs_engine_config* cfg, rvs_engine** out) {
         rvs_engine_destroy(h);
         return rc;
     }
+    if (cudaHostAlloc((void**)&h->pinned_count, 64, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        rvs_engine_destroy(h);
+        return fail(-3, "rvs_engine_create: cudaHostAlloc failed");
+    }
     reset_games_kernel<<<(v.G + 127) / 128, 128>>>(v);
     g_launches.fetch_add(1);
     h->launches++;
@@ -705,9 +754,11 @@ int rvs_engine_create(const rvs_engine_config* cfg, rvs_engine** out) {
 
 int rvs_engine_destroy(rvs_engine* h) {
     if (!h) return 0;
-    cudaSetDevice(h->cfg.device);
+    DeviceGuard dg;
+    dg.enter(h->cfg.device);
     cudaDeviceSynchronize();
     for (int i = 0; i < h->n_allocs; ++i) cudaFree(h->allocs[i]);
+    if (h->pinned_count) cudaFreeHost(h->pinned_count);
     if (h->io_stage) cudaFree(h->io_stage);
     if (h->ext_probs) cudaFree(h->ext_probs);
     if (h->ext_values) cudaFree(h->ext_values);
@@ -719,25 +770,32 @@ int rvs_engine_destroy(rvs_engine* h) {
 }
 
 int rvs_engine_reset(rvs_engine* h, void* stream) {
-    int rc = check_handle(h);
-    if (rc) return rc;
+    RVS_ENTER(h);
+    int rc = 0;
+    (void)rc;
     cudaStream_t s = (cudaStream_t)stream;
     RVS_ENGINE_LAUNCH(h, reset_games_kernel, (h->v.G + 127) / 128, 128, 0, s, h->v);
     RVS_CUDA(cudaMemsetAsync(h->v.ring_count, 0, 8, s));
     h->searching = false;
+    h->epoch = 0;
     return 0;
 }
 
 int rvs_engine_set_positions(rvs_engine* h, const uint64_t* black, const uint64_t* white, const uint8_t* side, int32_t n,
                              int mem, void* stream) {
-    int rc = check_handle(h);
-    if (rc) return rc;
+    RVS_ENTER(h);
+    int rc = 0;
     if (n < 0 || n > h->v.G || (n > 0 && (!black || !white || !side))) return fail(-1, "rvs_engine_set_positions: bad arguments");
+    if (mem < RVS_MEM_DEVICE || mem > RVS_MEM_HOST_ASYNC) return fail(-1, "rvs_engine_set_positions: bad mem %d", mem);
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     const uint64_t *db = black, *dw = white;
     const uint8_t* ds = side;
-    if (mem == RVS_MEM_HOST || mem == RVS_MEM_HOST_ASYNC) {
+    if (mem != RVS_MEM_DEVICE) {
+        for (int32_t i = 0; i < n; ++i)  // host inputs are validated before anything is uploaded
+            if ((side[i] != 1 && side[i] != 2) || (black[i] & white[i]))
+                return fail(-1, "rvs_engine_set_positions: position %d is invalid (side %d, %s)", i, (int)side[i],
+                            (black[i] & white[i]) ? "black and white discs overlap" : "side must be 1 or 2");
         void* st = nullptr;
         const size_t nb = (size_t)n * 8;
         if ((rc = io_stage(h, 2 * nb + n, &st))) return rc;
@@ -746,32 +804,38 @@ int rvs_engine_set_positions(rvs_engine* h, const uint64_t* black, const uint64_
         RVS_CUDA(cudaMemcpyAsync((char*)st + 2 * nb, side, n, cudaMemcpyHostToDevice, s));
         db = (const uint64_t*)st; dw = (const uint64_t*)((char*)st + nb); ds = (const uint8_t*)((char*)st + 2 * nb);
     }
+    const uint64_t epoch = h->epoch++;
     if (h->cfg.rules == RVS_RULES_STRICT)
-        RVS_ENGINE_LAUNCH(h, set_positions_kernel<RULES_STRICT>, (n + 127) / 128, 128, 0, s, h->v, db, dw, ds, n);
+        RVS_ENGINE_LAUNCH(h, set_positions_kernel<RULES_STRICT>, (n + 127) / 128, 128, 0, s, h->v, db, dw, ds, n, epoch);
     else
-        RVS_ENGINE_LAUNCH(h, set_positions_kernel<RULES_REF>, (n + 127) / 128, 128, 0, s, h->v, db, dw, ds, n);
+        RVS_ENGINE_LAUNCH(h, set_positions_kernel<RULES_REF>, (n + 127) / 128, 128, 0, s, h->v, db, dw, ds, n, epoch);
+    // pageable host memory: the staged copies above may still be reading the caller's arrays
+    if (mem == RVS_MEM_HOST) RVS_CUDA(cudaStreamSynchronize(s));
     h->searching = false;
     return 0;
 }
 
 int rvs_engine_get_positions(rvs_engine* h, uint64_t* black, uint64_t* white, uint8_t* side, uint8_t* flags, int32_t n,
                              int mem, void* stream) {
-    int rc = check_handle(h);
-    if (rc) return rc;
+    RVS_ENTER(h);
+    int rc = 0;
+    (void)rc;
     if (n < 0 || n > h->v.G) return fail(-1, "rvs_engine_get_positions: bad n");
     cudaStream_t s = (cudaStream_t)stream;
-    const cudaMemcpyKind kind = mem == RVS_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    const bool host = mem != RVS_MEM_DEVICE;
+    const cudaMemcpyKind kind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
     if (black) RVS_CUDA(cudaMemcpyAsync(black, h->v.black, (size_t)n * 8, kind, s));
     if (white) RVS_CUDA(cudaMemcpyAsync(white, h->v.white, (size_t)n * 8, kind, s));
     if (side) RVS_CUDA(cudaMemcpyAsync(side, h->v.side, n, kind, s));
     if (flags) RVS_CUDA(cudaMemcpyAsync(flags, h->v.flags, n, kind, s));
-    if (mem == RVS_MEM_HOST) RVS_CUDA(cudaStreamSynchronize(s));
+    if (host) RVS_CUDA(cudaStreamSynchronize(s));
     return 0;
 }
 
 int rvs_engine_search(rvs_engine* h, int32_t num_sims, int32_t wave, void* stream) {
-    int rc = check_handle(h);
-    if (rc) return rc;
+    RVS_ENTER(h);
+    int rc = 0;
+    (void)rc;
     if (num_sims < 1 || num_sims > h->cfg.max_sims) return fail(-1, "rvs_engine_search: num_sims %d outside [1,%d]", num_sims, h->cfg.max_sims);
     if (wave < 1 || wave > h->cfg.max_wave) return fail(-1, "rvs_engine_search: wave %d outside [1,%d]", wave, h->cfg.max_wave);
     cudaStream_t s = (cudaStream_t)stream;
@@ -818,8 +882,9 @@ int rvs_engine_search(rvs_engine* h, int32_t num_sims, int32_t wave, void* strea
 }
 
 int rvs_engine_begin_search(rvs_engine* h, void* stream) {
-    int rc = check_handle(h);
-    if (rc) return rc;
+    RVS_ENTER(h);
+    int rc = 0;
+    (void)rc;
     RVS_ENGINE_LAUNCH(h, begin_search_kernel, games_grid(h->v.G), kBlock, 0, (cudaStream_t)stream, h->v);
     h->searching = true;
     h->cur_k = 0;
@@ -828,8 +893,9 @@ int rvs_engine_begin_search(rvs_engine* h, void* stream) {
 }
 
 int rvs_engine_select(rvs_engine* h, int32_t k, void* stream) {
-    int rc = check_handle(h);
-    if (rc) return rc;
+    RVS_ENTER(h);
+    int rc = 0;
+    (void)rc;
     if (!h->searching) return fail(-1, "rvs_engine_select: call rvs_engine_begin_search first");
     if (k < 1 || k > h->cfg.max_wave) return fail(-1, "rvs_engine_select: k %d outside [1,%d]", k, h->cfg.max_wave);
     if (h->cur_k != 0) return fail(-1, "rvs_engine_select: previous wave not processed");
@@ -841,15 +907,16 @@ int rvs_engine_select(rvs_engine* h, int32_t k, void* stream) {
 }
 
 int rvs_engine_leaf_planes(rvs_engine* h, float* out_planes, uint8_t* out_valid, int mem, void* stream) {
-    int rc = check_handle(h);
-    if (rc) return rc;
+    RVS_ENTER(h);
+    int rc = 0;
+    (void)rc;
     if (h->cur_k == 0) return fail(-1, "rvs_engine_leaf_planes: no selected wave");
     if (!out_planes) return fail(-1, "rvs_engine_leaf_planes: null output");
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t slots = (int64_t)h->v.G * h->cur_k;
     float* dp = out_planes;
     uint8_t* dv = out_valid;
-    if (mem == RVS_MEM_HOST) {
+    if (mem != RVS_MEM_DEVICE) {
         const size_t need = (size_t)h->v.G * h->cfg.max_wave;
         if (!h->ext_planes) RVS_CUDA(cudaMalloc(&h->ext_planes, need * 192 * sizeof(float)));
         if (!h->ext_valid) RVS_CUDA(cudaMalloc(&h->ext_valid, need));
@@ -857,7 +924,7 @@ int rvs_engine_leaf_planes(rvs_engine* h, float* out_planes, uint8_t* out_valid,
         dv = h->ext_valid;
     }
     RVS_ENGINE_LAUNCH(h, leaf_planes_kernel, grid_for(slots * 48, 256), 256, 0, s, h->v, h->cur_k, (float4*)dp, dv);
-    if (mem == RVS_MEM_HOST) {
+    if (mem != RVS_MEM_DEVICE) {
         RVS_CUDA(cudaMemcpyAsync(out_planes, dp, slots * 192 * sizeof(float), cudaMemcpyDeviceToHost, s));
         if (out_valid) RVS_CUDA(cudaMemcpyAsync(out_valid, dv, slots, cudaMemcpyDeviceToHost, s));
         RVS_CUDA(cudaStreamSynchronize(s));
@@ -866,14 +933,15 @@ int rvs_engine_leaf_planes(rvs_engine* h, float* out_planes, uint8_t* out_valid,
 }
 
 int rvs_engine_process(rvs_engine* h, const float* probs, const float* values, int mem, void* stream) {
-    int rc = check_handle(h);
-    if (rc) return rc;
+    RVS_ENTER(h);
+    int rc = 0;
+    (void)rc;
     if (h->cur_k == 0) return fail(-1, "rvs_engine_process: no selected wave");
     if (!probs || !values) return fail(-1, "rvs_engine_process: null input");
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t slots = (int64_t)h->v.G * h->cur_k;
     const float *dp = probs, *dv = values;
-    if (mem == RVS_MEM_HOST) {
+    if (mem != RVS_MEM_DEVICE) {
         const size_t need = (size_t)h->v.G * h->cfg.max_wave;
         if (!h->ext_probs) RVS_CUDA(cudaMalloc(&h->ext_probs, need * 65 * sizeof(float)));
         if (!h->ext_values) RVS_CUDA(cudaMalloc(&h->ext_values, need * sizeof(float)));
@@ -889,8 +957,9 @@ int rvs_engine_process(rvs_engine* h, const float* probs, const float* values, i
 }
 
 int rvs_engine_root_visits(rvs_engine* h, int32_t* out, int32_t n, int mem, void* stream) {
-    int rc = check_handle(h);
-    if (rc) return rc;
+    RVS_ENTER(h);
+    int rc = 0;
+    (void)rc;
     if (!out || n < 0 || n > h->v.G) return fail(-1, "rvs_engine_root_visits: bad arguments");
     if (n == 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
@@ -905,15 +974,16 @@ int rvs_engine_root_visits(rvs_engine* h, int32_t* out, int32_t n, int mem, void
 }
 
 int rvs_engine_play(rvs_engine* h, float temperature, int recycle, uint8_t* out_moves, int mem, void* stream) {
-    int rc = check_handle(h);
-    if (rc) return rc;
+    RVS_ENTER(h);
+    int rc = 0;
+    (void)rc;
     if (temperature < 0.0f) return fail(-1, "rvs_engine_play: negative temperature");
     cudaStream_t s = (cudaStream_t)stream;
-    uint8_t* dm = out_moves ? (mem == RVS_MEM_HOST ? h->moves : out_moves) : nullptr;
+    uint8_t* dm = out_moves ? (mem != RVS_MEM_DEVICE ? h->moves : out_moves) : nullptr;
     if (h->cfg.rules == RVS_RULES_STRICT) RVS_ENGINE_LAUNCH(h, play_kernel<RULES_STRICT>, (h->v.G + 127) / 128, 128, 0, s, h->v, temperature, dm);
     else RVS_ENGINE_LAUNCH(h, play_kernel<RULES_REF>, (h->v.G + 127) / 128, 128, 0, s, h->v, temperature, dm);
     RVS_ENGINE_LAUNCH(h, finalize_kernel, games_grid(h->v.G), kBlock, 0, s, h->v, recycle);
-    if (out_moves && mem == RVS_MEM_HOST) {
+    if (out_moves && mem != RVS_MEM_DEVICE) {
         RVS_CUDA(cudaMemcpyAsync(out_moves, dm, h->v.G, cudaMemcpyDeviceToHost, s));
         RVS_CUDA(cudaStreamSynchronize(s));
     }
@@ -922,8 +992,9 @@ int rvs_engine_play(rvs_engine* h, float temperature, int recycle, uint8_t* out_
 }
 
 int rvs_engine_selfplay(rvs_engine* h, int32_t num_sims, float temperature, int64_t plies, int recycle, void* stream) {
-    int rc = check_handle(h);
-    if (rc) return rc;
+    RVS_ENTER(h);
+    int rc = 0;
+    (void)rc;
     if (num_sims < 1 || num_sims > h->cfg.max_sims) return fail(-1, "rvs_engine_selfplay: num_sims %d outside [1,%d]", num_sims, h->cfg.max_sims);
     if (plies < 0 || temperature < 0.0f) return fail(-1, "rvs_engine_selfplay: bad arguments");
     if (h->cfg.evaluator == RVS_EVAL_NN) {
@@ -963,23 +1034,32 @@ int rvs_engine_selfplay(rvs_engine* h, int32_t num_sims, float temperature, int6
     return 0;
 }
 
+// number of completed samples waiting in the ring, through the handle's pinned word (the copy is ordered after
+// everything enqueued on `s`, so the host waits for exactly the work the samples depend on and nothing else)
+static int ring_pending(rvs_engine* h, cudaStream_t s, int64_t* n) {
+    RVS_CUDA(cudaMemcpyAsync(h->pinned_count, h->v.ring_count, 8, cudaMemcpyDeviceToHost, s));
+    RVS_CUDA(cudaStreamSynchronize(s));
+    const unsigned long long cnt = *h->pinned_count;
+    *n = (int64_t)cnt < h->v.ring_cap ? (int64_t)cnt : h->v.ring_cap;
+    return 0;
+}
+
 int rvs_engine_drain_samples(rvs_engine* h, float* states, float* pi, float* z, int64_t capacity, int64_t* out_count,
                              int mem, void* stream) {
-    int rc = check_handle(h);
-    if (rc) return rc;
+    RVS_ENTER(h);
+    int rc = 0;
     if (!out_count) return fail(-1, "rvs_engine_drain_samples: null out_count");
     cudaStream_t s = (cudaStream_t)stream;
-    unsigned long long cnt = 0;
-    RVS_CUDA(cudaMemcpyAsync(&cnt, h->v.ring_count, 8, cudaMemcpyDeviceToHost, s));
-    RVS_CUDA(cudaStreamSynchronize(s));
-    int64_t n = (int64_t)cnt < h->v.ring_cap ? (int64_t)cnt : h->v.ring_cap;
+    int64_t n = 0;
+    if ((rc = ring_pending(h, s, &n))) return rc;
     *out_count = n;
     if (n == 0) return 0;
     if (!states || !pi || !z) return fail(-1, "rvs_engine_drain_samples: null output");
     if (capacity < n) return fail(-4, "rvs_engine_drain_samples: capacity %lld < %lld samples pending", (long long)capacity, (long long)n);
+    const bool host = mem != RVS_MEM_DEVICE;
     float *ds = states, *dp = pi, *dz = z;
     const size_t bs = (size_t)n * 192 * 4, bp = (size_t)n * 65 * 4, bz = (size_t)n * 4;
-    if (mem == RVS_MEM_HOST) {
+    if (host) {
         void* st = nullptr;
         if ((rc = io_stage(h, bs + bp + bz, &st))) return rc;
         ds = (float*)st; dp = (float*)((char*)st + bs); dz = (float*)((char*)st + bs + bp);
@@ -988,7 +1068,7 @@ int rvs_engine_drain_samples(rvs_engine* h, float* states, float* pi, float* z, 
     if (h->cfg.rules == RVS_RULES_STRICT) RVS_ENGINE_LAUNCH(h, drain_kernel<RULES_STRICT>, grid, 256, 0, s, h->v, n, (float4*)ds, dp, dz);
     else RVS_ENGINE_LAUNCH(h, drain_kernel<RULES_REF>, grid, 256, 0, s, h->v, n, (float4*)ds, dp, dz);
     RVS_CUDA(cudaMemsetAsync(h->v.ring_count, 0, 8, s));
-    if (mem == RVS_MEM_HOST) {
+    if (host) {
         RVS_CUDA(cudaMemcpyAsync(states, ds, bs, cudaMemcpyDeviceToHost, s));
         RVS_CUDA(cudaMemcpyAsync(pi, dp, bp, cudaMemcpyDeviceToHost, s));
         RVS_CUDA(cudaMemcpyAsync(z, dz, bz, cudaMemcpyDeviceToHost, s));
@@ -999,14 +1079,12 @@ int rvs_engine_drain_samples(rvs_engine* h, float* states, float* pi, float* z, 
 
 int rvs_engine_drain_packed(rvs_engine* h, uint64_t* black, uint64_t* white, uint8_t* side, int8_t* z, float* pi,
                             int64_t capacity, int64_t* out_count, int mem, void* stream) {
-    int rc = check_handle(h);
-    if (rc) return rc;
+    RVS_ENTER(h);
+    int rc = 0;
     if (!out_count) return fail(-1, "rvs_engine_drain_packed: null out_count");
     cudaStream_t s = (cudaStream_t)stream;
-    unsigned long long cnt = 0;
-    RVS_CUDA(cudaMemcpyAsync(&cnt, h->v.ring_count, 8, cudaMemcpyDeviceToHost, s));
-    RVS_CUDA(cudaStreamSynchronize(s));
-    const int64_t n = (int64_t)cnt < h->v.ring_cap ? (int64_t)cnt : h->v.ring_cap;
+    int64_t n = 0;
+    if ((rc = ring_pending(h, s, &n))) return rc;
     *out_count = n;
     if (n == 0) return 0;
     if (!black || !white || !side || !z || !pi) return fail(-1, "rvs_engine_drain_packed: null output");
@@ -1022,17 +1100,61 @@ int rvs_engine_drain_packed(rvs_engine* h, uint64_t* black, uint64_t* white, uin
     return 0;
 }
 
+int rvs_engine_drain_packed_async(rvs_engine* h, uint64_t* black, uint64_t* white, uint8_t* side, int8_t* z, float* pi,
+                                  int64_t capacity, int64_t* out_count_dev, void* stream) {
+    RVS_ENTER(h);
+    if (!out_count_dev || !black || !white || !side || !z || !pi || capacity < 0)
+        return fail(-1, "rvs_engine_drain_packed_async: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    // two launches: the copy reads the count, the second kernel moves the remainder to the front and
+    // publishes the count -- nothing visits the host
+    RVS_ENGINE_LAUNCH(h, drain_packed_kernel, grid_for(capacity * 17, 256), 256, 0, s, h->v, capacity, black, white, side, z, pi);
+    RVS_ENGINE_LAUNCH(h, drain_commit_kernel, 1, 1024, 0, s, h->v, capacity, out_count_dev);
+    return 0;
+}
+
 int rvs_engine_set_lanes_per_game(rvs_engine* h, int32_t lanes) {
-    int rc = check_handle(h);
-    if (rc) return rc;
+    RVS_ENTER(h);
+    int rc = 0;
+    (void)rc;
     if (lanes != 0 && lanes != 2 && lanes != 4 && lanes != 8) return fail(-1, "rvs_engine_set_lanes_per_game: %d not in {0, 2, 4, 8}", lanes);
     h->lanes_per_game = lanes;
     return 0;
 }
 
+int rvs_engine_set_option(rvs_engine* h, int32_t option, int64_t value) {
+    RVS_ENTER(h);
+    switch (option) {
+    case RVS_OPT_LANES_PER_GAME:
+        return rvs_engine_set_lanes_per_game(h, (int32_t)value);
+    case RVS_OPT_NET_GRAPH:
+        h->net_graph = value != 0;
+        return 0;
+    case RVS_OPT_SEARCH_MODE:
+        if (value != RVS_MODE_REF && value != RVS_MODE_FAST) return fail(-1, "rvs_engine_set_option: search mode %lld not in {REF, FAST}", (long long)value);
+        h->search_mode = (int)value;
+        return 0;
+    case RVS_OPT_GAME_LIMIT:
+        if (value < 0 || (value > 0 && value < h->v.G))
+            return fail(-1, "rvs_engine_set_option: game limit %lld must be 0 or >= n_games (%d)", (long long)value, h->v.G);
+        h->v.game_limit = (uint64_t)value;
+        return 0;
+    case RVS_OPT_NET_MAX_CTAS:
+        if (value < 0 || value > kNumSMs) return fail(-1, "rvs_engine_set_option: net_max_ctas %lld outside [0,%d]", (long long)value, kNumSMs);
+        h->net_max_ctas = (int)value;
+        return 0;
+    case RVS_OPT_NET_PIPELINE:
+        h->net_pipeline = value != 0;
+        return 0;
+    default:
+        return fail(-1, "rvs_engine_set_option: unknown option %d", option);
+    }
+}
+
 int rvs_engine_set_root_noise(rvs_engine* h, double alpha, float epsilon) {
-    int rc = check_handle(h);
-    if (rc) return rc;
+    RVS_ENTER(h);
+    int rc = 0;
+    (void)rc;
     if (!(epsilon >= 0.0f && epsilon <= 1.0f)) return fail(-1, "rvs_engine_set_root_noise: epsilon %g outside [0,1]", (double)epsilon);
     if (epsilon > 0.0f && !(alpha >= 1e-3 && alpha <= 1e3)) return fail(-1, "rvs_engine_set_root_noise: alpha %g outside [1e-3,1e3]", alpha);
     h->v.noise_alpha = alpha;
@@ -1041,14 +1163,13 @@ int rvs_engine_set_root_noise(rvs_engine* h, double alpha, float epsilon) {
 }
 
 int rvs_engine_stats_get(rvs_engine* h, rvs_engine_stats* out, void* stream) {
-    int rc = check_handle(h);
-    if (rc) return rc;
+    RVS_ENTER(h);
+    int rc = 0;
+    (void)rc;
     if (!out) return fail(-1, "rvs_engine_stats_get: null output");
     cudaStream_t s = (cudaStream_t)stream;
     unsigned long long st[ST_COUNT];
     RVS_CUDA(cudaMemcpyAsync(st, h->v.stats, sizeof(st), cudaMemcpyDeviceToHost, s));
-    int nn[1] = {0};
-    (void)nn;
     RVS_CUDA(cudaStreamSynchronize(s));
     out->sims = (int64_t)st[ST_SIMS];
     out->evals = (int64_t)st[ST_EVALS];
@@ -1062,14 +1183,16 @@ int rvs_engine_stats_get(rvs_engine* h, rvs_engine_stats* out, void* stream) {
     out->samples_dropped = (int64_t)st[ST_DROPPED];
     out->stalled = (int64_t)st[ST_STALLED];
     out->nn_evals = (int64_t)st[ST_NNEVALS];
+    out->bad_positions = (int64_t)st[ST_BADPOS];
     return 0;
 }
 
 }  // extern "C"
 
 int rvs_engine_process_mapped(rvs_engine* h, const float* probs, const float* values, const int* inv, cudaStream_t s) {
-    int rc = check_handle(h);
-    if (rc) return rc;
+    RVS_ENTER(h);
+    int rc = 0;
+    (void)rc;
     if (h->cur_k == 0) return fail(-1, "rvs_engine_process: no selected wave");
     RVS_ENGINE_LAUNCH(h, process_probs_kernel, games_grid(h->v.G), kBlock, 0, s, h->v, h->cur_k, probs, values, h->waves_done == 0 ? 1 : 0, inv);
     h->waves_done++;

@@ -8,7 +8,7 @@
 
 namespace rvs {
 
-enum : int { ST_SIMS = 0, ST_EVALS, ST_STEPS, ST_FINISHED, ST_SAMPLES, ST_OVERFLOW, ST_DROPPED, ST_STALLED, ST_BYTES, ST_NODES, ST_NNEVALS, ST_COUNT };
+enum : int { ST_SIMS = 0, ST_EVALS, ST_STEPS, ST_FINISHED, ST_SAMPLES, ST_OVERFLOW, ST_DROPPED, ST_STALLED, ST_BYTES, ST_NODES, ST_NNEVALS, ST_BADPOS, ST_COUNT };
 
 struct NetState;  // rvs_net.cu
 
@@ -19,6 +19,7 @@ struct EngineView {
     float noise_eps;     // Dirichlet root noise (rvs_noise.cuh); 0 = off
     double noise_alpha;
     uint64_t seed;
+    uint64_t game_limit;  // self-play: a slot restarts only while its next game id < game_limit (0 = unlimited)
     // game state per slot
     uint64_t* black; uint64_t* white; uint8_t* side; uint8_t* flags;
     uint64_t* game_id; int* ply; uint8_t* live; uint8_t* finished;
@@ -66,6 +67,12 @@ struct rvs_engine {
     rvs::EngineView v;
     int cur_k = 0;          // wave size of the last select (external path)
     int lanes_per_game = 0; // wave-1 kernels: 0 = choose by the number of games (rvs_engine_set_lanes_per_game)
+    int search_mode = 0;    // RVS_MODE_REF / RVS_MODE_FAST (RVS_OPT_SEARCH_MODE)
+    int net_graph = 0;      // RVS_OPT_NET_GRAPH
+    int net_max_ctas = 0;   // RVS_OPT_NET_MAX_CTAS
+    int net_pipeline = 1;   // RVS_OPT_NET_PIPELINE
+    uint64_t epoch = 0;     // set_positions calls since create / reset: game id of slot g = g + epoch * G
+    unsigned long long* pinned_count = nullptr;  // pinned host word for the sample count of the synchronous drains
     int waves_done = 0;     // waves processed since begin_search (root noise goes in after the first)
     bool searching = false;
     float* ext_probs = nullptr;   // staging for host-side probs/values/planes of the external path
@@ -81,6 +88,33 @@ struct rvs_engine {
     void* allocs[64];
     int n_allocs = 0;
 };
+
+namespace rvs {
+// restores the caller's current CUDA device when an entry point returns (a torchrun rank that called
+// torch.cuda.set_device(r) must not find its device switched by a handle that lives elsewhere)
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    int enter(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev != dev) {
+            cudaError_t e = cudaSetDevice(dev);
+            if (e != cudaSuccess) return fail(-100 - (int)e, "cudaSetDevice(%d) failed: %s", dev, cudaGetErrorString(e));
+            switched = true;
+        }
+        return 0;
+    }
+    ~DeviceGuard() {
+        if (switched && prev >= 0) cudaSetDevice(prev);
+    }
+};
+}  // namespace rvs
+
+// every engine entry point starts with this: validates the handle and makes its device current for the call
+#define RVS_ENTER(h)                                             \
+    if (!(h)) return ::rvs::fail(-1, "null engine handle");      \
+    ::rvs::DeviceGuard _dg;                                      \
+    if (int _rc = _dg.enter((h)->cfg.device)) return _rc
 
 // K4 hooks implemented in rvs_net.cu
 int rvs_net_search(rvs_engine* h, int32_t num_sims, int32_t wave, cudaStream_t s);

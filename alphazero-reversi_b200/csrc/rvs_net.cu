@@ -3,8 +3,8 @@
 //
 // Data layout: activations NHWC bf16 [B][8][8][C]; conv weights BN-folded bf16 [tap][Cout][Cin]
 // (tap = ky*3+kx, K-major for both GEMM operands); biases and the two small heads in f32.
-//   conv_tower_*     3x3 convolutions C->C: implicit GEMM on tcgen05 (rvs_conv_tc.cuh)
-//   conv3x3_direct   first layer (3->C, K = 27) and bring-up/debug path: CUDA cores
+//   conv3x3_tc2*     3x3 convolutions C->C: implicit GEMM on tcgen05 (rvs_conv_tc.cu)
+//   conv0_bits       first layer (3->C, K = 27) for 64 / 256 filters: CUDA cores, fused with the leaf encoding
 //   heads_kernel     policy 1x1 conv + FC + softmax, value 1x1 conv + FC + FC + tanh (fp32)
 #include "rvs_engine.cuh"
 
@@ -45,10 +45,9 @@ struct NetState {
     __nv_bfloat16 *a = nullptr, *b = nullptr, *c = nullptr;  // [tile][y][board][x][C] (act_row)
     float *probs = nullptr, *logits = nullptr, *values = nullptr;          // [B][65], [B][65], [B]
     float* feat = nullptr;                   // [B][192] head planes written by the fused last-layer epilogue
-    float head_host[3 * 256 + 4];            // host copy of the folded 1x1 head weights [3][C] + 3 biases
+    ConvHeadW head;                          // folded 1x1 head weights of THIS network for the fused last-layer epilogue
     float* flat = nullptr;  // staging of the raw state_dict
     bool loaded = false;
-    bool force_direct = false;  // RVS_NET_DIRECT=1: run the tower on the CUDA-core kernel (debug)
     std::vector<void*> allocs;  // 2 per tower layer: 80 for the 20-block network
     // one wave of the NN search (select -> encode -> tower -> heads -> expand/backup, ~16 launches) captured
     // as a CUDA graph and replayed for the remaining waves of a search
@@ -98,73 +97,6 @@ __global__ void fold_conv1x1_kernel(const float* __restrict__ w, const float* __
         const float scale = gamma[co] / sqrtf(var[co] + 1e-5f);
         wf[t] = w[t] * scale;
         if (t % cin == 0) bias[co] = beta[co] - mean[co] * scale;
-    }
-}
-
-// ---- direct 3x3 convolution on CUDA cores ----------------------------------------------------
-// one CTA per board: the board's input (with a zero halo) lives in shared memory; thread t owns
-// output channel (t % COUT_T) and a group of pixels; weights stream from L2 as 16-byte vectors.
-// out = relu(conv(in) + bias [+ residual])
-template <int CIN, bool PLAIN_IN>
-__global__ void __launch_bounds__(256) conv3x3_direct_kernel(const __nv_bfloat16* __restrict__ in,
-                                                              const __nv_bfloat16* __restrict__ w,
-                                                              const float* __restrict__ bias,
-                                                              const __nv_bfloat16* __restrict__ residual,
-                                                              __nv_bfloat16* __restrict__ out, int cout, int relu) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __nv_bfloat16* sx = reinterpret_cast<__nv_bfloat16*>(smem_raw);  // [10][10][CIN]
-    const int board = blockIdx.x;
-    const uint4* gin = reinterpret_cast<const uint4*>(in);
-    constexpr int V = CIN / 8;  // uint4 per pixel
-    for (int i = threadIdx.x; i < 100 * V; i += blockDim.x) {
-        const int p = i / V, v = i % V;
-        const int y = p / 10 - 1, x = p % 10 - 1;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (y >= 0 && y < 8 && x >= 0 && x < 8) {
-            const size_t row = PLAIN_IN ? (size_t)board * 64 + (y * 8 + x) : act_row(board, y * 8 + x);
-            val = gin[row * V + v];
-        }
-        reinterpret_cast<uint4*>(sx)[i] = val;
-    }
-    __syncthreads();
-    const int groups = blockDim.x / cout;  // cout in {64,128,256} -> 4, 2 or 1 pixel groups
-    const int co = threadIdx.x % cout, grp = threadIdx.x / cout;
-    const int ppg = 64 / groups;           // pixels per group
-    {
-        for (int p0 = grp * ppg; p0 < (grp + 1) * ppg; p0 += 16) {
-            float acc[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-            for (int tap = 0; tap < 9; ++tap) {
-                const int dy = tap / 3, dx = tap % 3;  // halo-shifted: input (y+dy, x+dx) in padded coords
-                const uint4* wrow = reinterpret_cast<const uint4*>(w + ((size_t)tap * cout + co) * CIN);
-                for (int v = 0; v < V; ++v) {
-                    const uint4 wv = wrow[v];
-                    const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&wv);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int p = p0 + i, y = p >> 3, x = p & 7;
-                        const uint4 xv = reinterpret_cast<const uint4*>(sx)[((y + dy) * 10 + (x + dx)) * V + v];
-                        const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(&xv);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float2 a = __bfloat1622float2(x2[q]), b = __bfloat1622float2(w2[q]);
-                            acc[i] = fmaf(a.x, b.x, acc[i]);
-                            acc[i] = fmaf(a.y, b.y, acc[i]);
-                        }
-                    }
-                }
-            }
-            const float bv = bias[co];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const size_t o = act_row(board, p0 + i) * cout + co;
-                float r = acc[i] + bv;
-                if (residual) r += __bfloat162float(residual[o]);
-                if (relu) r = fmaxf(r, 0.f);
-                out[o] = __float2bfloat16(r);
-            }
-        }
     }
 }
 
@@ -425,29 +357,6 @@ __global__ void __launch_bounds__(256) encode_positions_kernel(const uint64_t* _
     }
 }
 
-int launch_direct(const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
-                  int64_t B, int relu, cudaStream_t s) {
-    const int threads = 256;
-    if (L.cout > 256 || 256 % L.cout != 0) return fail(-6, "direct conv: unsupported cout %d", L.cout);
-    if (L.cin == 16) {
-        RVS_LAUNCH((conv3x3_direct_kernel<16, true>), (int)B, threads, 100 * 16 * 2, s, in, L.w, L.bias, residual, out, L.cout, relu);
-    } else if (L.cin == 64) {
-        RVS_LAUNCH((conv3x3_direct_kernel<64, false>), (int)B, threads, 100 * 64 * 2, s, in, L.w, L.bias, residual, out, L.cout, relu);
-    } else if (L.cin == 128) {
-        RVS_LAUNCH((conv3x3_direct_kernel<128, false>), (int)B, threads, 100 * 128 * 2, s, in, L.w, L.bias, residual, out, L.cout, relu);
-    } else if (L.cin == 256) {
-        static bool attr = false;
-        if (!attr) {
-            RVS_CUDA(cudaFuncSetAttribute(conv3x3_direct_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 256 * 2));
-            attr = true;
-        }
-        RVS_LAUNCH((conv3x3_direct_kernel<256, false>), (int)B, threads, 100 * 256 * 2, s, in, L.w, L.bias, residual, out, L.cout, relu);
-    } else {
-        return fail(-6, "direct conv: unsupported cin %d", L.cin);
-    }
-    return 0;
-}
-
 }  // namespace
 
 // forward pass on B boards whose bit planes are already in n->bits; results in n->probs/logits/values
@@ -457,7 +366,7 @@ int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s, cons
     if (B > n->max_batch) return fail(-7, "network batch %lld exceeds capacity %lld", (long long)B, (long long)n->max_batch);
     if (B == 0) return 0;
     int rc;
-    if (!n->force_direct && n->conv0.tc.valid) {  // first layer on the tensor cores: planes -> bf16 tiles -> tcgen05
+    if (n->conv0.tc.valid) {  // first layer on the tensor cores: planes -> bf16 tiles -> tcgen05
         const int64_t tiles = (B + 1) / 2;
         RVS_LAUNCH(planes_tiles_kernel, grid_for(tiles * 128, 256), 256, 0, s, n->bits, B, tiles, (uint4*)n->x0, n_dev);
         if ((rc = conv_tc_launch(n->conv0.tc, n->x0, nullptr, n->a, n->conv0.bias, B, s, nullptr, nullptr, n_dev))) return rc;
@@ -472,16 +381,11 @@ int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s, cons
     for (int i = 0; i < n->blocks; ++i) {  // ResBlock (network.py:23-28)
         const ConvLayer& c1 = n->tower[2 * i];
         const ConvLayer& c2 = n->tower[2 * i + 1];
-        if (n->force_direct || !c1.tc.valid) {
-            if ((rc = launch_direct(c1, x, nullptr, t, B, 1, s))) return rc;
-            if ((rc = launch_direct(c2, t, x, y, B, 1, s))) return rc;
-        } else {
-            if ((rc = conv_tc_launch(c1.tc, x, nullptr, t, c1.bias, B, s, nullptr, nullptr, n_dev))) return rc;
-            if (i == n->blocks - 1 && conv_tc_can_fuse_head(c2.tc)) {  // last layer: heads' 1x1 convs in the epilogue
-                if ((rc = conv_tc_launch(c2.tc, t, x, y, c2.bias, B, s, n->head_host, n->feat, n_dev))) return rc;
-                fused_head = true;
-            } else if ((rc = conv_tc_launch(c2.tc, t, x, y, c2.bias, B, s, nullptr, nullptr, n_dev))) return rc;
-        }
+        if ((rc = conv_tc_launch(c1.tc, x, nullptr, t, c1.bias, B, s, nullptr, nullptr, n_dev))) return rc;
+        if (i == n->blocks - 1 && conv_tc_can_fuse_head(c2.tc)) {  // last layer: heads' 1x1 convs in the epilogue
+            if ((rc = conv_tc_launch(c2.tc, t, x, y, c2.bias, B, s, &n->head, n->feat, n_dev))) return rc;
+            fused_head = true;
+        } else if ((rc = conv_tc_launch(c2.tc, t, x, y, c2.bias, B, s, nullptr, nullptr, n_dev))) return rc;
         __nv_bfloat16* tmp = x; x = y; y = tmp;
     }
     RVS_LAUNCH(heads_kernel, (int)((B + kHB - 1) / kHB), 256, 0, s, x, fused_head ? n->feat : (const float*)nullptr, n->C, B, n->pw, n->pb, n->pfw, n->pfb, n->vw, n->vb, n->v1w, n->v1b,
@@ -499,7 +403,6 @@ int net_create(rvs_engine* h) {
     n->blocks = blocks;
     n->C = C;
     n->max_batch = (int64_t)h->v.G * h->cfg.max_wave;
-    n->force_direct = getenv("RVS_NET_DIRECT") && atoi(getenv("RVS_NET_DIRECT")) != 0;
     const size_t B = (size_t)((n->max_batch + 1) / 2) * 2;  // whole tiles of two boards
     int rc = 0;
     n->tower = new ConvLayer[2 * blocks];
@@ -561,8 +464,8 @@ static int net_wave(rvs_engine* h, int k, cudaStream_t s) {
 
 // MCTS.search with the built-in network: per wave  select -> encode (K3) -> tower + heads (K4)
 // -> expand/backup with the softmax priors (K2).  No host round trip inside the loop.  Optionally
-// (RVS_NET_GRAPH=1) the first wave (root expansion, root noise, one-time kernel setup) is launched
-// directly and the following full waves replay one captured CUDA graph.
+// the first wave (root expansion, root noise, one-time kernel setup) is launched
+// directly and the following full waves replay one captured CUDA graph (RVS_OPT_NET_GRAPH).
 int rvs_net_search(rvs_engine* h, int32_t num_sims, int32_t wave, cudaStream_t s) {
     int rc;
     if ((rc = net_create(h))) return rc;
@@ -570,9 +473,8 @@ int rvs_net_search(rvs_engine* h, int32_t num_sims, int32_t wave, cudaStream_t s
     if (!n->loaded) return fail(-7, "RVS_EVAL_NN: call rvs_engine_load_weights before rvs_engine_search");
     if ((rc = rvs_engine_begin_search(h, s))) return rc;
     // Measured on B200 (5x128, 4096 games, 100 waves): 81.5 ms with the graph, 80.1 ms with plain launches --
-    // the wave loop is not launch bound (PDL already chains the tower), so replay is opt-in: RVS_NET_GRAPH=1
-    const char* ge = getenv("RVS_NET_GRAPH");
-    const bool use_graph = ge && atoi(ge) != 0;
+    // the wave loop is not launch bound (PDL already chains the tower), so replay is opt-in
+    const bool use_graph = h->net_graph != 0;  // RVS_OPT_NET_GRAPH
     for (int start = 0; start < num_sims; start += wave) {
         const int k = num_sims - start < wave ? num_sims - start : wave;
         const bool replayable = use_graph && n->graph_ok && start > 0 && k == wave && num_sims / wave >= 4;
@@ -626,8 +528,7 @@ int rvs_net_search(rvs_engine* h, int32_t num_sims, int32_t wave, cudaStream_t s
 extern "C" {
 
 int rvs_engine_load_weights(rvs_engine* h, const float* flat, int64_t n_floats, int mem, void* stream) {
-    if (!h) return fail(-1, "null engine handle");
-    RVS_CUDA(cudaSetDevice(h->cfg.device));
+    RVS_ENTER(h);
     int rc;
     if ((rc = net_create(h))) return rc;
     NetState* n = h->net;
@@ -641,7 +542,7 @@ int rvs_engine_load_weights(rvs_engine* h, const float* flat, int64_t n_floats, 
         n->wave_exec = nullptr;
     }
     if (!n->flat) RVS_CUDA(cudaMalloc(&n->flat, need * sizeof(float)));
-    RVS_CUDA(cudaMemcpyAsync(n->flat, flat, need * sizeof(float), mem == RVS_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
+    RVS_CUDA(cudaMemcpyAsync(n->flat, flat, need * sizeof(float), mem != RVS_MEM_DEVICE ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s));
     const float* p = n->flat;
     auto take = [&](int64_t k) { const float* q = p; p += k; return q; };
     {
@@ -674,35 +575,44 @@ int rvs_engine_load_weights(rvs_engine* h, const float* flat, int64_t n_floats, 
     for (int i = 0; i < 2 * blocks; ++i) {
         if ((rc = conv_tc_plan(n->tower[i].tc, n->tower[i].w, C, n->max_batch))) return rc;
     }
-    if (C == 128 && !(getenv("RVS_CONV_1SM") && atoi(getenv("RVS_CONV_1SM")) != 0)) {
+    if (C == 128) {  // 128 filters: the first layer runs on the tensor cores too (64 -> 128 variant, one K = 16 step per tap)
         if ((rc = conv_tc_plan(n->conv0.tc, n->conv0.w, C, n->max_batch, 64))) return rc;
     }
     RVS_CUDA(cudaStreamSynchronize(s));
-    // host copy of the folded 1x1 head weights for the fused last-layer epilogue (kernel parameter)
-    RVS_CUDA(cudaMemcpy(n->head_host, n->pw, (size_t)2 * C * 4, cudaMemcpyDeviceToHost));
-    RVS_CUDA(cudaMemcpy(n->head_host + 2 * C, n->vw, (size_t)C * 4, cudaMemcpyDeviceToHost));
-    RVS_CUDA(cudaMemcpy(n->head_host + 3 * C, n->pb, 8, cudaMemcpyDeviceToHost));
-    RVS_CUDA(cudaMemcpy(n->head_host + 3 * C + 2, n->vb, 4, cudaMemcpyDeviceToHost));
+    if (C <= 128) {  // host copy of the folded 1x1 head weights for the fused last-layer epilogue (kernel parameter)
+        float hw[3 * 128 + 4];
+        RVS_CUDA(cudaMemcpy(hw, n->pw, (size_t)2 * C * 4, cudaMemcpyDeviceToHost));
+        RVS_CUDA(cudaMemcpy(hw + 2 * C, n->vw, (size_t)C * 4, cudaMemcpyDeviceToHost));
+        RVS_CUDA(cudaMemcpy(hw + 3 * C, n->pb, 8, cudaMemcpyDeviceToHost));
+        RVS_CUDA(cudaMemcpy(hw + 3 * C + 2, n->vb, 4, cudaMemcpyDeviceToHost));
+        for (int j = 0; j < 3; ++j)
+            for (int c = 0; c < 128; ++c) n->head.w[j][c] = c < C ? hw[j * C + c] : 0.f;
+        for (int j = 0; j < 3; ++j) n->head.b[j] = hw[3 * C + j];
+        n->head.b[3] = 0.f;
+    }
     n->loaded = true;
     return 0;
 }
 
-int rvs_engine_predict(rvs_engine* h, const uint64_t* black, const uint64_t* white, const uint8_t* side, int64_t n_pos,
-                       float* out_logits, float* out_value, int mem, void* stream) {
-    if (!h) return fail(-1, "null engine handle");
-    RVS_CUDA(cudaSetDevice(h->cfg.device));
-    if (!h->net || !h->net->loaded) return fail(-7, "rvs_engine_predict: weights not loaded");
-    if (n_pos < 0 || (n_pos > 0 && (!black || !white || !side || !out_logits || !out_value))) return fail(-1, "rvs_engine_predict: bad arguments");
+// AlphaZeroNetwork.predict on packed positions; any of out_logits / out_probs may be null
+static int predict_impl(rvs_engine* h, const uint64_t* black, const uint64_t* white, const uint8_t* side, int64_t n_pos,
+                        float* out_logits, float* out_probs, float* out_value, int mem, void* stream, const char* who) {
+    RVS_ENTER(h);
+    if (!h->net || !h->net->loaded) return fail(-7, "%s: weights not loaded", who);
+    if (n_pos < 0 || (n_pos > 0 && (!black || !white || !side || !(out_logits || out_probs) || !out_value))) return fail(-1, "%s: bad arguments", who);
+    if (mem < RVS_MEM_DEVICE || mem > RVS_MEM_HOST_ASYNC) return fail(-1, "%s: bad mem %d", who, mem);
     NetState* n = h->net;
     cudaStream_t s = (cudaStream_t)stream;
+    const bool host = mem != RVS_MEM_DEVICE;  // RVS_MEM_HOST_ASYNC is treated like RVS_MEM_HOST here
+    const int hmem = host ? RVS_MEM_HOST : RVS_MEM_DEVICE;
     std::unique_lock<std::mutex> lk(g_stage_mu, std::defer_lock);
-    if (mem == RVS_MEM_HOST) lk.lock();
+    if (host) lk.lock();
     for (int64_t off = 0; off < n_pos; off += n->max_batch) {
         const int64_t B = n_pos - off < n->max_batch ? n_pos - off : n->max_batch;
         Arg ab, aw, as;
         int rc;
-        if ((rc = arg_in(ab, black + off, B * 8, mem, 0, s)) || (rc = arg_in(aw, white + off, B * 8, mem, 1, s)) ||
-            (rc = arg_in(as, side + off, B, mem, 2, s)))
+        if ((rc = arg_in(ab, black + off, B * 8, hmem, 0, s)) || (rc = arg_in(aw, white + off, B * 8, hmem, 1, s)) ||
+            (rc = arg_in(as, side + off, B, hmem, 2, s)))
             return rc;
         if (h->cfg.rules == RVS_RULES_STRICT)
             RVS_LAUNCH(encode_positions_kernel<RULES_STRICT>, grid_for(B, 256), 256, 0, s, (const uint64_t*)ab.dev,
@@ -710,13 +620,26 @@ int rvs_engine_predict(rvs_engine* h, const uint64_t* black, const uint64_t* whi
         else
             RVS_LAUNCH(encode_positions_kernel<RULES_REF>, grid_for(B, 256), 256, 0, s, (const uint64_t*)ab.dev,
                        (const uint64_t*)aw.dev, (const uint8_t*)as.dev, B, n->bits);
-        if ((rc = net_forward(h, B, true, s))) return rc;
-        const cudaMemcpyKind kind = mem == RVS_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-        RVS_CUDA(cudaMemcpyAsync(out_logits + off * 65, n->logits, B * 65 * 4, kind, s));
+        if ((rc = net_forward(h, B, out_logits != nullptr, s))) return rc;
+        const cudaMemcpyKind kind = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+        if (out_logits) RVS_CUDA(cudaMemcpyAsync(out_logits + off * 65, n->logits, B * 65 * 4, kind, s));
+        if (out_probs) RVS_CUDA(cudaMemcpyAsync(out_probs + off * 65, n->probs, B * 65 * 4, kind, s));
         RVS_CUDA(cudaMemcpyAsync(out_value + off, n->values, B * 4, kind, s));
-        if (mem == RVS_MEM_HOST) RVS_CUDA(cudaStreamSynchronize(s));
+        if (host) RVS_CUDA(cudaStreamSynchronize(s));
     }
     return 0;
+}
+
+int rvs_engine_predict(rvs_engine* h, const uint64_t* black, const uint64_t* white, const uint8_t* side, int64_t n_pos,
+                       float* out_logits, float* out_value, int mem, void* stream) {
+    if (!out_logits) return fail(-1, "rvs_engine_predict: bad arguments");
+    return predict_impl(h, black, white, side, n_pos, out_logits, nullptr, out_value, mem, stream, "rvs_engine_predict");
+}
+
+int rvs_engine_predict_probs(rvs_engine* h, const uint64_t* black, const uint64_t* white, const uint8_t* side, int64_t n_pos,
+                             float* out_probs, float* out_value, int mem, void* stream) {
+    if (!out_probs) return fail(-1, "rvs_engine_predict_probs: bad arguments");
+    return predict_impl(h, black, white, side, n_pos, nullptr, out_probs, out_value, mem, stream, "rvs_engine_predict_probs");
 }
 
 }  // extern "C"

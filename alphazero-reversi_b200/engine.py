@@ -10,7 +10,15 @@ class Engine:
     """One engine per device.  Not thread-safe (one host thread per handle)."""
 
     def __init__(self, n_games, max_sims, max_wave=64, evaluator=L.EVAL_E0, c_puct=1.0, rules=L.RULES_REF,
-                 seed=0, device=0, nodes_per_game=0, net_blocks=0, net_filters=0, sample_capacity=0):
+                 seed=0, device=None, nodes_per_game=0, net_blocks=0, net_filters=0, sample_capacity=0):
+        # device=None: the process's current CUDA device (torch.cuda.current_device()), so that a torchrun rank
+        # that called torch.cuda.set_device(local_rank) gets an engine on ITS GPU; the library restores the
+        # caller's current device after every call
+        if device is None:
+            device = L.current_device()
+        elif hasattr(device, "index"):  # torch.device
+            device = device.index if device.index is not None else L.current_device()
+        device = int(device)
         cfg = L.EngineConfig(C.sizeof(L.EngineConfig), device, n_games, max_sims, max_wave, rules, evaluator,
                              c_puct, seed, nodes_per_game, net_blocks, net_filters, sample_capacity)
         self._h = C.c_void_p()
@@ -31,17 +39,23 @@ class Engine:
         except Exception:
             pass
 
-    @staticmethod
-    def _s(stream):
-        return stream if stream is not None else L.current_stream()
+    def _s(self, stream):
+        # torch's current stream ON THE ENGINE'S DEVICE (a stream of another device would be an invalid handle)
+        return stream if stream is not None else L.current_stream(self.device)
+
+    def _check_device(self, *tensors):
+        for t in tensors:
+            if hasattr(t, "is_cuda") and t.is_cuda and t.device.index != self.device:
+                raise ValueError(f"tensor on {t.device} passed to an engine on cuda:{self.device}")
 
     def reset(self, stream=None):
         L.check(L.lib().rvs_engine_reset(self._h, self._s(stream)))
 
     def set_positions(self, black, white, side, stream=None):
         mem = L.mem_of(black, white, side)
-        L.check(L.lib().rvs_engine_set_positions(self._h, L.ptr(black)[0], L.ptr(white)[0], L.ptr(side)[0],
-                                                 len(black), mem, self._s(stream)))
+        self._check_device(black, white, side)
+        L.check(L.lib().rvs_engine_set_positions(self._h, L.ptr(black, "uint64")[0], L.ptr(white, "uint64")[0],
+                                                 L.ptr(side, "uint8")[0], len(black), mem, self._s(stream)))
 
     def get_positions(self, n=None, stream=None):
         n = self.n_games if n is None else n
@@ -81,7 +95,8 @@ class Engine:
 
     def process(self, probs, values, stream=None):
         mem = L.mem_of(probs, values)
-        L.check(L.lib().rvs_engine_process(self._h, L.ptr(probs)[0], L.ptr(values)[0], mem, self._s(stream)))
+        self._check_device(probs, values)
+        L.check(L.lib().rvs_engine_process(self._h, L.ptr(probs, "float32")[0], L.ptr(values, "float32")[0], mem, self._s(stream)))
         self.cur_k = 0
 
     def root_visits(self, n=None, device=None, stream=None):
@@ -155,6 +170,30 @@ class Engine:
         it); epsilon = 0 switches it off"""
         L.check(L.lib().rvs_engine_set_root_noise(self._h, float(alpha), float(epsilon)))
 
+    def set_option(self, option, value):
+        """rvs_engine_set_option (L.OPT_*): search mode REF/FAST, game limit, CUDA-graph replay, tower grid cap ..."""
+        L.check(L.lib().rvs_engine_set_option(self._h, int(option), int(value)))
+
+    def set_search_mode(self, mode):
+        """L.MODE_REF: the reference's wave semantics (graded); L.MODE_FAST: effective virtual-loss leaf batching"""
+        self.set_option(L.OPT_SEARCH_MODE, mode)
+
+    def drain_packed_async(self, capacity, device, count_out=None, stream=None):
+        """rvs_engine_drain_packed_async: no host synchronisation.  Returns (PackedSamples of `capacity` rows on
+        `device`, count tensor); only the first count[0] rows are samples -- read the count after synchronising
+        `stream` (count_out: a pinned host or device int64[1] tensor; default a fresh device tensor)"""
+        import torch
+        from .replay import PackedSamples
+        cap = int(capacity)
+        bl = torch.empty(cap, dtype=torch.int64, device=device); wh = torch.empty(cap, dtype=torch.int64, device=device)
+        sd = torch.empty(cap, dtype=torch.uint8, device=device); z = torch.empty(cap, dtype=torch.int8, device=device)
+        pi = torch.empty((cap, 65), dtype=torch.float32, device=device)
+        cnt = count_out if count_out is not None else torch.zeros(1, dtype=torch.int64, device=device)
+        self._check_device(bl)
+        L.check(L.lib().rvs_engine_drain_packed_async(self._h, bl.data_ptr(), wh.data_ptr(), sd.data_ptr(), z.data_ptr(),
+                                                      pi.data_ptr(), cap, cnt.data_ptr(), self._s(stream)))
+        return PackedSamples(bl, wh, sd, z, pi), cnt
+
     def set_lanes_per_game(self, lanes):
         """wave-1 kernels: lanes of a warp per game (8 / 4 / 2, 0 = automatic); never changes results"""
         L.check(L.lib().rvs_engine_set_lanes_per_game(self._h, int(lanes)))
@@ -169,8 +208,9 @@ class Engine:
         L.check(L.lib().rvs_engine_load_weights(self._h, L.ptr(flat)[0], flat.numel() if hasattr(flat, "numel") else flat.size,
                                                 L.ptr(flat)[1], self._s(stream)))
 
-    def predict(self, black, white, side, stream=None):
-        """AlphaZeroNetwork.predict on packed positions -> (logits [n,65] f32, value [n] f32)"""
+    def predict(self, black, white, side, stream=None, probs=False):
+        """AlphaZeroNetwork.predict on packed positions -> (logits [n,65] f32, value [n] f32); probs=True returns
+        the head kernel's softmax(logits) instead (rvs_engine_predict_probs: what the built-in NN search consumes)"""
         n = len(black)
         if hasattr(black, "data_ptr"):
             import torch
@@ -180,6 +220,8 @@ class Engine:
             logits = np.empty((n, 65), dtype=np.float32)
             value = np.empty(n, dtype=np.float32)
         mem = L.mem_of(black, white, side, logits, value)
-        L.check(L.lib().rvs_engine_predict(self._h, L.ptr(black)[0], L.ptr(white)[0], L.ptr(side)[0], n,
-                                           L.ptr(logits)[0], L.ptr(value)[0], mem, self._s(stream)))
+        self._check_device(black, white, side)
+        fn = L.lib().rvs_engine_predict_probs if probs else L.lib().rvs_engine_predict
+        L.check(fn(self._h, L.ptr(black, "uint64")[0], L.ptr(white, "uint64")[0], L.ptr(side, "uint8")[0], n,
+                   L.ptr(logits)[0], L.ptr(value)[0], mem, self._s(stream)))
         return logits, value

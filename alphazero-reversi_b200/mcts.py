@@ -41,7 +41,7 @@ class _Root:
 class MCTS:
     def __init__(self, model, c_puct: float = 1.0, num_simulations: int = 800, batch_size: int = 64,
                  num_threads: int = 1, use_transposition: bool = True, rules: int = L.RULES_REF,
-                 device: int = 0):
+                 device=None):
         self.model = model
         self.c_puct = c_puct
         self.num_simulations = num_simulations

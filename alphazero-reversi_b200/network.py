@@ -112,11 +112,14 @@ class RvsNetwork:
         return cls(*pack_state_dict(sd))
 
     @classmethod
-    def from_checkpoint(cls, path: str) -> "RvsNetwork":
+    def from_checkpoint(cls, path: str, trusted: bool = False) -> "RvsNetwork":
         """a reference checkpoint file: `checkpoint_XXXX.pth` (dict with 'model_state_dict',
         pipeline.py:463-480) or `best_model.pth` (bare state_dict, pipeline.py:482-485), with or
         without the `_script_module.` duplicates of a TorchScript-compiled model (mcts.py:459-479)"""
-        obj = torch.load(path, map_location="cpu", weights_only=False)
+        # weights_only=True: a checkpoint is data, not code.  Reference checkpoints (state_dict, or a dict of
+        # state_dicts + primitives) load with the safe unpickler; only a caller who vouches for the file
+        # (trusted=True) gets the arbitrary-code pickle path (e.g. a whole pickled nn.Module).
+        obj = torch.load(path, map_location="cpu", weights_only=not trusted)
         if isinstance(obj, dict) and "model_state_dict" in obj:
             obj = obj["model_state_dict"]
         if hasattr(obj, "state_dict"):

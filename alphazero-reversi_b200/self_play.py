@@ -35,9 +35,10 @@ class SelfPlay:
             self.model.eval()
         else:
             self.device = None
+        self.cuda_device = args.get("device", None)  # CUDA device index of the engines (None: the current device)
         self.mcts = MCTS(model=model, c_puct=args.get("c_puct", 1.0),
                          num_simulations=args.get("num_simulations", 800),
-                         batch_size=args.get("batch_size", 64))
+                         batch_size=args.get("batch_size", 64), device=self.cuda_device)
         self.save_dir = args.get("save_dir", None)
         if self.save_dir:
             os.makedirs(self.save_dir, exist_ok=True)
@@ -74,7 +75,7 @@ class SelfPlay:
         T = self.args.get("temperature", 1.0)
         slots = min(parallel, num_games)
         eng = Engine(slots, S, K, evaluator=self._builtin, c_puct=self.args.get("c_puct", 1.0),
-                     seed=self.args.get("seed", getattr(self.model, "seed", 0)),
+                     seed=self.args.get("seed", getattr(self.model, "seed", 0)), device=self.cuda_device,
                      sample_capacity=64 * max(slots, 1) * 2, net_blocks=getattr(self.model, "net_blocks", 0),
                      net_filters=getattr(self.model, "net_filters", 0))
         if hasattr(self.model, "attach"):
@@ -83,6 +84,10 @@ class SelfPlay:
             # engine feature: the reference accepts dirichlet_alpha / dirichlet_epsilon and never applies
             # them (self_play.py:18-47), so the noise needs this explicit switch
             eng.set_root_noise(self.args.get("dirichlet_alpha", 0.3), self.args.get("dirichlet_epsilon", 0.25))
+        # exactly `num_games` games are started (ids 0 .. num_games-1): a slot restarts only while its next game id
+        # stays below the limit, so no surplus game is searched and the set returned does not depend on which
+        # games happen to finish first (the reference plays its games one after another, self_play.py:66)
+        eng.set_option(L.OPT_GAME_LIMIT, num_games)
         persistent = K == 1 and self._builtin in (L.EVAL_E0, L.EVAL_ROLLOUT, L.EVAL_NN)
         games: List[Dict] = []
         collected = 0
@@ -91,7 +96,7 @@ class SelfPlay:
                 eng.selfplay(S, plies=16 * slots, temperature=T, recycle=True)
             else:
                 eng.search(S, K)
-                eng.play(T, recycle=True)  # finished slots restart at once; surplus games are discarded
+                eng.play(T, recycle=True)  # finished slots restart at once, up to the game limit
             st = eng.stats()
             if st["overflow"] or st["stalled"] or st["samples_dropped"]:
                 raise L.RvsError(f"engine error counters non-zero: {st}")

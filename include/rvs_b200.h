@@ -33,8 +33,9 @@ extern "C" {
 #define RVS_MEM_HOST 1
 /* host pointers in PINNED memory, copies only enqueued on `stream`: the call returns without
  * synchronising, so several engine handles can be pipelined on several streams; the caller
- * synchronises the stream before reading outputs / reusing inputs (accepted by
- * rvs_engine_set_positions and rvs_engine_root_visits; everywhere else it means RVS_MEM_HOST) */
+ * synchronises the stream before reading outputs / reusing inputs (honoured by
+ * rvs_engine_set_positions and rvs_engine_root_visits; every other entry point treats it exactly
+ * like RVS_MEM_HOST: staged copies, outputs complete on return) */
 #define RVS_MEM_HOST_ASYNC 2
 
 #define RVS_RULES_REF 0    /* bug-compatible with src/game/board.py (graded) */
@@ -54,6 +55,21 @@ extern "C" {
 #define RVS_EVAL_ROLLOUT 1  /* uniform prior, value = one uniform random playout */
 #define RVS_EVAL_EXTERNAL 2 /* caller evaluates leaves (any model.predict duck type) */
 #define RVS_EVAL_NN 3       /* built-in bf16 ResNet on tcgen05 (K4) */
+
+/* wave semantics of the search (RVS_OPT_SEARCH_MODE) */
+#define RVS_MODE_REF 0  /* the reference's waves, bugs included (src/mcts/mcts.py:96-100,113,355-392): graded */
+#define RVS_MODE_FAST 1 /* effective virtual-loss leaf batching: the simulations of a wave spread over distinct leaves */
+
+/* rvs_engine_set_option keys.  Only RVS_OPT_SEARCH_MODE changes results. */
+#define RVS_OPT_LANES_PER_GAME 1 /* = rvs_engine_set_lanes_per_game */
+#define RVS_OPT_NET_GRAPH 2      /* RVS_EVAL_NN: waves 2.. of a search replay one captured CUDA graph (0 / 1, default 0) */
+#define RVS_OPT_SEARCH_MODE 3    /* RVS_MODE_REF (default) / RVS_MODE_FAST */
+#define RVS_OPT_GAME_LIMIT 4     /* self-play: a finished slot restarts only while its next game id stays below this
+                                    value (0 = no limit); with n slots, game ids 0 .. limit-1 are each played exactly once */
+#define RVS_OPT_NET_MAX_CTAS 5   /* RVS_EVAL_NN: cap of the persistent tcgen05 grids (0 = all SMs); leaves SMs to the tree
+                                    kernels of the other half-batch when a search is pipelined */
+#define RVS_OPT_NET_PIPELINE 6   /* RVS_EVAL_NN, wave 1: 0 = one lockstep batch per wave, 1 = two half-batches ping-pong
+                                    on two streams so that tree kernels overlap the tower (default 1) */
 
 const char *rvs_last_error(void);
 int rvs_version(void);
@@ -128,6 +144,7 @@ typedef struct rvs_engine_stats {
     int64_t samples_dropped; /* samples lost because the ring was full (drain more often) */
     int64_t stalled;     /* slots parked after an illegal move choice (num_sims <= wave hazard) */
     int64_t nn_evals;    /* RVS_EVAL_NN: boards actually run through the network (terminal / duplicate leaves of a wave are compacted away) */
+    int64_t bad_positions; /* positions rejected by rvs_engine_set_positions from DEVICE memory (side not 1/2 or overlapping discs): their slots are parked */
 } rvs_engine_stats;
 
 int rvs_engine_create(const rvs_engine_config *cfg, rvs_engine **out);
@@ -135,7 +152,11 @@ int rvs_engine_destroy(rvs_engine *h);
 
 /* every slot back to the start position with a fresh game id (ReversiGame(), game.py:14-26) */
 int rvs_engine_reset(rvs_engine *h, void *stream);
-/* root positions for slots [0,n): MCTS.search(game) takes the caller's game (mcts.py:322) */
+/* root positions for slots [0,n): MCTS.search(game) takes the caller's game (mcts.py:322).
+ * Every position must have side in {1,2} and disjoint disc sets: host inputs are validated before the upload
+ * (error -1), device inputs on the device (bad slots are parked and counted in stats.bad_positions).
+ * RNG streams: slot g of the e-th set_positions call on a handle (e = 0 after create / reset) plays game id
+ * g + e * n_games, so successive searches through this entry point draw independent rollout / noise streams. */
 int rvs_engine_set_positions(rvs_engine *h, const uint64_t *black, const uint64_t *white,
                              const uint8_t *side, int32_t n, int mem, void *stream);
 int rvs_engine_get_positions(rvs_engine *h, uint64_t *black, uint64_t *white, uint8_t *side,
@@ -194,6 +215,14 @@ int rvs_engine_drain_samples(rvs_engine *h, float *states, float *pi, float *z, 
 int rvs_engine_drain_packed(rvs_engine *h, uint64_t *black, uint64_t *white, uint8_t *side, int8_t *z,
                             float *pi, int64_t capacity, int64_t *out_count, int mem, void *stream);
 
+/* rvs_engine_drain_packed without any host synchronisation: DEVICE output buffers, and the number of samples
+ * is written ON `stream` to *out_count_dev (device memory, or pinned host memory mapped into the device's address
+ * space).  At most `capacity` samples are taken (the oldest first); the rest stay in the ring.  The caller orders
+ * its consumers after this call on `stream` (or on an event recorded there): used to gather a generation's samples
+ * on a side stream while the next generation is already searching. */
+int rvs_engine_drain_packed_async(rvs_engine *h, uint64_t *black, uint64_t *white, uint8_t *side, int8_t *z,
+                                  float *pi, int64_t capacity, int64_t *out_count_dev, void *stream);
+
 /* Dirichlet noise on the root priors: P' = (1-eps) P + eps Dir(alpha), mixed in right after the root
  * is expanded by every following search (BASELINE config 4).  The reference only CONFIGURES this
  * (dirichlet_alpha / dirichlet_epsilon, src/config.py:25-26, src/self_play/self_play.py:18-47) and
@@ -206,6 +235,9 @@ int rvs_engine_set_root_noise(rvs_engine *h, double alpha, float epsilon);
  * 4 up to 24576, else 2).  Results never depend on it.  Worth setting to 4 when several handles are pipelined on one
  * GPU, i.e. when far more games are in flight than one handle holds. */
 int rvs_engine_set_lanes_per_game(rvs_engine *h, int32_t lanes);
+
+/* Engine options, see the RVS_OPT_* keys above. */
+int rvs_engine_set_option(rvs_engine *h, int32_t option, int64_t value);
 
 int rvs_engine_stats_get(rvs_engine *h, rvs_engine_stats *out, void *stream);
 
@@ -221,6 +253,13 @@ int rvs_engine_load_weights(rvs_engine *h, const float *flat, int64_t n_floats, 
 int rvs_engine_predict(rvs_engine *h, const uint64_t *black, const uint64_t *white,
                        const uint8_t *side, int64_t n, float *out_logits, float *out_value,
                        int mem, void *stream);
+/* The same forward pass, returning what the built-in NN search consumes: probs [n,65] f32 =
+ * softmax(logits) as computed by the engine's own head kernel (the reference applies F.softmax to the
+ * logits, src/mcts/mcts.py:596) and value [n].  Feeding these to rvs_engine_process reproduces
+ * rvs_engine_search(RVS_EVAL_NN) visit for visit. */
+int rvs_engine_predict_probs(rvs_engine *h, const uint64_t *black, const uint64_t *white,
+                             const uint8_t *side, int64_t n, float *out_probs, float *out_value,
+                             int mem, void *stream);
 
 #ifdef __cplusplus
 }

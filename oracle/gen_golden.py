@@ -380,9 +380,16 @@ def perturb_bn(model, seed):
     model.value_fc2.weight.data.mul_(0.05)  # keep tanh out of saturation
 
 
-def gen_net():
-    from src.model.network import AlphaZeroNetwork
-    out = {}
+def tame(model):
+    """a deep random-init tower saturates (20x256: |logits| ~ 1e3, value = +-1): damp the residual branches
+    and the policy head so that priors and values of the deep network are informative test targets"""
+    for blk in model.res_blocks:
+        blk.bn2.weight.data.mul_(0.1)
+        blk.bn2.bias.data.mul_(0.1)
+    model.policy_fc.weight.data.mul_(0.1)
+
+
+def net_positions():
     pos = midgame_positions()
     rng = random.Random(5)
     for _ in range(19):
@@ -394,9 +401,16 @@ def gen_net():
             g.make_move(*vm[rng.randrange(len(vm))])
         if not g.is_game_over():
             pos.append((g.board.black, g.board.white, g.current_player))
+    return pos
+
+
+def gen_net(which=(("5x128", 5, 128), ("2x64", 2, 64)), fname="net.npz"):
+    from src.model.network import AlphaZeroNetwork
+    out = {}
+    pos = net_positions()
     planes = np.array([set_position(*p).get_canonical_state() for p in pos], dtype=np.float32)
     out["pos"] = np.array(pos, dtype=np.uint64)
-    for tag, nb, nf in (("5x128", 5, 128), ("2x64", 2, 64)):
+    for tag, nb, nf in which:
         torch.manual_seed(42)
         net = AlphaZeroNetwork(8, nb, nf)
         sd = {k: v for k, v in net.state_dict().items()}
@@ -422,7 +436,23 @@ def gen_net():
         out[f"{tag}_bn_logits_autocast"] = lg16.float().numpy()
         out[f"{tag}_bn_values_autocast"] = vl16.float().numpy()
         print(tag, lg.abs().max().item(), vl[:5].tolist())
-    np.savez_compressed(os.path.join(OUT, "net.npz"), **out)
+        if nb >= 20:  # third variant for the deep tower: perturbed BN + damped residual branches (unsaturated outputs)
+            torch.manual_seed(42)
+            net = AlphaZeroNetwork(8, nb, nf)
+            with torch.no_grad():
+                perturb_bn(net, 43)
+                tame(net)
+            net.eval()
+            with torch.no_grad():
+                lg, vl = net.predict(torch.from_numpy(planes))
+                with torch.autocast("cpu", dtype=torch.bfloat16):
+                    lg16, vl16 = net.forward(torch.from_numpy(planes))
+            out[f"{tag}_tamed_logits"] = lg.numpy()
+            out[f"{tag}_tamed_values"] = vl.numpy()
+            out[f"{tag}_tamed_logits_autocast"] = lg16.float().numpy()
+            out[f"{tag}_tamed_values_autocast"] = vl16.float().numpy()
+            print(tag, "tamed", lg.abs().max().item(), vl[:5].tolist())
+    np.savez_compressed(os.path.join(OUT, fname), **out)
 
 
 if __name__ == "__main__":
@@ -441,3 +471,5 @@ if __name__ == "__main__":
         gen_selfplay()
     if "net" in todo:
         gen_net()
+    if "net20" in todo:  # BASELINE config 4's network at full depth: AlphaZeroNetwork(8, 20, 256) (network.py:80-117)
+        gen_net((("20x256", 20, 256),), "net20.npz")

@@ -62,3 +62,11 @@ def perturb_bn(model, seed):
             m.weight.data.copy_(torch.rand(m.num_features, generator=gen) * 0.5 + 0.5)
             m.bias.data.copy_(torch.randn(m.num_features, generator=gen) * 0.1)
     model.value_fc2.weight.data.mul_(0.05)
+
+
+def tame(model):
+    """restates oracle/gen_golden.py:tame (damped residual branches + policy head for the deep-tower goldens)"""
+    for blk in model.res_blocks:
+        blk.bn2.weight.data.mul_(0.1)
+        blk.bn2.bias.data.mul_(0.1)
+    model.policy_fc.weight.data.mul_(0.1)

@@ -38,7 +38,7 @@ def test_header_symbols_exported(az):
 
 def test_struct_layouts_match_header(az):
     assert C.sizeof(az._lib.EngineConfig) == 56
-    assert C.sizeof(az._lib.EngineStats) == 96
+    assert C.sizeof(az._lib.EngineStats) == 104
 
 
 def test_sm100a_only(az):

@@ -56,6 +56,19 @@ def _worker(rank, world, port, q):
                           (torch.randint(0, 3, (m,), generator=g2) - 1).to(torch.int8), torch.rand((m, 65), generator=g2)))
         exp = [torch.cat([p[i] for p in parts]) for i in range(5)]
         packed_ok = all(torch.equal(a, b) for a, b in zip((gk.black, gk.white, gk.side, gk.z, gk.pi), exp))
+    # ragged case: rank 1 has nothing to contribute (more ranks than games); exact-size transfers, no padding
+    info = {}
+    empty = az.PackedSamples(torch.empty(0, dtype=torch.int64), torch.empty(0, dtype=torch.int64), torch.empty(0, dtype=torch.uint8),
+                             torch.empty(0, dtype=torch.int8), torch.empty((0, 65)))
+    ge = azd.gather_packed(pk if rank == 0 else empty, dst=0, info=info)
+    if rank == 0:
+        packed_ok = packed_ok and len(ge) == 3 and torch.equal(ge.black, pk.black) and info["bytes_received"] == 0
+    info2 = {}
+    ge2 = azd.gather_packed(empty if rank == 0 else pk, dst=0, info=info2)
+    if rank == 0:
+        packed_ok = packed_ok and len(ge2) == 5 and info2["bytes_received"] == 5 * 280
+    else:
+        assert ge2 is None and info2["bytes_sent"] == 5 * 280
     first, count = azd.shard_range(65536 + 1, rank, world)
     q.put((rank, ok_w, None if out is None else (out[0].shape[0], out[0][:, 0, 0, 0].tolist(), out[2].tolist()),
            first, count, azd.rank_seed(7, rank), packed_ok))

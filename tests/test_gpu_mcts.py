@@ -168,16 +168,15 @@ def test_batched_search_vs_oracle(az, evaluator, S, K):
 def test_root_dirichlet_noise_vs_oracle(az, evaluator, S, K, alpha, eps, lpg):
     """engine feature (BASELINE config 4): Dirichlet noise mixed into the root priors after the root
     expansion; the oracle restates the sampler, visit counts must stay bit exact.  Covers the
-    several-games-per-warp wave-1 kernels (lanes per game forced through RVS_K1_LPG), the fused wave
+    several-games-per-warp wave-1 kernels (lanes per game forced through rvs_engine_set_lanes_per_game), the fused wave
     kernel, and -- with an E0 evaluator driven from the host -- the external select/process path."""
-    import os
     n = 192
     bl, wh, sd = _random_roots(n, 500 + S + K)
-    if lpg:
-        os.environ["RVS_K1_LPG"] = str(lpg)
     orc.set_root_noise(alpha, eps)
     try:
         eng = az.Engine(n, S, K, evaluator=evaluator, seed=777)
+        if lpg:
+            eng.set_lanes_per_game(lpg)
         eng.set_root_noise(alpha, eps)
         eng.set_positions(bl, wh, sd)
         eng.search(S, K)
@@ -211,7 +210,6 @@ def test_root_dirichlet_noise_vs_oracle(az, evaluator, S, K, alpha, eps, lpg):
             assert changed > n // 4, changed
     finally:
         orc.set_root_noise(0.0, 0.0)
-        os.environ.pop("RVS_K1_LPG", None)
 
 
 @pytest.mark.parametrize("rules,c_puct,lpg,evaluator", [(1, 0.7, 8, 1), (1, 2.5, 4, 0), (1, 1.0, 2, 1), (0, 0.7, 4, 1), (0, 2.5, 2, 0), (0, 1.5, 8, 1)])

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 import orc
-from stubs import perturb_bn
+from stubs import perturb_bn, tame
 
 pytestmark = pytest.mark.gpu
 
@@ -28,17 +28,24 @@ def _softmax(x):
 def _build(az, nb, nf, variant):
     torch.manual_seed(42)
     net = az.AlphaZeroNetwork(8, nb, nf)
-    if variant == "bn":
+    if variant in ("bn", "tamed"):
         with torch.no_grad():
             perturb_bn(net, 43)
+            if variant == "tamed":
+                tame(net)
     net.eval()
     return net
 
 
-@pytest.mark.parametrize("tag,nb,nf", [("5x128", 5, 128), ("2x64", 2, 64)])
-@pytest.mark.parametrize("variant", ["fresh", "bn"])
+@pytest.mark.parametrize("tag,nb,nf,variant", [("5x128", 5, 128, "fresh"), ("5x128", 5, 128, "bn"), ("2x64", 2, 64, "fresh"),
+                                               ("2x64", 2, 64, "bn"), ("20x256", 20, 256, "fresh"), ("20x256", 20, 256, "bn"),
+                                               ("20x256", 20, 256, "tamed")])
 def test_predict_vs_reference_golden(az, golden, tag, nb, nf, variant):
-    g = golden["net"]
+    """logits / values recorded from the reference AlphaZeroNetwork (src/model/network.py:80-117), including
+    BASELINE config 4's tower at its full depth: AlphaZeroNetwork(8, 20, 256), where bf16 error has 41
+    layers to grow (fresh and perturbed-BN weights saturate -- |logits| ~ 1e3, one-hot priors --, so the
+    damped 'tamed' variant is what exercises priors and values there)."""
+    g = golden["net20" if nb >= 20 else "net"]
     net = _build(az, nb, nf, variant)
     # the mirror module reproduces the reference's random init exactly (weight checksums)
     if variant == "fresh":
@@ -54,21 +61,25 @@ def test_predict_vs_reference_golden(az, golden, tag, nb, nf, variant):
     with torch.no_grad():
         planes = torch.from_numpy(az.board_ops.encode_planes(bl, wh, sd))
         tl, tv = net(planes)
-    assert np.allclose(tl.numpy(), ref_l, atol=2e-3, rtol=1e-3)
+    assert np.allclose(tl.numpy(), ref_l, atol=2e-3 * max(1.0, np.abs(ref_l).max() / 10), rtol=1e-3)
     # calibration baseline: torch's own bf16 autocast of the same module against its fp32 output
     with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
         al, av = net(planes)
     base_l = np.abs(al.float().numpy() - ref_l).max()
     base_v = np.abs(av.float().numpy() - ref_v).max()
     base_p = np.abs(_softmax(al.float().numpy()) - _softmax(ref_l)).max()
-    if variant == "bn":  # the recorded autocast outputs of the reference agree with the live ones
-        assert abs(base_l - np.abs(g[f"{tag}_bn_logits_autocast"] - ref_l).max()) < 0.05
+    if variant != "fresh":  # the recorded autocast outputs of the reference agree with the live ones
+        rec = np.abs(g[f"{tag}_{variant}_logits_autocast"] - ref_l).max()
+        assert abs(base_l - rec) < 0.05 * max(1.0, rec)
     err_l = np.abs(logits - ref_l).max()
     err_p = np.abs(_softmax(logits) - _softmax(ref_l)).max()
     err_v = np.abs(value - ref_v).max()
     print(f"{tag} {variant}: logits err {err_l:.4f} (autocast {base_l:.4f}) rel-L2 "
           f"{np.linalg.norm(logits - ref_l) / np.linalg.norm(ref_l):.4f} priors {err_p:.5f} (autocast {base_p:.5f}) value {err_v:.5f} (autocast {base_v:.5f})")
+    rel_l = np.linalg.norm(logits - ref_l) / np.linalg.norm(ref_l)
+    base_rel = np.linalg.norm(al.float().numpy() - ref_l) / np.linalg.norm(ref_l)
     assert err_l <= max(2 * base_l, 0.05)
+    assert rel_l <= max(2 * base_rel, 1e-3)
     assert err_p <= max(2 * base_p, 2e-2)
     assert err_v <= max(2 * base_v, 3e-2)
     eng.close()
@@ -83,19 +94,10 @@ def test_weight_loading_errors(az):
     eng.close()
 
 
-def test_nn_search_consistency(az):
-    """NN-evaluated search (select -> encode -> tower -> heads+softmax -> expand/backup, all on
-    device) against the SAME search driven through the external path with the engine's own
-    predictions: the two must give identical visit counts (same priors/values, same tree code)."""
-    nb, nf, S = 2, 64, 64
-    net = _build(az, nb, nf, "bn")
-    rn = az.RvsNetwork.from_module(net)
-    g = 16
-    rng = np.random.default_rng(3)
-    bl, wh, wi, pl = orc.random_playouts(g, 5)
-    # mid-game roots
-    L = orc.lib()
+def _midgame_roots(g, seed):
     import ctypes as C
+    rng = np.random.default_rng(seed)
+    L = orc.lib()
     roots = []
     for i in range(g):
         b = orc.make_board(*orc.START)
@@ -106,44 +108,57 @@ def test_nn_search_consistency(az):
             bits = [q for q in range(64) if (lm >> q) & 1]
             L.orc_apply(C.byref(b), bits[int(rng.integers(0, len(bits)))], 0)
         roots.append((b.black, b.white, b.side))
-    rb = np.array([r[0] for r in roots], dtype=np.uint64)
-    rw = np.array([r[1] for r in roots], dtype=np.uint64)
-    rs = np.array([r[2] for r in roots], dtype=np.uint8)
-    import os
-    for K, graph in ((1, "0"), (8, "0"), (1, "1"), (32, "0")):
-        os.environ["RVS_NET_GRAPH"] = graph  # "1": waves 2.. replay a captured CUDA graph
-        eng = az.Engine(g, S, K, evaluator=az.EVAL_NN, net_blocks=nb, net_filters=nf)
-        rn.attach(eng)
-        eng.set_positions(rb, rw, rs)
-        eng.search(S, K)
-        v_nn = eng.root_visits()
-        assert eng.stats()["overflow"] == 0
-        # external path, evaluator = the engine's own predict() + float32 softmax on the device
-        ext = az.Engine(g, S, K, evaluator=az.EVAL_EXTERNAL)
-        ext.set_positions(rb, rw, rs)
-        ext.begin_search()
-        w = (1 << np.arange(64, dtype=np.uint64))
-        for start in range(0, S, K):
-            k = min(K, S - start)
-            ext.select(k)
-            planes, valid = ext.leaf_planes()
-            n = len(valid)
-            own = ((planes[:, 0].reshape(n, 64) > 0.5).astype(np.uint64) * w).sum(axis=1).astype(np.uint64)
-            opp = ((planes[:, 1].reshape(n, 64) > 0.5).astype(np.uint64) * w).sum(axis=1).astype(np.uint64)
-            lg, val = eng.predict(own, opp, np.ones(n, dtype=np.uint8))
-            probs = torch.softmax(torch.from_numpy(lg).cuda(), dim=1).cpu().numpy()
-            probs[valid == 0] = 0
-            val[valid == 0] = 0
-            ext.process(probs, val)
-        v_ext = ext.root_visits()
-        # softmax differs by an ulp or two between the fused head kernel and torch: allow a few
-        # games to diverge, the bulk must be identical
-        same = (v_nn == v_ext).all(axis=1).mean()
-        assert same >= 0.75, (K, same)
-        assert np.array_equal(v_nn.sum(axis=1), v_ext.sum(axis=1))
-        eng.close()
-        ext.close()
-    os.environ.pop("RVS_NET_GRAPH", None)
+    return (np.array([r[0] for r in roots], dtype=np.uint64), np.array([r[1] for r in roots], dtype=np.uint64),
+            np.array([r[2] for r in roots], dtype=np.uint8))
+
+
+@pytest.mark.parametrize("K,graph,pipeline,S", [(1, 0, 0, 64), (1, 0, 1, 64), (1, 1, 0, 64), (8, 0, 0, 64), (8, 1, 0, 64), (32, 0, 0, 96),
+                                                (64, 0, 0, 200), (64, 1, 0, 200)])
+def test_nn_search_consistency(az, K, graph, pipeline, S):
+    """The fused NN search (select -> compaction + de-duplication of the leaf batch -> tower -> heads + softmax
+    -> slot -> row remap -> expand/backup, all on the device; optionally as a replayed CUDA graph / as two
+    pipelined half-batches) against the SAME search driven through the external select / process path and fed
+    the engine's OWN probabilities (rvs_engine_predict_probs: the head kernel's softmax, bit for bit what the
+    fused path consumes).  Same priors, same values, same tree code => visit counts identical in EVERY game
+    -- waves of 8 / 32 / 64 contain many duplicate leaves (reference wave semantics), so a wrong remap row
+    cannot hide."""
+    nb, nf = 2, 64
+    net = _build(az, nb, nf, "bn")
+    rn = az.RvsNetwork.from_module(net)
+    g = 48
+    rb, rw, rs = _midgame_roots(g, 3)
+    eng = az.Engine(g, S, K, evaluator=az.EVAL_NN, net_blocks=nb, net_filters=nf)
+    eng.set_option(az._lib.OPT_NET_GRAPH, graph)
+    eng.set_option(az._lib.OPT_NET_PIPELINE, pipeline)
+    rn.attach(eng)
+    eng.set_positions(rb, rw, rs)
+    eng.search(S, K)
+    v_nn = eng.root_visits()
+    st = eng.stats()
+    assert st["overflow"] == 0 and st["sims"] == g * S
+    if K > 1:
+        assert st["nn_evals"] < st["evals"]  # duplicates of a wave were evaluated once
+    ext = az.Engine(g, S, K, evaluator=az.EVAL_EXTERNAL)
+    ext.set_positions(rb, rw, rs)
+    ext.begin_search()
+    w = (1 << np.arange(64, dtype=np.uint64))
+    for start in range(0, S, K):
+        k = min(K, S - start)
+        ext.select(k)
+        planes, valid = ext.leaf_planes()
+        n = len(valid)
+        own = ((planes[:, 0].reshape(n, 64) > 0.5).astype(np.uint64) * w).sum(axis=1).astype(np.uint64)
+        opp = ((planes[:, 1].reshape(n, 64) > 0.5).astype(np.uint64) * w).sum(axis=1).astype(np.uint64)
+        # canonical planes = (own, opponent): side 1 with black := own reproduces the network input exactly
+        probs, val = eng.predict(own, opp, np.ones(n, dtype=np.uint8), probs=True)
+        probs[valid == 0] = 0
+        val[valid == 0] = 0
+        ext.process(probs, val)
+    v_ext = ext.root_visits()
+    bad = np.nonzero((v_nn != v_ext).any(axis=1))[0]
+    assert len(bad) == 0, (K, graph, bad[:8], v_nn[bad[:1]], v_ext[bad[:1]])
+    eng.close()
+    ext.close()
 
 
 def test_mcts_and_selfplay_with_rvs_network(az):
@@ -166,45 +181,36 @@ def test_mcts_and_selfplay_with_rvs_network(az):
 
 
 @pytest.mark.parametrize("nb,nf,n", [(1, 64, 2), (1, 128, 2), (1, 64, 1500), (1, 128, 1501), (2, 128, 37), (5, 128, 512),
-                                     (1, 256, 2), (1, 256, 1501), (2, 256, 37), (3, 256, 600)])
-def test_tcgen05_tower_matches_direct_kernel(az, nb, nf, n):
-    """the tensor-core implicit GEMM (TMA + tcgen05 + TMEM) against the CUDA-core direct kernel on
-    the same bf16 weights/activations: only the f32 summation order differs"""
-    import os
-    net = _build(az, nb, nf, "bn")
+                                     (1, 256, 2), (1, 256, 1501), (2, 256, 37), (3, 256, 600), (20, 256, 64)])
+def test_tcgen05_tower_matches_torch_emulation(az, nb, nf, n):
+    """the tensor-core implicit GEMM (TMA + tcgen05 + TMEM) against a plain torch restatement of the same
+    arithmetic on the same bf16 weights / activations (tests/net_emul.py): only the f32 summation order differs"""
+    from net_emul import emulate
+    net = _build(az, nb, nf, "tamed" if nb >= 20 else "bn")
     rn = az.RvsNetwork.from_module(net)
-    bl, wh, wi, pl = orc.random_playouts(n, 77)
     rng = np.random.default_rng(1)
     # random (not necessarily reachable) disc sets exercise every input pattern
     occ = rng.integers(0, 2**64, n, dtype=np.uint64)
     pick = rng.integers(0, 2**64, n, dtype=np.uint64)
     bl, wh = occ & pick, occ & ~pick
     sd = rng.integers(1, 3, n).astype(np.uint8)
-    outs = {}
-    # "1": CUDA-core direct kernel; "0": tcgen05 2-CTA (cta_group::2) kernel; "1sm": 1-CTA kernel
-    for mode in ("1", "0", "1sm"):
-        os.environ["RVS_NET_DIRECT"] = "1" if mode == "1" else "0"
-        os.environ["RVS_CONV_1SM"] = "1" if mode == "1sm" else "0"
-        eng = az.Engine(n, 8, 1, evaluator=az.EVAL_NN, net_blocks=nb, net_filters=nf)
-        rn.attach(eng)
-        outs[mode] = eng.predict(bl, wh, sd)
-        eng.close()
-    os.environ.pop("RVS_NET_DIRECT")
-    os.environ.pop("RVS_CONV_1SM")
-    # the two tensor-core variants differ only in the first layer (bf16 tcgen05 vs f32 bit-plane kernel)
-    assert np.abs(outs["0"][0] - outs["1sm"][0]).max() <= 0.02 * max(np.abs(outs["0"][0]).max(), 1.0)
-    dl = np.abs(outs["1"][0] - outs["0"][0]).max()
-    dv = np.abs(outs["1"][1] - outs["0"][1]).max()
-    scale = np.abs(outs["1"][0]).max()
-    # both against the fp32 torch module: deep towers amplify bf16 rounding differences, so the
-    # criterion is "the tensor-core path is as close to fp32 as the direct path", plus near-equality
-    # for shallow towers where no amplification happens
+    eng = az.Engine(n, 8, 1, evaluator=az.EVAL_NN, net_blocks=nb, net_filters=nf)
+    rn.attach(eng)
+    lg, val = eng.predict(bl, wh, sd)
+    eng.close()
+    planes = torch.from_numpy(az.board_ops.encode_planes(bl, wh, sd))
+    el, ev = emulate(net, planes)
+    el, ev = el.numpy(), ev.numpy()
     with torch.no_grad():
-        tl, tv = net(torch.from_numpy(az.board_ops.encode_planes(bl, wh, sd)))
-    e_dir = np.abs(outs["1"][0] - tl.numpy()).max()
-    e_tc = np.abs(outs["0"][0] - tl.numpy()).max()
-    print(f"{nb}x{nf} n={n}: direct vs tcgen05 logits max diff {dl:.5f} (scale {scale:.2f}) value diff {dv:.5f}; "
-          f"vs fp32: direct {e_dir:.5f} tcgen05 {e_tc:.5f}")
-    assert e_tc <= 1.5 * e_dir + 0.01
+        tl, tv = net.cpu()(planes)
+    scale = max(np.abs(el).max(), 1.0)
+    dl, dv = np.abs(lg - el).max(), np.abs(val - ev).max()
+    e_emul, e_tc = np.abs(el - tl.numpy()).max(), np.abs(lg - tl.numpy()).max()
+    print(f"{nb}x{nf} n={n}: tcgen05 vs emulation logits max diff {dl:.5f} (scale {scale:.2f}) value diff {dv:.5f}; "
+          f"vs fp32: emulation {e_emul:.5f} tcgen05 {e_tc:.5f}")
+    # deep towers amplify last-bit differences through the bf16 roundings, so the criterion there is "as close
+    # to fp32 as the emulation"; shallow towers must agree with the emulation almost exactly
+    assert e_tc <= 1.5 * e_emul + 0.01
+    assert dl <= (0.004 if nb == 1 else 0.02 * nb) * scale
     if nb == 1:
-        assert dl <= 0.004 * max(scale, 1.0) and dv <= 0.01
+        assert dv <= 0.01

@@ -132,11 +132,10 @@ def test_persistent_selfplay_budget_and_recycling(az):
 def test_group_kernels_ragged_sizes_and_lane_counts(az, lpg, n):
     """the several-games-per-warp wave-1 kernels (rvs_treeg.cuh) with 8 / 4 / 2 lanes per game and game
     counts that leave groups of the last warp empty: persistent self-play samples == oracle"""
-    import os
-    os.environ["RVS_K1_LPG"] = str(lpg)
     try:
         S, T = 40, 1.0
         eng = az.Engine(n, S, 1, evaluator=az.EVAL_ROLLOUT, seed=77)
+        eng.set_lanes_per_game(lpg)
         eng.selfplay(S, plies=n * 64, temperature=T, recycle=False)
         st = eng.stats()
         assert st["overflow"] == 0 and st["games_finished"] == n
@@ -159,18 +158,17 @@ def test_group_kernels_ragged_sizes_and_lane_counts(az, lpg, n):
             assert np.array_equal(gz, np.array([s.z for s in samples], dtype=np.int8))
         eng.close()
     finally:
-        os.environ.pop("RVS_K1_LPG", None)
+        pass
 
 
 def test_more_games_than_resident_groups(az):
     """12 000 games x 8 lanes = 3000 warps > the 2368 resident one-warp CTAs: groups own several slots
     (search: one after the other; persistent self-play: round-robin).  Visit counts of a strided sample of
     games equal the oracle's, and a budgeted self-play launch spends exactly its budget."""
-    import os
-    os.environ["RVS_K1_LPG"] = "8"
     try:
         n, S = 12000, 24
         eng = az.Engine(n, S, 1, evaluator=az.EVAL_ROLLOUT, seed=5)
+        eng.set_lanes_per_game(8)
         eng.search(S, 1)
         v = eng.root_visits()
         st = eng.stats()
@@ -184,4 +182,4 @@ def test_more_games_than_resident_groups(az):
         assert s1["sims"] - s0["sims"] == (3 * n + 5) * S and s1["overflow"] == 0 and s1["stalled"] == 0
         eng.close()
     finally:
-        os.environ.pop("RVS_K1_LPG", None)
+        pass

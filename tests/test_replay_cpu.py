@@ -82,3 +82,23 @@ def test_checkpoint_formats(tmp_path):
         rn = az.RvsNetwork.from_checkpoint(path)
         assert (rn.net_blocks, rn.net_filters) == (2, 64) and torch.equal(rn.flat, ref.flat)
     assert ref.flat.numel() == sum(v.numel() for k, v in sd.items() if "num_batches_tracked" not in k)
+
+
+def test_checkpoint_loader_is_safe_by_default(tmp_path):
+    import torch
+    import alphazero_reversi_b200 as az
+    torch.manual_seed(42)
+    net = az.AlphaZeroNetwork(8, 2, 64).eval()
+    p1 = tmp_path / "best_model.pth"
+    torch.save(net.state_dict(), p1)                                            # pipeline.py:482-485
+    p2 = tmp_path / "checkpoint_0001.pth"
+    torch.save({"model_state_dict": net.state_dict(), "iteration": 1, "optimizer_state_dict": {}}, p2)  # pipeline.py:463-480
+    a = az.RvsNetwork.from_checkpoint(str(p1))
+    b = az.RvsNetwork.from_checkpoint(str(p2))
+    assert torch.equal(a.flat, b.flat) and a.net_blocks == 2 and a.net_filters == 64
+    p3 = tmp_path / "module.pth"
+    torch.save(net, p3)                                                         # a pickled module = code
+    with pytest.raises(Exception):
+        az.RvsNetwork.from_checkpoint(str(p3))
+    c = az.RvsNetwork.from_checkpoint(str(p3), trusted=True)
+    assert torch.equal(c.flat, a.flat)
