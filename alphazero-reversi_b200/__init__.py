@@ -7,7 +7,7 @@ All computation happens in librvs_b200.so (hand-written sm_100a CUDA, C ABI in i
 There is no CPU fallback: importing is cheap, the first call raises if the library or GPU is absent.
 """
 from . import _lib, board_ops
-from ._lib import (EVAL_E0, EVAL_EXTERNAL, EVAL_NN, EVAL_ROLLOUT, RULES_REF, RULES_STRICT, RvsError)
+from ._lib import (EVAL_E0, EVAL_EXTERNAL, EVAL_NN, EVAL_ROLLOUT, MODE_FAST, MODE_REF, RULES_REF, RULES_STRICT, RvsError)
 from .engine import Engine
 from .game import Board, ReversiGame
 from .mcts import MCTS, UniformDiscDiff, UniformRollout
@@ -26,4 +26,4 @@ def __getattr__(name):  # torch-dependent members are imported lazily
 
 __all__ = ["Board", "ReversiGame", "MCTS", "SelfPlay", "Engine", "board_ops", "UniformDiscDiff",
            "UniformRollout", "RvsError", "RULES_REF", "RULES_STRICT", "EVAL_E0", "EVAL_ROLLOUT",
-           "EVAL_EXTERNAL", "EVAL_NN", "replay", "PackedSamples", "Arena", "ELOPlayer", "ELORatingSystem"]
+           "EVAL_EXTERNAL", "EVAL_NN", "MODE_REF", "MODE_FAST", "replay", "PackedSamples", "Arena", "ELOPlayer", "ELORatingSystem"]

@@ -93,10 +93,7 @@ def _cuda_index(device):
     """'cuda' / 'cuda:1' / torch.device / int -> CUDA device index for the engines (None = the current device)"""
     if device is None or isinstance(device, int):
         return device
-    idx = getattr(device, "index", None)
-    if idx is not None:
-        return idx
-    d = str(device)
+    d = str(device)  # 'cuda', 'cuda:1', or str(torch.device)
     return int(d.split(":", 1)[1]) if ":" in d else None
 
 

@@ -97,16 +97,21 @@ __global__ void __launch_bounds__(kBlock) search_fused_kernel(EngineView ev, int
     const WaveScratch ws = scratch_of(ev, g);
     unsigned long long lane_steps = 0;
     init_root(cx, root.side);
-    for (int start = 0; start < S; start += K) {
-        const int k = (S - start) < K ? (S - start) : K;
-        select_wave(cx, root, ws, k);
+    const bool fast = ev.mode == RVS_MODE_FAST;
+    for (int start = 0; start < S;) {
+        // FAST: the first wave is a single simulation (it expands the root)
+        const int k = (fast && start == 0) ? 1 : ((S - start) < K ? (S - start) : K);
+        if (fast) select_wave_fast(cx, root, ws, k);
+        else select_wave(cx, root, ws, k);
         eval_wave<RULES, EVAL>(ev, cx, ws, k, game_id, search_id, start, lane_steps);
-        process_wave(cx, ws, k, [](int, int) { return 1.0f / 65.0f; });
+        if (fast) process_wave_fast(cx, ws, k, [](int, int) { return 1.0f / 65.0f; });
+        else process_wave(cx, ws, k, [](int, int) { return 1.0f / 65.0f; });
         if (start == 0 && ev.noise_eps > 0.0f) {
             __syncwarp();
             if (cx.lane == 0) root_noise_apply(ev, g, game_id, search_id);
             __syncwarp();
         }
+        start += k;
     }
     if (cx.lane == 0) ev.n_nodes[g] = cx.n_nodes;
     flush_stats(ev, cx, lane_steps);
@@ -128,7 +133,8 @@ __global__ void __launch_bounds__(kBlock) select_kernel(EngineView ev, int k) {
     TreeCtx cx{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, ev.n_nodes[g], ev.c_puct, (int)(threadIdx.x & 31), 0, 0, 0, 0, 0, 0, make_dir<RULES>(threadIdx.x & 7)};
     const Board root{ev.black[g], ev.white[g], ev.side[g], ev.flags[g]};
     const WaveScratch ws = scratch_of(ev, g);
-    select_wave(cx, root, ws, k);
+    if (ev.mode == RVS_MODE_FAST) select_wave_fast(cx, root, ws, k);
+    else select_wave(cx, root, ws, k);
     // legal masks of the leaves (reused by leaf_planes and process)
     for (int j = cx.lane; j < k; j += 32) {
         if (ws.node[j] < 0) { ws.lm[j] = 0; continue; }
@@ -162,7 +168,8 @@ __global__ void __launch_bounds__(kBlock) process_probs_kernel(EngineView ev, in
         ws.val[j] = r >= 0 ? values[r] : 0.0f;
     }
     __syncwarp();
-    process_wave(cx, ws, k, [&](int j, int sq) { return probs[row_of(j) * 65 + sq]; });
+    if (ev.mode == RVS_MODE_FAST) process_wave_fast(cx, ws, k, [&](int j, int sq) { return probs[row_of(j) * 65 + sq]; });
+    else process_wave(cx, ws, k, [&](int j, int sq) { return probs[row_of(j) * 65 + sq]; });
     if (first_wave && ev.noise_eps > 0.0f) {
         __syncwarp();
         if (cx.lane == 0) root_noise_apply(ev, g, ev.game_id[g], (uint64_t)ev.ply[g]);
@@ -620,8 +627,9 @@ __global__ void set_positions_kernel(EngineView ev, const uint64_t* __restrict__
     if (g >= n) return;
     Board b{black[g], white[g], side[g], 0};
     ev.game_id[g] = (uint64_t)g + epoch * (uint64_t)ev.G;
-    if ((b.side != 1 && b.side != 2) || (b.black & b.white)) {  // not a position: park the slot, count it
-        ev.black[g] = kStartBlack; ev.white[g] = kStartWhite; ev.side[g] = 1; ev.flags[g] = 0;
+    if ((b.side != 1 && b.side != 2) || (b.black & b.white)) {
+        // not a position: the slot is parked on an empty finished board (a search sees a terminal root: no visits)
+        ev.black[g] = 0; ev.white[g] = 0; ev.side[g] = 1; ev.flags[g] = F_OVER;
         ev.ply[g] = 0; ev.live[g] = 0; ev.finished[g] = 0; ev.n_nodes[g] = 0;
         atomicAdd(&ev.stats[ST_BADPOS], 1ULL);
         return;
@@ -717,6 +725,7 @@ int rvs_engine_create(const rvs_engine_config* cfg, rvs_engine** out) {
     v.noise_alpha = 0.0;
     v.seed = cfg->seed;
     v.game_limit = 0;
+    v.mode = RVS_MODE_REF;
     v.ring_cap = cfg->sample_capacity > 0 ? cfg->sample_capacity : (int64_t)64 * v.G;
     const size_t G = v.G, GK = G * v.kmax, GN = G * (size_t)v.cap;
     int rc = 0;
@@ -726,7 +735,7 @@ int rvs_engine_create(const rvs_engine_config* cfg, rvs_engine** out) {
         (rc = dalloc(h, &v.cold, GN)) || (rc = dalloc(h, &v.n_nodes, G)) || (rc = dalloc(h, &v.order, G)) || (rc = dalloc(h, &v.w_node, GK)) ||
         (rc = dalloc(h, &v.w_plen, GK)) || (rc = dalloc(h, &v.w_path, GK * kMaxPath)) || (rc = dalloc(h, &v.w_black, GK)) ||
         (rc = dalloc(h, &v.w_white, GK)) || (rc = dalloc(h, &v.w_sf, GK)) || (rc = dalloc(h, &v.w_lm, GK)) ||
-        (rc = dalloc(h, &v.w_val, GK)) || (rc = dalloc(h, &v.s_black, G * 64)) || (rc = dalloc(h, &v.s_white, G * 64)) ||
+        (rc = dalloc(h, &v.w_val, GK)) || (rc = dalloc(h, &v.w_sides, GK)) || (rc = dalloc(h, &v.s_black, G * 64)) || (rc = dalloc(h, &v.s_white, G * 64)) ||
         (rc = dalloc(h, &v.s_side, G * 64)) || (rc = dalloc(h, &v.s_pi, G * 64 * 65)) ||
         (rc = dalloc(h, &v.r_black, (size_t)v.ring_cap)) || (rc = dalloc(h, &v.r_white, (size_t)v.ring_cap)) ||
         (rc = dalloc(h, &v.r_side, (size_t)v.ring_cap)) || (rc = dalloc(h, &v.r_z, (size_t)v.ring_cap)) ||
@@ -841,7 +850,7 @@ int rvs_engine_search(rvs_engine* h, int32_t num_sims, int32_t wave, void* strea
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = games_grid(h->v.G);
     const bool strict = h->cfg.rules == RVS_RULES_STRICT;
-    if (wave == 1 && (h->cfg.evaluator == RVS_EVAL_E0 || h->cfg.evaluator == RVS_EVAL_ROLLOUT)) {
+    if (wave == 1 && h->v.mode == RVS_MODE_REF && (h->cfg.evaluator == RVS_EVAL_E0 || h->cfg.evaluator == RVS_EVAL_ROLLOUT)) {
         const bool e0 = h->cfg.evaluator == RVS_EVAL_E0;
         {
             RVS_ENGINE_LAUNCH(h, phase_order_kernel, 1, 1024, 0, s, h->v);
@@ -997,12 +1006,16 @@ int rvs_engine_selfplay(rvs_engine* h, int32_t num_sims, float temperature, int6
     (void)rc;
     if (num_sims < 1 || num_sims > h->cfg.max_sims) return fail(-1, "rvs_engine_selfplay: num_sims %d outside [1,%d]", num_sims, h->cfg.max_sims);
     if (plies < 0 || temperature < 0.0f) return fail(-1, "rvs_engine_selfplay: bad arguments");
-    if (h->cfg.evaluator == RVS_EVAL_NN) {
-        // the network evaluates all leaves of a wave in one batch, so NN self-play advances in lockstep:
-        // ceil(plies / n_games) rounds of (search with wave 1, play); all launches stay on `stream`
+    if (h->cfg.evaluator == RVS_EVAL_EXTERNAL)
+        return fail(-1, "rvs_engine_selfplay: the external evaluator is driven by the caller (begin_search / select / process + play)");
+    if (h->cfg.evaluator == RVS_EVAL_NN || h->v.mode == RVS_MODE_FAST) {
+        // the network evaluates all leaves of a wave in one batch (and FAST waves are lockstep by construction), so
+        // this self-play advances in lockstep: ceil(plies / n_games) rounds of (search, play) on `stream`.
+        // REF mode: wave 1 (= MCTS(batch_size=1)); FAST mode: waves of max_wave
         const int64_t rounds = (plies + h->v.G - 1) / h->v.G;
+        const int wave = h->v.mode == RVS_MODE_FAST ? h->cfg.max_wave : 1;
         for (int64_t r = 0; r < rounds; ++r) {
-            if ((rc = rvs_engine_search(h, num_sims, 1, stream))) return rc;
+            if ((rc = rvs_engine_search(h, num_sims, wave, stream))) return rc;
             if ((rc = rvs_engine_play(h, temperature, recycle, nullptr, RVS_MEM_DEVICE, stream))) return rc;
         }
         return 0;
@@ -1132,7 +1145,7 @@ int rvs_engine_set_option(rvs_engine* h, int32_t option, int64_t value) {
         return 0;
     case RVS_OPT_SEARCH_MODE:
         if (value != RVS_MODE_REF && value != RVS_MODE_FAST) return fail(-1, "rvs_engine_set_option: search mode %lld not in {REF, FAST}", (long long)value);
-        h->search_mode = (int)value;
+        h->v.mode = (int)value;
         return 0;
     case RVS_OPT_GAME_LIMIT:
         if (value < 0 || (value > 0 && value < h->v.G))

@@ -19,6 +19,7 @@ struct EngineView {
     float noise_eps;     // Dirichlet root noise (rvs_noise.cuh); 0 = off
     double noise_alpha;
     uint64_t seed;
+    int mode;             // RVS_MODE_REF (reference wave semantics) / RVS_MODE_FAST (virtual-loss PUCT, rvs_tree.cuh)
     uint64_t game_limit;  // self-play: a slot restarts only while its next game id < game_limit (0 = unlimited)
     // game state per slot
     uint64_t* black; uint64_t* white; uint8_t* side; uint8_t* flags;
@@ -28,7 +29,7 @@ struct EngineView {
     int* order;  // slots sorted by game phase (disc count): the four games of a warp have similar rollout lengths
     // wave scratch [G*kmax]
     int* w_node; int* w_plen; int* w_path; uint64_t* w_black; uint64_t* w_white; uint16_t* w_sf;
-    uint64_t* w_lm; float* w_val;
+    uint64_t* w_lm; float* w_val; uint64_t* w_sides;
     // per-slot sample staging [G*64]
     uint64_t* s_black; uint64_t* s_white; uint8_t* s_side; float* s_pi;  // s_pi [G*64*65]
     // completed-sample ring [ring_cap]
@@ -57,7 +58,7 @@ static __device__ __noinline__ void root_noise_apply(const EngineView& ev, int g
 __device__ __forceinline__ WaveScratch scratch_of(const EngineView& ev, int g) {
     const size_t o = (size_t)g * ev.kmax;
     return WaveScratch{ev.w_node + o, ev.w_plen + o, ev.w_path + o * kMaxPath, ev.w_black + o, ev.w_white + o,
-                       ev.w_sf + o,   ev.w_lm + o,   ev.w_val + o};
+                       ev.w_sf + o,   ev.w_lm + o,   ev.w_val + o,  ev.w_sides + o};
 }
 
 }  // namespace rvs
@@ -67,7 +68,6 @@ struct rvs_engine {
     rvs::EngineView v;
     int cur_k = 0;          // wave size of the last select (external path)
     int lanes_per_game = 0; // wave-1 kernels: 0 = choose by the number of games (rvs_engine_set_lanes_per_game)
-    int search_mode = 0;    // RVS_MODE_REF / RVS_MODE_FAST (RVS_OPT_SEARCH_MODE)
     int net_graph = 0;      // RVS_OPT_NET_GRAPH
     int net_max_ctas = 0;   // RVS_OPT_NET_MAX_CTAS
     int net_pipeline = 1;   // RVS_OPT_NET_PIPELINE

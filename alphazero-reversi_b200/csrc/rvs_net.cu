@@ -475,8 +475,9 @@ int rvs_net_search(rvs_engine* h, int32_t num_sims, int32_t wave, cudaStream_t s
     // Measured on B200 (5x128, 4096 games, 100 waves): 81.5 ms with the graph, 80.1 ms with plain launches --
     // the wave loop is not launch bound (PDL already chains the tower), so replay is opt-in
     const bool use_graph = h->net_graph != 0;  // RVS_OPT_NET_GRAPH
-    for (int start = 0; start < num_sims; start += wave) {
-        const int k = num_sims - start < wave ? num_sims - start : wave;
+    const bool fast = h->v.mode == RVS_MODE_FAST;
+    for (int start = 0, k = 0; start < num_sims; start += k) {
+        k = (fast && start == 0) ? 1 : (num_sims - start < wave ? num_sims - start : wave);  // FAST: wave 0 expands the root alone
         const bool replayable = use_graph && n->graph_ok && start > 0 && k == wave && num_sims / wave >= 4;
         if (!replayable) {
             if ((rc = net_wave(h, k, s))) return rc;

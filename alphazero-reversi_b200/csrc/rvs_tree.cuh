@@ -71,6 +71,7 @@ struct WaveScratch {
     uint16_t* sf;       // side | flags << 8
     uint64_t* lm;       // legal mask of the leaf (filled by precompute)
     float* val;         // evaluator value
+    uint64_t* sides;    // FAST mode: bit d = the side to move at path node d is WHITE
 };
 
 // MCTSNode.ucb_score (mcts.py:96-114) for a visited child without a valid cache
@@ -273,6 +274,167 @@ __device__ __forceinline__ void process_wave(TreeCtx& cx, const WaveScratch& ws,
         int p0, p1, plen;
         load_path(ws, j, cx.lane, p0, p1, plen);
         backup_path(cx, p0, p1, plen, ws.val[j]);
+    }
+}
+
+// ================================================================================================
+// RVS_MODE_FAST: virtual-loss PUCT with effective per-wave leaf batching.  NOT reference behaviour (the
+// reference sends all simulations of a wave down one path: src/mcts/mcts.py:96-100,113,355-392); the
+// specification is restated independently in oracle/rvs_oracle.c (mcts_search_fast) and these kernels
+// match it bit for bit.  Differences from the functions above: no +inf for unvisited children, no score
+// cache, virtual losses count as losses in q and as visits in u, the LEAF gets a virtual loss too, W is
+// kept from the perspective of the player who moved into the node (actual movers, auto-passes respected),
+// priors are bf16-rounded, and the first wave of a search is a single simulation (root expansion).
+// ================================================================================================
+__device__ __forceinline__ float score_child_fast(int N, float W, int VL, float P, float c_puct, float sq) {
+    const int n = N + VL;
+    const float q = n > 0 ? __fdiv_rn(__fsub_rn(W, (float)VL), (float)n) : 0.0f;
+    float u = __fmul_rn(c_puct, P);
+    u = __fmul_rn(u, sq);
+    u = __fdiv_rn(u, (float)(1 + n));
+    return __fadd_rn(q, u);
+}
+
+// v_black: the value from BLACK's perspective; path node d receives it from the perspective of the player
+// who moved into it = the side to move at node d-1 (the root: its own side to move)
+__device__ __forceinline__ void backup_path_fast(TreeCtx& cx, int p0, int p1, int plen, uint64_t sides, float v_black) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int d = cx.lane + 32 * half;
+        if (d < plen) {
+            const int n = half ? p1 : p0;
+            int4 h = cx.hot[n];
+            const bool white = (sides >> (d > 0 ? d - 1 : 0)) & 1ULL;
+            h.x += 1;
+            h.y = __float_as_int(__fadd_rn(__int_as_float(h.y), white ? -v_black : v_black));
+            int vl = h.z & kVLMask;
+            if (vl > 0) --vl;
+            h.z = (h.z & ~kVLMask) | vl;
+            cx.hot[n] = h;
+        }
+    }
+    cx.bytes += 32u * (unsigned)plen;
+    __syncwarp();
+}
+
+__device__ __forceinline__ int select_one_fast(TreeCtx& cx, CoopBoard& b, int& p0, int& p1, int& plen, int& leaf_vlf,
+                                               uint64_t& sides) {
+    int node = 0;
+    p0 = 0; p1 = 0;
+    plen = 1;
+    sides = b.side == 2 ? 1ULL : 0ULL;
+    int4 h = cx.hot[0];
+    int4 c = cx.cold[0];
+    cx.bytes += 32;
+    const unsigned key_floor = ordered_key(-INFINITY);
+    while (true) {
+        const int nchild = c.z & 0xFF;
+        if (nchild == 0 || (h.z & kTerminal)) break;
+        h.z += 1;  // VL[node] += 1
+        if (cx.lane == 0) reinterpret_cast<int*>(&cx.hot[node])[2] = h.z;
+        const float sq = __fsqrt_rn((float)(h.x + (h.z & kVLMask)));
+        const int fc = c.y;
+        cx.bytes += 32u * (unsigned)nchild;
+        unsigned best_key = key_floor;
+        int best_i = -1;
+        int4 bh = h, bc = c;
+        for (int base = 0; base < nchild; base += 32) {
+            const int i = base + cx.lane;
+            int4 ch = make_int4(0, 0, 0, 0), cc = make_int4(0, 0, 0, 0);
+            unsigned key = 0;
+            if (i < nchild) {
+                ch = cx.hot[fc + i];
+                cc = cx.cold[fc + i];
+                const float score = score_child_fast(ch.x, __int_as_float(ch.y), ch.z & kVLMask, __int_as_float(cc.x), cx.c_puct, sq);
+                key = (score == score) ? ordered_key(__fadd_rn(score, 0.0f)) : 0u;
+            }
+            const unsigned mx = __reduce_max_sync(kFull, key);
+            if (mx > best_key) {
+                const int src = __ffs(__ballot_sync(kFull, key == mx)) - 1;
+                best_key = mx;
+                best_i = base + src;
+                bh = shfl4(ch, src);
+                bc = shfl4(cc, src);
+            }
+        }
+        if (best_i < 0) { cx.overflow |= 2; break; }
+        coop_apply_move(cx.dir, b, (bc.z >> 8) & 0xFF);
+        ++cx.steps;
+        node = fc + best_i;
+        h = bh;
+        c = bc;
+        if (plen < kMaxPath) {
+            if (cx.lane == (plen & 31)) { if (plen < 32) p0 = node; else p1 = node; }
+            if (b.side == 2) sides |= 1ULL << plen;
+            ++plen;
+        } else {
+            cx.overflow |= 4;
+            break;
+        }
+    }
+    h.z += 1;  // the leaf carries a virtual loss too: later simulations of the wave avoid it
+    if (cx.lane == 0) reinterpret_cast<int*>(&cx.hot[node])[2] = h.z;
+    leaf_vlf = h.z;
+    __syncwarp();
+    return node;
+}
+
+__device__ __forceinline__ float term_black_value(int vlf) { return term_value_of(vlf); }  // codes are absolute: +1 black, -1 white
+
+__device__ __forceinline__ void select_wave_fast(TreeCtx& cx, const Board& root, const WaveScratch& ws, int k) {
+    const CoopBoard root_c = coop_load(cx.dir, root);
+    for (int j = 0; j < k; ++j) {
+        CoopBoard b = root_c;
+        int p0, p1, plen, vlf;
+        uint64_t sides;
+        const int node = select_one_fast(cx, b, p0, p1, plen, vlf, sides);
+        ++cx.sims;
+        if (vlf & kTerminal) {
+            backup_path_fast(cx, p0, p1, plen, sides, term_black_value(vlf));
+            if (cx.lane == 0) ws.node[j] = -1;
+        } else {
+            store_leaf(ws, j, cx.lane, node, p0, p1, plen, coop_store(cx.dir, b));
+            if (cx.lane == 0) ws.sides[j] = sides;
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ float bf16_round_f32(float x) {  // round-to-nearest-even to bf16 precision (finite inputs)
+    unsigned u = __float_as_uint(x);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return __uint_as_float(u & 0xFFFF0000u);
+}
+
+// the FAST counterpart of process_wave(): ws.val[j] is the evaluator's value from the LEAF MOVER's perspective
+template <typename PriorFn>
+__device__ __forceinline__ void process_wave_fast(TreeCtx& cx, const WaveScratch& ws, int k, PriorFn prior_for_slot) {
+    for (int j = 0; j < k; ++j) {
+        const int node = ws.node[j];
+        if (node < 0 || ws.lm[j] != 0) continue;
+        int p0, p1, plen;
+        load_path(ws, j, cx.lane, p0, p1, plen);
+        const int flags = ws.sf[j] >> 8;
+        const int w = (flags & F_WIN_MASK) >> F_WIN_SHIFT;
+        const int code = !(flags & F_OVER) ? 0 : (w == 1 ? 1 : (w == 2 ? 2 : 0));
+        if (cx.lane == 0) {
+            int* z = &reinterpret_cast<int*>(&cx.hot[node])[2];
+            *z = (*z & ~(3 << kTermShift)) | kTerminal | (code << kTermShift);
+        }
+        __syncwarp();
+        backup_path_fast(cx, p0, p1, plen, ws.sides[j], code == 1 ? 1.0f : (code == 2 ? -1.0f : 0.0f));
+    }
+    for (int j = 0; j < k; ++j) {
+        const int node = ws.node[j];
+        if (node < 0) continue;
+        const uint64_t lm = ws.lm[j];
+        if (lm == 0) continue;
+        ++cx.evals;
+        expand_node(cx, node, lm, [&](int sq) { return bf16_round_f32(prior_for_slot(j, sq)); });
+        int p0, p1, plen;
+        load_path(ws, j, cx.lane, p0, p1, plen);
+        const float v = ws.val[j];
+        backup_path_fast(cx, p0, p1, plen, ws.sides[j], (ws.sf[j] & 0xFF) == 1 ? v : -v);
     }
 }
 

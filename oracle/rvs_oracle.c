@@ -383,12 +383,215 @@ static void eval_e0(const orc_board *lv, int n, float *probs, float *values) {
     }
 }
 
+/* ---------------- FAST search mode (engine feature; NOT reference behaviour) ----------------
+ * Parity status: UNPINNED BY THE REFERENCE.  The reference's "batched" search sends every simulation of a
+ * wave down one path (+inf for unvisited children whatever the virtual loss, stale cached UCB, backups only
+ * after the wave: src/mcts/mcts.py:96-100,113,355-392), so a wave of K costs K evaluations of
+ * about one unique leaf.  RVS_MODE_FAST is this engine's own specification of the textbook alternative --
+ * virtual-loss PUCT -- and this function is its independent restatement; the CUDA kernels must match it bit
+ * for bit (tests/test_gpu_fast.py).  Specification:
+ *   - W of a node is the value sum from the perspective of the player who moved INTO it (the side to move at
+ *     its parent, as actually played: auto-passes are respected); the root's W is from the root mover's side.
+ *   - wave schedule: the first wave is ONE simulation (it expands the root); then waves of min(K, remaining).
+ *   - descent while the node is expanded and not terminal: VL[node] += 1; Nt = N + VL of the node;
+ *       score(child) = q + u,  n = N_c + VL_c,  q = n > 0 ? (W_c - f32(VL_c)) / f32(n) : 0,
+ *       u = ((c_puct * P_c) * f32(sqrt(Nt))) / f32(1 + n)      (IEEE f32, no FMA, this operation order)
+ *     first maximum in creation order wins; no score cache, no +inf.  The LEAF gets VL += 1 as well, so the
+ *     following simulations of the wave are steered to other leaves.
+ *   - a terminal-flagged leaf is backed up at once; after the wave, in selection order: a leaf without legal
+ *     moves is flagged terminal with its outcome; the others are evaluated (one evaluation per distinct node),
+ *     expanded if still unexpanded with priors rounded to bf16 (round-to-nearest-even), and backed up.
+ *   - backup, leaf to root: VL -= 1 (if > 0), N += 1, W += value for the player who moved into the node
+ *     (evaluator value v is from the leaf mover's perspective; terminal: +1 / -1 / 0 by the winner).
+ *   - Dirichlet root noise as in the reference-compatible mode (after the root expansion).
+ */
+static int g_search_mode = 0;
+void orc_set_search_mode(int mode) { g_search_mode = mode; }
+
+static float bf16_round(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    u &= 0xFFFF0000u;
+    memcpy(&x, &u, 4);
+    return x;
+}
+
+typedef struct { int node; int plen; int path[64]; uint8_t side[64]; orc_board b; int sim; } fleaf;
+
+static void backprop_fast(otree *t, const fleaf *L, float v_black) {
+    for (int i = L->plen - 1; i >= 0; i--) {
+        onode *x = &t->nodes[L->path[i]];
+        int mover = i == 0 ? L->side[0] : L->side[i - 1]; /* who moved into path[i] */
+        if (x->VL > 0) x->VL--;
+        x->N++;
+        x->W = x->W + (mover == 1 ? v_black : -v_black);
+    }
+}
+
+static int mcts_search_fast(const orc_board *root, int num_sims, int wave, float c_puct, int rules,
+                            int evaluator, orc_eval_fn fn, void *ctx, uint64_t seed, uint64_t game_id,
+                            uint64_t search_id, int32_t *visits, int32_t *root_n, float *root_w,
+                            int64_t *n_evals, int64_t *n_unique) {
+    otree t;
+    t.cap = 2 + num_sims * 34;
+    t.nodes = (onode *)malloc(sizeof(onode) * (size_t)t.cap);
+    t.n = 0;
+    t.c_puct = c_puct;
+    fleaf *leaves = (fleaf *)malloc(sizeof(fleaf) * (size_t)wave);
+    orc_board *lb = (orc_board *)malloc(sizeof(orc_board) * (size_t)wave);
+    float *probs = (float *)malloc(sizeof(float) * 65 * (size_t)wave);
+    float *values = (float *)malloc(sizeof(float) * (size_t)wave);
+    int *lidx = (int *)malloc(sizeof(int) * (size_t)wave);
+    int *rep = (int *)malloc(sizeof(int) * (size_t)wave);
+    int64_t evals = 0, unique = 0;
+    int rc = 0;
+    tree_new(&t, 1.0f, root->side, 255);
+    for (int start = 0; start < num_sims && rc >= 0;) {
+        int k = start == 0 ? 1 : (num_sims - start < wave ? num_sims - start : wave);
+        int nleaf = 0;
+        for (int j = 0; j < k; j++) {
+            fleaf *L = &leaves[nleaf];
+            L->b = *root;
+            L->plen = 0;
+            L->sim = start + j;
+            int node = 0;
+            L->side[0] = L->b.side;
+            L->path[L->plen++] = 0;
+            while (t.nodes[node].nchild > 0 && !t.nodes[node].terminal) {
+                t.nodes[node].VL++;
+                int Nt = t.nodes[node].N + t.nodes[node].VL;
+                float sq = (float)sqrt((double)Nt);
+                float best = -INFINITY;
+                int next = -1;
+                int fc = t.nodes[node].first_child, nc = t.nodes[node].nchild;
+                for (int c = fc; c < fc + nc; c++) {
+                    onode *x = &t.nodes[c];
+                    int n = x->N + x->VL;
+                    float q = n > 0 ? (x->W - (float)x->VL) / (float)n : 0.0f;
+                    float u = t.c_puct * x->P;
+                    u = u * sq;
+                    u = u / (float)(1 + n);
+                    float sc = q + u;
+                    if (sc > best) { best = sc; next = c; }
+                }
+                if (next < 0) { rc = -2; break; }
+                orc_apply(&L->b, t.nodes[next].move, rules);
+                node = next;
+                if (L->plen >= 64) { rc = -3; break; }
+                L->side[L->plen] = L->b.side;
+                L->path[L->plen++] = node;
+            }
+            if (rc < 0) break;
+            L->node = node;
+            t.nodes[node].VL++; /* the leaf carries a virtual loss too */
+            if (t.nodes[node].terminal) {
+                backprop_fast(&t, L, t.nodes[node].term_value);
+                continue;
+            }
+            nleaf++;
+        }
+        if (rc < 0) break;
+        int ne = 0;
+        for (int i = 0; i < nleaf; i++) {
+            fleaf *L = &leaves[i];
+            uint64_t lm = orc_board_legal(&L->b, rules);
+            if (lm == 0) { /* flagged with the outcome from BLACK's perspective (0 when not over) */
+                onode *x = &t.nodes[L->node];
+                x->terminal = 1;
+                x->term_value = !L->b.over ? 0.0f : L->b.winner == 1 ? 1.0f : L->b.winner == 2 ? -1.0f : 0.0f;
+                backprop_fast(&t, L, x->term_value);
+                continue;
+            }
+            rep[ne] = -1;
+            for (int q = 0; q < ne; q++)
+                if (leaves[lidx[q]].node == L->node) { rep[ne] = q; break; }
+            lb[ne] = L->b;
+            lidx[ne] = i;
+            ne++;
+        }
+        if (ne > 0) {
+            if (evaluator == ORC_EVAL_E0) {
+                eval_e0(lb, ne, probs, values);
+            } else if (evaluator == ORC_EVAL_ROLLOUT) {
+                for (int i = 0; i < ne; i++) {
+                    for (int q = 0; q < 65; q++) probs[i * 65 + q] = 1.0f / 65.0f;
+                    orc_board c = lb[i];
+                    uint64_t st = orc_stream_seed(seed, game_id, (search_id << 16) | (uint64_t)leaves[lidx[i]].sim);
+                    orc_random_playout(&c, st, rules);
+                    values[i] = (!c.over || c.winner == 0) ? 0.0f : (c.winner == lb[i].side ? 1.0f : -1.0f);
+                }
+            } else {
+                fn(ctx, lb, ne, probs, values);
+            }
+            evals += ne;
+            for (int i = 0; i < ne; i++) {
+                fleaf *L = &leaves[lidx[i]];
+                onode *x = &t.nodes[L->node];
+                if (rep[i] < 0) unique++;
+                if (x->nchild == 0) {
+                    uint64_t lm = orc_board_legal(&L->b, rules);
+                    int nc = popc(lm);
+                    if (t.n + nc > t.cap) { rc = -1; break; }
+                    int fc = t.n;
+                    while (lm) {
+                        int sq = __builtin_ctzll(lm);
+                        lm &= lm - 1;
+                        tree_new(&t, bf16_round(probs[i * 65 + sq]), 3 - x->turn, sq);
+                    }
+                    x = &t.nodes[L->node];
+                    x->first_child = fc;
+                    x->nchild = nc;
+                }
+                /* a duplicate leaf of the wave shares the evaluation of its first occurrence (rollout
+                 * evaluators draw per simulation, so each copy keeps its own value there) */
+                float v = (rep[i] >= 0 && evaluator != ORC_EVAL_ROLLOUT) ? values[rep[i]] : values[i];
+                backprop_fast(&t, L, lb[i].side == 1 ? v : -v);
+            }
+        }
+        if (start == 0 && g_noise_eps > 0.0f && t.nodes[0].nchild > 0 && t.nodes[0].nchild <= 64) {
+            float eta[64];
+            int fc = t.nodes[0].first_child, nc = t.nodes[0].nchild;
+            orc_dirichlet(g_noise_alpha, nc, orc_stream_seed(seed, game_id, 0xD1000000ULL + search_id), eta);
+            for (int c = 0; c < nc; c++) {
+                float keep = (1.0f + (-g_noise_eps)) * t.nodes[fc + c].P;
+                float add = g_noise_eps * eta[c];
+                t.nodes[fc + c].P = keep + add;
+            }
+        }
+        start += k;
+    }
+    for (int i = 0; i < 65; i++) visits[i] = 0;
+    if (rc >= 0) {
+        onode *r = &t.nodes[0];
+        for (int c = r->first_child; c >= 0 && c < r->first_child + r->nchild; c++) visits[t.nodes[c].move] = t.nodes[c].N;
+        if (root_n) *root_n = r->N;
+        if (root_w) *root_w = r->W;
+        rc = t.n;
+    }
+    if (n_evals) *n_evals = evals;
+    if (n_unique) *n_unique = unique;
+    free(t.nodes); free(leaves); free(lb); free(probs); free(values); free(lidx); free(rep);
+    return rc;
+}
+
+int orc_mcts_search_fast(const orc_board *root, int num_sims, int wave, float c_puct, int rules, int evaluator,
+                         orc_eval_fn fn, void *ctx, uint64_t seed, uint64_t game_id, uint64_t search_id,
+                         int32_t *visits, int32_t *root_n, float *root_w, int64_t *n_evals, int64_t *n_unique) {
+    if (wave < 1) wave = 1;
+    return mcts_search_fast(root, num_sims, wave, c_puct, rules, evaluator, fn, ctx, seed, game_id, search_id, visits,
+                            root_n, root_w, n_evals, n_unique);
+}
+
 typedef struct { int node; int plen; int path[64]; orc_board b; int sim; } oleaf;
 
 int orc_mcts_search(const orc_board *root, int num_sims, int wave, float c_puct, int rules,
                     int evaluator, orc_eval_fn fn, void *ctx, uint64_t seed,
                     uint64_t game_id, uint64_t search_id, int32_t *visits, int32_t *root_n,
                     float *root_w, int64_t *n_evals) {
+    if (g_search_mode == 1) /* orc_set_search_mode(1): the engine's FAST mode, see above */
+        return orc_mcts_search_fast(root, num_sims, wave, c_puct, rules, evaluator, fn, ctx, seed, game_id, search_id,
+                                    visits, root_n, root_w, n_evals, 0);
     otree t;
     t.cap = 2 + num_sims * 34;
     if (wave < 1) wave = 1;

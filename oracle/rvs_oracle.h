@@ -63,6 +63,14 @@ int orc_mcts_search(const orc_board *root, int num_sims, int wave, float c_puct,
                     uint64_t game_id, uint64_t search_id, int32_t *visits, int32_t *root_n,
                     float *root_w, int64_t *n_evals);
 
+/* RVS_MODE_FAST (engine feature, virtual-loss PUCT; specification in rvs_oracle.c).  PARITY UNPINNED BY THE
+ * REFERENCE: the reference has no such mode, the oracle is the specification the CUDA kernels are held to.
+ * orc_set_search_mode(1) routes orc_mcts_search / orc_self_play_game / orc_search_batch through it. */
+void orc_set_search_mode(int mode);
+int orc_mcts_search_fast(const orc_board *root, int num_sims, int wave, float c_puct, int rules, int evaluator,
+                         orc_eval_fn fn, void *ctx, uint64_t seed, uint64_t game_id, uint64_t search_id,
+                         int32_t *visits, int32_t *root_n, float *root_w, int64_t *n_evals, int64_t *n_unique);
+
 /* Dirichlet noise on the root priors (engine feature, see rvs_oracle.c): applied by every following
  * orc_mcts_search / orc_self_play_game right after the root expansion; eps == 0 switches it off */
 void orc_set_root_noise(double alpha, float eps);

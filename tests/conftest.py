@@ -17,5 +17,5 @@ def pytest_configure(config):
 def golden():
     import numpy as np
     g = os.path.join(ROOT, "tests", "golden")
-    return {k: dict(np.load(os.path.join(g, k + ".npz"))) for k in ("board", "mcts", "net", "selfplay")
+    return {k: dict(np.load(os.path.join(g, k + ".npz"))) for k in ("board", "mcts", "net", "net20", "selfplay")
             if os.path.exists(os.path.join(g, k + ".npz"))}

@@ -81,6 +81,13 @@ def lib():
                                       C.c_void_p, u64, u64, u64, C.POINTER(C.c_int32),
                                       C.POINTER(C.c_int32), C.POINTER(C.c_float),
                                       C.POINTER(C.c_int64)]
+        L.orc_set_search_mode.restype = None
+        L.orc_set_search_mode.argtypes = [i32]
+        L.orc_mcts_search_fast.restype = i32
+        L.orc_mcts_search_fast.argtypes = [C.POINTER(Board), i32, i32, C.c_float, i32, i32, EVAL_FN,
+                                           C.c_void_p, u64, u64, u64, C.POINTER(C.c_int32),
+                                           C.POINTER(C.c_int32), C.POINTER(C.c_float),
+                                           C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.orc_action_probs.argtypes = [C.POINTER(C.c_int32), C.c_double, C.POINTER(C.c_double)]
         L.orc_self_play_game.restype = i32
         L.orc_self_play_game.argtypes = [i32, i32, C.c_float, i32, i32, EVAL_FN, C.c_void_p, u64,
@@ -162,6 +169,29 @@ def mcts_search(pos, num_sims, wave, c_puct=1.0, rules=RULES_REF, evaluator=EVAL
     if rc < 0:
         raise RuntimeError(f"orc_mcts_search failed rc={rc}")
     return np.array(vis[:], dtype=np.int32), rn.value, np.float32(rw.value), ne.value
+
+
+def mcts_search_fast(pos, num_sims, wave, c_puct=1.0, rules=RULES_REF, evaluator=EVAL_E0, pyfn=None,
+                     seed=0, game_id=0, search_id=0):
+    """the engine's FAST search mode (virtual-loss PUCT; specification in oracle/rvs_oracle.c -- not reference
+    behaviour).  Returns (visits, root_n, root_w, evals consumed, unique evaluations)."""
+    b = make_board(*pos, rules=rules)
+    vis = (C.c_int32 * 65)()
+    rn = C.c_int32(0)
+    rw = C.c_float(0)
+    ne = C.c_int64(0)
+    nu = C.c_int64(0)
+    fn = _wrap_eval(pyfn) if pyfn is not None else EVAL_FN()
+    rc = lib().orc_mcts_search_fast(C.byref(b), num_sims, wave, c_puct, rules, evaluator, fn, None, seed,
+                                    game_id, search_id, vis, C.byref(rn), C.byref(rw), C.byref(ne), C.byref(nu))
+    if rc < 0:
+        raise RuntimeError(f"orc_mcts_search_fast failed rc={rc}")
+    return np.array(vis[:], dtype=np.int32), rn.value, np.float32(rw.value), ne.value, nu.value
+
+
+def set_search_mode(mode):
+    """0 = reference-compatible (graded), 1 = FAST: routes mcts_search / self_play_game / search_batch"""
+    lib().orc_set_search_mode(int(mode))
 
 
 def set_root_noise(alpha, eps):

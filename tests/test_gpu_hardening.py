@@ -146,7 +146,8 @@ def test_set_positions_validates_and_draws_fresh_streams(az):
     eng.set_positions(tb, tw, ts)
     eng.search(60, 1)
     st = eng.stats()
-    assert st["bad_positions"] == 1 and st["sims"] == 15 * 60
+    v = eng.root_visits()
+    assert st["bad_positions"] == 1 and v[5].sum() == 0 and (np.delete(v, 5, axis=0).sum(axis=1) == 59).all()
     eng.close()
     # successive set_positions calls on one handle play game ids g, g + G, g + 2G, ...: the rollout streams of
     # two searches of the SAME roots differ (they were identical in round 1), and each equals the oracle's
