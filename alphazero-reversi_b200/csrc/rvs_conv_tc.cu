@@ -35,8 +35,12 @@ constexpr int kThreads = 192;
 struct Impl {
     CUtensorMap w_map2;   // box of C/2 weight rows (one CTA's half of a tap)
     int cin = 0;
-    const void* act_ptr[4] = {nullptr, nullptr, nullptr, nullptr};
-    CUtensorMap act_map[4];
+    // TMA descriptors of the activation buffers this layer has been launched on, keyed by (base pointer, capacity):
+    // 3 ping-pong buffers x 2 half-batches of a pipelined search
+    static constexpr int kActSlots = 8;
+    const void* act_ptr[kActSlots] = {};
+    int64_t act_cap[kActSlots] = {};
+    CUtensorMap act_map[kActSlots];
     int n_act = 0;
 };
 
@@ -651,28 +655,31 @@ int conv_tc_plan(ConvTcPlan& plan, const __nv_bfloat16* w, int C, int64_t max_ba
 
 int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
                    const float* bias, int64_t B, cudaStream_t s, const ConvHeadW* head, float* feat, const int* n_dev,
-                   int max_ctas) {
+                   int max_ctas, int64_t cap_boards) {
     if (!plan.valid || !plan.impl) return fail(-8, "tcgen05 convolution: no plan");
     Impl* im = static_cast<Impl*>(plan.impl);
     static const ConvHeadW zero_head = {};
     if (!(feat && head)) { feat = nullptr; head = &zero_head; }
+    const int64_t cap = cap_boards > 0 ? cap_boards : plan.max_batch;  // boards addressable from `in`
+    if (B > cap) return fail(-8, "tcgen05 convolution: batch %lld exceeds the buffer capacity %lld", (long long)B, (long long)cap);
     int slot = -1;
     for (int i = 0; i < im->n_act; ++i)
-        if (im->act_ptr[i] == in) slot = i;
+        if (im->act_ptr[i] == in && im->act_cap[i] == cap) slot = i;
     if (slot < 0) {
-        if (im->n_act == 4) im->n_act = 0;
+        if (im->n_act == Impl::kActSlots) im->n_act = 0;
         slot = im->n_act++;
-        int rc = encode_act_map(&im->act_map[slot], in, im->cin, (plan.max_batch + 1) / 2);
+        int rc = encode_act_map(&im->act_map[slot], in, im->cin, (cap + 1) / 2);  // tiles beyond the map are zero-filled by TMA
         if (rc) return rc;
         im->act_ptr[slot] = in;
+        im->act_cap[slot] = cap;
     }
     const int n_tiles = (int)((B + 1) / 2);
     const int C = plan.C;
     // CTA pairs: grid = 2 x pairs, at most one CTA per SM (max_ctas < 148 leaves SMs to concurrent tree kernels)
-    int cap = (max_ctas > 0 && max_ctas < kNumSMs ? max_ctas : kNumSMs) / 2;
-    if (cap < 1) cap = 1;
+    int pair_cap = (max_ctas > 0 && max_ctas < kNumSMs ? max_ctas : kNumSMs) / 2;
+    if (pair_cap < 1) pair_cap = 1;
     int pairs = (n_tiles + 1) / 2;
-    if (pairs > cap) pairs = cap;
+    if (pairs > pair_cap) pairs = pair_cap;
     const CUtensorMap& am = im->act_map[slot];
     if (C == 256) return launch_pdl_s(2 * pairs, s, am, im->w_map2, residual, out, bias, n_tiles, n_dev);
     if (C == 64) {

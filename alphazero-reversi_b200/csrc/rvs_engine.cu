@@ -179,6 +179,64 @@ __global__ void __launch_bounds__(kBlock) process_probs_kernel(EngineView ev, in
     flush_stats(ev, cx, 0);
 }
 
+// One wave-1 step of the NN-evaluated search for the games [g0, g1), everything the tree does between two network
+// passes in ONE kernel: (flags & 1) MCTS._process_batch of the pending leaf with the network's outputs (row `rows[g]` of
+// probs / values; mcts.py:596-623), (flags & 4) root noise after the root expansion, then (flags & 2) the next
+// MCTS._traverse (mcts.py:409-444), the leaf's legal mask and K3 with compaction: a leaf that needs an evaluation
+// appends its three bit planes to the half-batch (one atomic) and remembers its row.  n_next is the counter of the
+// following wave, zeroed here because nothing else uses it while this kernel runs.
+template <int RULES>
+__global__ void __launch_bounds__(kBlock) nn_step_kernel(EngineView ev, int g0, int g1, int flags, const float* __restrict__ probs,
+                                                          const float* __restrict__ values, int* __restrict__ rows,
+                                                          uint64_t* __restrict__ bits_out, int* __restrict__ n_cur,
+                                                          int* __restrict__ n_next) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n_next) *n_next = 0;
+    const int g = g0 + blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (g >= g1) return;
+    TreeCtx cx{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, ev.n_nodes[g], ev.c_puct, (int)(threadIdx.x & 31), 0, 0, 0, 0, 0, 0, make_dir<RULES>(threadIdx.x & 7)};
+    const WaveScratch ws = scratch_of(ev, g);
+    const bool fast = ev.mode == RVS_MODE_FAST;
+    if (flags & 1) {
+        const int row = rows[g];
+        if (cx.lane == 0) ws.val[0] = row >= 0 ? values[row] : 0.0f;
+        __syncwarp();
+        auto prior = [&](int, int sq) { return probs[(size_t)row * 65 + sq]; };  // only called for evaluated leaves (row >= 0)
+        if (fast) process_wave_fast(cx, ws, 1, prior);
+        else process_wave(cx, ws, 1, prior);
+        if ((flags & 4) && ev.noise_eps > 0.0f) {
+            __syncwarp();
+            if (cx.lane == 0) root_noise_apply(ev, g, ev.game_id[g], (uint64_t)ev.ply[g]);
+            __syncwarp();
+        }
+    }
+    if (flags & 2) {
+        const Board root{ev.black[g], ev.white[g], ev.side[g], ev.flags[g]};
+        if (fast) select_wave_fast(cx, root, ws, 1);
+        else select_wave(cx, root, ws, 1);
+        if (cx.lane == 0) {
+            const int node = ws.node[0];
+            uint64_t lm = 0;
+            int row = -1;
+            if (node >= 0) {
+                const uint16_t sf = ws.sf[0];
+                const Board b{ws.black[0], ws.white[0], (uint8_t)(sf & 0xFF), (uint8_t)(sf >> 8)};
+                lm = board_legal<RULES>(b);
+                if (lm) {
+                    row = atomicAdd(n_cur, 1);
+                    const bool blk = b.side == 1;
+                    bits_out[(size_t)row * 3] = blk ? b.black : b.white;
+                    bits_out[(size_t)row * 3 + 1] = blk ? b.white : b.black;
+                    bits_out[(size_t)row * 3 + 2] = lm;
+                }
+            }
+            ws.lm[0] = lm;
+            rows[g] = row;
+        }
+    }
+    if (cx.lane == 0) ev.n_nodes[g] = cx.n_nodes;
+    flush_stats(ev, cx, 0);
+}
+
 // canonical planes of the selected leaves (game.py:131-162), 48 threads x float4 per slot
 __global__ void __launch_bounds__(256) leaf_planes_kernel(EngineView ev, int k, float4* __restrict__ out,
                                                            uint8_t* __restrict__ valid) {
@@ -1210,5 +1268,14 @@ int rvs_engine_process_mapped(rvs_engine* h, const float* probs, const float* va
     RVS_ENGINE_LAUNCH(h, process_probs_kernel, games_grid(h->v.G), kBlock, 0, s, h->v, h->cur_k, probs, values, h->waves_done == 0 ? 1 : 0, inv);
     h->waves_done++;
     h->cur_k = 0;
+    return 0;
+}
+
+int rvs_engine_nn_step(rvs_engine* h, int g0, int g1, int flags, const float* probs, const float* values, int* rows,
+                       uint64_t* bits_out, int* n_cur, int* n_next, cudaStream_t s) {
+    if (g1 <= g0) return 0;
+    const int grid = (g1 - g0 + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    if (h->cfg.rules == RVS_RULES_STRICT) RVS_ENGINE_LAUNCH(h, nn_step_kernel<RULES_STRICT>, grid, kBlock, 0, s, h->v, g0, g1, flags, probs, values, rows, bits_out, n_cur, n_next);
+    else RVS_ENGINE_LAUNCH(h, nn_step_kernel<RULES_REF>, grid, kBlock, 0, s, h->v, g0, g1, flags, probs, values, rows, bits_out, n_cur, n_next);
     return 0;
 }

@@ -70,7 +70,7 @@ struct rvs_engine {
     int lanes_per_game = 0; // wave-1 kernels: 0 = choose by the number of games (rvs_engine_set_lanes_per_game)
     int net_graph = 0;      // RVS_OPT_NET_GRAPH
     int net_max_ctas = 0;   // RVS_OPT_NET_MAX_CTAS
-    int net_pipeline = 1;   // RVS_OPT_NET_PIPELINE
+    int net_pipeline = 0;   // RVS_OPT_NET_PIPELINE (measured slower than lockstep on B200, DESIGN.md K4: opt-in)
     uint64_t epoch = 0;     // set_positions calls since create / reset: game id of slot g = g + epoch * G
     unsigned long long* pinned_count = nullptr;  // pinned host word for the sample count of the synchronous drains
     int waves_done = 0;     // waves processed since begin_search (root noise goes in after the first)
@@ -121,3 +121,6 @@ int rvs_net_search(rvs_engine* h, int32_t num_sims, int32_t wave, cudaStream_t s
 // rvs_engine_process with device probs / values addressed through the compaction map of rvs_net.cu
 int rvs_engine_process_mapped(rvs_engine* h, const float* probs, const float* values, const int* inv, cudaStream_t s);
 void rvs_net_destroy(rvs::NetState* n);
+// one fused tree step (process pending leaf | select next | encode) of the wave-1 NN search for games [g0, g1)
+int rvs_engine_nn_step(rvs_engine* h, int g0, int g1, int flags, const float* probs, const float* values, int* rows,
+                       uint64_t* bits_out, int* n_cur, int* n_next, cudaStream_t s);

@@ -18,6 +18,38 @@
 
 namespace rvs {
 
+// -DRVS_TIMELINE (debug builds only, never in the shipped library): CUDA events at the phase boundaries of a
+// few waves of rvs_net_search_w1 / net_forward, printed as offsets from the first one (tools/probe_nn_search.py)
+#ifdef RVS_TIMELINE
+struct TimelineRec { const char* what; int wave, half; };
+static std::vector<TimelineRec> g_tl;
+static unsigned long long* g_tl_buf = nullptr;  // device: %globaltimer stamps
+static bool g_tl_on = false;
+static int g_tl_wave = 0, g_tl_half = 0;
+__global__ void tl_stamp_kernel(unsigned long long* out) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *out = t;
+}
+static void tl_mark(const char* what, cudaStream_t s) {
+    if (!g_tl_on || g_tl.size() >= 4096) return;
+    if (!g_tl_buf) cudaMalloc(&g_tl_buf, 4096 * 8);
+    tl_stamp_kernel<<<1, 1, 0, s>>>(g_tl_buf + g_tl.size());
+    g_tl.push_back({what, g_tl_wave, g_tl_half});
+}
+static void tl_dump() {
+    cudaDeviceSynchronize();
+    std::vector<unsigned long long> t(g_tl.size());
+    cudaMemcpy(t.data(), g_tl_buf, t.size() * 8, cudaMemcpyDeviceToHost);
+    for (size_t i = 0; i < g_tl.size(); ++i)
+        fprintf(stderr, "TL wave %d half %d %-12s %9.1f us\n", g_tl[i].wave, g_tl[i].half, g_tl[i].what, (double)(t[i] - t[0]) * 1e-3);
+    g_tl.clear();
+}
+#define TL_MARK(what, s) tl_mark(what, s)
+#else
+#define TL_MARK(what, s) do { } while (0)
+#endif
+
 struct ConvLayer {
     __nv_bfloat16* w = nullptr;  // [9][Cout][Cin]
     float* bias = nullptr;       // [Cout]
@@ -37,7 +69,11 @@ struct NetState {
     float *v1w = nullptr, *v1b = nullptr;    // fc1 TRANSPOSED [64][256], [256]
     float *w0f = nullptr, *b0f = nullptr;    // first conv for the bit-plane kernel: [27][C] f32, [C]
     uint64_t* bits = nullptr;                // [B][3] own / opponent / legal bit planes (K3 output)
-    int* n_valid = nullptr;                  // [1] boards in the compacted leaf batch of the current wave
+    int* n_valid = nullptr;                  // [8] boards in the compacted leaf batch of the current wave ([0]: lockstep path;
+                                             // [2 + 2 * half + parity]: the pipelined wave-1 path, see rvs_net_search_w1)
+    int* rows = nullptr;                     // [G] pipelined path: row of each game's pending leaf in its half's batch (-1: none)
+    cudaStream_t side = nullptr;             // second stream of the pipelined search (the caller's stream is the first)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int* inv = nullptr;                      // [B] wave slot -> row of the compacted batch (-1: none, <= -2: same as slot -2-inv of its game)
     __nv_bfloat16* x0 = nullptr;             // [tile][y][board][x][64] bf16 input planes (3 used) for the tcgen05 first layer
     float *v2w = nullptr, *v2b = nullptr;    // fc2 [256], [1]
@@ -359,37 +395,50 @@ __global__ void __launch_bounds__(256) encode_positions_kernel(const uint64_t* _
 
 }  // namespace
 
-// forward pass on B boards whose bit planes are already in n->bits; results in n->probs/logits/values
-int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s, const int* n_dev = nullptr) {
+// forward pass on B boards whose bit planes are already in n->bits (+ off boards); results in n->probs / logits /
+// values (+ off).  `off` (even: whole tiles) and `cap` select a sub-range of every buffer: the half-batches of a
+// pipelined search run their own forward passes on their own streams.
+int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s, const int* n_dev = nullptr, int64_t off = 0,
+                int64_t cap = 0) {
     NetState* n = h->net;
     if (!n || !n->loaded) return fail(-7, "network weights not loaded: call rvs_engine_load_weights first");
-    if (B > n->max_batch) return fail(-7, "network batch %lld exceeds capacity %lld", (long long)B, (long long)n->max_batch);
+    if (cap <= 0) cap = n->max_batch - off;
+    if (B > cap || off + cap > n->max_batch + 1 || (off & 1)) return fail(-7, "network batch %lld (+%lld) exceeds capacity %lld", (long long)B, (long long)off, (long long)n->max_batch);
     if (B == 0) return 0;
     int rc;
+    const int C = n->C;
+    const int mc = h->net_max_ctas;
+    const uint64_t* bits = n->bits + off * 3;
+    __nv_bfloat16* x0 = n->x0 + off * 64 * 64;
+    __nv_bfloat16 *x = n->a + off * 64 * C, *t = n->b + off * 64 * C, *y = n->c + off * 64 * C;
+    float* feat = n->feat + off * 192;
     if (n->conv0.tc.valid) {  // first layer on the tensor cores: planes -> bf16 tiles -> tcgen05
         const int64_t tiles = (B + 1) / 2;
-        RVS_LAUNCH(planes_tiles_kernel, grid_for(tiles * 128, 256), 256, 0, s, n->bits, B, tiles, (uint4*)n->x0, n_dev);
-        if ((rc = conv_tc_launch(n->conv0.tc, n->x0, nullptr, n->a, n->conv0.bias, B, s, nullptr, nullptr, n_dev))) return rc;
+        RVS_LAUNCH(planes_tiles_kernel, grid_for(tiles * 128, 256), 256, 0, s, bits, B, tiles, (uint4*)x0, n_dev);
+        TL_MARK("planes", s);
+        if ((rc = conv_tc_launch(n->conv0.tc, x0, nullptr, x, n->conv0.bias, B, s, nullptr, nullptr, n_dev, mc, cap))) return rc;
+        TL_MARK("conv0", s);
     } else {  // network.py:97, fused with the leaf encoding (CUDA cores)
         const int tiles = (int)((B + 1) / 2);
-        if (n->C == 64) RVS_LAUNCH(conv0_bits_kernel<64>, tiles, 256, 0, s, n->bits, B, n->w0f, n->b0f, n->a, n_dev);
-        else if (n->C == 128) RVS_LAUNCH(conv0_bits_kernel<128>, tiles, 256, 0, s, n->bits, B, n->w0f, n->b0f, n->a, n_dev);
-        else RVS_LAUNCH(conv0_bits_kernel<256>, tiles, 256, 0, s, n->bits, B, n->w0f, n->b0f, n->a, n_dev);
+        if (C == 64) RVS_LAUNCH(conv0_bits_kernel<64>, tiles, 256, 0, s, bits, B, n->w0f, n->b0f, x, n_dev);
+        else if (C == 128) RVS_LAUNCH(conv0_bits_kernel<128>, tiles, 256, 0, s, bits, B, n->w0f, n->b0f, x, n_dev);
+        else RVS_LAUNCH(conv0_bits_kernel<256>, tiles, 256, 0, s, bits, B, n->w0f, n->b0f, x, n_dev);
     }
-    __nv_bfloat16 *x = n->a, *t = n->b, *y = n->c;
     bool fused_head = false;
     for (int i = 0; i < n->blocks; ++i) {  // ResBlock (network.py:23-28)
         const ConvLayer& c1 = n->tower[2 * i];
         const ConvLayer& c2 = n->tower[2 * i + 1];
-        if ((rc = conv_tc_launch(c1.tc, x, nullptr, t, c1.bias, B, s, nullptr, nullptr, n_dev))) return rc;
+        if ((rc = conv_tc_launch(c1.tc, x, nullptr, t, c1.bias, B, s, nullptr, nullptr, n_dev, mc, cap))) return rc;
         if (i == n->blocks - 1 && conv_tc_can_fuse_head(c2.tc)) {  // last layer: heads' 1x1 convs in the epilogue
-            if ((rc = conv_tc_launch(c2.tc, t, x, y, c2.bias, B, s, &n->head, n->feat, n_dev))) return rc;
+            if ((rc = conv_tc_launch(c2.tc, t, x, y, c2.bias, B, s, &n->head, feat, n_dev, mc, cap))) return rc;
             fused_head = true;
-        } else if ((rc = conv_tc_launch(c2.tc, t, x, y, c2.bias, B, s, nullptr, nullptr, n_dev))) return rc;
+        } else if ((rc = conv_tc_launch(c2.tc, t, x, y, c2.bias, B, s, nullptr, nullptr, n_dev, mc, cap))) return rc;
         __nv_bfloat16* tmp = x; x = y; y = tmp;
     }
-    RVS_LAUNCH(heads_kernel, (int)((B + kHB - 1) / kHB), 256, 0, s, x, fused_head ? n->feat : (const float*)nullptr, n->C, B, n->pw, n->pb, n->pfw, n->pfb, n->vw, n->vb, n->v1w, n->v1b,
-               n->v2w, n->v2b, want_logits ? n->logits : nullptr, n->probs, n->values, n_dev, n_dev ? h->v.stats + ST_NNEVALS : nullptr);
+    TL_MARK("tower", s);
+    RVS_LAUNCH(heads_kernel, (int)((B + kHB - 1) / kHB), 256, 0, s, x, fused_head ? feat : (const float*)nullptr, C, B, n->pw, n->pb, n->pfw, n->pfb, n->vw, n->vb, n->v1w, n->v1b,
+               n->v2w, n->v2b, want_logits ? n->logits + off * 65 : nullptr, n->probs + off * 65, n->values + off, n_dev, n_dev ? h->v.stats + ST_NNEVALS : nullptr);
+    TL_MARK("heads", s);
     return 0;
 }
 
@@ -403,7 +452,7 @@ int net_create(rvs_engine* h) {
     n->blocks = blocks;
     n->C = C;
     n->max_batch = (int64_t)h->v.G * h->cfg.max_wave;
-    const size_t B = (size_t)((n->max_batch + 1) / 2) * 2;  // whole tiles of two boards
+    const size_t B = (size_t)((n->max_batch + 1) / 2) * 2 + 2;  // whole tiles of two boards (+ one tile: the two half-batches of a pipelined search start on tile boundaries)
     int rc = 0;
     n->tower = new ConvLayer[2 * blocks];
     if ((rc = nalloc(n, &n->conv0.w, (size_t)9 * C * 64)) || (rc = nalloc(n, &n->conv0.bias, (size_t)C)) ||
@@ -419,7 +468,7 @@ int net_create(rvs_engine* h) {
     if ((rc = nalloc(n, &n->pw, (size_t)2 * C)) || (rc = nalloc(n, &n->pb, 2)) || (rc = nalloc(n, &n->pfw, 65 * 128)) ||
         (rc = nalloc(n, &n->pfb, 65)) || (rc = nalloc(n, &n->vw, (size_t)C)) || (rc = nalloc(n, &n->vb, 1)) ||
         (rc = nalloc(n, &n->v1w, 256 * 64)) || (rc = nalloc(n, &n->v1b, 256)) || (rc = nalloc(n, &n->v2w, 256)) ||
-        (rc = nalloc(n, &n->v2b, 1)) || (rc = nalloc(n, &n->bits, B * 3)) || (rc = nalloc(n, &n->n_valid, 1)) || (rc = nalloc(n, &n->inv, B)) || (rc = nalloc(n, &n->w0f, (size_t)27 * C)) || (rc = nalloc(n, &n->b0f, (size_t)C)) || (rc = nalloc(n, &n->a, B * 64 * C)) ||
+        (rc = nalloc(n, &n->v2b, 1)) || (rc = nalloc(n, &n->bits, B * 3)) || (rc = nalloc(n, &n->n_valid, 8)) || (rc = nalloc(n, &n->rows, (size_t)h->v.G)) || (rc = nalloc(n, &n->inv, B)) || (rc = nalloc(n, &n->w0f, (size_t)27 * C)) || (rc = nalloc(n, &n->b0f, (size_t)C)) || (rc = nalloc(n, &n->a, B * 64 * C)) ||
         (rc = nalloc(n, &n->b, B * 64 * C)) || (rc = nalloc(n, &n->c, B * 64 * C)) || (rc = nalloc(n, &n->probs, B * 65)) ||
         (rc = nalloc(n, &n->logits, B * 65)) || (rc = nalloc(n, &n->values, B)) || (rc = nalloc(n, &n->feat, B * 192)))
         return rc;
@@ -441,6 +490,9 @@ using namespace rvs;
 void rvs_net_destroy(rvs::NetState* n) {
     if (!n) return;
     if (n->wave_exec) cudaGraphExecDestroy(n->wave_exec);
+    if (n->side) cudaStreamDestroy(n->side);
+    if (n->ev_fork) cudaEventDestroy(n->ev_fork);
+    if (n->ev_join) cudaEventDestroy(n->ev_join);
     for (void* q : n->allocs) cudaFree(q);
     if (n->flat) cudaFree(n->flat);
     for (int i = 0; i < 2 * n->blocks; ++i) conv_tc_destroy(n->tower[i].tc);
@@ -462,6 +514,65 @@ static int net_wave(rvs_engine* h, int k, cudaStream_t s) {
     return rvs_engine_process_mapped(h, h->net->probs, h->net->values, h->net->inv, s);
 }
 
+// MCTS.search with the built-in network and batch_size 1 (the configs[2] / configs[3] path): per wave and per
+// half-batch  [process pending leaf | select | encode] (ONE tree kernel, rvs_engine_nn_step) -> tower -> heads.
+// With RVS_OPT_NET_PIPELINE (default) the games are split into two half-batches that ping-pong on two streams:
+// while the tcgen05 tower of one half owns the SMs' shared memory, the tree kernel of the other half (no shared
+// memory, few registers) runs beside it, so selection / expansion / backup leave the critical path.  Per-game
+// results do not depend on the split: every game's tree is touched by its own warp only, and the network
+// treats boards independently.
+static int rvs_net_search_w1(rvs_engine* h, int32_t num_sims, cudaStream_t s) {
+    NetState* n = h->net;
+    int rc;
+    const int G = h->v.G;
+    const bool two = h->net_pipeline && G >= 512;
+    if (two && !n->side) {
+        RVS_CUDA(cudaStreamCreateWithFlags(&n->side, cudaStreamNonBlocking));
+        RVS_CUDA(cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming));
+        RVS_CUDA(cudaEventCreateWithFlags(&n->ev_join, cudaEventDisableTiming));
+    }
+    const int nh = two ? 2 : 1;
+    const int split = two ? ((G / 2) & ~1) : G;  // even: the second half starts on a tile boundary
+    const int g0[2] = {0, split}, g1[2] = {split, G};
+    cudaStream_t st[2] = {s, two ? n->side : s};
+    RVS_CUDA(cudaMemsetAsync(n->n_valid, 0, 8 * sizeof(int), s));
+    if (two) {
+        RVS_CUDA(cudaEventRecord(n->ev_fork, s));
+        RVS_CUDA(cudaStreamWaitEvent(n->side, n->ev_fork, 0));
+    }
+    const bool fast = h->v.mode == RVS_MODE_FAST;
+    (void)fast;  // wave 1: the FAST schedule (first wave = one simulation) is the ordinary one
+    for (int w = 0; w <= num_sims; ++w) {
+        for (int hf = 0; hf < nh; ++hf) {
+#ifdef RVS_TIMELINE
+            g_tl_on = (w >= 40 && w < 43);
+            g_tl_wave = w; g_tl_half = hf;
+            TL_MARK("begin", st[hf]);
+#endif
+            const int64_t off = g0[hf], cap = g1[hf] - g0[hf];
+            int* cur = n->n_valid + 2 + 2 * hf + (w & 1);
+            int* nxt = n->n_valid + 2 + 2 * hf + ((w + 1) & 1);
+            const int flags = (w > 0 ? 1 : 0) | (w < num_sims ? 2 : 0) | (w == 1 ? 4 : 0);
+            if ((rc = rvs_engine_nn_step(h, g0[hf], g1[hf], flags, n->probs + off * 65, n->values + off, n->rows, n->bits + off * 3,
+                                         cur, nxt, st[hf])))
+                return rc;
+            TL_MARK("tree", st[hf]);
+            if (w < num_sims && (rc = net_forward(h, cap, false, st[hf], cur, off, cap))) return rc;
+        }
+    }
+#ifdef RVS_TIMELINE
+    g_tl_on = false;
+    if (!g_tl.empty()) tl_dump();
+#endif
+    if (two) {
+        RVS_CUDA(cudaEventRecord(n->ev_join, n->side));
+        RVS_CUDA(cudaStreamWaitEvent(s, n->ev_join, 0));
+    }
+    h->cur_k = 0;
+    h->searching = false;
+    return 0;
+}
+
 // MCTS.search with the built-in network: per wave  select -> encode (K3) -> tower + heads (K4)
 // -> expand/backup with the softmax priors (K2).  No host round trip inside the loop.  Optionally
 // the first wave (root expansion, root noise, one-time kernel setup) is launched
@@ -472,6 +583,7 @@ int rvs_net_search(rvs_engine* h, int32_t num_sims, int32_t wave, cudaStream_t s
     NetState* n = h->net;
     if (!n->loaded) return fail(-7, "RVS_EVAL_NN: call rvs_engine_load_weights before rvs_engine_search");
     if ((rc = rvs_engine_begin_search(h, s))) return rc;
+    if (wave == 1 && !h->net_graph) return rvs_net_search_w1(h, num_sims, s);
     // Measured on B200 (5x128, 4096 games, 100 waves): 81.5 ms with the graph, 80.1 ms with plain launches --
     // the wave loop is not launch bound (PDL already chains the tower), so replay is opt-in
     const bool use_graph = h->net_graph != 0;  // RVS_OPT_NET_GRAPH

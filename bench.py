@@ -49,6 +49,29 @@ def peaks():
         return 6650.0, "of fallback (B200_PROFILING.md)"
 
 
+# sources that define the dominant kernel: a committed ncu figure is only valid for the code it was captured on
+KERNEL_SOURCES = ["rvs_treeg.cuh", "rvs_tree.cuh", "rvs_board.cuh", "rvs_engine.cu", "rvs_engine.cuh", "rvs_noise.cuh"]
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "traffic_r2.json")
+
+
+def kernel_source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    for f in KERNEL_SOURCES:
+        h.update(open(os.path.join(ROOT, "alphazero-reversi_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def committed_capture():
+    """profiles/traffic_r2.json: ncu figures of the dominant kernel (DRAM bytes per step, warp instructions per
+    simulation, issue-active) stamped with the commit and the hash of the kernel sources they were captured on"""
+    try:
+        d = json.load(open(TRAFFIC_FILE))
+    except Exception:
+        return None, True
+    return d, d.get("kernel_source_hash") != kernel_source_hash()
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region"""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -123,6 +146,84 @@ def position_pool(az, n, seed):
     return bl, wh, sd
 
 
+def generation_leg(az, dist, dev, rank, world, local, games, barrier):
+    """BASELINE configs[4] (config 5) as ONE timed generation per rank: NCCL broadcast of the trainer rank's weights
+    -> `games` games of ResNet 5x128 self-play (100 sims/move, one slot per game) played to completion -> replay
+    samples gathered on rank 0.  The drain is asynchronous (rvs_engine_drain_packed_async) and the gather runs on a
+    SIDE stream while the next generation's first ply is already searching on the main stream."""
+    import torch
+    from alphazero_reversi_b200 import dist as azd
+    L = az._lib
+    torch.manual_seed(42)
+    rn = az.RvsNetwork.from_module(az.AlphaZeroNetwork(8, 5, 128).eval())
+    eng = az.Engine(games, N_SIMS, 1, evaluator=az.EVAL_NN, c_puct=1.0, seed=azd.rank_seed(7, rank), device=local,
+                    net_blocks=5, net_filters=128, sample_capacity=64 * games)
+    eng.set_option(L.OPT_GAME_LIMIT, games)
+    main, side = torch.cuda.current_stream(), torch.cuda.Stream(device=dev)
+    E = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    b0, b1, g1, c0, c1, drained = E(), E(), E(), E(), E(), E()
+    cnt = torch.zeros(1, dtype=torch.int64).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    b0.record()
+    flat = rn.flat.to(dev) if rank == 0 else torch.empty_like(rn.flat, device=dev)
+    azd.broadcast_weights(flat, src=0)
+    b1.record()
+    eng.load_weights(flat)
+    rounds = 0
+    s0 = eng.stats()
+    while True:
+        eng.selfplay(N_SIMS, plies=games, temperature=1.0, recycle=True)  # one lockstep ply of every live game
+        rounds += 1
+        if rounds >= 58:
+            st = eng.stats()
+            if st["games_finished"] >= games or rounds > 70:
+                break
+    g1.record()
+    pk, cnt = eng.drain_packed_async(64 * games, dev, count_out=cnt)
+    drained.record()
+    # the NEXT generation starts searching at once (main stream); its first ply overlaps the gather below
+    eng.reset()
+    eng.selfplay(N_SIMS, plies=games, temperature=1.0, recycle=True)
+    drained.synchronize()  # waits for this generation's drain only, not for the work enqueued after it
+    k = int(cnt[0])
+    info = {}
+    with torch.cuda.stream(side):
+        side.wait_event(drained)
+        c0.record(side)
+        mine = az.PackedSamples(pk.black[:k], pk.white[:k], pk.side[:k], pk.z[:k], pk.pi[:k])
+        res = azd.gather_packed(mine, dst=0, info=info)
+        c1.record(side)
+    side.synchronize()
+    wall = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    s1 = eng.stats()
+    if s1["overflow"] or s1["samples_dropped"] or s1["stalled"]:
+        raise SystemExit(f"generation leg: engine error counters non-zero: {s1}")
+    eng.close()
+    vals = torch.tensor([wall * 1e3, b0.elapsed_time(b1), b1.elapsed_time(g1), c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
+    sums = torch.tensor([float(k), float(st["sims"] - s0["sims"]), float(st["games_finished"])], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    wall_ms, bc_ms, sp_ms, ga_ms = vals.tolist()
+    samples, sims, finished = sums.tolist()
+    if rank != 0:
+        return None
+    got = len(res) if res is not None else 0
+    assert got == int(samples), (got, samples)
+    nbytes = info.get("bytes_received", 0)
+    return {"config": f"configs[4]: {world} x {games} games of ResNet 5x128 self-play to completion, 100 sims/move, wave 1; "
+                      "NCCL weight broadcast before, packed-sample gather (280 B/sample) to rank 0 after",
+            "games": int(finished), "samples_gathered_rank0": got, "rounds": rounds, "wall_s": wall_ms * 1e-3,
+            "selfplay_s": sp_ms * 1e-3, "sims_per_sec": sims / (wall_ms * 1e-3),
+            "broadcast_ms": bc_ms, "broadcast_bytes": int(flat.numel() * 4),
+            "gather_ms": ga_ms, "gather_bytes": int(nbytes), "gather_gbs": (nbytes / (ga_ms * 1e-3) / 1e9) if ga_ms > 0 else None,
+            "collective_share": (bc_ms + ga_ms) / wall_ms,
+            "overlap": "gather on a side stream, concurrent with the first ply of the next generation on the main stream; "
+                       "times are device events (max over ranks), wall is the host clock from before the broadcast to the end of the gather"}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -146,8 +247,10 @@ def run_ours(args):
     lib = az._lib.lib()
     stream = torch.cuda.current_stream().cuda_stream
     wave = args.wave
+    # sample ring: the timed region may be repeated up to the duration floor (about 1 ms per step at the fastest)
+    ring_steps = args.steps + int(args.min_seconds * 1000) + args.steps_per_launch + 100
     eng = az.Engine(N_GAMES, N_SIMS, max(wave, 64), evaluator=az.EVAL_ROLLOUT, c_puct=1.0, seed=1000 + rank, device=local,
-                    sample_capacity=(args.steps + args.warmup + args.presteps + 72) * N_GAMES)
+                    sample_capacity=ring_steps * N_GAMES)
 
     persistent = wave == 1 and not args.lockstep
     ppl = max(1, args.steps_per_launch)
@@ -165,31 +268,54 @@ def run_ours(args):
     # function of the ply instead of the workload.
     pb0, pw0, ps0 = position_pool(az, N_GAMES, 99 + rank)
     eng.set_positions(pb0, pw0, ps0, stream=stream)
-    for _ in range(max(args.warmup, 3) + args.presteps):
+    # untimed: `presteps` plies that spread the games over all phases, then W >= 3 warm-up steps
+    warmup_run = max(args.warmup, 3)
+    for _ in range(args.presteps + warmup_run):
         step(eng)
     torch.cuda.synchronize()
+    # duration floor: a K-step region is ~1.4 ms x K (29 ms at the driver's K = 20, shorter than one clock sample), so
+    # the K-step region is repeated back to back `reps` times inside ONE event pair until >= --min-seconds are timed
+    # (steps stays K; ms_per_step = total / (K x reps))
+    reps = 1
+    if persistent and args.min_seconds > 0:
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        eng.selfplay(N_SIMS, plies=N_GAMES * min(ppl, args.steps), temperature=1.0, recycle=True, stream=stream)
+        c1.record()
+        torch.cuda.synchronize()
+        est = c0.elapsed_time(c1) * 1e-3 * args.steps / min(ppl, args.steps)
+        reps = max(1, int(args.min_seconds / max(est, 1e-6) + 0.999))
+    if dist is not None:  # every rank times the same number of steps
+        rt = torch.tensor([reps], dtype=torch.int64, device=dev)
+        dist.all_reduce(rt, op=dist.ReduceOp.MAX)
+        reps = int(rt.item())
 
+    eng.drain_packed(device=dev)  # samples of the untimed steps are not part of the measured generation
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     s0 = eng.stats()
     l0 = lib.rvs_launch_count()
-    ks = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ks = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps * reps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     if persistent:
-        # K steps = K x N_GAMES game-plies, issued as persistent launches of `ppl` steps each
-        done = 0
-        while done < args.steps:
-            n = min(ppl, args.steps - done)
-            ks[done][0].record()
-            eng.selfplay(N_SIMS, plies=N_GAMES * n, temperature=1.0, recycle=True, stream=stream)
-            ks[done][1].record()
-            done += n
-        ks = [ks[i] for i in range(0, args.steps, ppl)]
+        # K steps = K x N_GAMES game-plies, issued as persistent launches of `ppl` steps each (x reps, see above)
+        used = []
+        for r in range(reps):
+            done = 0
+            while done < args.steps:
+                n = min(ppl, args.steps - done)
+                ev = ks[r * args.steps + done]
+                ev[0].record()
+                eng.selfplay(N_SIMS, plies=N_GAMES * n, temperature=1.0, recycle=True, stream=stream)
+                ev[1].record()
+                used.append(ev)
+                done += n
+        ks = used
     else:
-        for i in range(args.steps):
+        for i in range(args.steps * reps):
             ks[i][0].record()
             eng.search(N_SIMS, wave, stream=stream)
             ks[i][1].record()
@@ -202,6 +328,7 @@ def run_ours(args):
     s1 = eng.stats()
     launches = lib.rvs_launch_count() - l0
     kernel_ms = sum(a.elapsed_time(b) for a, b in ks) / len(ks)  # average launch duration of the dominant kernel
+    total_steps = args.steps * reps
     d = {k: s1[k] - s0[k] for k in s1}
     d["n_search_launches"] = len(ks)
     if s1["overflow"] or s1["samples_dropped"] or s1["stalled"]:
@@ -216,44 +343,51 @@ def run_ours(args):
     hb.numpy()[:] = pb.view(np.int64)
     hw.numpy()[:] = pw.view(np.int64)
     hs.numpy()[:] = ps
-    # The lockstep search call ends with a tail (the longest, early-game searches), so the e2e leg
+    # The lockstep search call ends with a tail (the longest, early-game searches), so the headline e2e leg
     # pipelines `depth` engine handles round-robin on their own CUDA streams through the asynchronous
     # host mode of the C ABI (RVS_MEM_HOST_ASYNC): while one batch drains its tail the next fills the SMs.
-    depth = max(1, args.e2e_depth)
-    streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
-    hvs = [torch.empty((N_GAMES, 65), dtype=torch.int32).pin_memory() for _ in range(depth)]
-    engs = [az.Engine(N_GAMES, N_SIMS, max(wave, 64), evaluator=az.EVAL_ROLLOUT, c_puct=1.0, seed=2000 + rank, device=local)
-            for _ in range(depth)]
-    for e in engs:  # depth x 4096 games are in flight: the many-games setting of the wave-1 kernels
-        e.set_lanes_per_game(args.e2e_lanes if args.e2e_lanes else (4 if depth >= 3 else 0))
+    # The same loop at depth 1 (one handle, one stream, 4096 games in flight = the concurrency of `value`)
+    # is reported as e2e_depth1.
     MH = az._lib.MEM_HOST_ASYNC
 
-    def e2e_step(i):
-        o = (i % pool_steps) * N_GAMES
-        j = i % depth
-        st, e = streams[j], engs[j]
-        st.synchronize()  # results of this handle's previous step are complete and consumed
-        az._lib.check(lib.rvs_engine_set_positions(e._h, hb[o:].data_ptr(), hw[o:].data_ptr(), hs[o:].data_ptr(),
-                                                   N_GAMES, MH, st.cuda_stream))
-        az._lib.check(lib.rvs_engine_search(e._h, N_SIMS, wave, st.cuda_stream))
-        az._lib.check(lib.rvs_engine_root_visits(e._h, hvs[j].data_ptr(), N_GAMES, MH, st.cuda_stream))
+    def measure_e2e(depth, lanes):
+        streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+        hvs = [torch.empty((N_GAMES, 65), dtype=torch.int32).pin_memory() for _ in range(depth)]
+        engs = [az.Engine(N_GAMES, N_SIMS, max(wave, 64), evaluator=az.EVAL_ROLLOUT, c_puct=1.0, seed=2000 + rank, device=local)
+                for _ in range(depth)]
+        for e in engs:  # depth x 4096 games are in flight: the many-games setting of the wave-1 kernels
+            e.set_lanes_per_game(lanes)
 
-    for i in range(3 * depth):
-        e2e_step(i)
-    torch.cuda.synchronize()
-    e2e_steps = max(4 * depth, args.steps // 2)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        e2e_step(i)
-    torch.cuda.synchronize()
-    e2e_wall = (time.perf_counter() - t0) * 1e3
-    barrier()
-    e2e_ms = e2e_wall  # host wall clock around H2D + search + D2H of every step, all streams drained
-    for hv in hvs:
-        assert int(hv.numpy().sum()) > 0
-    for e in engs:
-        e.close()
+        def e2e_step(i):
+            o = (i % pool_steps) * N_GAMES
+            j = i % depth
+            st, e = streams[j], engs[j]
+            st.synchronize()  # results of this handle's previous step are complete and consumed
+            az._lib.check(lib.rvs_engine_set_positions(e._h, hb[o:].data_ptr(), hw[o:].data_ptr(), hs[o:].data_ptr(),
+                                                       N_GAMES, MH, st.cuda_stream))
+            az._lib.check(lib.rvs_engine_search(e._h, N_SIMS, wave, st.cuda_stream))
+            az._lib.check(lib.rvs_engine_root_visits(e._h, hvs[j].data_ptr(), N_GAMES, MH, st.cuda_stream))
+
+        for i in range(3 * depth):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        steps_ = max(4 * depth, args.steps // 2, 24)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps_):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3  # host clock around H2D + search + D2H of every step, all streams drained
+        barrier()
+        for hv in hvs:
+            assert int(hv.numpy().sum()) > 0
+        for e in engs:
+            e.close()
+        return steps_, wall
+
+    depth = max(1, args.e2e_depth)
+    e2e_steps, e2e_ms = measure_e2e(depth, args.e2e_lanes if args.e2e_lanes else (4 if depth >= 3 else 0))
+    e2e1_steps, e2e1_ms = measure_e2e(1, 0) if depth != 1 else (e2e_steps, e2e_ms)
 
     # ---- config-1 side metric: register-resident uniform-random playouts ------------------
     n_po = 1 << 20
@@ -345,9 +479,36 @@ def run_ours(args):
         torch.cuda.synchronize()
         u1 = eng3.stats()
         wms = m0.elapsed_time(m1)
+        # FAST mode (engine feature, virtual-loss PUCT): the waves spread over distinct leaves, so wave > 1 buys search
+        fastm = {}
+        for K in (8, 16, 64):
+            engf = az.Engine(N_GAMES, N_SIMS, K, evaluator=az.EVAL_NN, c_puct=1.0, seed=3600 + rank, device=local,
+                             net_blocks=5, net_filters=128)
+            engf.set_search_mode(az.MODE_FAST)
+            rn.attach(engf)
+            engf.set_positions(pb0, pw0, ps0, stream=stream)
+            engf.search(N_SIMS, K, stream=stream); engf.play(1.0, recycle=True, stream=stream)
+            torch.cuda.synchronize()
+            f0 = engf.stats()
+            y0, y1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            y0.record()
+            for _ in range(2):
+                engf.search(N_SIMS, K, stream=stream); engf.play(1.0, recycle=True, stream=stream)
+            y1.record()
+            torch.cuda.synchronize()
+            f1 = engf.stats()
+            fms = y0.elapsed_time(y1)
+            fastm[f"wave{K}"] = {"sims_per_sec": (f1["sims"] - f0["sims"]) / (fms * 1e-3),
+                                 "network_evals_per_sec": (f1["nn_evals"] - f0["nn_evals"]) / (fms * 1e-3),
+                                 "unique_evals_per_sim": (f1["nn_evals"] - f0["nn_evals"]) / max(1, f1["sims"] - f0["sims"]),
+                                 "tflops": (f1["nn_evals"] - f0["nn_evals"]) * flops_per_eval / (fms * 1e-3) / 1e12}
+            engf.close()
+        nn["fast_mode"] = dict(fastm, config="RVS_MODE_FAST (virtual-loss PUCT leaf batching, DESIGN.md): same network and games; "
+                                             "reference-compatible waves evaluate ~1 unique leaf per wave (wave64 block)")
         nn["wave64"] = {"sims_per_sec": (u1["sims"] - u0["sims"]) / (wms * 1e-3),
                         "network_evals_per_sec": (u1["nn_evals"] - u0["nn_evals"]) / (wms * 1e-3),
                         "consumed_evals_per_sec": (u1["evals"] - u0["evals"]) / (wms * 1e-3), "ms_per_step": wms / 5,
+                        "unique_evals_per_sim": (u1["nn_evals"] - u0["nn_evals"]) / max(1, u1["sims"] - u0["sims"]),
                         "config": "same network and games with the reference's default MCTS(batch_size=64) wave semantics"}
         eng3.close()
 
@@ -394,29 +555,51 @@ def run_ours(args):
     else:
         gathered = len(pk_)
 
+    # ---- config 5 as a timed leg: broadcast -> N x 8192 NN self-play games to completion -> gather ----------
+    generation = None
+    if (dist is not None or args.generation) and not args.no_nn and not args.no_generation:
+        generation = generation_leg(az, dist, dev, rank, world, local, args.gen_games, barrier)
+
     # ---- reductions over ranks --------------------------------------------------------------
-    vals = torch.tensor([ms, e2e_ms, kernel_ms], dtype=torch.float64, device=dev)
+    rank_sims_per_sec = d["sims"] / (ms * 1e-3)  # this rank's GPU (roofline of the dominant kernel)
+    vals = torch.tensor([ms, e2e_ms, kernel_ms, e2e1_ms], dtype=torch.float64, device=dev)
     sums = torch.tensor([d["sims"], d["board_steps"], d["evals"], float(launches), e2e_steps * N_GAMES * N_SIMS,
-                         po_steps / (po_ms * 1e-3)], dtype=torch.float64, device=dev)
+                         po_steps / (po_ms * 1e-3), e2e1_steps * N_GAMES * N_SIMS,
+                         0.0 if big is None else big["sims_per_sec"]], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    ms, e2e_ms, kernel_ms = vals.tolist()
-    sims, bsteps, evals, launches_all, e2e_sims, po_rate = sums.tolist()
+    ms, e2e_ms, kernel_ms, e2e1_ms = vals.tolist()
+    sims, bsteps, evals, launches_all, e2e_sims, po_rate, e2e1_sims, big_all = sums.tolist()
 
     if rank == 0:
         hbm, which = peaks()
         # algorithmic bytes of the fused search kernel per launch (this rank), from its counters
         tree_bytes = algorithmic_bytes(d)
         achieved = tree_bytes / (kernel_ms * 1e-3) / 1e9
+        cap, stale = committed_capture()
+        kcap = (cap or {}).get("selfplay_k1g_kernel", {}) if persistent else {}
         traffic = args.traffic  # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
-        tpath = os.path.join(ROOT, "profiles", "traffic_r1.json")
-        if traffic is None and persistent and os.path.exists(tpath):
-            traffic = json.load(open(tpath))["selfplay_k1g_kernel"]["dram_bytes_per_step"] * min(ppl, args.steps)
+        if traffic is None and kcap.get("dram_bytes_per_step") is not None:
+            traffic = kcap["dram_bytes_per_step"] * min(ppl, args.steps)
+        # The binding roof of the dominant kernel is the ISSUE rate, not HBM (rollouts are register resident; DRAM
+        # traffic is a few % of peak): achieved = warp instructions per simulation (ncu smsp__inst_executed.sum /
+        # simulations of the committed capture, stamped with the hash of the kernel sources) x measured sims/s;
+        # peak = 148 SMs x 4 schedulers x 1 warp instruction per cycle x the SM clock sampled under this load
+        sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+        issue_peak = 148 * 4 * sm_mhz * 1e6
+        wips = kcap.get("warp_inst_per_sim")
+        issue_ach = wips * rank_sims_per_sec if wips else None
+        kname = ("selfplay_k1g_kernel<REF,ROLLOUT,8>" if persistent else
+                 ("search_k1g_kernel<REF,ROLLOUT,8>" if wave == 1 else "search_fused_kernel<REF,ROLLOUT>"))
         out = {
             "metric": METRIC, "value": sims / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3) + args.presteps, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": ms / total_steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64+f32", "data": "synthetic",
+            "timing": {"timed_repeats": reps, "timed_steps_total": total_steps, "timed_ms": ms, "warmup_steps_run": warmup_run,
+                       "presteps": args.presteps,
+                       "note": "the K-step region is repeated back to back inside one CUDA-event pair until >= min_seconds are "
+                               "timed; presteps spread the games over all phases before the warm-up", "min_seconds": args.min_seconds},
             "config": {"workload": "configs[1]: pure MCTS, uniform prior + uniform-random rollout value, 100 sims/move, "
                                    "4096 concurrent games per GPU, REF rules, self-play with recycling",
                        "games_per_gpu": N_GAMES, "sims_per_move": N_SIMS, "wave": wave, "c_puct": 1.0, "temperature": 1.0,
@@ -426,22 +609,36 @@ def run_ours(args):
             "board_steps_per_sec": bsteps / (ms * 1e-3),
             "unique_evals_per_sec": evals / (ms * 1e-3),
             "playout_board_steps_per_sec": po_rate,
+            "value_16384": (big_all if big is not None else None),
             "e2e": {"value": e2e_sims / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": N_GAMES * 17,
                     "d2h_bytes_per_step": N_GAMES * 65 * 4, "steps": e2e_steps, "pipeline_depth": depth, "games_in_flight": depth * N_GAMES,
                     "api": "rvs_engine_set_positions(host) -> rvs_engine_search -> rvs_engine_root_visits(host), "
                            "RVS_MEM_HOST_ASYNC on one stream per engine handle; timed with the host clock"},
+            "e2e_depth1": {"value": e2e1_sims / (e2e1_ms * 1e-3), "unit": UNIT, "steps": e2e1_steps, "pipeline_depth": 1,
+                           "games_in_flight": N_GAMES,
+                           "note": "the same host-buffer loop with ONE engine handle: the concurrency `value` is measured at; each call "
+                                   "ends in the tail of its longest searches, which the pipelined e2e hides"},
             "gpu_launches": int(launches_all),
             "samples_gathered_rank0": gathered,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                         "traffic": traffic, "peak_source": which, "kernel": ("selfplay_k1g_kernel<REF,ROLLOUT,8>" if persistent else
-                                    ("search_k1g_kernel<REF,ROLLOUT,8>" if wave == 1 else "search_fused_kernel<REF,ROLLOUT>")),
+            "roofline": {"bound": "issue", "achieved": (issue_ach / 1e9 if issue_ach else None), "peak": issue_peak / 1e9,
+                         "unit": "Gwarp-inst/s", "frac": (issue_ach / issue_peak if issue_ach else None),
+                         "traffic": traffic, "traffic_stale": bool(stale),
+                         "kernel": kname, "warp_inst_per_sim": wips, "sm_mhz_used": sm_mhz,
+                         "peak_source": "148 SMs x 4 schedulers x SM clock sampled by nvidia-smi during the timed region",
+                         "capture": ({"file": os.path.relpath(TRAFFIC_FILE, ROOT), "commit": cap.get("commit"),
+                                      "kernel_source_hash": cap.get("kernel_source_hash"), "current_hash": kernel_source_hash(),
+                                      "issue_active_pct_under_ncu": kcap.get("issue_active_pct")} if cap else None),
                          "steps_per_launch": min(ppl, args.steps) if persistent else 1,
                          "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms * len(ks) / ms,
-                         "note": "not HBM bound: rollouts are register resident (0 B); at 4096 games the kernel is bound by the "
-                                 "latency of one rollout ply's dependency chain (1.7 warps per scheduler), see DESIGN.md K2",
-                         "issue": issue_evidence()},
+                         "hbm": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                                 "peak_source": which, "algorithmic_bytes_per_sim": d["tree_bytes"] / max(1, d["sims"])},
+                         "note": "rollouts are register resident (0 B), so HBM is not the roof (secondary `hbm` block); the kernel is "
+                                 "bound by instruction issue and, at 4096 games, by the latency of a rollout ply's dependency chain "
+                                 "(see DESIGN.md K2)"},
             "clocks": clocks,
         }
+        if generation is not None:
+            out["generation"] = generation
         out["perft8"] = {"leaves": int(perft_nodes), "ms": perft_ms, "expected": 391210}
         if big is not None:
             out["games_16384"] = big
@@ -465,23 +662,6 @@ def run_ours(args):
         _emit(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
-
-
-def issue_evidence():
-    """instruction-side figures of the dominant kernel from the committed ncu capture (profiles/)"""
-    import re
-    path = os.path.join(ROOT, "profiles", "ncu_selfplay_k1g_r1.txt")
-    if not os.path.exists(path):
-        return None
-    t = open(path).read()
-
-    def grab(pat):
-        m = re.search(pat, t)
-        return float(m.group(1)) if m else None
-    return {"warp_inst_per_sim": grab(r"warp instructions per unit:\s+([\d.]+)"),
-            "issue_active_pct": grab(r"smsp__issue_active\S*\s+([\d.]+)"),
-            "warps_eligible_per_cycle": grab(r"smsp__warps_eligible\S*\s+([\d.]+)"),
-            "source": "profiles/ncu_selfplay_k1g_r1.txt"}
 
 
 def algorithmic_bytes(d):
@@ -528,10 +708,40 @@ def cpu_baseline(wave, threads, budget_s):
     tq = time.perf_counter()
     p8 = orc.perft(8)
     p8_ms = (time.perf_counter() - tq) * 1e3
-    return {"value": sims / dt, "unit": UNIT, "cores": threads, "kind": "port",
+    port = {"value": sims / dt, "unit": UNIT, "cores": threads, "kind": "port",
             "board_steps_per_sec": steps / dt, "perft8_ms_one_thread": p8_ms, "perft8_leaves": int(p8),
             "sample": f"{rounds} x {n} mid-game roots x {N_SIMS} sims (wave {wave}), C oracle (oracle/rvs_oracle.c), "
                       f"{threads} host threads, {dt:.1f} s"}
+    out = dict(port)
+    out["port"] = port
+    out["python_reference"] = python_reference()
+    return out
+
+
+def python_reference():
+    """The reference's OWN Python path.  It is pure Python, /root/reference does not exist on
+    the GPU box and reference sources may not be copied into the repo, so it cannot run here: if it IS importable
+    (a checkout at $RVS_REFERENCE or /root/reference) the committed script is run live in a CUDA_VISIBLE_DEVICES=""
+    subprocess; otherwise the figures measured with that script in the build container are reported, labelled."""
+    ref = os.environ.get("RVS_REFERENCE", "/root/reference")
+    script = os.path.join(ROOT, "oracle", "time_python_reference.py")
+    if os.path.isdir(os.path.join(ref, "src", "mcts")):
+        try:
+            tmp = os.path.join("/tmp", f"pyref_{os.getpid()}.json")
+            env = dict(os.environ, CUDA_VISIBLE_DEVICES="", RVS_REFERENCE=ref)
+            subprocess.run([sys.executable, script, "--quick", "--out", tmp], env=env, check=True, capture_output=True, timeout=600)
+            live = json.load(open(tmp))
+            live["where"] = "live on this host (quick sample)"
+            return live
+        except Exception as ex:  # noqa: BLE001
+            return {"unavailable": f"reference present but the timing script failed: {ex!r}"}
+    path = os.path.join(ROOT, "profiles", "python_reference_cpu_r2.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        d["where"] = ("NOT this host: the reference is not importable here (no /root/reference on the GPU box); figures measured "
+                      "in the build container by oracle/time_python_reference.py and committed under profiles/")
+        return d
+    return None
 
 
 def run_reference(args):
@@ -543,7 +753,7 @@ def run_reference(args):
     import numpy as np
     import orc
     import ctypes as C
-    n = 512  # bounded sample of the 4096-game step
+    n = N_GAMES  # the full 4096-game step (the C port needs ~0.3 s per step on 16 threads)
     rng = np.random.default_rng(3)
     L = orc.lib()
     pos_b = np.zeros(n, dtype=np.uint64); pos_w = np.zeros(n, dtype=np.uint64); pos_s = np.ones(n, dtype=np.uint8)
@@ -574,10 +784,11 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64+f32", "data": "synthetic",
         "config": {"workload": "configs[1]: pure MCTS, uniform prior + uniform-random rollout value, 100 sims/move, "
-                               f"bounded sample of {n} of the 4096 games per step", "sims_per_move": N_SIMS,
+                               f"{n} concurrent games per step (searches of mid-game roots)", "sims_per_move": N_SIMS,
                    "wave": args.wave},
         "board_steps_per_sec": steps_total / dt,
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "python_reference": python_reference()},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -612,6 +823,10 @@ def main():
     ap.add_argument("--e2e-lanes", type=int, default=0, help="lanes per game of the e2e engines (0: 4 when pipelined)")
     ap.add_argument("--no-big", action="store_true", help="skip the 16384-game side measurement")
     ap.add_argument("--no-nn", action="store_true", help="skip the config-3 (ResNet) side measurement")
+    ap.add_argument("--min-seconds", type=float, default=0.5, help="floor of the timed region (the K steps are repeated)")
+    ap.add_argument("--generation", action="store_true", help="run the config-5 generation leg on one GPU too")
+    ap.add_argument("--no-generation", action="store_true")
+    ap.add_argument("--gen-games", type=int, default=8192, help="games per rank of the generation leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -161,6 +161,31 @@ def test_nn_search_consistency(az, K, graph, pipeline, S):
     ext.close()
 
 
+def test_pipelined_half_batches_equal_lockstep(az):
+    """RVS_OPT_NET_PIPELINE: two half-batches ping-pong on two streams (tree kernel of one half beside the tower of
+    the other).  Per-game results cannot depend on the split; odd game counts exercise the tile-boundary split."""
+    net = _build(az, 2, 64, "bn")
+    rn = az.RvsNetwork.from_module(net)
+    for g in (1001, 512, 2050):
+        rb, rw, rs = _midgame_roots(g, 11)
+        out = []
+        for pipe in (0, 1):
+            eng = az.Engine(g, 30, 1, evaluator=az.EVAL_NN, net_blocks=2, net_filters=64, seed=9)
+            eng.set_option(az._lib.OPT_NET_PIPELINE, pipe)
+            rn.attach(eng)
+            eng.set_positions(rb, rw, rs)
+            eng.search(30, 1)
+            out.append(eng.root_visits())
+            st = eng.stats()
+            assert st["overflow"] == 0 and st["sims"] == g * 30
+            # a self-play ply on top (play kernels run on the caller's stream after the join)
+            eng.play(1.0, recycle=True)
+            eng.search(30, 1)
+            out.append(eng.root_visits())
+            eng.close()
+        assert np.array_equal(out[0], out[2]) and np.array_equal(out[1], out[3]), g
+
+
 def test_mcts_and_selfplay_with_rvs_network(az):
     net = _build(az, 2, 64, "bn")
     rn = az.RvsNetwork.from_module(net)
