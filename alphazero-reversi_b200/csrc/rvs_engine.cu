@@ -429,7 +429,7 @@ __device__ __forceinline__ void flush_stats_g(const EngineView& ev, const TreeCt
 
 template <int LPG>
 __device__ __forceinline__ TreeCtxG<LPG> make_ctx_g(const EngineView& ev, int g, const Grp<LPG>& grp) {
-    return TreeCtxG<LPG>{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, 1, ev.c_puct, 0, 0, 0, 0, 0, 0, grp};
+    return TreeCtxG<LPG>{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, 1, ev.c_puct, 0, 0, 0, 0, 0, 0, grp, nullptr, 0, 0u};
 }
 
 template <int LPG>
@@ -510,8 +510,10 @@ __global__ void __launch_bounds__(1024) phase_order_kernel(EngineView ev) {
 // owns the slots gidx, gidx + n_groups, ... (phase order), so any G runs on a resident grid.
 constexpr int kMaxWarpsG = kNumSMs * 16;  // 16 one-warp CTAs per SM (__launch_bounds__(32, 16): <= 128 registers)
 
-template <int RULES, int EVAL, int LPG>
-__global__ void __launch_bounds__(kBlockG, 16) search_k1g_kernel(EngineView ev, int S) {
+// MINB = resident one-warp CTAs per SM the launch is compiled for: 16 (<= 128 registers) when the grid needs them all,
+// 8 (<= 255 registers: no spills in the simulation loop) when the games fit in 148 x 8 warps (e.g. 4096 games x 8 lanes)
+template <int RULES, int EVAL, int LPG, int MINB>
+__global__ void __launch_bounds__(kBlockG, MINB) search_k1g_kernel(EngineView ev, int S) {
     constexpr int GPB = kBlockG / LPG;
     __shared__ uint8_t lut[256 * 8];
     __shared__ int spath[GPB][kMaxPath + 1];
@@ -520,10 +522,12 @@ __global__ void __launch_bounds__(kBlockG, 16) search_k1g_kernel(EngineView ev, 
     __syncthreads();
     const int n_groups = gridDim.x * GPB;
     const Grp<LPG> grp = make_grp<RULES, LPG>(threadIdx.x & 31, lut, spath[threadIdx.x / LPG], LPG == 8 ? sgather[threadIdx.x / LPG] : nullptr);
+    __shared__ int4 sstage[GPB][2 * (1 + StageCfg<LPG>::kRows) + 2];  // hot node rows of each group's search
     for (int slot = blockIdx.x * GPB + (int)threadIdx.x / LPG; __any_sync(kFull, slot < ev.G); slot += n_groups) {
         const bool act = slot < ev.G;
         const int g = act ? ev.order[slot] : 0;
         TreeCtxG<LPG> cx = make_ctx_g(ev, g, grp);
+        cx.stage = sstage[threadIdx.x / LPG];
         const Board root{ev.black[g], ev.white[g], ev.side[g], ev.flags[g]};
         const uint64_t game_id = ev.game_id[g];
         const uint64_t search_id = (uint64_t)ev.ply[g];
@@ -532,11 +536,15 @@ __global__ void __launch_bounds__(kBlockG, 16) search_k1g_kernel(EngineView ev, 
         for (int sim = 0; sim < S; ++sim) {
             const uint64_t st = EVAL == RVS_EVAL_ROLLOUT ? stream_seed(ev.seed, game_id, (search_id << 16) | (uint64_t)sim) : 0ULL;
             simulate_one_g<EVAL>(cx, root_g, st, act);
-            if (sim == 0 && ev.noise_eps > 0.0f) {
-                if (act && grp.lane == 0) root_noise_apply(ev, g, game_id, search_id);
-                __syncwarp();
+            if (sim == 0) {
+                if (ev.noise_eps > 0.0f) {
+                    if (act && grp.lane == 0) root_noise_apply(ev, g, game_id, search_id);
+                    __syncwarp();
+                }
+                stage_root(cx, act);  // the root was expanded by simulation 0: its rows move to shared memory
             }
         }
+        unstage_root(cx);
         if (act && grp.lane == 0) ev.n_nodes[g] = cx.n_nodes;
         flush_stats_g(ev, cx, act);
     }
@@ -555,8 +563,8 @@ __device__ __noinline__ void end_of_ply(const EngineView& ev, int g, int lane, f
 // Persistent self-play (SelfPlay.generate_games, self_play.py:66-131, with MCTS batch_size 1), an LPG-lane
 // group per game, work-conserving: every group
 // keeps playing plies of its slots, round-robin, until the launch-wide budget of game-plies is used up
-template <int RULES, int EVAL, int LPG>
-__global__ void __launch_bounds__(kBlockG, 16) selfplay_k1g_kernel(EngineView ev, int S, float temperature,
+template <int RULES, int EVAL, int LPG, int MINB>
+__global__ void __launch_bounds__(kBlockG, MINB) selfplay_k1g_kernel(EngineView ev, int S, float temperature,
                                                                    unsigned long long budget, int recycle) {
     constexpr int GPB = kBlockG / LPG;
     __shared__ uint8_t lut[256 * 8];
@@ -568,6 +576,7 @@ __global__ void __launch_bounds__(kBlockG, 16) selfplay_k1g_kernel(EngineView ev
     const int slot0 = blockIdx.x * GPB + (int)threadIdx.x / LPG;
     const int n_mine = slot0 < ev.G ? (ev.G - slot0 + n_groups - 1) / n_groups : 0;  // slots of this group
     const Grp<LPG> grp = make_grp<RULES, LPG>(threadIdx.x & 31, lut, spath[threadIdx.x / LPG], LPG == 8 ? sgather[threadIdx.x / LPG] : nullptr);
+    __shared__ int4 sstage[GPB][2 * (1 + StageCfg<LPG>::kRows) + 2];  // hot node rows of each group's search
     bool quit = n_mine == 0;
     int k = 0, idle = 0;  // current slot of the round-robin; consecutive slots found parked / finished
     while (true) {
@@ -581,6 +590,7 @@ __global__ void __launch_bounds__(kBlockG, 16) selfplay_k1g_kernel(EngineView ev
         t = __shfl_sync(kFull, t, 0, LPG);
         if (alive && t >= budget) { alive = false; quit = true; }
         TreeCtxG<LPG> cx = make_ctx_g(ev, g, grp);
+        cx.stage = sstage[threadIdx.x / LPG];
         const uint64_t game_id = ev.game_id[g];
         const uint64_t search_id = (uint64_t)ev.ply[g];
         init_root_g(cx, root.side, alive);
@@ -589,11 +599,15 @@ __global__ void __launch_bounds__(kBlockG, 16) selfplay_k1g_kernel(EngineView ev
             for (int sim = 0; sim < S; ++sim) {
                 const uint64_t st = EVAL == RVS_EVAL_ROLLOUT ? stream_seed(ev.seed, game_id, (search_id << 16) | (uint64_t)sim) : 0ULL;
                 simulate_one_g<EVAL>(cx, root_g, st, alive);
-                if (sim == 0 && ev.noise_eps > 0.0f) {
-                    if (alive && grp.lane == 0) root_noise_apply(ev, g, game_id, search_id);
-                    __syncwarp();
+                if (sim == 0) {
+                    if (ev.noise_eps > 0.0f) {
+                        if (alive && grp.lane == 0) root_noise_apply(ev, g, game_id, search_id);
+                        __syncwarp();
+                    }
+                    stage_root(cx, alive);  // the root was expanded by simulation 0: its rows move to shared memory
                 }
             }
+            unstage_root(cx);
         }
         if (alive && grp.lane == 0) ev.n_nodes[g] = cx.n_nodes;
         flush_stats_g(ev, cx, alive);
@@ -913,19 +927,25 @@ int rvs_engine_search(rvs_engine* h, int32_t num_sims, int32_t wave, void* strea
         {
             RVS_ENGINE_LAUNCH(h, phase_order_kernel, 1, 1024, 0, s, h->v);
             const int lpg = lanes_per_game(h);
+#define RVS_SEARCH_GM(LPG, MINB)                                                                                                  \
+    do {                                                                                                                          \
+        if (strict && e0) RVS_ENGINE_LAUNCH(h, (search_k1g_kernel<RULES_STRICT, RVS_EVAL_E0, LPG, MINB>), gridg, kBlockG, 0, s, h->v, num_sims); \
+        else if (strict) RVS_ENGINE_LAUNCH(h, (search_k1g_kernel<RULES_STRICT, RVS_EVAL_ROLLOUT, LPG, MINB>), gridg, kBlockG, 0, s, h->v, num_sims); \
+        else if (e0) RVS_ENGINE_LAUNCH(h, (search_k1g_kernel<RULES_REF, RVS_EVAL_E0, LPG, MINB>), gridg, kBlockG, 0, s, h->v, num_sims); \
+        else RVS_ENGINE_LAUNCH(h, (search_k1g_kernel<RULES_REF, RVS_EVAL_ROLLOUT, LPG, MINB>), gridg, kBlockG, 0, s, h->v, num_sims);  \
+    } while (0)
 #define RVS_SEARCH_G(LPG)                                                                                                         \
     do {                                                                                                                          \
         const int need = (h->v.G * LPG + kBlockG - 1) / kBlockG;                                                                  \
         const int gridg = need < kMaxWarpsG ? need : kMaxWarpsG;                                                                  \
-        if (strict && e0) RVS_ENGINE_LAUNCH(h, (search_k1g_kernel<RULES_STRICT, RVS_EVAL_E0, LPG>), gridg, kBlockG, 0, s, h->v, num_sims); \
-        else if (strict) RVS_ENGINE_LAUNCH(h, (search_k1g_kernel<RULES_STRICT, RVS_EVAL_ROLLOUT, LPG>), gridg, kBlockG, 0, s, h->v, num_sims); \
-        else if (e0) RVS_ENGINE_LAUNCH(h, (search_k1g_kernel<RULES_REF, RVS_EVAL_E0, LPG>), gridg, kBlockG, 0, s, h->v, num_sims); \
-        else RVS_ENGINE_LAUNCH(h, (search_k1g_kernel<RULES_REF, RVS_EVAL_ROLLOUT, LPG>), gridg, kBlockG, 0, s, h->v, num_sims);  \
+        if (need <= kNumSMs * 8) RVS_SEARCH_GM(LPG, 8);                                                                           \
+        else RVS_SEARCH_GM(LPG, 16);                                                                                              \
     } while (0)
             if (lpg == 8) RVS_SEARCH_G(8);
             else if (lpg == 2) RVS_SEARCH_G(2);
             else RVS_SEARCH_G(4);
 #undef RVS_SEARCH_G
+#undef RVS_SEARCH_GM
         }
         h->searching = false;
         return 0;
@@ -1087,19 +1107,25 @@ int rvs_engine_selfplay(rvs_engine* h, int32_t num_sims, float temperature, int6
     {
         RVS_ENGINE_LAUNCH(h, phase_order_kernel, 1, 1024, 0, s, h->v);
         const int lpg = lanes_per_game(h);
+#define RVS_SELFPLAY_GM(LPG, MINB)                                                                                                \
+    do {                                                                                                                          \
+        if (strict && e0) RVS_ENGINE_LAUNCH(h, (selfplay_k1g_kernel<RULES_STRICT, RVS_EVAL_E0, LPG, MINB>), gridg, kBlockG, 0, s, h->v, num_sims, temperature, budget, recycle); \
+        else if (strict) RVS_ENGINE_LAUNCH(h, (selfplay_k1g_kernel<RULES_STRICT, RVS_EVAL_ROLLOUT, LPG, MINB>), gridg, kBlockG, 0, s, h->v, num_sims, temperature, budget, recycle); \
+        else if (e0) RVS_ENGINE_LAUNCH(h, (selfplay_k1g_kernel<RULES_REF, RVS_EVAL_E0, LPG, MINB>), gridg, kBlockG, 0, s, h->v, num_sims, temperature, budget, recycle); \
+        else RVS_ENGINE_LAUNCH(h, (selfplay_k1g_kernel<RULES_REF, RVS_EVAL_ROLLOUT, LPG, MINB>), gridg, kBlockG, 0, s, h->v, num_sims, temperature, budget, recycle); \
+    } while (0)
 #define RVS_SELFPLAY_G(LPG)                                                                                                       \
     do {                                                                                                                          \
         const int need = (h->v.G * LPG + kBlockG - 1) / kBlockG;                                                                  \
         const int gridg = need < kMaxWarpsG ? need : kMaxWarpsG;                                                                  \
-        if (strict && e0) RVS_ENGINE_LAUNCH(h, (selfplay_k1g_kernel<RULES_STRICT, RVS_EVAL_E0, LPG>), gridg, kBlockG, 0, s, h->v, num_sims, temperature, budget, recycle); \
-        else if (strict) RVS_ENGINE_LAUNCH(h, (selfplay_k1g_kernel<RULES_STRICT, RVS_EVAL_ROLLOUT, LPG>), gridg, kBlockG, 0, s, h->v, num_sims, temperature, budget, recycle); \
-        else if (e0) RVS_ENGINE_LAUNCH(h, (selfplay_k1g_kernel<RULES_REF, RVS_EVAL_E0, LPG>), gridg, kBlockG, 0, s, h->v, num_sims, temperature, budget, recycle); \
-        else RVS_ENGINE_LAUNCH(h, (selfplay_k1g_kernel<RULES_REF, RVS_EVAL_ROLLOUT, LPG>), gridg, kBlockG, 0, s, h->v, num_sims, temperature, budget, recycle); \
+        if (need <= kNumSMs * 8) RVS_SELFPLAY_GM(LPG, 8);                                                                         \
+        else RVS_SELFPLAY_GM(LPG, 16);                                                                                            \
     } while (0)
         if (lpg == 8) RVS_SELFPLAY_G(8);
         else if (lpg == 2) RVS_SELFPLAY_G(2);
         else RVS_SELFPLAY_G(4);
 #undef RVS_SELFPLAY_G
+#undef RVS_SELFPLAY_GM
     }
     h->searching = false;
     return 0;

@@ -335,7 +335,71 @@ struct TreeCtxG {
     int overflow;
     unsigned steps, sims, evals, bytes, created;
     Grp<LPG> g;
+    // shared-memory staging of the HOT NODE ROWS of the search: the root and its children (every simulation scans
+    // and backs up exactly these rows).  stage = generic address of this group's block of (1 + kStageRows) 32-byte
+    // rows {hot, cold} in shared memory; nc0 = staged children (0: nothing staged, all rows live in HBM/L1)
+    int4* stage;
+    int fc0;
+    unsigned nc0;
 };
+
+// rows a group can stage: the root + its children (REF rules: up to ~33 legal squares incl. phantom moves)
+template <int LPG>
+struct StageCfg { static constexpr int kRows = LPG == 8 ? 32 : (LPG == 4 ? 24 : 0); };
+
+// address of a node's hot / cold row: the staged copy when the node is the root or one of its staged children.
+// One generic-space access serves both cases, so groups of a warp that sit at different tree levels do not diverge.
+template <int LPG>
+__device__ __forceinline__ int4* hot_at(const TreeCtxG<LPG>& cx, int node) {
+    if constexpr (StageCfg<LPG>::kRows == 0) return &cx.hot[node];
+    const unsigned rel = (unsigned)(node - cx.fc0);
+    const bool st = cx.nc0 != 0u && (node == 0 || rel < cx.nc0);
+    return st ? cx.stage + 2 * (node == 0 ? 0 : 1 + (int)rel) : &cx.hot[node];
+}
+template <int LPG>
+__device__ __forceinline__ int4* cold_at(const TreeCtxG<LPG>& cx, int node) {
+    if constexpr (StageCfg<LPG>::kRows == 0) return &cx.cold[node];
+    const unsigned rel = (unsigned)(node - cx.fc0);
+    const bool st = cx.nc0 != 0u && (node == 0 || rel < cx.nc0);
+    return st ? cx.stage + 2 * (node == 0 ? 0 : 1 + (int)rel) + 1 : &cx.cold[node];
+}
+
+// after the root expansion (and the root noise): copy the root row and its children into the group's block
+template <int LPG>
+__device__ __forceinline__ void stage_root(TreeCtxG<LPG>& cx, bool act) {
+    if constexpr (StageCfg<LPG>::kRows != 0) {
+        unsigned nc = 0;
+        int fc = 0;
+        if (act) {
+            const int4 c = cx.cold[0];
+            nc = (unsigned)(c.z & 0xFF);
+            fc = c.y;
+            if (nc > (unsigned)StageCfg<LPG>::kRows) nc = 0;  // does not fit: this search stays in HBM/L1
+        }
+        for (unsigned i = cx.g.lane; i < nc + (nc ? 1u : 0u); i += LPG) {
+            const int node = i == 0 ? 0 : fc + (int)i - 1;
+            cx.stage[2 * i] = cx.hot[node];
+            cx.stage[2 * i + 1] = cx.cold[node];
+        }
+        __syncwarp();
+        cx.fc0 = fc;
+        cx.nc0 = nc;
+    }
+}
+// end of the search: the hot rows (N, W, VL, cached score) go back to HBM, where the move choice reads them
+template <int LPG>
+__device__ __forceinline__ void unstage_root(TreeCtxG<LPG>& cx) {
+    if constexpr (StageCfg<LPG>::kRows != 0) {
+        __syncwarp();
+        const unsigned nc = cx.nc0;
+        for (unsigned i = cx.g.lane; i < nc + (nc ? 1u : 0u); i += LPG) {
+            const int node = i == 0 ? 0 : cx.fc0 + (int)i - 1;
+            cx.hot[node] = cx.stage[2 * i];
+        }
+        cx.nc0 = 0u;
+        __syncwarp();
+    }
+}
 
 // MCTS._backpropagate_path (mcts.py:625-640): lane l owns path nodes l, l+LPG, ...
 template <int LPG>
@@ -343,14 +407,15 @@ __device__ __forceinline__ void backup_path_g(TreeCtxG<LPG>& cx, int plen, float
     const int n_upd = act ? plen : 0;
     for (int d = cx.g.lane; d < n_upd; d += LPG) {
         const int n = lds_s32(cx.g.path + 4 * d);
-        int4 h = cx.hot[n];
+        int4* hp = hot_at(cx, n);
+        int4 h = *hp;
         const float sv = ((plen - 1 - d) & 1) ? -v : v;
         h.x += 1;
         h.y = __float_as_int(__fadd_rn(__int_as_float(h.y), sv));
         int vl = h.z & kVLMask;
         if (vl > 0) --vl;
         h.z = (h.z & ~(kVLMask | kCacheValid)) | vl;
-        cx.hot[n] = h;
+        *hp = h;
     }
     cx.bytes += 32u * (unsigned)n_upd;
     __syncwarp();
@@ -365,8 +430,8 @@ __device__ __forceinline__ int select_one_g(TreeCtxG<LPG>& cx, GBoard& b, int& p
     int4 h = make_int4(0, 0, 0, 0), c = make_int4(0, 0, 0, 0);
     if (act) {
         if (g.lane == 0) sts_s32(g.path, 0);
-        h = cx.hot[0];
-        c = cx.cold[0];
+        h = *hot_at(cx, 0);
+        c = *cold_at(cx, 0);
         cx.bytes += 32;
     }
     const unsigned key_floor = ordered_key(-INFINITY);
@@ -379,7 +444,7 @@ __device__ __forceinline__ int select_one_g(TreeCtxG<LPG>& cx, GBoard& b, int& p
         if (!__any_sync(kFull, going)) break;
         if (going) {
             h.z += 1;  // node.virtual_loss += 1 (mcts.py:416)
-            if (g.lane == 0) reinterpret_cast<int*>(&cx.hot[node])[2] = h.z;
+            if (g.lane == 0) reinterpret_cast<int*>(hot_at(cx, node))[2] = h.z;
             cx.bytes += 32u * (unsigned)nchild;
         }
         const float sq = __fsqrt_rn((float)h.x);
@@ -393,8 +458,9 @@ __device__ __forceinline__ int select_one_g(TreeCtxG<LPG>& cx, GBoard& b, int& p
             int4 ch = make_int4(0, 0, 0, 0), cc = make_int4(0, 0, 0, 0);
             unsigned key = 0;
             if (i < nscan) {
-                ch = cx.hot[fc + i];
-                cc = cx.cold[fc + i];
+                int4* hp = hot_at(cx, fc + i);
+                ch = *hp;
+                cc = *cold_at(cx, fc + i);
                 float score;
                 if (ch.x == 0) {
                     score = INFINITY;  // mcts.py:96-97
@@ -405,7 +471,7 @@ __device__ __forceinline__ int select_one_g(TreeCtxG<LPG>& cx, GBoard& b, int& p
                                         (cc.z >> 16) & 3, cx.c_puct, sq);
                     ch.w = __float_as_int(score);
                     ch.z |= kCacheValid;
-                    reinterpret_cast<int2*>(&cx.hot[fc + i])[1] = make_int2(ch.z, ch.w);
+                    reinterpret_cast<int2*>(hp)[1] = make_int2(ch.z, ch.w);
                 }
                 key = (score == score) ? ordered_key(score) : 0u;
             }
@@ -453,7 +519,8 @@ template <int LPG>
 __device__ __forceinline__ void expand_node_g(TreeCtxG<LPG>& cx, int node, uint64_t lm, float prior, bool act) {
     const Grp<LPG>& g = cx.g;
     if (act) {
-        int4 c = cx.cold[node];
+        int4* cp = cold_at(cx, node);
+        int4 c = *cp;
         const int nc = popc64(lm);
         if ((c.z & 0xFF) != 0) {
             // 'if action not in self.children' (mcts.py:154): already expanded, nothing to add
@@ -474,7 +541,7 @@ __device__ __forceinline__ void expand_node_g(TreeCtxG<LPG>& cx, int node, uint6
             if (g.lane == 0) {
                 c.y = fc;
                 c.z = (c.z & ~0xFF) | nc;
-                cx.cold[node] = c;
+                *cp = c;
             }
             cx.n_nodes += nc;
             cx.created += (unsigned)nc;
@@ -510,7 +577,7 @@ __device__ __forceinline__ void simulate_one_g(TreeCtxG<LPG>& cx, const GBoard& 
         const int w = (b.flags & F_WIN_MASK) >> F_WIN_SHIFT;
         const int code = !(b.flags & F_OVER) ? 0 : (w == 1 ? 1 : (w == 2 ? 2 : 0));
         if (cx.g.lane == 0) {
-            int* z = &reinterpret_cast<int*>(&cx.hot[node])[2];
+            int* z = &reinterpret_cast<int*>(hot_at(cx, node))[2];
             *z = (*z & ~(3 << kTermShift)) | kTerminal | (code << kTermShift);
         }
         v = code == 1 ? 1.0f : (code == 2 ? -1.0f : 0.0f);

@@ -109,8 +109,9 @@ def gather_packed(s, dst: int = 0, info: Optional[dict] = None):
                     bytes_received=(total - counts[dst]) * PACKED_ROW_WORDS * 4 if rank == dst else 0,
                     bytes_sent=0 if rank == dst else len(s) * PACKED_ROW_WORDS * 4)
     if rank != dst:
-        if len(s):
-            dist.send(row, dst=dst)
+        if len(s):  # batched P2P: not serialised with the other collectives of the group
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, row, dst)]):
+                w.wait()
         return None
     allr = torch.empty((total, PACKED_ROW_WORDS), dtype=torch.int32, device=dev)
     off = [0]
