@@ -29,7 +29,15 @@ namespace rvs {
 namespace {
 
 constexpr int kTileRows = 128;              // pixels per tile (2 boards)
-constexpr int kABytes = 10 * 2 * 8 * 128;   // one activation stage: 160 rows x 128 B
+constexpr int kABytes = 10 * 2 * 8 * 128;   // one activation stage of the streamed (256-filter) kernel: 160 rows x 128 B
+// Resident-weight kernels (C <= 128): ONE activation box per 64-channel chunk serves all nine taps.  The box is
+// 10 rows of y (halo -1..8) x 2 boards x 16 x-slots (x = -1..14; x < 0 and x > 7 are zero-filled by the TMA unit)
+// x 64 channels, so a (y, board) line is exactly two 1024-byte swizzle atoms and a horizontal tap shift dx is a
+// start-address offset of dx rows (128 B) INSIDE the atom (make_desc_x).  Compared with one shifted box per dx this fetches every input element once instead of three
+// times (L2 -> SM traffic per tile 40 KB instead of 120 KB per chunk pair) and writes 80 KB instead of 120 KB of
+// shared memory per tile -- the 128-filter layer was bound by exactly these two.
+constexpr int kXSlots = 16;
+constexpr int kABytesX = 10 * 2 * kXSlots * 128;  // 40 KB
 constexpr int kThreads = 192;
 
 struct Impl {
@@ -102,6 +110,14 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// the same with 2048 B between 8-row groups (16 x-slots per (y, board) line).  The start address may sit 1 or 2 rows
+// (128 / 256 B) into a swizzle atom (horizontal tap shift): the tensor core applies the 128-byte swizzle to the
+// ABSOLUTE shared-memory address bits, exactly like the TMA unit that wrote the box, so no descriptor field has to
+// describe the phase.  Measured on B200: with the descriptor's base-offset field [49,52) set to the row phase the
+// results are wrong, with 0 all network goldens pass (tests/test_gpu_net.py).
+__device__ __forceinline__ uint64_t make_desc_x(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(2048 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16
 // [10,13)=1, A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)  -> Cfg2::IDESC / Cfg2S::IDESC
 
@@ -161,19 +177,26 @@ __device__ __forceinline__ void tc2_commit_mc(uint32_t bar) {  // arrive on `bar
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}" ::"r"(bar)
         : "memory");
 }
+// Barrier traffic inside the pair carries NO generic-proxy memory dependency: operands travel TMA -> shared memory ->
+// tensor core (async proxy, ordered by complete_tx / tcgen05.commit) and results tensor core -> TMEM -> registers
+// (ordered by tcgen05.fence / tcgen05.wait::ld).  So the remote arrive and the waits use the default CTA-scope
+// semantics, as CUTLASS's ClusterBarrier does.  The `.release.cluster` / `.acquire.cluster` forms used in round 1
+// compiled to MEMBAR.ALL.GPU + ERRBAR per arrive and to CCTL.IVALL (invalidate all of L1) per successful wait: a
+// GPU-wide fence per epilogue warp per tile that waited for the tile's 32 KB of output stores to drain (ncu:
+// stall_membar 17 % of the epilogue warps' samples).
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {  // arrive on the leader CTA's barrier from either CTA
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar)
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar)
         : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquire at cluster scope
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t done;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
             : "r"(bar), "r"(parity)
@@ -193,12 +216,12 @@ struct Cfg2 {
     static constexpr int NH = C / 2;                        // weight rows (couts) held by each CTA
     static constexpr int W_TILE = NH * 128;                 // bytes of one (tap, kc) weight tile per CTA
     static constexpr int W_TILES = 9 * KC;
-    static constexpr int STAGES = (C == 128 && CIN == 128) ? 4 : 6;  // 128->128: 144 KB weights + 4 x 20 KB = 224 KB
+    static constexpr int STAGES = (C == 128 && CIN == 128) ? 2 : (C == 128 ? 3 : 4);  // 128->128: 144 KB weights + 2 x 40 KB = 224 KB
     static constexpr int TMEM_COLS = 2 * C;                 // two accumulators of C fp32 columns
     // K = 16 steps per 64-channel chunk.  The 64 -> 128 instantiation is the network's FIRST layer: only
     // channels 0..2 of its input tiles are non-zero, so the steps over channels 16..63 would multiply zeros
     static constexpr int KSTEPS = (C == 128 && CIN == 64) ? 1 : 4;
-    static constexpr int SMEM = W_TILES * W_TILE + STAGES * kABytes + 1024 /*align*/ + 1280 /*barriers, bias*/;
+    static constexpr int SMEM = W_TILES * W_TILE + STAGES * kABytesX + 1024 /*align*/ + 1280 /*barriers, bias*/;
     static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 };
 
@@ -217,7 +240,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
     unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t w_s = base;
     const uint32_t a_s = base + K::W_TILES * K::W_TILE;
-    unsigned char* tail = gen + K::W_TILES * K::W_TILE + K::STAGES * kABytes;
+    unsigned char* tail = gen + K::W_TILES * K::W_TILE + K::STAGES * kABytesX;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 192);
     float* sbias = reinterpret_cast<float*>(tail + 256);  // [C] <= 256 floats
@@ -261,13 +284,12 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
             int stage = 0, phase = 0;
             for (int it = 0; it < n_iters; ++it) {
                 const int tile = (it * n_pairs + pair) * 2 + (int)rank;  // may be >= n_tiles: TMA zero-fills
-                for (int dx = 0; dx < 3; ++dx)
-                    for (int kc = 0; kc < K::KC; ++kc) {
-                        mbar_wait_cluster(EMPTY(stage), phase ^ 1);
-                        if (rank == 0) mbar_expect_tx(FULL(stage), 2 * kABytes);
-                        tma2_load_5d(&a_map, FULL(stage), a_s + stage * kABytes, kc * 64, dx - 1, 0, -1, tile);
-                        if (++stage == K::STAGES) { stage = 0; phase ^= 1; }
-                    }
+                for (int kc = 0; kc < K::KC; ++kc) {
+                    mbar_wait_cluster(EMPTY(stage), phase ^ 1);
+                    if (rank == 0) mbar_expect_tx(FULL(stage), 2 * kABytesX);
+                    tma2_load_5d(&a_map, FULL(stage), a_s + stage * kABytesX, kc * 64, -1, 0, -1, tile);
+                    if (++stage == K::STAGES) { stage = 0; phase ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
@@ -280,23 +302,27 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)(acc * C);
                 uint32_t accum = 0;
-                for (int dx = 0; dx < 3; ++dx)
-                    for (int kc = 0; kc < K::KC; ++kc) {
-                        mbar_wait_cluster(FULL(stage), phase);
-                        tc_fence_after();
-                        const uint32_t a0 = a_s + stage * kABytes;
+                for (int kc = 0; kc < K::KC; ++kc) {
+                    mbar_wait_cluster(FULL(stage), phase);
+                    tc_fence_after();
+                    const uint32_t a0 = a_s + stage * kABytesX;
 #pragma unroll
-                        for (int dy = 0; dy < 3; ++dy) {
+                    for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
                             const uint32_t wt = w_s + ((dy * 3 + dx) * K::KC + kc) * K::W_TILE;
+                            // tap (dy, dx): input pixel (y + dy - 1, x + dx - 1) = box row ((y + dy) * 2 + board) * 16 + x + dx
+                            const uint32_t at = a0 + (uint32_t)(dy * 2 * kXSlots + dx) * 128u;
 #pragma unroll
                             for (int k = 0; k < K::KSTEPS; ++k) {
-                                tc2_mma(d, make_desc(a0 + dy * 2048 + k * 32), make_desc(wt + k * 32), K::IDESC, accum);
+                                tc2_mma(d, make_desc_x(at + k * 32), make_desc(wt + k * 32), K::IDESC, accum);
                                 accum = 1;
                             }
                         }
-                        tc2_commit_mc(EMPTY(stage));
-                        if (++stage == K::STAGES) { stage = 0; phase ^= 1; }
                     }
+                    tc2_commit_mc(EMPTY(stage));
+                    if (++stage == K::STAGES) { stage = 0; phase ^= 1; }
+                }
                 tc2_commit_mc(ACC_FULL(acc));
             }
         }
@@ -597,13 +623,13 @@ int launch_pdl_s(int grid, cudaStream_t s, const CUtensorMap& a_map, const CUten
     return 0;
 }
 
-int encode_act_map(CUtensorMap* m, const void* ptr, int C /*channels of this buffer*/, int64_t n_tiles) {
+int encode_act_map(CUtensorMap* m, const void* ptr, int C /*channels of this buffer*/, int64_t n_tiles, int x_slots) {
     EncodeFn enc = get_encode();
     if (!enc) return fail(-9, "cuTensorMapEncodeTiled entry point not available");
     // tiled activation layout [tile][y][board][x][c]  (dims innermost first)
     const cuuint64_t dims[5] = {(cuuint64_t)C, 8, 2, 8, (cuuint64_t)n_tiles};
     const cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * 8, (cuuint64_t)C * 2 * 16, (cuuint64_t)C * 2 * 128};
-    const cuuint32_t box[5] = {64, 8, 2, 10, 1};
+    const cuuint32_t box[5] = {64, (cuuint32_t)x_slots, 2, 10, 1};  // 8: one box per dx (streamed kernel); 16: one box for all taps
     const cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -668,7 +694,7 @@ int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_b
     if (slot < 0) {
         if (im->n_act == Impl::kActSlots) im->n_act = 0;
         slot = im->n_act++;
-        int rc = encode_act_map(&im->act_map[slot], in, im->cin, (cap + 1) / 2);  // tiles beyond the map are zero-filled by TMA
+        int rc = encode_act_map(&im->act_map[slot], in, im->cin, (cap + 1) / 2, plan.C == 256 ? 8 : kXSlots);  // tiles beyond the map are zero-filled by TMA
         if (rc) return rc;
         im->act_ptr[slot] = in;
         im->act_cap[slot] = cap;

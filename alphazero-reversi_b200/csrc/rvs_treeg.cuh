@@ -33,7 +33,13 @@ struct Grp {
     int sh;              // first lane of the group inside the warp
     int lane;            // 0..LPG-1 inside the group
     uint64_t below;      // squares of the rows owned by lower lanes
+    uint64_t belowd;     // the same set in the lane's OWN domain (LPG == 8: bit-reversed for odd lanes; else = below)
+    uint64_t oned;       // square 0 in the lane's own domain
+    int bsh;             // LPG == 8: index (0..7) of this lane's row byte inside an own-domain mask
+    int flip63;          // LPG == 8: 63 for lanes that work on bit-reversed boards (square s = bit 63 - s), else 0
     uint32_t lut;        // shared-window address: lut[byte * 8 + j] = position of the j-th set bit of byte
+    uint32_t lutd;       // the table for own-domain row bytes: odd lanes of 8-lane groups see their row bit-reversed
+                         // (lut + 2048: lutr[byte * 8 + j] = lut[rev8(byte) * 8 + j])
     uint32_t gather;     // shared-window address: 3 x 64-byte exchange buffers of the group (grp_or64_own8)
     uint32_t path;       // shared-window address: int[kMaxPath + 1] nodes of the current path; the extra word
                          // is the group's broadcast slot (grp_nth_set_bit)
@@ -41,9 +47,13 @@ struct Grp {
     DirLane d[ND];       // this lane's directions; d[j].neg == (j & 1) when ND >= 2
 };
 
+// lut[0 .. 2048): select-in-byte; lut[2048 .. 4096): the same for a bit-reversed byte (positions still count from
+// the least significant bit of the NORMAL byte)
+constexpr int kLutBytes = 2 * 256 * 8;
 __device__ __forceinline__ void lut_init(uint8_t* lut, int tid, int nthreads) {
-    for (int e = tid; e < 256 * 8; e += nthreads) {
-        unsigned b = (unsigned)(e >> 3);
+    for (int e = tid; e < kLutBytes; e += nthreads) {
+        unsigned b = (unsigned)(e >> 3) & 0xFFu;
+        if (e >= 256 * 8) b = __brev(b) >> 24;
         int j = e & 7, pos = 0;
         for (int i = 0; i < 8; ++i)
             if ((b >> i) & 1u) {
@@ -54,15 +64,28 @@ __device__ __forceinline__ void lut_init(uint8_t* lut, int tid, int nthreads) {
     }
 }
 
+// word offset of the 3 x 16-word exchange buffers of 8-lane group gi inside the CTA's gather array (kGatherWords words)
+constexpr int kGatherWords = 264;
+__device__ __forceinline__ int gather_off(int gi) { return gi == 0 ? 0 : (gi == 1 ? 68 : (gi == 2 ? 144 : 212)); }
+
 template <int RULES, int LPG>
 __device__ __forceinline__ Grp<LPG> make_grp(int lane32, const uint8_t* lut, int* path, const void* gather = nullptr) {
     Grp<LPG> g;
     g.sh = lane32 & ~(LPG - 1);
     g.lane = lane32 & (LPG - 1);
     g.below = Grp<LPG>::RPL * g.lane == 0 ? 0ULL : ((1ULL << (8 * Grp<LPG>::RPL * g.lane)) - 1ULL);
+    const bool own_rev = LPG == 8 && (g.lane & 1);  // make_dir: odd directions are right shifts = bit-reversed boards
+    g.belowd = own_rev ? brev64(g.below) : g.below;
+    g.oned = own_rev ? (1ULL << 63) : 1ULL;
+    g.bsh = own_rev ? 7 - g.lane : g.lane;
+    g.flip63 = own_rev ? 63 : 0;
     g.lut = (uint32_t)__cvta_generic_to_shared(lut);
+    g.lutd = g.lut + (own_rev ? 256u * 8u : 0u);
     g.path = (uint32_t)__cvta_generic_to_shared(path);
-    g.gather = gather ? (uint32_t)__cvta_generic_to_shared(gather) : 0u;
+    // 8-lane groups: the four groups of a warp read their exchange buffers with the same LDS.128 instructions, so
+    // the buffers start 4 / 16 / 20 banks apart (kGatherOff): the 8 distinct 16-byte chunks of one load instruction
+    // (4 groups x 2 domains) then cover all 32 banks once -- no bank conflicts
+    g.gather = gather ? (uint32_t)__cvta_generic_to_shared(gather) + 4u * (uint32_t)gather_off(lane32 >> 3) : 0u;
 #pragma unroll
     for (int j = 0; j < Grp<LPG>::ND; ++j) g.d[j] = make_dir<RULES>(g.lane * Grp<LPG>::ND + j);
     return g;
@@ -161,26 +184,44 @@ __device__ __forceinline__ unsigned grp_slice(const Grp<LPG>& g, uint64_t m) {
     }
 }
 
-// k-th (0-based) set bit of a group-uniform mask with more than k bits
+// k-th (0-based) set bit (ascending squares) of a group-uniform mask with more than k bits, in two halves so that
+// the rollout can run the first half (pure register work + one table lookup) in the shadow of the previous ply's
+// vote.  `md` is the mask in the lane's OWN domain (LPG == 8: bit-reversed for odd lanes; otherwise normal).
+struct NthPrep {
+    bool hit;  // this lane's rows hold the bit
+    int pos;   // its square (normal numbering), valid when hit
+};
 template <int LPG>
-__device__ __forceinline__ int grp_nth_set_bit(const Grp<LPG>& g, uint64_t m, int k) {
+__device__ __forceinline__ NthPrep grp_nth_prep(const Grp<LPG>& g, uint64_t md, int k) {
     constexpr int RPL = Grp<LPG>::RPL;
-    unsigned slice = grp_slice(g, m);
-    int j = k - popc64(m & g.below);
-    const bool hit = (unsigned)j < (unsigned)__popc(slice);
-    int row = 0;
+    NthPrep r;
+    if constexpr (LPG == 8) {
+        const unsigned byte = __byte_perm((unsigned)md, (unsigned)(md >> 32), (unsigned)g.bsh) & 0xFFu;  // one PRMT
+        const int j = k - popc64(md & g.belowd);
+        r.hit = (unsigned)j < (unsigned)__popc(byte);
+        r.pos = g.lane * 8 + (int)lds_u8(g.lutd + byte * 8 + (j & 7));
+    } else {
+        unsigned slice = grp_slice(g, md);
+        int j = k - popc64(md & g.below);
+        r.hit = (unsigned)j < (unsigned)__popc(slice);
+        int row = 0;
 #pragma unroll
-    for (int r = 0; r + 1 < RPL; ++r) {  // walk to the row of the slice that holds bit j
-        const int n = __popc(slice & 0xFFu);
-        const bool next = j >= n && row == r;
-        j = next ? j - n : j;
-        slice = next ? slice >> 8 : slice;
-        row = next ? r + 1 : row;
+        for (int q = 0; q + 1 < RPL; ++q) {  // walk to the row of the slice that holds bit j
+            const int n = __popc(slice & 0xFFu);
+            const bool next = j >= n && row == q;
+            j = next ? j - n : j;
+            slice = next ? slice >> 8 : slice;
+            row = next ? q + 1 : row;
+        }
+        r.pos = (g.lane * RPL + row) * 8 + (int)lds_u8(g.lut + (slice & 0xFFu) * 8 + (j & 7));
     }
-    const int pos = (g.lane * RPL + row) * 8 + (int)lds_u8(g.lut + (slice & 0xFFu) * 8 + (j & 7));
-    // exactly one lane of the group holds the bit: it posts the square in the group's shared slot
-    // (STS -> LDS is ~45 cycles shorter than ballot + find-first-set + SHFL on the critical path)
-    if (hit) sts_s32(g.path + 4 * kMaxPath, pos);
+    return r;
+}
+// exactly one lane of the group holds the bit: it posts the square in the group's shared slot
+// (STS -> LDS is ~45 cycles shorter than ballot + find-first-set + SHFL on the critical path)
+template <int LPG>
+__device__ __forceinline__ int grp_nth_post(const Grp<LPG>& g, const NthPrep& p) {
+    if (p.hit) sts_s32(g.path + 4 * kMaxPath, p.pos);
     __syncwarp();
     const int sq = lds_s32(g.path + 4 * kMaxPath);
     __syncwarp();
@@ -209,11 +250,12 @@ __device__ __forceinline__ bool dir_neg(const Grp<LPG>& g, int j) {
     return Grp<LPG>::ND >= 2 ? (j & 1) != 0 : g.d[0].neg;  // compile-time unless a lane owns a single direction
 }
 
-// Board.get_valid_moves for side P against O (both domains given), group-uniform result
+// Board.get_valid_moves for side P against O (both domains given), group-uniform result in the lane's OWN domain
+// (LPG == 8: bit-reversed for odd lanes -- popcounts, emptiness and grp_nth_prep do not need the normal form)
 template <int LPG, int BUF = 1>
-__device__ __forceinline__ uint64_t grp_legal(const Grp<LPG>& g, const uint64_t (&P)[2], const uint64_t (&O)[2]) {
-    if constexpr (Grp<LPG>::ND == 1)  // boards and partial masks in the lane's own domain, result normalised once
-        return to_dom(grp_or64_own8<BUF>(g, legal_raw(g.d[0], P[0], O[0])), g.d[0].neg);
+__device__ __forceinline__ uint64_t grp_legal_own(const Grp<LPG>& g, const uint64_t (&P)[2], const uint64_t (&O)[2]) {
+    if constexpr (Grp<LPG>::ND == 1)  // boards and partial masks in the lane's own domain
+        return grp_or64_own8<BUF>(g, legal_raw(g.d[0], P[0], O[0]));
     uint64_t xn = 0, xr = 0;
 #pragma unroll
     for (int j = 0; j < Grp<LPG>::ND; ++j) {
@@ -222,10 +264,20 @@ __device__ __forceinline__ uint64_t grp_legal(const Grp<LPG>& g, const uint64_t 
     }
     return grp_or64<LPG>(xn | brev64(xr));
 }
+template <int LPG>
+__device__ __forceinline__ uint64_t own_to_normal(const Grp<LPG>& g, uint64_t md) {
+    if constexpr (Grp<LPG>::ND == 1) return to_dom(md, g.d[0].neg);
+    return md;
+}
+// the same in the normal domain
+template <int LPG, int BUF = 1>
+__device__ __forceinline__ uint64_t grp_legal(const Grp<LPG>& g, const uint64_t (&P)[2], const uint64_t (&O)[2]) {
+    return own_to_normal(g, grp_legal_own<LPG, BUF>(g, P, O));
+}
 
 struct MoveOut {
     uint64_t P[2], O[2];  // mover / opponent after the flips (roles not swapped yet)
-    uint64_t lm_opp;      // legal mask of the opponent
+    uint64_t lm_opp;      // legal mask of the opponent, in the lane's OWN domain (grp_legal_own)
 };
 
 // flips of move idx by the side to move + the opponent's reply mask (board.py:181-240)
@@ -233,7 +285,7 @@ template <int LPG>
 __device__ __forceinline__ MoveOut grp_flip(const Grp<LPG>& g, const GBoard& c, int idx) {
     MoveOut m;
     if constexpr (Grp<LPG>::ND == 1) {  // everything in the lane's own domain
-        const uint64_t mv = 1ULL << (g.d[0].neg ? 63 - idx : idx);
+        const uint64_t mv = 1ULL << (idx ^ g.flip63);
         const uint64_t f = grp_or64_own8<0>(g, flip_raw(g.d[0], c.P[0], c.O[0], mv));
         m.P[0] = c.P[0] ^ (mv | f); m.P[1] = 0ULL;
         m.O[0] = c.O[0] ^ f;        m.O[1] = 0ULL;
@@ -250,7 +302,7 @@ __device__ __forceinline__ MoveOut grp_flip(const Grp<LPG>& g, const GBoard& c, 
         m.P[0] = c.P[0] ^ (mvn | f); m.P[1] = c.P[1] ^ (mvr | fb);
         m.O[0] = c.O[0] ^ f;         m.O[1] = c.O[1] ^ fb;
     }
-    m.lm_opp = grp_legal(g, m.O, m.P);
+    m.lm_opp = grp_legal_own(g, m.O, m.P);
     return m;
 }
 
@@ -265,7 +317,7 @@ __device__ __forceinline__ int over_flags(const GBoard& c, uint64_t P, uint64_t 
 template <int LPG>
 __device__ __forceinline__ uint64_t grp_apply_move(const Grp<LPG>& g, GBoard& c, int idx, bool act) {
     const MoveOut m = grp_flip(g, c, act ? idx : 0);
-    uint64_t lm = m.lm_opp;
+    uint64_t lm = own_to_normal(g, m.lm_opp);
     const bool pass = act && lm == 0;
     if (__any_sync(kFull, pass)) {  // rare, warp-uniform branch: auto-pass (board.py:242-249)
         const uint64_t lm2 = grp_legal<LPG, 2>(g, m.P, m.O);
@@ -286,28 +338,39 @@ __device__ __forceinline__ uint64_t grp_apply_move(const Grp<LPG>& g, GBoard& c,
 // random_playout() of one position per group.  A group whose game has ended keeps executing the
 // loop body on a dead position (cheaper than predicating every state update); its result was
 // captured when the game ended.  Returns the winner (0 draw, 1 black, 2 white); plies are counted
-// into `plies`.  lm == 0 on entry means "no rollout for this group".
+// into `plies`.  lm (normal domain) == 0 on entry means "no rollout for this group".
+//
+// The loop is software-pipelined around its dependency chain (move square -> flips -> exchange -> move generation ->
+// exchange -> next square): the random draw of the NEXT ply is taken at the top of a ply, and the register half of
+// the next square selection (grp_nth_prep, incl. its table lookup) is issued BEFORE the branch on the pass vote, so
+// both run in the shadow of the exchanges / the vote instead of extending the chain.  The legal mask stays in the
+// lane's own domain from one ply to the next (no bit reversal on the chain).  The draws consumed per ply are the
+// same as in the plain loop (one roll_next per ply, in order; an auto-pass consumes none).
 template <int LPG>
-__device__ __forceinline__ int grp_random_playout(const Grp<LPG>& g, GBoard c, uint64_t lm, uint64_t stream, int& plies) {
+__device__ __forceinline__ int grp_random_playout(const Grp<LPG>& g, GBoard c, uint64_t lm_normal, uint64_t stream, int& plies) {
     uint32_t rs = roll_init(stream);
-    bool done = lm == 0;
+    bool done = lm_normal == 0;
     int winner = 0;
     plies = 0;
-    if (done) lm = 1;  // a dead group plays square 0 over and over; nothing of it is read
-    bool all_done = __all_sync(kFull, done);
-    while (!all_done) {  // one vote per ply on the common path: `done` only changes inside the pass branch
-        const int n = popc64(lm);
-        const int k = roll_pick(roll_next(rs), n);
-        const int idx = grp_nth_set_bit(g, lm, k) & 63;
+    if (__all_sync(kFull, done)) return 0;
+    // a dead group plays square 0 over and over; nothing of it is read
+    uint64_t lm = done ? g.oned : (Grp<LPG>::ND == 1 ? to_dom(lm_normal, g.d[0].neg) : lm_normal);
+    uint32_t r = roll_next(rs);  // the draw of the first ply
+    NthPrep np = grp_nth_prep(g, lm, roll_pick(r, popc64(lm)));
+    while (true) {
+        r = roll_next(rs);  // the draw of the next ply
+        const int idx = grp_nth_post(g, np);
         const MoveOut m = grp_flip(g, c, idx);
         plies += done ? 0 : 1;
         lm = m.lm_opp;
         const bool pass = !done && lm == 0;
+        const bool any_pass = __any_sync(kFull, pass);
         // default: the opponent moves next
         c.P[0] = m.O[0]; c.P[1] = m.O[1]; c.O[0] = m.P[0]; c.O[1] = m.P[1];
         c.side = 3 - c.side;
-        if (__any_sync(kFull, pass)) {  // rare: auto-pass or game over (board.py:242-249)
-            const uint64_t lm2 = grp_legal<LPG, 2>(g, m.P, m.O);
+        np = grp_nth_prep(g, lm, roll_pick(r, popc64(lm)));  // speculative: right unless this group passes
+        if (any_pass) {  // rare: auto-pass or game over (board.py:242-249)
+            const uint64_t lm2 = grp_legal_own<LPG, 2>(g, m.P, m.O);
             if (pass) {
                 c.side = 3 - c.side;  // the mover keeps the turn
                 c.P[0] = m.P[0]; c.P[1] = m.P[1]; c.O[0] = m.O[0]; c.O[1] = m.O[1];
@@ -317,8 +380,9 @@ __device__ __forceinline__ int grp_random_playout(const Grp<LPG>& g, GBoard c, u
                     done = true;
                 }
             }
-            if (done) lm = 1;  // keep the dead group's ply well defined
-            all_done = __all_sync(kFull, done);
+            if (done) lm = g.oned;  // keep the dead group's ply well defined
+            if (__all_sync(kFull, done)) break;
+            np = grp_nth_prep(g, lm, roll_pick(r, popc64(lm)));  // same draw, the mask after the pass
         }
     }
     return winner;
