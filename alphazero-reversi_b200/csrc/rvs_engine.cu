@@ -14,12 +14,12 @@ constexpr int kBlock = 32 * kWarpsPerBlock;
 __device__ __forceinline__ void flush_stats(const EngineView& ev, const TreeCtx& cx, unsigned long long lane_steps) {
     for (int o = 16; o; o >>= 1) lane_steps += __shfl_down_sync(kFull, lane_steps, o);
     if (cx.lane == 0) {
-        atomicAdd(&ev.stats[ST_SIMS], (unsigned long long)cx.sims);
-        atomicAdd(&ev.stats[ST_EVALS], (unsigned long long)cx.evals);
-        atomicAdd(&ev.stats[ST_STEPS], (unsigned long long)cx.steps + lane_steps);
-        atomicAdd(&ev.stats[ST_BYTES], (unsigned long long)cx.bytes);
-        atomicAdd(&ev.stats[ST_NODES], (unsigned long long)cx.created);
-        if (cx.overflow) atomicAdd(&ev.stats[ST_OVERFLOW], 1ULL);
+        atomicAdd(stat_at(ev, ST_SIMS), (unsigned long long)cx.sims);
+        atomicAdd(stat_at(ev, ST_EVALS), (unsigned long long)cx.evals);
+        atomicAdd(stat_at(ev, ST_STEPS), (unsigned long long)cx.steps + lane_steps);
+        atomicAdd(stat_at(ev, ST_BYTES), (unsigned long long)cx.bytes);
+        atomicAdd(stat_at(ev, ST_NODES), (unsigned long long)cx.created);
+        if (cx.overflow) atomicAdd(stat_at(ev, ST_OVERFLOW), 1ULL);
     }
 }
 
@@ -211,26 +211,55 @@ __global__ void __launch_bounds__(kBlock) nn_step_kernel(EngineView ev, int g0, 
     }
     if (flags & 2) {
         const Board root{ev.black[g], ev.white[g], ev.side[g], ev.flags[g]};
-        if (fast) select_wave_fast(cx, root, ws, 1);
-        else select_wave(cx, root, ws, 1);
-        if (cx.lane == 0) {
-            const int node = ws.node[0];
+        if (fast) {
+            select_wave_fast(cx, root, ws, 1);
+            if (cx.lane == 0) {
+                const int node = ws.node[0];
+                uint64_t lm = 0;
+                int row = -1;
+                if (node >= 0) {
+                    const uint16_t sf = ws.sf[0];
+                    const Board b{ws.black[0], ws.white[0], (uint8_t)(sf & 0xFF), (uint8_t)(sf >> 8)};
+                    lm = board_legal<RULES>(b);
+                    if (lm) {
+                        row = atomicAdd(n_cur, 1);
+                        const bool blk = b.side == 1;
+                        bits_out[(size_t)row * 3] = blk ? b.black : b.white;
+                        bits_out[(size_t)row * 3 + 1] = blk ? b.white : b.black;
+                        bits_out[(size_t)row * 3 + 2] = lm;
+                    }
+                }
+                ws.lm[0] = lm;
+                rows[g] = row;
+            }
+        } else {
+            // select_wave(k = 1) with the leaf kept in registers: its legal mask comes from the direction-sliced
+            // warp-cooperative scan instead of one lane re-reading the wave scratch and scanning 8 directions alone
+            CoopBoard b = coop_load(cx.dir, root);
+            int p0, p1, plen, vlf;
+            const int node = select_one(cx, b, p0, p1, plen, vlf);
+            ++cx.sims;
             uint64_t lm = 0;
             int row = -1;
-            if (node >= 0) {
-                const uint16_t sf = ws.sf[0];
-                const Board b{ws.black[0], ws.white[0], (uint8_t)(sf & 0xFF), (uint8_t)(sf >> 8)};
-                lm = board_legal<RULES>(b);
-                if (lm) {
+            if (vlf & kTerminal) {  // warp-uniform (mcts.py:364-366)
+                backup_path(cx, p0, p1, plen, term_value_of(vlf));
+                if (cx.lane == 0) ws.node[0] = -1;
+            } else {
+                const Board lb = coop_store(cx.dir, b);
+                store_leaf(ws, 0, cx.lane, node, p0, p1, plen, lb);
+                lm = coop_legal(cx.dir, b);
+                if (cx.lane == 0 && lm) {
                     row = atomicAdd(n_cur, 1);
-                    const bool blk = b.side == 1;
-                    bits_out[(size_t)row * 3] = blk ? b.black : b.white;
-                    bits_out[(size_t)row * 3 + 1] = blk ? b.white : b.black;
+                    const bool blk = lb.side == 1;
+                    bits_out[(size_t)row * 3] = blk ? lb.black : lb.white;
+                    bits_out[(size_t)row * 3 + 1] = blk ? lb.white : lb.black;
                     bits_out[(size_t)row * 3 + 2] = lm;
                 }
             }
-            ws.lm[0] = lm;
-            rows[g] = row;
+            if (cx.lane == 0) {
+                ws.lm[0] = lm;
+                rows[g] = row;
+            }
         }
     }
     if (cx.lane == 0) ev.n_nodes[g] = cx.n_nodes;
@@ -347,10 +376,10 @@ __device__ __noinline__ int play_game(const EngineView& ev, int g, float tempera
     if (!try_move<RULES>(b, mv, nl)) {
         // the reference would spin forever here (SURVEY.md 8(a) A7 hazard); park the slot instead
         ev.live[g] = 0;
-        atomicAdd(&ev.stats[ST_STALLED], 1ULL);
+        atomicAdd(stat_at(ev, ST_STALLED), 1ULL);
         return 255;
     }
-    atomicAdd(&ev.stats[ST_STEPS], 1ULL);
+    atomicAdd(stat_at(ev, ST_STEPS), 1ULL);
     ev.black[g] = b.black; ev.white[g] = b.white; ev.side[g] = b.side; ev.flags[g] = b.flags;
     ev.ply[g] = ply + 1;
     if (is_over(b)) ev.finished[g] = 1;
@@ -391,9 +420,9 @@ __device__ __forceinline__ void finalize_game(const EngineView& ev, int g, int l
         ++stored;
     }
     if (lane == 0) {
-        atomicAdd(&ev.stats[ST_FINISHED], 1ULL);
-        atomicAdd(&ev.stats[ST_SAMPLES], (unsigned long long)stored);
-        if (stored < n) atomicAdd(&ev.stats[ST_DROPPED], (unsigned long long)(n - stored));
+        atomicAdd(stat_at(ev, ST_FINISHED), 1ULL);
+        atomicAdd(stat_at(ev, ST_SAMPLES), (unsigned long long)stored);
+        if (stored < n) atomicAdd(stat_at(ev, ST_DROPPED), (unsigned long long)(n - stored));
         ev.finished[g] = 0;
         if (recycle && (ev.game_limit == 0 || ev.game_id[g] + (uint64_t)ev.G < ev.game_limit)) {
             ev.black[g] = kStartBlack; ev.white[g] = kStartWhite; ev.side[g] = 1; ev.flags[g] = 0;
@@ -418,12 +447,12 @@ constexpr int kBlockG = 32;  // one warp per CTA: the finest grain for the block
 template <int LPG>
 __device__ __forceinline__ void flush_stats_g(const EngineView& ev, const TreeCtxG<LPG>& cx, bool act) {
     if (act && cx.g.lane == 0) {
-        atomicAdd(&ev.stats[ST_SIMS], (unsigned long long)cx.sims);
-        atomicAdd(&ev.stats[ST_EVALS], (unsigned long long)cx.evals);
-        atomicAdd(&ev.stats[ST_STEPS], (unsigned long long)cx.steps);
-        atomicAdd(&ev.stats[ST_BYTES], (unsigned long long)cx.bytes);
-        atomicAdd(&ev.stats[ST_NODES], (unsigned long long)cx.created);
-        if (cx.overflow) atomicAdd(&ev.stats[ST_OVERFLOW], 1ULL);
+        atomicAdd(stat_at(ev, ST_SIMS), (unsigned long long)cx.sims);
+        atomicAdd(stat_at(ev, ST_EVALS), (unsigned long long)cx.evals);
+        atomicAdd(stat_at(ev, ST_STEPS), (unsigned long long)cx.steps);
+        atomicAdd(stat_at(ev, ST_BYTES), (unsigned long long)cx.bytes);
+        atomicAdd(stat_at(ev, ST_NODES), (unsigned long long)cx.created);
+        if (cx.overflow) atomicAdd(stat_at(ev, ST_OVERFLOW), 1ULL);
     }
 }
 
@@ -466,9 +495,9 @@ __device__ __forceinline__ void finalize_game_g(const EngineView& ev, int g, int
         ++stored;
     }
     if (fin && lane == 0) {
-        atomicAdd(&ev.stats[ST_FINISHED], 1ULL);
-        atomicAdd(&ev.stats[ST_SAMPLES], (unsigned long long)stored);
-        if (stored < n) atomicAdd(&ev.stats[ST_DROPPED], (unsigned long long)(n - stored));
+        atomicAdd(stat_at(ev, ST_FINISHED), 1ULL);
+        atomicAdd(stat_at(ev, ST_SAMPLES), (unsigned long long)stored);
+        if (stored < n) atomicAdd(stat_at(ev, ST_DROPPED), (unsigned long long)(n - stored));
         ev.finished[g] = 0;
         if (recycle && (ev.game_limit == 0 || ev.game_id[g] + (uint64_t)ev.G < ev.game_limit)) {
             ev.black[g] = kStartBlack; ev.white[g] = kStartWhite; ev.side[g] = 1; ev.flags[g] = 0;
@@ -703,7 +732,7 @@ __global__ void set_positions_kernel(EngineView ev, const uint64_t* __restrict__
         // not a position: the slot is parked on an empty finished board (a search sees a terminal root: no visits)
         ev.black[g] = 0; ev.white[g] = 0; ev.side[g] = 1; ev.flags[g] = F_OVER;
         ev.ply[g] = 0; ev.live[g] = 0; ev.finished[g] = 0; ev.n_nodes[g] = 0;
-        atomicAdd(&ev.stats[ST_BADPOS], 1ULL);
+        atomicAdd(stat_at(ev, ST_BADPOS), 1ULL);
         return;
     }
     if (board_legal<RULES>(b) == 0) {
@@ -812,7 +841,7 @@ int rvs_engine_create(const rvs_engine_config* cfg, rvs_engine** out) {
         (rc = dalloc(h, &v.r_black, (size_t)v.ring_cap)) || (rc = dalloc(h, &v.r_white, (size_t)v.ring_cap)) ||
         (rc = dalloc(h, &v.r_side, (size_t)v.ring_cap)) || (rc = dalloc(h, &v.r_z, (size_t)v.ring_cap)) ||
         (rc = dalloc(h, &v.r_pi, (size_t)v.ring_cap * 65)) || (rc = dalloc(h, &v.ring_count, 1)) || (rc = dalloc(h, &v.ply_counter, 1)) ||
-        (rc = dalloc(h, &v.stats, (size_t)ST_COUNT)) || (rc = dalloc(h, &h->visits, G * 65)) || (rc = dalloc(h, &h->moves, G))) {
+        (rc = dalloc(h, &v.stats, (size_t)kStatStripes * kStatStride)) || (rc = dalloc(h, &h->visits, G * 65)) || (rc = dalloc(h, &h->moves, G))) {
         rvs_engine_destroy(h);
         return rc;
     }
@@ -1265,9 +1294,11 @@ int rvs_engine_stats_get(rvs_engine* h, rvs_engine_stats* out, void* stream) {
     (void)rc;
     if (!out) return fail(-1, "rvs_engine_stats_get: null output");
     cudaStream_t s = (cudaStream_t)stream;
-    unsigned long long st[ST_COUNT];
-    RVS_CUDA(cudaMemcpyAsync(st, h->v.stats, sizeof(st), cudaMemcpyDeviceToHost, s));
+    unsigned long long raw[kStatStripes * kStatStride], st[ST_COUNT] = {};
+    RVS_CUDA(cudaMemcpyAsync(raw, h->v.stats, sizeof(raw), cudaMemcpyDeviceToHost, s));
     RVS_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < kStatStripes; ++i)
+        for (int k = 0; k < ST_COUNT; ++k) st[k] += raw[i * kStatStride + k];
     out->sims = (int64_t)st[ST_SIMS];
     out->evals = (int64_t)st[ST_EVALS];
     out->board_steps = (int64_t)st[ST_STEPS];

@@ -37,8 +37,18 @@ struct EngineView {
     uint64_t* r_black; uint64_t* r_white; uint8_t* r_side; int8_t* r_z; float* r_pi;
     unsigned long long* ring_count;
     unsigned long long* ply_counter;  // game-plies claimed in the current persistent self-play launch
-    unsigned long long* stats;  // [ST_COUNT]
+    unsigned long long* stats;  // [kStatStripes][kStatStride] counters, striped (stat_at): summed by rvs_engine_stats_get
 };
+
+// Counters are striped over kStatStripes 128-byte lines chosen by the CTA index: thousands of warps add to them at
+// the end of every tree kernel, and same-address atomics serialise in one L2 slice (ncu on the NN step kernel: ~15 %
+// of its stall samples sat on these six atomics when all of them hit one 32-byte sector).
+constexpr int kStatStripes = 64;
+constexpr int kStatStride = 16;  // >= ST_COUNT, 128 bytes
+static_assert(ST_COUNT <= kStatStride, "stat stripe too small");
+__device__ __forceinline__ unsigned long long* stat_at(const EngineView& ev, int k) {
+    return ev.stats + (size_t)(blockIdx.x & (kStatStripes - 1)) * kStatStride + k;
+}
 
 // Dirichlet noise into the priors of the root's children (rvs_noise.cuh), by ONE thread, right
 // after the expansion of the root; children still have N == 0, so no cached score is stale

@@ -138,11 +138,18 @@ __global__ void fold_conv1x1_kernel(const float* __restrict__ w, const float* __
 
 // ---- heads (network.py:103-117) + softmax (mcts.py:596) ---------------------------------------
 // One CTA (256 threads) evaluates kHB = 8 boards: (1) the three 1x1 convolutions + BN + ReLU, one
-// thread per pixel streaming its C channels with 16-byte loads; (2) policy_fc (65 rows) and
-// value_fc1 (256 rows) with TRANSPOSED weights so that consecutive threads read consecutive
-// addresses, each weight reused for the 8 boards; (3) one warp per board: softmax over the 65
-// logits (no legal-move masking: mcts.py:596 applies the plain softmax), value_fc2 + tanh.
+// thread per pixel streaming its C channels with 16-byte loads (skipped when the last tower layer's
+// epilogue already produced the planes); (2) policy_fc (65 rows) and value_fc1 (256 rows) with
+// TRANSPOSED weights so that consecutive threads read consecutive addresses, each weight reused for
+// the boards of the thread; (3) one warp per board: softmax over the 65 logits (no legal-move
+// masking: mcts.py:596 applies the plain softmax), value_fc2 + tanh.
+// The FC loops fetch their weights 16 rows at a time into registers before the multiply-adds: the
+// first version loaded one weight per iteration and was a serial chain of 128 L2 latencies (ncu:
+// 42 us for 4096 boards, issue-active 16 %, long-scoreboard stalls); features sit in shared memory
+// board-minor ([feature][board]) so that one 16-byte load serves four boards.  The summation order
+// over the features is unchanged (ascending), so outputs are bit-identical to the first version.
 constexpr int kHB = 8;
+constexpr int kFcBatch = 16;
 __global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ feat_in, int C, int64_t B,
                                                      const float* __restrict__ pw, const float* __restrict__ pb,
                                                      const float* __restrict__ pfwT, const float* __restrict__ pfb,
@@ -157,19 +164,22 @@ __global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restr
         if (nn_evals && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(nn_evals, (unsigned long long)B);
         if ((int64_t)blockIdx.x * kHB >= B) return;
     }
-    __shared__ float w1x1[3 * 256];        // [3][C] (C <= 256)
-    __shared__ float feat[kHB][192];       // [0,128): policy planes channel-major (ch*64+px); [128,192): value plane
+    __shared__ float w1x1[3 * 256];                    // [3][C] (C <= 256)
+    __shared__ __align__(16) float featT[192][kHB];    // [0,128): policy planes channel-major (ch*64+px); [128,192): value plane
     __shared__ float hid[kHB][256];
     __shared__ float lg[kHB][68];
     const int t = threadIdx.x;
     const int64_t board0 = (int64_t)blockIdx.x * kHB;
     if (feat_in) {  // (1') the last tower layer already produced the three head planes (fused epilogue)
-        for (int i = t; i < kHB * 192; i += 256) {
-            const int bi = i / 192;
-            feat[bi][i - bi * 192] = board0 + bi < B ? feat_in[(size_t)(board0 + bi) * 192 + (i - bi * 192)] : 0.f;
+#pragma unroll
+        for (int r = 0; r < kHB * 192 / 256; ++r) {
+            const int i = t + 256 * r;
+            const int bi = i / 192, j = i - bi * 192;
+            featT[j][bi] = board0 + bi < B ? feat_in[(size_t)(board0 + bi) * 192 + j] : 0.f;
         }
+    } else {
+        for (int i = t; i < 3 * C; i += 256) w1x1[i] = i < 2 * C ? pw[i] : vw[i - 2 * C];
     }
-    for (int i = t; i < 3 * C; i += 256) w1x1[i] = i < 2 * C ? pw[i] : vw[i - 2 * C];
     __syncthreads();
     for (int p = t; p < kHB * 64 && !feat_in; p += 256) {  // (1) 1x1 convs
         const int bi = p >> 6, px = p & 63;
@@ -190,40 +200,62 @@ __global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restr
                 }
             }
         }
-        feat[bi][px] = fmaxf(a0 + pb[0], 0.f);
-        feat[bi][64 + px] = fmaxf(a1 + pb[1], 0.f);
-        feat[bi][128 + px] = fmaxf(a2 + vb[0], 0.f);
+        featT[px][bi] = fmaxf(a0 + pb[0], 0.f);
+        featT[64 + px][bi] = fmaxf(a1 + pb[1], 0.f);
+        featT[128 + px][bi] = fmaxf(a2 + vb[0], 0.f);
     }
     __syncthreads();
     {  // (2a) value_fc1 + ReLU: row t of [256][64], transposed weights [64][256]
         float acc[kHB];
 #pragma unroll
         for (int b = 0; b < kHB; ++b) acc[b] = v1b[t];
-        for (int i = 0; i < 64; ++i) {
-            const float w = v1wT[i * 256 + t];
 #pragma unroll
-            for (int b = 0; b < kHB; ++b) acc[b] = fmaf(w, feat[b][128 + i], acc[b]);
+        for (int i0 = 0; i0 < 64; i0 += kFcBatch) {
+            float w[kFcBatch];
+#pragma unroll
+            for (int u = 0; u < kFcBatch; ++u) w[u] = v1wT[(i0 + u) * 256 + t];
+#pragma unroll
+            for (int u = 0; u < kFcBatch; ++u) {
+                const float4 f0 = *reinterpret_cast<const float4*>(&featT[128 + i0 + u][0]);
+                const float4 f1 = *reinterpret_cast<const float4*>(&featT[128 + i0 + u][4]);
+                acc[0] = fmaf(w[u], f0.x, acc[0]); acc[1] = fmaf(w[u], f0.y, acc[1]);
+                acc[2] = fmaf(w[u], f0.z, acc[2]); acc[3] = fmaf(w[u], f0.w, acc[3]);
+                acc[4] = fmaf(w[u], f1.x, acc[4]); acc[5] = fmaf(w[u], f1.y, acc[5]);
+                acc[6] = fmaf(w[u], f1.z, acc[6]); acc[7] = fmaf(w[u], f1.w, acc[7]);
+            }
         }
 #pragma unroll
         for (int b = 0; b < kHB; ++b) hid[b][t] = fmaxf(acc[b], 0.f);
     }
-    if (t < 65) {  // (2b) policy_fc: view(batch,-1) is channel-major (network.py:107); weights [128][65]
-        float acc[kHB];
+    if (t < 130) {  // (2b) policy_fc: view(batch,-1) is channel-major (network.py:107); weights [128][65];
+                    // thread = (logit o, half of the boards)
+        const int o = t < 65 ? t : t - 65, bh = t < 65 ? 0 : 4;
+        float acc[4];
 #pragma unroll
-        for (int b = 0; b < kHB; ++b) acc[b] = pfb[t];
-        for (int i = 0; i < 128; ++i) {
-            const float w = pfwT[i * 65 + t];
+        for (int b = 0; b < 4; ++b) acc[b] = pfb[o];
+#pragma unroll 2
+        for (int i0 = 0; i0 < 128; i0 += kFcBatch) {
+            float w[kFcBatch];
 #pragma unroll
-            for (int b = 0; b < kHB; ++b) acc[b] = fmaf(w, feat[b][i], acc[b]);
+            for (int u = 0; u < kFcBatch; ++u) w[u] = pfwT[(i0 + u) * 65 + o];
+#pragma unroll
+            for (int u = 0; u < kFcBatch; ++u) {
+                const float4 f = *reinterpret_cast<const float4*>(&featT[i0 + u][bh]);
+                acc[0] = fmaf(w[u], f.x, acc[0]); acc[1] = fmaf(w[u], f.y, acc[1]);
+                acc[2] = fmaf(w[u], f.z, acc[2]); acc[3] = fmaf(w[u], f.w, acc[3]);
+            }
         }
 #pragma unroll
-        for (int b = 0; b < kHB; ++b) lg[b][t] = acc[b];
+        for (int b = 0; b < 4; ++b) lg[bh + b][o] = acc[b];
     }
     __syncthreads();
     {  // (3) warp w <-> board w
         const int w = t >> 5, l = t & 31;
         const int64_t board = board0 + w;
         if (board < B) {
+            float v2[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v2[i] = v2w[l + 32 * i];
             float m = fmaxf(lg[w][l], lg[w][l + 32]);
             if (l == 0) m = fmaxf(m, lg[w][64]);
             for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -243,7 +275,8 @@ __global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restr
                 if (l == 0) lo[64] = lg[w][64];
             }
             float acc = 0.f;
-            for (int i = l; i < 256; i += 32) acc = fmaf(v2w[i], hid[w][i], acc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc = fmaf(v2[i], hid[w][l + 32 * i], acc);
             for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (l == 0) values[board] = tanhf(acc + v2b[0]);
         }
