@@ -230,7 +230,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap w_map,
                    const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
                    const float* __restrict__ bias, int n_tiles_arg, const __grid_constant__ HeadW head,
-                   float* __restrict__ feat, const int* __restrict__ n_boards_dev) {
+                   float* __restrict__ feat, const int* __restrict__ n_boards_dev, int rev) {
     using K = Cfg2<C, CIN>;
     // compacted leaf batches: the number of boards is only known on the device (written at least two
     // kernels upstream, so it is visible even when this launch overlaps its predecessor's tail)
@@ -283,7 +283,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
             pdl_wait();  // weights are constants; activations come from the previous layer
             int stage = 0, phase = 0;
             for (int it = 0; it < n_iters; ++it) {
-                const int tile = (it * n_pairs + pair) * 2 + (int)rank;  // may be >= n_tiles: TMA zero-fills
+                const int tile = ((rev ? n_iters - 1 - it : it) * n_pairs + pair) * 2 + (int)rank;  // may be >= n_tiles: TMA zero-fills
                 for (int kc = 0; kc < K::KC; ++kc) {
                     mbar_wait_cluster(EMPTY(stage), phase ^ 1);
                     if (rank == 0) mbar_expect_tx(FULL(stage), 2 * kABytesX);
@@ -332,7 +332,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
         pdl_wait();
         for (int it = 0; it < n_iters; ++it) {
             const int acc = it & 1;
-            const int tile = (it * n_pairs + pair) * 2 + (int)rank;
+            const int tile = ((rev ? n_iters - 1 - it : it) * n_pairs + pair) * 2 + (int)rank;
             const size_t off = ((size_t)tile * kTileRows + row) * C;
             const bool live = tile < n_tiles;
             // residual row prefetched into registers BEFORE waiting for the accumulator: its HBM/L2
@@ -432,7 +432,7 @@ struct Cfg2S {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv3x3_tc2s_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap w_map,
                     const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out,
-                    const float* __restrict__ bias, int n_tiles_arg, const int* __restrict__ n_boards_dev) {
+                    const float* __restrict__ bias, int n_tiles_arg, const int* __restrict__ n_boards_dev, int rev) {
     using K = Cfg2S;
     const int n_tiles = n_boards_dev ? (*n_boards_dev + 1) >> 1 : n_tiles_arg;
     constexpr int C = K::C;
@@ -476,7 +476,7 @@ conv3x3_tc2s_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_cons
             pdl_wait();
             int stage = 0, phase = 0;
             for (int it = 0; it < n_iters; ++it) {
-                const int tile = (it * n_pairs + pair) * 2 + (int)rank;  // may be >= n_tiles: TMA zero-fills
+                const int tile = ((rev ? n_iters - 1 - it : it) * n_pairs + pair) * 2 + (int)rank;  // may be >= n_tiles: TMA zero-fills
                 for (int dx = 0; dx < 3; ++dx)
                     for (int kc = 0; kc < K::KC; ++kc) {
                         mbar_wait_cluster(EMPTY(stage), phase ^ 1);
@@ -524,7 +524,7 @@ conv3x3_tc2s_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_cons
         pdl_wait();
         for (int it = 0; it < n_iters; ++it) {
             const int acc = it & 1;
-            const int tile = (it * n_pairs + pair) * 2 + (int)rank;
+            const int tile = ((rev ? n_iters - 1 - it : it) * n_pairs + pair) * 2 + (int)rank;
             const size_t off = ((size_t)tile * kTileRows + row) * C;
             const bool live = tile < n_tiles;
             const bool has_res = residual != nullptr && live;
@@ -590,7 +590,7 @@ conv3x3_tc2s_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_cons
 template <typename Kern>
 int launch_pdl(Kern kern, int grid, int smem, cudaStream_t s, const CUtensorMap& a_map, const CUtensorMap& w_map,
                const __nv_bfloat16* residual, __nv_bfloat16* out, const float* bias, int n_tiles, const HeadW& head,
-               float* feat, const int* n_dev) {
+               float* feat, const int* n_dev, int rev) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
@@ -601,13 +601,13 @@ int launch_pdl(Kern kern, int grid, int smem, cudaStream_t s, const CUtensorMap&
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    RVS_CUDA(cudaLaunchKernelEx(&cfg, kern, a_map, w_map, residual, out, bias, n_tiles, head, feat, n_dev));
+    RVS_CUDA(cudaLaunchKernelEx(&cfg, kern, a_map, w_map, residual, out, bias, n_tiles, head, feat, n_dev, rev));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
 
 int launch_pdl_s(int grid, cudaStream_t s, const CUtensorMap& a_map, const CUtensorMap& w_map, const __nv_bfloat16* residual,
-                 __nv_bfloat16* out, const float* bias, int n_tiles, const int* n_dev) {
+                 __nv_bfloat16* out, const float* bias, int n_tiles, const int* n_dev, int rev) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
@@ -618,7 +618,7 @@ int launch_pdl_s(int grid, cudaStream_t s, const CUtensorMap& a_map, const CUten
     attrs[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = 1;
-    RVS_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2s_kernel, a_map, w_map, residual, out, bias, n_tiles, n_dev));
+    RVS_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_tc2s_kernel, a_map, w_map, residual, out, bias, n_tiles, n_dev, rev));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
@@ -681,7 +681,7 @@ int conv_tc_plan(ConvTcPlan& plan, const __nv_bfloat16* w, int C, int64_t max_ba
 
 int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
                    const float* bias, int64_t B, cudaStream_t s, const ConvHeadW* head, float* feat, const int* n_dev,
-                   int max_ctas, int64_t cap_boards) {
+                   int max_ctas, int64_t cap_boards, int rev) {
     if (!plan.valid || !plan.impl) return fail(-8, "tcgen05 convolution: no plan");
     Impl* im = static_cast<Impl*>(plan.impl);
     static const ConvHeadW zero_head = {};
@@ -707,15 +707,15 @@ int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_b
     int pairs = (n_tiles + 1) / 2;
     if (pairs > pair_cap) pairs = pair_cap;
     const CUtensorMap& am = im->act_map[slot];
-    if (C == 256) return launch_pdl_s(2 * pairs, s, am, im->w_map2, residual, out, bias, n_tiles, n_dev);
+    if (C == 256) return launch_pdl_s(2 * pairs, s, am, im->w_map2, residual, out, bias, n_tiles, n_dev, rev);
     if (C == 64) {
-        if (feat) return launch_pdl(conv3x3_tc2_kernel<64, 64, true>, 2 * pairs, Cfg2<64, 64>::SMEM, s, am, im->w_map2, residual, out, bias, n_tiles, *head, feat, n_dev);
-        return launch_pdl(conv3x3_tc2_kernel<64, 64, false>, 2 * pairs, Cfg2<64, 64>::SMEM, s, am, im->w_map2, residual, out, bias, n_tiles, *head, feat, n_dev);
+        if (feat) return launch_pdl(conv3x3_tc2_kernel<64, 64, true>, 2 * pairs, Cfg2<64, 64>::SMEM, s, am, im->w_map2, residual, out, bias, n_tiles, *head, feat, n_dev, rev);
+        return launch_pdl(conv3x3_tc2_kernel<64, 64, false>, 2 * pairs, Cfg2<64, 64>::SMEM, s, am, im->w_map2, residual, out, bias, n_tiles, *head, feat, n_dev, rev);
     }
     if (im->cin == 64)  // first layer of a 128-filter tower: 64 (3 used) -> 128
-        return launch_pdl(conv3x3_tc2_kernel<128, 64, false>, 2 * pairs, Cfg2<128, 64>::SMEM, s, am, im->w_map2, residual, out, bias, n_tiles, *head, nullptr, n_dev);
-    if (feat) return launch_pdl(conv3x3_tc2_kernel<128, 128, true>, 2 * pairs, Cfg2<128, 128>::SMEM, s, am, im->w_map2, residual, out, bias, n_tiles, *head, feat, n_dev);
-    return launch_pdl(conv3x3_tc2_kernel<128, 128, false>, 2 * pairs, Cfg2<128, 128>::SMEM, s, am, im->w_map2, residual, out, bias, n_tiles, *head, feat, n_dev);
+        return launch_pdl(conv3x3_tc2_kernel<128, 64, false>, 2 * pairs, Cfg2<128, 64>::SMEM, s, am, im->w_map2, residual, out, bias, n_tiles, *head, nullptr, n_dev, rev);
+    if (feat) return launch_pdl(conv3x3_tc2_kernel<128, 128, true>, 2 * pairs, Cfg2<128, 128>::SMEM, s, am, im->w_map2, residual, out, bias, n_tiles, *head, feat, n_dev, rev);
+    return launch_pdl(conv3x3_tc2_kernel<128, 128, false>, 2 * pairs, Cfg2<128, 128>::SMEM, s, am, im->w_map2, residual, out, bias, n_tiles, *head, feat, n_dev, rev);
 }
 
 void conv_tc_destroy(ConvTcPlan& plan) {

@@ -37,9 +37,12 @@ int conv_tc_plan(ConvTcPlan& plan, const __nv_bfloat16* w, int C, int64_t max_ba
 // max_ctas (optional): cap of the persistent grid (default: all 148 SMs)
 // cap_boards (optional): boards addressable from `in` (default plan.max_batch): sizes the TMA descriptor when `in`
 // points into the middle of a buffer (second half-batch of a pipelined search)
+// rev: walk the tiles in DESCENDING order.  Consecutive layers alternate the direction, so a layer starts on the
+// tiles its predecessor wrote last -- the part of the previous output (and of the residual) that is still in L2
+// (a 4096-board activation tensor is 62 MB, two of them fill the L2: in one direction every read missed)
 int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_bfloat16* residual, __nv_bfloat16* out,
                    const float* bias, int64_t B, cudaStream_t s, const ConvHeadW* head = nullptr, float* feat = nullptr,
-                   const int* n_dev = nullptr, int max_ctas = 0, int64_t cap_boards = 0);
+                   const int* n_dev = nullptr, int max_ctas = 0, int64_t cap_boards = 0, int rev = 0);
 bool conv_tc_can_fuse_head(const ConvTcPlan& plan);
 void conv_tc_destroy(ConvTcPlan& plan);
 

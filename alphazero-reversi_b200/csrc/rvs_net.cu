@@ -449,7 +449,7 @@ int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s, cons
         const int64_t tiles = (B + 1) / 2;
         RVS_LAUNCH(planes_tiles_kernel, grid_for(tiles * 128, 256), 256, 0, s, bits, B, tiles, (uint4*)x0, n_dev);
         TL_MARK("planes", s);
-        if ((rc = conv_tc_launch(n->conv0.tc, x0, nullptr, x, n->conv0.bias, B, s, nullptr, nullptr, n_dev, mc, cap))) return rc;
+        if ((rc = conv_tc_launch(n->conv0.tc, x0, nullptr, x, n->conv0.bias, B, s, nullptr, nullptr, n_dev, mc, cap, 0))) return rc;
         TL_MARK("conv0", s);
     } else {  // network.py:97, fused with the leaf encoding (CUDA cores)
         const int tiles = (int)((B + 1) / 2);
@@ -461,11 +461,11 @@ int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s, cons
     for (int i = 0; i < n->blocks; ++i) {  // ResBlock (network.py:23-28)
         const ConvLayer& c1 = n->tower[2 * i];
         const ConvLayer& c2 = n->tower[2 * i + 1];
-        if ((rc = conv_tc_launch(c1.tc, x, nullptr, t, c1.bias, B, s, nullptr, nullptr, n_dev, mc, cap))) return rc;
+        if ((rc = conv_tc_launch(c1.tc, x, nullptr, t, c1.bias, B, s, nullptr, nullptr, n_dev, mc, cap, 1))) return rc;  // layers alternate the tile direction (L2 reuse)
         if (i == n->blocks - 1 && conv_tc_can_fuse_head(c2.tc)) {  // last layer: heads' 1x1 convs in the epilogue
-            if ((rc = conv_tc_launch(c2.tc, t, x, y, c2.bias, B, s, &n->head, feat, n_dev, mc, cap))) return rc;
+            if ((rc = conv_tc_launch(c2.tc, t, x, y, c2.bias, B, s, &n->head, feat, n_dev, mc, cap, 0))) return rc;
             fused_head = true;
-        } else if ((rc = conv_tc_launch(c2.tc, t, x, y, c2.bias, B, s, nullptr, nullptr, n_dev, mc, cap))) return rc;
+        } else if ((rc = conv_tc_launch(c2.tc, t, x, y, c2.bias, B, s, nullptr, nullptr, n_dev, mc, cap, 0))) return rc;
         __nv_bfloat16* tmp = x; x = y; y = tmp;
     }
     TL_MARK("tower", s);
