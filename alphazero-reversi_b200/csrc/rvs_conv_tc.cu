@@ -36,7 +36,10 @@ constexpr int kABytes = 10 * 2 * 8 * 128;   // one activation stage of the strea
 // start-address offset of dx rows (128 B) INSIDE the atom (make_desc_x).  Compared with one shifted box per dx this fetches every input element once instead of three
 // times (L2 -> SM traffic per tile 40 KB instead of 120 KB per chunk pair) and writes 80 KB instead of 120 KB of
 // shared memory per tile -- the 128-filter layer was bound by exactly these two.
-constexpr int kXSlots = 16;
+#ifndef RVS_CONV_XSLOTS
+#define RVS_CONV_XSLOTS 16
+#endif
+constexpr int kXSlots = RVS_CONV_XSLOTS;
 constexpr int kABytesX = 10 * 2 * kXSlots * 128;  // 40 KB
 constexpr int kThreads = 192;
 
@@ -116,7 +119,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 // describe the phase.  Measured on B200: with the descriptor's base-offset field [49,52) set to the row phase the
 // results are wrong, with 0 all network goldens pass (tests/test_gpu_net.py).
 __device__ __forceinline__ uint64_t make_desc_x(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(2048 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)((kXSlots * 128) >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16
 // [10,13)=1, A/B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)  -> Cfg2::IDESC / Cfg2S::IDESC
@@ -216,7 +219,7 @@ struct Cfg2 {
     static constexpr int NH = C / 2;                        // weight rows (couts) held by each CTA
     static constexpr int W_TILE = NH * 128;                 // bytes of one (tap, kc) weight tile per CTA
     static constexpr int W_TILES = 9 * KC;
-    static constexpr int STAGES = (C == 128 && CIN == 128) ? 2 : (C == 128 ? 3 : 4);  // 128->128: 144 KB weights + 2 x 40 KB = 224 KB
+    static constexpr int STAGES = (C == 128 && CIN == 128) ? (kXSlots <= 10 ? 3 : 2) : (C == 128 ? 3 : 4);  // 128->128: 144 KB weights + 2 x 40 KB = 224 KB
     static constexpr int TMEM_COLS = 2 * C;                 // two accumulators of C fp32 columns
     // K = 16 steps per 64-channel chunk.  The 64 -> 128 instantiation is the network's FIRST layer: only
     // channels 0..2 of its input tiles are non-zero, so the steps over channels 16..63 would multiply zeros
@@ -370,8 +373,11 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
                             const int col = c16 * 16 + 2 * i;
                             const __nv_bfloat162 r2 = *reinterpret_cast<const __nv_bfloat162*>(&res[h * 32 + c16 * 8 + i]);
                             const float2 t = __bfloat1622float2(r2);
-                            const float f0 = __uint_as_float(v[col]) + sbias[h * 64 + col] + t.x;
-                            const float f1 = __uint_as_float(v[col + 1]) + sbias[h * 64 + col + 1] + t.y;
+                            float f0 = __uint_as_float(v[col]), f1 = __uint_as_float(v[col + 1]);
+                            if constexpr (!(C == 128 && CIN == 64)) {  // the first layer has its bias in K and no residual
+                                f0 += sbias[h * 64 + col] + t.x;
+                                f1 += sbias[h * 64 + col + 1] + t.y;
+                            }
                             const __nv_bfloat162 ob = __floats2bfloat162_rn(fmaxf(f0, 0.f), fmaxf(f1, 0.f));
                             if (HEAD) {  // the heads see the same bf16-rounded activations as the unfused path
                                 const float2 a = __bfloat1622float2(ob);

@@ -300,6 +300,17 @@ __global__ void fold_conv0_kernel(const float* __restrict__ w, const float* __re
     }
 }
 
+// tensor-core first layer: the folded bias becomes weights of the two constant-one input channels (3: the bf16
+// head of the bias, 4: the bf16 remainder; together 16 significant bits) at the centre tap, which never reads padding
+__global__ void conv0_bias_in_k_kernel(__nv_bfloat16* __restrict__ w /*[9][C][64]*/, const float* __restrict__ bias, int C) {
+    for (int co = blockIdx.x * blockDim.x + threadIdx.x; co < C; co += gridDim.x * blockDim.x) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(bias[co]);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(bias[co] - __bfloat162float(hi));
+        w[((size_t)4 * C + co) * 64 + 3] = hi;
+        w[((size_t)4 * C + co) * 64 + 4] = lo;
+    }
+}
+
 // K3 + first convolution fused (network.py:97): the network input is never materialised.  The
 // three input planes are bit masks (own discs, opponent discs, legal squares), so the 3->C 3x3
 // convolution is, per output pixel, a sum of at most 27 weight rows selected by neighbour bits.
@@ -367,17 +378,20 @@ __global__ void __launch_bounds__(256) planes_tiles_kernel(const uint64_t* __res
         const int64_t tile = r >> 7;
         const int row = (int)(r & 127), y = row >> 4, b = (row >> 3) & 1, x = row & 7;
         const int64_t board = tile * 2 + b;
-        uint32_t c01 = 0, c2 = 0;
+        uint32_t c01 = 0, c23 = 0, c45 = 0;
         if (board < B) {
             const int sq = y * 8 + x;
             const uint32_t one = 0x3F80u;
             c01 = (((bits[board * 3] >> sq) & 1) ? one : 0u) | ((((bits[board * 3 + 1] >> sq) & 1) ? one : 0u) << 16);
-            c2 = ((bits[board * 3 + 2] >> sq) & 1) ? one : 0u;
+            // channels 3 and 4 are constant 1 on every real pixel: the first layer's folded bias rides on them as two
+            // bf16 weights (hi + lo) of the centre tap (conv0_bias_in_k_kernel), so its epilogue adds nothing
+            c23 = (((bits[board * 3 + 2] >> sq) & 1) ? one : 0u) | (one << 16);
+            c45 = one;
         }
         // only channels 0..15 (the first 32 bytes of the 128-byte row) are ever read by the first layer's single
         // K = 16 step (Cfg2::KSTEPS); the rest of the buffer stays at its initial zero
         uint4* o = out + r * 8;
-        o[0] = make_uint4(c01, c2, 0u, 0u);
+        o[0] = make_uint4(c01, c23, c45, 0u);
         o[1] = make_uint4(0u, 0u, 0u, 0u);
     }
 }
@@ -696,6 +710,7 @@ int rvs_engine_load_weights(rvs_engine* h, const float* flat, int64_t n_floats, 
         const float *g = take(C), *b = take(C), *m = take(C), *v = take(C);
         RVS_LAUNCH(fold_conv3x3_kernel, 64, 256, 0, s, w, g, b, m, v, C, 3, 64, n->conv0.w, n->conv0.bias);
         RVS_LAUNCH(fold_conv0_kernel, 16, 256, 0, s, w, g, b, m, v, C, n->w0f, n->b0f);
+        if (C == 128) RVS_LAUNCH(conv0_bias_in_k_kernel, 1, 128, 0, s, n->conv0.w, n->conv0.bias, C);  // tensor-core first layer
     }
     for (int i = 0; i < 2 * blocks; ++i) {
         const float* w = take((int64_t)C * C * 9);
