@@ -189,7 +189,7 @@ template <int RULES>
 __global__ void __launch_bounds__(kBlock) nn_step_kernel(EngineView ev, int g0, int g1, int flags, const float* __restrict__ probs,
                                                           const float* __restrict__ values, int* __restrict__ rows,
                                                           uint64_t* __restrict__ bits_out, int* __restrict__ n_cur,
-                                                          int* __restrict__ n_next) {
+                                                          int* __restrict__ n_next, uint4* __restrict__ tiles_out) {
     if (blockIdx.x == 0 && threadIdx.x == 0 && n_next) *n_next = 0;
     const int g = g0 + blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (g >= g1) return;
@@ -211,26 +211,16 @@ __global__ void __launch_bounds__(kBlock) nn_step_kernel(EngineView ev, int g0, 
     }
     if (flags & 2) {
         const Board root{ev.black[g], ev.white[g], ev.side[g], ev.flags[g]};
+        // lane 0 ends up with: the leaf's legal mask, its row in the batch (-1: nothing to evaluate), its position
+        uint64_t lm = 0;
+        int row = -1;
+        Board lb{0, 0, 1, 0};
         if (fast) {
             select_wave_fast(cx, root, ws, 1);
-            if (cx.lane == 0) {
-                const int node = ws.node[0];
-                uint64_t lm = 0;
-                int row = -1;
-                if (node >= 0) {
-                    const uint16_t sf = ws.sf[0];
-                    const Board b{ws.black[0], ws.white[0], (uint8_t)(sf & 0xFF), (uint8_t)(sf >> 8)};
-                    lm = board_legal<RULES>(b);
-                    if (lm) {
-                        row = atomicAdd(n_cur, 1);
-                        const bool blk = b.side == 1;
-                        bits_out[(size_t)row * 3] = blk ? b.black : b.white;
-                        bits_out[(size_t)row * 3 + 1] = blk ? b.white : b.black;
-                        bits_out[(size_t)row * 3 + 2] = lm;
-                    }
-                }
-                ws.lm[0] = lm;
-                rows[g] = row;
+            if (cx.lane == 0 && ws.node[0] >= 0) {
+                const uint16_t sf = ws.sf[0];
+                lb = Board{ws.black[0], ws.white[0], (uint8_t)(sf & 0xFF), (uint8_t)(sf >> 8)};
+                lm = board_legal<RULES>(lb);
             }
         } else {
             // select_wave(k = 1) with the leaf kept in registers: its legal mask comes from the direction-sliced
@@ -239,26 +229,43 @@ __global__ void __launch_bounds__(kBlock) nn_step_kernel(EngineView ev, int g0, 
             int p0, p1, plen, vlf;
             const int node = select_one(cx, b, p0, p1, plen, vlf);
             ++cx.sims;
-            uint64_t lm = 0;
-            int row = -1;
             if (vlf & kTerminal) {  // warp-uniform (mcts.py:364-366)
                 backup_path(cx, p0, p1, plen, term_value_of(vlf));
                 if (cx.lane == 0) ws.node[0] = -1;
             } else {
-                const Board lb = coop_store(cx.dir, b);
+                lb = coop_store(cx.dir, b);
                 store_leaf(ws, 0, cx.lane, node, p0, p1, plen, lb);
                 lm = coop_legal(cx.dir, b);
-                if (cx.lane == 0 && lm) {
-                    row = atomicAdd(n_cur, 1);
-                    const bool blk = lb.side == 1;
-                    bits_out[(size_t)row * 3] = blk ? lb.black : lb.white;
-                    bits_out[(size_t)row * 3 + 1] = blk ? lb.white : lb.black;
-                    bits_out[(size_t)row * 3 + 2] = lm;
-                }
             }
-            if (cx.lane == 0) {
-                ws.lm[0] = lm;
-                rows[g] = row;
+        }
+        const bool blk = lb.side == 1;
+        const uint64_t own = blk ? lb.black : lb.white, opp = blk ? lb.white : lb.black;
+        if (cx.lane == 0) {
+            if (lm) {
+                row = atomicAdd(n_cur, 1);
+                bits_out[(size_t)row * 3] = own;
+                bits_out[(size_t)row * 3 + 1] = opp;
+                bits_out[(size_t)row * 3 + 2] = lm;
+            }
+            ws.lm[0] = lm;
+            rows[g] = row;
+        }
+        if (tiles_out) {
+            // K3 fused: the warp writes the leaf's three input planes (+ the two constant-one bias channels) straight
+            // into the bf16 input tile of the tensor-core first layer -- the same 32 bytes per pixel that
+            // planes_tiles_kernel (rvs_net.cu) derives from the bit planes, without the extra kernel in every wave
+            row = __shfl_sync(kFull, row, 0);
+            if (row >= 0) {
+                const uint64_t P = __shfl_sync(kFull, own, 0), O = __shfl_sync(kFull, opp, 0), M = __shfl_sync(kFull, lm, 0);
+                const uint32_t one = 0x3F80u;
+#pragma unroll
+                for (int hp = 0; hp < 2; ++hp) {
+                    const int sq = cx.lane + 32 * hp, y = sq >> 3, x = sq & 7;
+                    uint4* o = tiles_out + ((size_t)(row >> 1) * 128 + y * 16 + (row & 1) * 8 + x) * 8;
+                    o[0] = make_uint4((((P >> sq) & 1) ? one : 0u) | ((((O >> sq) & 1) ? one : 0u) << 16),
+                                      (((M >> sq) & 1) ? one : 0u) | (one << 16), one, 0u);
+                    o[1] = make_uint4(0u, 0u, 0u, 0u);
+                }
             }
         }
     }
@@ -1329,10 +1336,10 @@ int rvs_engine_process_mapped(rvs_engine* h, const float* probs, const float* va
 }
 
 int rvs_engine_nn_step(rvs_engine* h, int g0, int g1, int flags, const float* probs, const float* values, int* rows,
-                       uint64_t* bits_out, int* n_cur, int* n_next, cudaStream_t s) {
+                       uint64_t* bits_out, int* n_cur, int* n_next, void* tiles_out, cudaStream_t s) {
     if (g1 <= g0) return 0;
     const int grid = (g1 - g0 + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    if (h->cfg.rules == RVS_RULES_STRICT) RVS_ENGINE_LAUNCH(h, nn_step_kernel<RULES_STRICT>, grid, kBlock, 0, s, h->v, g0, g1, flags, probs, values, rows, bits_out, n_cur, n_next);
-    else RVS_ENGINE_LAUNCH(h, nn_step_kernel<RULES_REF>, grid, kBlock, 0, s, h->v, g0, g1, flags, probs, values, rows, bits_out, n_cur, n_next);
+    if (h->cfg.rules == RVS_RULES_STRICT) RVS_ENGINE_LAUNCH(h, nn_step_kernel<RULES_STRICT>, grid, kBlock, 0, s, h->v, g0, g1, flags, probs, values, rows, bits_out, n_cur, n_next, (uint4*)tiles_out);
+    else RVS_ENGINE_LAUNCH(h, nn_step_kernel<RULES_REF>, grid, kBlock, 0, s, h->v, g0, g1, flags, probs, values, rows, bits_out, n_cur, n_next, (uint4*)tiles_out);
     return 0;
 }

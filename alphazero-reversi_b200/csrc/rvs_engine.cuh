@@ -131,6 +131,7 @@ int rvs_net_search(rvs_engine* h, int32_t num_sims, int32_t wave, cudaStream_t s
 // rvs_engine_process with device probs / values addressed through the compaction map of rvs_net.cu
 int rvs_engine_process_mapped(rvs_engine* h, const float* probs, const float* values, const int* inv, cudaStream_t s);
 void rvs_net_destroy(rvs::NetState* n);
-// one fused tree step (process pending leaf | select next | encode) of the wave-1 NN search for games [g0, g1)
+// one fused tree step (process pending leaf | select next | encode) of the wave-1 NN search for games [g0, g1);
+// tiles_out (optional): bf16 input tiles of the tensor-core first layer, written by the same kernel
 int rvs_engine_nn_step(rvs_engine* h, int g0, int g1, int flags, const float* probs, const float* values, int* rows,
-                       uint64_t* bits_out, int* n_cur, int* n_next, cudaStream_t s);
+                       uint64_t* bits_out, int* n_cur, int* n_next, void* tiles_out, cudaStream_t s);

@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(256) encode_positions_kernel(const uint64_t* _
 // values (+ off).  `off` (even: whole tiles) and `cap` select a sub-range of every buffer: the half-batches of a
 // pipelined search run their own forward passes on their own streams.
 int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s, const int* n_dev = nullptr, int64_t off = 0,
-                int64_t cap = 0) {
+                int64_t cap = 0, bool tiles_written = false) {
     NetState* n = h->net;
     if (!n || !n->loaded) return fail(-7, "network weights not loaded: call rvs_engine_load_weights first");
     if (cap <= 0) cap = n->max_batch - off;
@@ -461,7 +461,8 @@ int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s, cons
     float* feat = n->feat + off * 192;
     if (n->conv0.tc.valid) {  // first layer on the tensor cores: planes -> bf16 tiles -> tcgen05
         const int64_t tiles = (B + 1) / 2;
-        RVS_LAUNCH(planes_tiles_kernel, grid_for(tiles * 128, 256), 256, 0, s, bits, B, tiles, (uint4*)x0, n_dev);
+        // (the wave-1 search's tree step kernel writes the tiles itself: tiles_written)
+        if (!tiles_written) RVS_LAUNCH(planes_tiles_kernel, grid_for(tiles * 128, 256), 256, 0, s, bits, B, tiles, (uint4*)x0, n_dev);
         TL_MARK("planes", s);
         if ((rc = conv_tc_launch(n->conv0.tc, x0, nullptr, x, n->conv0.bias, B, s, nullptr, nullptr, n_dev, mc, cap, 0))) return rc;
         TL_MARK("conv0", s);
@@ -600,11 +601,12 @@ static int rvs_net_search_w1(rvs_engine* h, int32_t num_sims, cudaStream_t s) {
             int* cur = n->n_valid + 2 + 2 * hf + (w & 1);
             int* nxt = n->n_valid + 2 + 2 * hf + ((w + 1) & 1);
             const int flags = (w > 0 ? 1 : 0) | (w < num_sims ? 2 : 0) | (w == 1 ? 4 : 0);
+            void* tiles = n->conv0.tc.valid ? (void*)(n->x0 + off * 64 * 64) : nullptr;  // first layer on the tensor cores
             if ((rc = rvs_engine_nn_step(h, g0[hf], g1[hf], flags, n->probs + off * 65, n->values + off, n->rows, n->bits + off * 3,
-                                         cur, nxt, st[hf])))
+                                         cur, nxt, tiles, st[hf])))
                 return rc;
             TL_MARK("tree", st[hf]);
-            if (w < num_sims && (rc = net_forward(h, cap, false, st[hf], cur, off, cap))) return rc;
+            if (w < num_sims && (rc = net_forward(h, cap, false, st[hf], cur, off, cap, tiles != nullptr))) return rc;
         }
     }
 #ifdef RVS_TIMELINE
