@@ -627,14 +627,16 @@ def run_ours(args):
                          "peak_source": "148 SMs x 4 schedulers x SM clock sampled by nvidia-smi during the timed region",
                          "capture": ({"file": os.path.relpath(TRAFFIC_FILE, ROOT), "commit": cap.get("commit"),
                                       "kernel_source_hash": cap.get("kernel_source_hash"), "current_hash": kernel_source_hash(),
-                                      "issue_active_pct_under_ncu": kcap.get("issue_active_pct")} if cap else None),
+                                      "issue_active_pct_under_ncu": kcap.get("issue_active_pct"),
+                                      "alu_pipe_active_pct_under_ncu": kcap.get("alu_pipe_active_pct")} if cap else None),
                          "steps_per_launch": min(ppl, args.steps) if persistent else 1,
                          "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms * len(ks) / ms,
                          "hbm": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                                  "peak_source": which, "algorithmic_bytes_per_sim": d["tree_bytes"] / max(1, d["sims"])},
                          "note": "rollouts are register resident (0 B), so HBM is not the roof (secondary `hbm` block); the kernel is "
-                                 "bound by instruction issue and, at 4096 games, by the latency of a rollout ply's dependency chain "
-                                 "(see DESIGN.md K2)"},
+                                 "bound by instruction issue: its 64-bit shift/logic floods run on the half-rate ALU pipe, which a "
+                                 "single warp already saturates during a flood, and at 4096 games (1.7 warps per scheduler) the "
+                                 "exchange / vote latencies between floods stay exposed (see DESIGN.md K2)"},
             "clocks": clocks,
         }
         if generation is not None:
