@@ -43,6 +43,30 @@ inline int fail(int code, const char* fmt, ...) {
         RVS_CUDA(cudaGetLastError());                                                        \
     } while (0)
 
+// The same with programmatic dependent launch: the kernel may become resident while its predecessor in the stream is
+// still running (after the predecessor's griddepcontrol.launch_dependents, or at its end) and MUST execute
+// pdl_grid_wait() before it touches anything the predecessor reads or writes.  Hides the launch latency between the
+// small kernels of an NN search wave (tree step -> first layer -> tower -> heads -> tree step ...).
+#define RVS_LAUNCH_PDL(kernel, grid_, block_, smem_, stream_, ...)                               \
+    do {                                                                                     \
+        cudaLaunchConfig_t cfg_ = {};                                                        \
+        cfg_.gridDim = dim3(grid_);                                                          \
+        cfg_.blockDim = dim3(block_);                                                        \
+        cfg_.dynamicSmemBytes = (smem_);                                                     \
+        cfg_.stream = (stream_);                                                             \
+        cudaLaunchAttribute attr_[1];                                                        \
+        attr_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                    \
+        attr_[0].val.programmaticStreamSerializationAllowed = 1;                             \
+        cfg_.attrs = attr_;                                                                  \
+        cfg_.numAttrs = 1;                                                                   \
+        RVS_CUDA(cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__));                            \
+        ::rvs::g_launches.fetch_add(1, std::memory_order_relaxed);                           \
+    } while (0)
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_grid_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 // RVS_MEM_HOST_ASYNC is only honoured by rvs_engine_set_positions / rvs_engine_root_visits; everywhere else it
 // is RVS_MEM_HOST (staged copies under the staging lock, outputs complete on return)
 #define RVS_NORMALISE_MEM(mem)                                                                   \

@@ -186,10 +186,12 @@ __global__ void __launch_bounds__(kBlock) process_probs_kernel(EngineView ev, in
 // appends its three bit planes to the half-batch (one atomic) and remembers its row.  n_next is the counter of the
 // following wave, zeroed here because nothing else uses it while this kernel runs.
 template <int RULES>
-__global__ void __launch_bounds__(kBlock) nn_step_kernel(EngineView ev, int g0, int g1, int flags, const float* __restrict__ probs,
+__global__ void __launch_bounds__(kBlock, 7) nn_step_kernel(EngineView ev, int g0, int g1, int flags, const float* __restrict__ probs,
                                                           const float* __restrict__ values, int* __restrict__ rows,
                                                           uint64_t* __restrict__ bits_out, int* __restrict__ n_cur,
                                                           int* __restrict__ n_next, uint4* __restrict__ tiles_out) {
+    pdl_trigger();    // the first layer's CTAs may load their weights while this kernel runs
+    pdl_grid_wait();  // probs / values come from the heads kernel launched just before
     if (blockIdx.x == 0 && threadIdx.x == 0 && n_next) *n_next = 0;
     const int g = g0 + blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (g >= g1) return;
@@ -1279,6 +1281,9 @@ int rvs_engine_set_option(rvs_engine* h, int32_t option, int64_t value) {
     case RVS_OPT_NET_PIPELINE:
         h->net_pipeline = value != 0;
         return 0;
+    case RVS_OPT_NET_TOWER:
+        h->net_tower = value != 0;
+        return 0;
     default:
         return fail(-1, "rvs_engine_set_option: unknown option %d", option);
     }
@@ -1339,7 +1344,8 @@ int rvs_engine_nn_step(rvs_engine* h, int g0, int g1, int flags, const float* pr
                        uint64_t* bits_out, int* n_cur, int* n_next, void* tiles_out, cudaStream_t s) {
     if (g1 <= g0) return 0;
     const int grid = (g1 - g0 + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    if (h->cfg.rules == RVS_RULES_STRICT) RVS_ENGINE_LAUNCH(h, nn_step_kernel<RULES_STRICT>, grid, kBlock, 0, s, h->v, g0, g1, flags, probs, values, rows, bits_out, n_cur, n_next, (uint4*)tiles_out);
-    else RVS_ENGINE_LAUNCH(h, nn_step_kernel<RULES_REF>, grid, kBlock, 0, s, h->v, g0, g1, flags, probs, values, rows, bits_out, n_cur, n_next, (uint4*)tiles_out);
+    if (h->cfg.rules == RVS_RULES_STRICT) RVS_LAUNCH_PDL(nn_step_kernel<RULES_STRICT>, grid, kBlock, 0, s, h->v, g0, g1, flags, probs, values, rows, bits_out, n_cur, n_next, (uint4*)tiles_out);
+    else RVS_LAUNCH_PDL(nn_step_kernel<RULES_REF>, grid, kBlock, 0, s, h->v, g0, g1, flags, probs, values, rows, bits_out, n_cur, n_next, (uint4*)tiles_out);
+    h->launches++;
     return 0;
 }
