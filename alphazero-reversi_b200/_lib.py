@@ -11,7 +11,7 @@ RULES_REF, RULES_STRICT = 0, 1
 PLANES_F32_NCHW, PLANES_BF16_NHWC = 0, 1
 EVAL_E0, EVAL_ROLLOUT, EVAL_EXTERNAL, EVAL_NN = 0, 1, 2, 3
 MODE_REF, MODE_FAST = 0, 1
-OPT_LANES_PER_GAME, OPT_NET_GRAPH, OPT_SEARCH_MODE, OPT_GAME_LIMIT, OPT_NET_MAX_CTAS, OPT_NET_PIPELINE = 1, 2, 3, 4, 5, 6
+OPT_LANES_PER_GAME, OPT_NET_GRAPH, OPT_SEARCH_MODE, OPT_GAME_LIMIT, OPT_NET_MAX_CTAS, OPT_NET_PIPELINE, OPT_NET_TOWER = 1, 2, 3, 4, 5, 6, 7
 FLAG_OVER, FLAG_WINNER_SHIFT, FLAG_WINNER_MASK, FLAG_PASSED = 1, 1, 6, 8
 
 u64p = C.POINTER(C.c_uint64)

@@ -99,6 +99,12 @@ __device__ __forceinline__ void ldg256(const void* p, uint32_t* v) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "l"(p));
 }
+// the same through L2 only: for data that the TMA unit (async proxy) wrote, which an earlier L1 line would not reflect
+__device__ __forceinline__ void ldg256_cg(const void* p, uint32_t* v) {
+    asm volatile("ld.global.cg.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p));
+}
 __device__ __forceinline__ void stg256(void* p, const uint32_t* v) {
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
                  "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
@@ -215,6 +221,7 @@ using HeadW = ConvHeadW;  // rvs_conv_tc.cuh
 
 #ifdef RVS_CONV_PROBE  // debug variant only (tools/probe_conv.py): where the roles of the 128-filter kernel wait
 __device__ long long g_conv_probe[148 * 16];
+__device__ long long g_conv_layer[148 * 48];  // tower kernel's MMA issuer: clock at the start of every layer
 #define PROBE_T0() const long long _pt = clock64()
 #define PROBE_ADD(x) (x) += clock64() - _pt
 #else
@@ -394,7 +401,9 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
             if constexpr (HEAD) {
                 // The three head planes are dot products over ALL channels of a row in a fixed order: the hh = 0 warp of each
                 // quarter walks the whole row, its hh = 1 partner only releases the accumulator.
-                float hd0 = 0.f, hd1 = 0.f, hd2 = 0.f;
+                // plane = sum(channels 0..63) + sum(channels 64..127), each in ascending order (the whole-network kernel sums the
+                // two halves in two warps: same order, same bits)
+                float hd0 = 0.f, hd1 = 0.f, hd2 = 0.f, hs0 = 0.f, hs1 = 0.f, hs2 = 0.f;
                 uint32_t res[C / 2];
                 if (hh == 0) {
                     if (residual && live) {
@@ -435,7 +444,9 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
                                 hd2 = fmaf(a.x, head.w[2][cc], fmaf(a.y, head.w[2][cc + 1], hd2));
                             }
                         }
+                        if (h == 0 && C > 64) { hs0 = hd0; hs1 = hd1; hs2 = hd2; hd0 = hd1 = hd2 = 0.f; }
                     }
+                    if (C > 64) { hd0 = hs0 + hd0; hd1 = hs1 + hd1; hd2 = hs2 + hd2; }
                     if (live) {  // feat[board][plane*64 + px], plane 0/1 policy, 2 value
                         const int y = row >> 4, b = (row >> 3) & 1, x = row & 7;
                         float* fp = feat + ((size_t)tile * 2 + b) * 192 + y * 8 + x;
@@ -512,6 +523,472 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
     }
 }
 
+
+// =============================================================================================
+// Whole residual tower in ONE persistent kernel (C = 128).
+//
+// A tile is two whole boards, so a 3x3 convolution never reads across tiles, and every layer maps tile slot `it`
+// of pair p to the same CTA: a CTA only ever consumes activations it produced itself.  The tower therefore needs NO
+// grid-wide synchronisation between layers: each CTA pair walks its own tiles through all layers, and the only
+// cross-layer dependencies are inside the CTA --
+//   * input tile of layer l  <- the CTA's own epilogue stores of layer l-1: per-epilogue-warp counters in shared
+//     memory (`done`), published after a generic->async proxy fence because the stores are generic-proxy writes and
+//     the TMA loads that read them back are async-proxy reads;
+//   * the resident weights of layer l replace those of layer l-1 in place, one 64-channel half at a time: the half
+//     read by the kc = 0 MMAs of the previous layer's last tile is reloaded while its kc = 1 MMAs run (WEMPTY /
+//     WFULL barriers per half), so the tensor pipe does not drain at a layer boundary.
+// Compared with one launch per layer (conv3x3_tc2_kernel) this removes, per layer: the launch gap, the serial weight
+// prologue (the next layer's CTA cannot become resident before this one frees its 224 KB of shared memory: ~1800
+// cycles waiting for weights + ~1500 for the first activation box, tools/probe_conv.py), and the tail where early
+// CTAs idle until the slowest one finishes.  The arithmetic (MMA order, epilogue) is the per-layer kernel's, so
+// the results are bit-identical to it (tests/test_gpu_net.py::test_tower_kernel_matches_per_layer).
+// Tile order: consecutive layers walk the CTA's tiles in opposite directions (the most recently written tiles are
+// still in L2), rotated by two so that the first tile a layer needs was stored two epilogues ago.
+// =============================================================================================
+struct TowerArgs {
+    __nv_bfloat16* buf[3];   // x (block input / residual), t (mid), y (block output); roles rotate per block
+    const float* bias;       // [n_layers][C]
+    float* feat;             // fused heads' output of the LAST layer (when head != 0)
+    const int* n_boards_dev;
+    int n_tiles;
+    int n_layers;            // 2 x blocks
+    int head;
+    int conv0;               // 1: the network's first layer (64 -> C, input tiles of 64 channels) runs here too, as layer 0
+};
+
+__device__ __forceinline__ int posmod(int x, int n) { const int r = x % n; return r < 0 ? r + n : r; }
+
+// x-slots of the tower's activation boxes: 10 = exactly the slots the nine taps read (x = -1..8).  A (y, board) line
+// is then 1280 B, not a whole number of swizzle atoms, which the tensor core does not mind (the swizzle acts on absolute
+// address bits, the descriptor's stride between 8-row groups is 1280 B); the 15 KB per stage this saves against 16
+// slots are what pays for the epilogue's staging buffers.
+constexpr int kTowerXS = 10;
+constexpr int kTowerABytes = 10 * 2 * kTowerXS * 128;  // 25 KB
+constexpr int kTowerStaging = 8 * 2048;                // per epilogue warp: 32 rows x 64 B (32 of the 64 channels it converts)
+constexpr int kTowerThreads = 320;                     // warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue
+__device__ __forceinline__ uint64_t make_desc_t(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)((kTowerXS * 128) >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <int C>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTowerThreads, 1)
+conv_tower_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__ CUtensorMap m1,
+                  const __grid_constant__ CUtensorMap m2, const __grid_constant__ CUtensorMap s0,
+                  const __grid_constant__ CUtensorMap s1, const __grid_constant__ CUtensorMap s2,
+                  const __grid_constant__ CUtensorMap w_map, const __grid_constant__ CUtensorMap mx0,
+                  const __grid_constant__ CUtensorMap w0_map, const __grid_constant__ TowerArgs ta,
+                  const __grid_constant__ HeadW head) {
+    using K = Cfg2<C, C>;
+    static_assert(K::KC == 2, "the weight halves are tied to the two stages of the 128-filter configuration");
+    constexpr int kABytesX = kTowerABytes;  // (shadows the per-layer kernels' 16-slot box)
+    constexpr int kXSlots = kTowerXS;
+    int n_tiles = ta.n_tiles;  // compacted leaf batches: re-read from the device by every role after its griddepcontrol.wait
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    unsigned char* gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t w_s = base;
+    const uint32_t a_s = base + K::W_TILES * K::W_TILE;
+    const uint32_t stg_base = a_s + 2 * kABytesX;  // 1024-aligned: 147456 + 2 x 25600
+    unsigned char* stg_gen = gen + K::W_TILES * K::W_TILE + 2 * kABytesX;
+    unsigned char* tail = gen + K::W_TILES * K::W_TILE + 2 * kABytesX + kTowerStaging;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+    uint32_t* done = reinterpret_cast<uint32_t*>(tail + 128);   // [8] tiles stored so far, per epilogue warp
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 192);
+    float* sbias = reinterpret_cast<float*>(tail + 256);  // [3][C]: three layers' biases in rotation (epilogue warps may be in different layers)
+    const uint32_t bar0 = smem_u32(bars);
+    auto FULL = [&](int s) { return bar0 + 8u * s; };              // leader
+    auto EMPTY = [&](int s) { return bar0 + 8u * (2 + s); };       // both CTAs (multicast commit)
+    auto WFULL = [&](int kc) { return bar0 + 8u * (4 + kc); };     // leader: weight half kc of the current layer has landed
+    auto WEMPTY = [&](int kc) { return bar0 + 8u * (6 + kc); };    // both CTAs: weight half kc of the finished layer is no longer read
+    auto ACC_FULL = [&](int a) { return bar0 + 8u * (8 + a); };    // both CTAs
+    auto ACC_EMPTY = [&](int a) { return bar0 + 8u * (10 + a); };  // leader, 16 arrivals (8 epilogue warps x 2 CTAs)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    // Layer L of this launch: with ta.conv0, L = 0 is the network's FIRST convolution (network.py:97): input tiles of 64
+    // channels (3 planes + the two constant-one bias channels), one 64-channel chunk and one K = 16 step per tap, no
+    // bias / residual in the epilogue; the residual tower's layer l is L = l + has0.
+    const int has0 = ta.conv0 ? 1 : 0;
+    const int nL = ta.n_layers + has0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) { mbar_init(FULL(s), 1); mbar_init(EMPTY(s), 1); mbar_init(WFULL(s), 1); mbar_init(WEMPTY(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(ACC_FULL(a), 1); mbar_init(ACC_EMPTY(a), 16); }
+        for (int i = 0; i < 8; ++i) done[i] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(K::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) pdl_launch_dependents();
+
+    // Layer 0's weights do not depend on the previous kernel: the producer thread requests them, then EVERY thread waits
+    // for the previous kernel and reads the batch size -- in uniform control flow.  (Read inside the single-lane role
+    // branches, the tile count is a divergent value for the compiler, the MMA issuer's descriptor arithmetic leaves the
+    // uniform datapath -- 5 R2UR per tcgen05.mma -- and an MMA takes ~80 instead of ~68 cycles to issue.)
+    auto load_weights = [&](int L, int kc) {
+        if (rank == 0) mbar_expect_tx(WFULL(kc), 2 * 9 * K::W_TILE);  // both CTAs' halves report to the leader
+        for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t dst = w_s + (tap * K::KC + kc) * K::W_TILE;
+            if (has0 && L == 0) tma2_load_2d(&w0_map, WFULL(kc), dst, 0, tap * C + (int)rank * K::NH);
+            else tma2_load_2d(&w_map, WFULL(kc), dst, kc * 64, ((L - has0) * 9 + tap) * C + (int)rank * K::NH);
+        }
+    };
+    if (threadIdx.x == 0) {
+        load_weights(0, 0);
+        if (!has0) load_weights(0, 1);
+    }
+    pdl_wait();
+    if (ta.n_boards_dev) n_tiles = (__ldcg(ta.n_boards_dev) + 1) >> 1;
+    const int n = (n_tiles + 2 * n_pairs - 1) / (2 * n_pairs);  // tiles per CTA and layer (same in both CTAs of a pair)
+    const int rot = n >= 8 ? 4 : (n >= 4 ? 2 : 0);             // rotation of the tile order between layers
+    // tile slot visited at position i of layer l: (sa * i + sb) mod n; next layer = this one reversed, rotated by `rot`
+    auto next_order = [&](int& sa, int& sb) { sb = posmod(sa * (n - 1 - rot) + sb, n); sa = -sa; };
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer (both CTAs): own tiles, own half of the weight rows =====
+            long long p_done = 0, p_empty = 0, p_wempty = 0; (void)p_done; (void)p_empty; (void)p_wempty;
+            int sa = -1, sb = n - 1, pa = 0, pb = 0;  // layer 0 walks downwards: the previous kernel stored the high tiles last
+            int xi = 0, ti = 1, yi = 2;
+            int stage = 0, sph = 0;      // activation stage ring (two stages)
+            int wuse0 = 0, wuse1 = 0;    // layers that have used weight half 0 / 1 so far (= loads of that half issued)
+            for (int L = 0; L < nL; ++L) {
+                const bool first = has0 && L == 0;
+                const int l = L - has0;  // tower layer
+                const int in_idx = (l & 1) ? ti : xi;
+                const CUtensorMap* amap = first ? &mx0 : (in_idx == 0 ? &m0 : (in_idx == 1 ? &m1 : &m2));
+                const int kcs = first ? 1 : 2;
+                for (int i = 0; i < n; ++i) {
+                    const int slot = posmod(sa * i + sb, n);
+                    const int tile = (slot * n_pairs + pair) * 2 + (int)rank;  // may be >= n_tiles: TMA zero-fills
+                    if (L > 0) {  // this tile was stored by the CTA's own epilogue warps in the previous layer
+                        const uint32_t need = (uint32_t)((L - 1) * n + posmod(pa * (slot - pb), n) + 1);
+                        PROBE_T0();
+                        for (int w = 0; w < 8; ++w) {
+                            uint32_t v;
+                            do {
+                                asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(done + w)) : "memory");
+                            } while (v < need);
+                        }
+                        PROBE_ADD(p_done);
+                    }
+#pragma unroll
+                    for (int kc = 0; kc < 2; ++kc) {
+                        if (kc >= kcs) break;
+                        { PROBE_T0(); mbar_wait_cluster(EMPTY(stage), sph ^ 1); PROBE_ADD(p_empty); }
+                        if (rank == 0) mbar_expect_tx(FULL(stage), 2 * kABytesX);
+                        tma2_load_5d(amap, FULL(stage), a_s + stage * kABytesX, kc * 64, -1, 0, -1, tile);
+                        if (++stage == 2) { stage = 0; sph ^= 1; }
+                        if (i == 0 && L > 0) {
+                            // bring in this layer's half kc once the MMAs of the last layer that used it are done
+                            const int used = kc == 0 ? wuse0 : wuse1;
+                            if (used > 0) { PROBE_T0(); mbar_wait_cluster(WEMPTY(kc), (used - 1) & 1); PROBE_ADD(p_wempty); }
+                            load_weights(L, kc);
+                        }
+                    }
+                }
+                wuse0 += 1;
+                if (kcs == 2) wuse1 += 1;
+                pa = sa; pb = sb;
+                next_order(sa, sb);
+                if (!first && (l & 1)) { const int tmp = xi; xi = yi; yi = tmp; }
+            }
+#ifdef RVS_CONV_PROBE
+            g_conv_probe[blockIdx.x * 16 + 0] = p_empty;
+            g_conv_probe[blockIdx.x * 16 + 5] = p_done;
+            g_conv_probe[blockIdx.x * 16 + 6] = p_wempty;
+#endif
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {  // ===== MMA issuer (leader only) =====
+            uint32_t g = 0;  // tiles issued so far: the accumulator ping-pong runs across layers
+            long long p_w = 0, p_acc = 0, p_full = 0, p_start = 0; (void)p_w; (void)p_acc; (void)p_full; (void)p_start;
+#ifdef RVS_CONV_PROBE
+            p_start = clock64();
+#endif
+            int stage = 0, sph = 0;
+            int wuse0 = 0, wuse1 = 0;
+            for (int L = 0; L < nL; ++L) {
+#ifdef RVS_CONV_PROBE
+                if (L < 47) g_conv_layer[blockIdx.x * 48 + L] = clock64() - p_start;
+#endif
+                const bool first = has0 && L == 0;
+                const int kcs = first ? 1 : 2;
+                const int ksteps = first ? 1 : 4;  // first layer: only channels 0..15 of its input tiles are non-zero
+                for (int i = 0; i < n; ++i, ++g) {
+                    const int acc = g & 1;
+                    { PROBE_T0(); mbar_wait_cluster(ACC_EMPTY(acc), ((g >> 1) & 1) ^ 1); PROBE_ADD(p_acc); }
+                    tc_fence_after();
+                    const uint32_t d = tmem_base + (uint32_t)(acc * C);
+                    uint32_t accum = 0;
+#pragma unroll
+                    for (int kc = 0; kc < 2; ++kc) {
+                        if (kc >= kcs) break;
+                        if (i == 0) { PROBE_T0(); mbar_wait_cluster(WFULL(kc), (kc == 0 ? wuse0 : wuse1) & 1); PROBE_ADD(p_w); }
+                        { PROBE_T0(); mbar_wait_cluster(FULL(stage), sph); PROBE_ADD(p_full); }
+                        tc_fence_after();
+                        const uint32_t a0 = a_s + stage * kABytesX;
+#pragma unroll
+                        for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+                            for (int dx = 0; dx < 3; ++dx) {
+                                const uint32_t wt = w_s + ((dy * 3 + dx) * K::KC + kc) * K::W_TILE;
+                                const uint32_t at = a0 + (uint32_t)(dy * 2 * kXSlots + dx) * 128u;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    if (k < ksteps) {
+                                        tc2_mma(d, make_desc_t(at + k * 32), make_desc(wt + k * 32), K::IDESC, accum);
+                                        accum = 1;
+                                    }
+                                }
+                            }
+                        }
+                        tc2_commit_mc(EMPTY(stage));
+                        if (i == n - 1) tc2_commit_mc(WEMPTY(kc));
+                        if (++stage == 2) { stage = 0; sph ^= 1; }
+                    }
+                    tc2_commit_mc(ACC_FULL(acc));
+                }
+                wuse0 += 1;
+                if (kcs == 2) wuse1 += 1;
+            }
+#ifdef RVS_CONV_PROBE
+            g_conv_probe[blockIdx.x * 16 + 1] = p_w;
+            g_conv_probe[blockIdx.x * 16 + 2] = p_acc;
+            g_conv_probe[blockIdx.x * 16 + 3] = p_full;
+            g_conv_probe[blockIdx.x * 16 + 4] = clock64() - p_start;
+            g_conv_probe[blockIdx.x * 16 + 7] = n * nL;
+            if (nL < 48) g_conv_layer[blockIdx.x * 48 + nL] = clock64() - p_start;
+#endif
+        }
+    } else {  // ===== epilogue (both CTAs, own tiles) =====
+        // TMEM -> registers -> (+bias, +residual, ReLU, bf16) -> swizzled staging block in shared memory -> TMA store.
+        // EIGHT warps: warp (q, hh) converts TMEM lane quarter q (its 32 pixel rows) x channel half hh.  One epilogue
+        // warp per scheduler ran the ~900 instructions of a tile's conversion at 0.25 IPC (3600 cycles per tile, more
+        // than the tile's MMAs need once the layer boundaries are gone: tools/probe_conv.py); two per scheduler
+        // interleave.  The rows leave through a staging block and the TMA unit rather than 32-byte global stores at a
+        // 256-byte stride (32 L1 wavefronts per warp instruction).
+        const int q = warp & 3;             // TMEM lane quarter this warp may read (hardware rule: warp id % 4)
+        const int hh = (warp - 2) >> 2;     // channel half: couts [64 hh, 64 hh + 64)
+        const int ew = (warp - 2);          // epilogue warp index 0..7
+        const int row = q * 32 + lane;
+        const uint32_t stg_blk = stg_base + (uint32_t)ew * 2048u;             // 32 rows x 64 B, SWIZZLE_64B
+        const uint32_t stg = stg_blk + (uint32_t)lane * 64u;                  // this thread's staging row
+        const uint32_t sw = (uint32_t)((lane >> 1) & 3);                      // 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3)
+        int sa = -1, sb = n - 1;
+        int xi = 0, ti = 1, yi = 2;
+        uint32_t g = 0;
+        bool pending = false;  // TMA stores of the previous tile not yet known complete (and not yet published)
+        long long p_af = 0, p_e0 = 0, p_ld = 0, p_ms = 0, p_pub = 0, p_res = 0; (void)p_af; (void)p_e0; (void)p_ld; (void)p_ms; (void)p_pub; (void)p_res;
+#ifdef RVS_CONV_PROBE
+        p_e0 = clock64();
+#endif
+        // Tells the producer thread which of this warp's tiles are in memory.  Every tile commits exactly two bulk groups
+        // (empty ones when it stores nothing), so "at most 2 * lag groups pending" means "all tiles but the last `lag`
+        // have landed".  With enough tiles per CTA the tile order gives the next layer a head start of rot >= 4 tiles,
+        // and publishing runs two tiles late: a TMA store then has two tile times to complete and is never waited for
+        // (waiting for the previous tile's store at every tile cost the short first-layer tiles ~6000 cycles each).
+        const bool lag2 = rot >= 4;
+        auto publish = [&](uint32_t tiles_issued, bool flush) {
+            if (lane == 0) {
+                uint32_t upto = tiles_issued;
+                if (lag2 && !flush) {
+                    asm volatile("cp.async.bulk.wait_group 4;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging block itself is free again
+                    upto = tiles_issued >= 2 ? tiles_issued - 2 : 0;
+                } else {
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                }
+                asm volatile("fence.proxy.async.global;" ::: "memory");  // async-proxy writes -> the warp's later generic residual loads
+                asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(done + ew)), "r"(upto) : "memory");
+            }
+            __syncwarp();
+        };
+        for (int L = 0; L < nL; ++L) {
+            const bool first = has0 && L == 0;
+            const int l = L - has0;  // tower layer (-1: the first convolution, whose folded bias rides in its K dimension)
+            const bool is_head = ta.head && L == nL - 1;
+            const __nv_bfloat16* residual = (!first && (l & 1)) ? ta.buf[xi] : nullptr;
+            const int oi = first ? xi : ((l & 1) ? yi : ti);
+            const CUtensorMap* omap = oi == 0 ? &s0 : (oi == 1 ? &s1 : &s2);
+            float* sbl = sbias + (L % 3) * C;
+            // every epilogue warp writes the whole (identical) bias row: no barrier between the warps is needed, and
+            // three rotating rows keep a warp that is a layer ahead off the row a slower warp still reads
+            for (int j = lane; j < C; j += 32) sbl[j] = first ? 0.f : ta.bias[l * C + j];
+            __syncwarp();
+            for (int i = 0; i < n; ++i, ++g) {
+                const int acc = g & 1;
+                const int slot = posmod(sa * i + sb, n);
+                const int tile = (slot * n_pairs + pair) * 2 + (int)rank;
+                const size_t off = ((size_t)tile * kTileRows + row) * C;
+                const bool live = tile < n_tiles;
+#ifdef RVS_CONV_PROBE
+                long long _t1 = clock64();
+#endif
+                if (pending) {  // earlier tiles' stores have had time to land (this also frees the staging block)
+                    PROBE_T0();
+                    publish(g, false);
+                    pending = false;
+                    PROBE_ADD(p_pub);
+                }
+                if (is_head) {
+                    // The three head planes (policy x2, value) are dot products over the 128 channels of a row: each warp sums
+                    // its 64 channels in ascending order, the hh = 1 warp hands its partial sums to its hh = 0 partner through
+                    // its own (idle) staging block, and plane = sum(channels 0..63) + sum(channels 64..127) -- the order the
+                    // per-layer kernel uses too, so both paths give identical bits.
+                    uint32_t res[32];
+                    if (residual && live) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) ldg256_cg(residual + off + hh * 64 + j * 16, res + j * 8);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) res[j] = 0u;
+                    }
+                    { PROBE_T0(); mbar_wait_cluster(ACC_FULL(acc), (g >> 1) & 1); PROBE_ADD(p_af); }
+                    tc_fence_after();
+                    uint32_t v[64];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C + hh * 64);
+                    tc_ld32(taddr, v);
+                    tc_ld32(taddr + 32, v + 32);
+                    tc_wait_ld();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(ACC_EMPTY(acc));
+                    float hd0 = 0.f, hd1 = 0.f, hd2 = 0.f;
+                    if (live) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = 2 * j;
+                            const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&res[j]));
+                            const float f0 = __uint_as_float(v[col]) + (sbl[hh * 64 + col] + t.x);
+                            const float f1 = __uint_as_float(v[col + 1]) + (sbl[hh * 64 + col + 1] + t.y);
+                            // the heads see the same bf16-rounded activations as the unfused path
+                            const float2 a = __bfloat1622float2(__floats2bfloat162_rn(fmaxf(f0, 0.f), fmaxf(f1, 0.f)));
+                            const int cc = hh * 64 + col;
+                            hd0 = fmaf(a.x, head.w[0][cc], fmaf(a.y, head.w[0][cc + 1], hd0));
+                            hd1 = fmaf(a.x, head.w[1][cc], fmaf(a.y, head.w[1][cc + 1], hd1));
+                            hd2 = fmaf(a.x, head.w[2][cc], fmaf(a.y, head.w[2][cc + 1], hd2));
+                        }
+                    }
+                    // exchange slot: in the hh = 1 warp's own staging block (free: its stores were waited for above), two
+                    // slots alternate so that the partner may still read tile g while tile g + 1 is being summed
+                    float* xch = reinterpret_cast<float*>(stg_gen + (size_t)(4 + (ew & 3)) * 2048 + (size_t)(g & 1) * 512);
+                    if (hh == 1) { xch[lane] = hd0; xch[32 + lane] = hd1; xch[64 + lane] = hd2; }
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // the two warps of quarter q
+                    if (hh == 0 && live) {  // feat[board][plane*64 + px], plane 0/1 policy, 2 value
+                        hd0 += xch[lane]; hd1 += xch[32 + lane]; hd2 += xch[64 + lane];
+                        const int y = row >> 4, b = (row >> 3) & 1, x = row & 7;
+                        float* fp = ta.feat + ((size_t)tile * 2 + b) * 192 + y * 8 + x;
+                        fp[0] = fmaxf(hd0 + head.b[0], 0.f);
+                        fp[64] = fmaxf(hd1 + head.b[1], 0.f);
+                        fp[128] = fmaxf(hd2 + head.b[2], 0.f);
+                    }
+                    if (lane == 0) { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+                    if (rot > 0) pending = true;
+                    continue;
+                }
+                uint32_t res[32];  // this warp's 64 channels of the residual row
+                if (residual && live) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) ldg256_cg(residual + off + hh * 64 + j * 16, res + j * 8);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) res[j] = 0u;
+                }
+#ifdef RVS_CONV_PROBE
+                p_res += clock64() - _t1;
+#endif
+                { PROBE_T0(); mbar_wait_cluster(ACC_FULL(acc), (g >> 1) & 1); PROBE_ADD(p_af); }
+                tc_fence_after();
+                uint32_t v[64];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C + hh * 64);
+#ifdef RVS_CONV_PROBE
+                long long _t2 = clock64();
+#endif
+                tc_ld32(taddr, v);
+                tc_ld32(taddr + 32, v + 32);
+                tc_wait_ld();
+                tc_fence_before();  // all of this warp's TMEM reads of the accumulator are done
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(ACC_EMPTY(acc));
+#ifdef RVS_CONV_PROBE
+                { const long long _t3 = clock64(); p_ld += _t3 - _t2; p_ms -= _t3; }
+#endif
+                if (live) {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {  // 32 channels per round through the 2-KB staging block
+                        uint32_t o[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int col = r * 32 + 2 * j;
+                            const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&res[r * 16 + j]));
+                            const float f0 = __uint_as_float(v[col]) + (sbl[hh * 64 + col] + t.x);
+                            const float f1 = __uint_as_float(v[col + 1]) + (sbl[hh * 64 + col + 1] + t.y);
+                            const __nv_bfloat162 ob = __floats2bfloat162_rn(fmaxf(f0, 0.f), fmaxf(f1, 0.f));
+                            o[j] = *reinterpret_cast<const uint32_t*>(&ob);
+                        }
+                        if (r > 0) {  // the TMA unit must have read the first round out of the staging block
+                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                            __syncwarp();
+                        }
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            sts128(stg + (((uint32_t)c ^ sw) << 4), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy STS -> async-proxy read by the TMA store
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(omap, stg_blk, hh * 64 + r * 32, tile * kTileRows + q * 32);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                    }
+                } else if (lane == 0) {  // keep the group count per tile fixed (publish)
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+#ifdef RVS_CONV_PROBE
+                p_ms += clock64();
+#endif
+                if (rot > 0) pending = true;      // published at the top of a later tile: by then the stores have landed
+                else publish(g + 1, true);        // few tiles per CTA: the next layer needs this tile at once
+            }
+            next_order(sa, sb);
+            if (!first && (l & 1)) { const int tmp = xi; xi = yi; yi = tmp; }
+        }
+        publish(g, true);  // nothing may be in flight when the CTA exits
+#ifdef RVS_CONV_PROBE
+        if (warp == 2 && lane == 0) {
+            g_conv_probe[blockIdx.x * 16 + 8] = 0;
+            g_conv_probe[blockIdx.x * 16 + 9] = 0;
+            g_conv_probe[blockIdx.x * 16 + 10] = p_af;
+            g_conv_probe[blockIdx.x * 16 + 11] = clock64() - p_e0;
+            g_conv_probe[blockIdx.x * 16 + 12] = p_ld;
+            g_conv_probe[blockIdx.x * 16 + 13] = p_ms;
+            g_conv_probe[blockIdx.x * 16 + 14] = p_pub;
+            g_conv_probe[blockIdx.x * 16 + 15] = p_res;
+        }
+#endif
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the peer's shared memory / TMEM stay valid until the leader's MMAs are done
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(K::TMEM_COLS));
+    }
+}
 
 // =============================================================================================
 // 256-filter variant (BASELINE config 4: 20 blocks x 256 filters): the 1.18 MB of one layer's
@@ -833,6 +1310,126 @@ int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_b
     return launch_pdl(conv3x3_tc2_kernel<128, 128, false, false>, Cfg2<128, 128>::THREADS, 2 * pairs, Cfg2<128, 128>::SMEM, s, am, im->w_map2, residual, out, bias, n_tiles, *head, feat, n_dev, rev);
 }
 
+// ---- persistent tower (conv_tower_kernel) ----------------------------------------------------
+namespace {
+struct TowerImpl {
+    CUtensorMap w_map;      // all layers' folded weights: [n_layers * 9 * C rows][C] bf16, box = 64 cin x C/2 couts
+    const void* act_ptr[3] = {};
+    int64_t act_cap = -1;
+    CUtensorMap act_map[3];   // loads: 5-D boxes (10 y x 2 boards x 10 x-slots x 64 channels)
+    CUtensorMap w0_map;       // first layer's folded weights [9 * C rows][64] (optional)
+    bool has_w0 = false;
+    const void* x0_ptr = nullptr;
+    CUtensorMap x0_map;       // first layer's input tiles (64 channels)
+    CUtensorMap st_map[3];    // stores: [tile rows][C], box = 32 rows x 32 channels (half of an epilogue warp's block), SWIZZLE_64B
+};
+constexpr int kTowerSmem = Cfg2<128, 128>::W_TILES * Cfg2<128, 128>::W_TILE + 2 * kTowerABytes + kTowerStaging + 1024 /*align*/ + 256 + 3 * 128 * 4;
+static_assert(kTowerSmem <= 232448, "persistent tower: shared memory over the 227 KB per-CTA limit");
+}  // namespace
+
+int conv_tower_plan(ConvTowerPlan& plan, const __nv_bfloat16* w_slab, const float* bias_slab, int C, int n_layers, int64_t max_batch,
+                    const __nv_bfloat16* w0) {
+    plan.valid = false;
+    if (C != 128 || n_layers < 2 || (n_layers & 1)) return 0;  // other widths keep the per-layer kernels
+    EncodeFn enc = get_encode();
+    if (!enc) return fail(-9, "cuTensorMapEncodeTiled entry point not available");
+    TowerImpl* im = plan.impl ? static_cast<TowerImpl*>(plan.impl) : new TowerImpl();
+    plan.impl = im;
+    im->act_cap = -1;
+    const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)n_layers * 9 * C};
+    const cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    const cuuint32_t es[2] = {1, 1};
+    const cuuint32_t box2[2] = {64, (cuuint32_t)(C / 2)};
+    CUresult r = enc(&im->w_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(w_slab), dims, strides, box2, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-9, "cuTensorMapEncodeTiled(tower weights) failed: %d", (int)r);
+    im->has_w0 = w0 != nullptr;
+    im->x0_ptr = nullptr;
+    if (w0) {  // first layer: [9 * C rows (tap, cout)][64 cin], box = 64 cin x C/2 couts
+        const cuuint64_t d0[2] = {64, (cuuint64_t)9 * C};
+        const cuuint64_t s0[1] = {64 * 2};
+        r = enc(&im->w0_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(w0), d0, s0, box2, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(-9, "cuTensorMapEncodeTiled(first-layer weights) failed: %d", (int)r);
+    } else {
+        im->w0_map = im->w_map;  // unused placeholder (kernel parameters must be valid descriptors)
+    }
+    RVS_CUDA(cudaFuncSetAttribute(conv_tower_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTowerSmem));
+    plan.C = C;
+    plan.n_layers = n_layers;
+    plan.bias = bias_slab;
+    plan.max_batch = max_batch;
+    plan.valid = true;
+    return 0;
+}
+
+int conv_tower_launch(const ConvTowerPlan& plan, __nv_bfloat16* x, __nv_bfloat16* t, __nv_bfloat16* y, int64_t B, cudaStream_t s,
+                      const ConvHeadW& head, float* feat, const int* n_dev, int max_ctas, int64_t cap_boards, const __nv_bfloat16* x0) {
+    if (!plan.valid || !plan.impl) return fail(-8, "persistent tower: no plan");
+    TowerImpl* im = static_cast<TowerImpl*>(plan.impl);
+    const int64_t cap = cap_boards > 0 ? cap_boards : plan.max_batch;
+    if (B > cap) return fail(-8, "persistent tower: batch %lld exceeds the buffer capacity %lld", (long long)B, (long long)cap);
+    if (im->act_ptr[0] != x || im->act_ptr[1] != t || im->act_ptr[2] != y || im->act_cap != cap) {
+        const void* ptrs[3] = {x, t, y};
+        for (int i = 0; i < 3; ++i) {
+            int rc = encode_act_map(&im->act_map[i], ptrs[i], plan.C, (cap + 1) / 2, kTowerXS);
+            if (rc) return rc;
+            const cuuint64_t dims[2] = {(cuuint64_t)plan.C, (cuuint64_t)((cap + 1) / 2) * kTileRows};
+            const cuuint64_t strides[1] = {(cuuint64_t)plan.C * 2};
+            const cuuint32_t box[2] = {32, 32};
+            const cuuint32_t es[2] = {1, 1};
+            CUresult r = get_encode()(&im->st_map[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptrs[i]), dims, strides, box, es,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(-9, "cuTensorMapEncodeTiled(tower stores) failed: %d", (int)r);
+            im->act_ptr[i] = ptrs[i];
+        }
+        im->act_cap = cap;
+        im->x0_ptr = nullptr;
+    }
+    if (x0 && !im->has_w0) return fail(-8, "persistent tower: first-layer input given but the plan has no first-layer weights");
+    if (x0 && im->x0_ptr != x0) {
+        int rc = encode_act_map(&im->x0_map, x0, 64, (cap + 1) / 2, kTowerXS);
+        if (rc) return rc;
+        im->x0_ptr = x0;
+    }
+    const int n_tiles = (int)((B + 1) / 2);
+    int pair_cap = (max_ctas > 0 && max_ctas < kNumSMs ? max_ctas : kNumSMs) / 2;
+    if (pair_cap < 1) pair_cap = 1;
+    int pairs = (n_tiles + 1) / 2;
+    if (pairs > pair_cap) pairs = pair_cap;
+    TowerArgs ta;
+    ta.conv0 = x0 != nullptr;
+    ta.buf[0] = x; ta.buf[1] = t; ta.buf[2] = y;
+    ta.bias = plan.bias;
+    ta.feat = feat;
+    ta.n_boards_dev = n_dev;
+    ta.n_tiles = n_tiles;
+    ta.n_layers = plan.n_layers;
+    ta.head = feat != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kTowerThreads);
+    cfg.dynamicSmemBytes = kTowerSmem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RVS_CUDA(cudaLaunchKernelEx(&cfg, conv_tower_kernel<128>, im->act_map[0], im->act_map[1], im->act_map[2], im->st_map[0], im->st_map[1],
+                                im->st_map[2], im->w_map, x0 ? im->x0_map : im->act_map[0], im->w0_map, ta, head));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+void conv_tower_destroy(ConvTowerPlan& plan) {
+    if (plan.impl) delete static_cast<TowerImpl*>(plan.impl);
+    plan.impl = nullptr;
+    plan.valid = false;
+}
+
 void conv_tc_destroy(ConvTcPlan& plan) {
     if (plan.impl) delete static_cast<Impl*>(plan.impl);
     plan.impl = nullptr;
@@ -840,6 +1437,9 @@ void conv_tc_destroy(ConvTcPlan& plan) {
 }
 
 #ifdef RVS_CONV_PROBE
+extern "C" int rvs_debug_conv_layers(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, g_conv_layer, sizeof(long long) * 148 * 48);
+}
 extern "C" int rvs_debug_conv_probe(long long* out) {
     return (int)cudaMemcpyFromSymbol(out, g_conv_probe, sizeof(long long) * 148 * 16);
 }

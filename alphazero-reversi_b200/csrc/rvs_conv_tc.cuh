@@ -46,6 +46,28 @@ int conv_tc_launch(const ConvTcPlan& plan, const __nv_bfloat16* in, const __nv_b
                    const int* n_dev = nullptr, int max_ctas = 0, int64_t cap_boards = 0, int rev = 0, int count_is_fresh = 0);
 bool conv_tc_can_fuse_head(const ConvTcPlan& plan);
 
+// The whole residual tower (2 x blocks layers, C = 128) as ONE persistent launch: a CTA pair walks its own tiles
+// through every layer (tiles are whole boards, so layers never exchange data between CTAs), the next layer's weights
+// replace the current ones in shared memory half by half under the last tile's MMAs.  Bit-identical to the chain of
+// conv_tc_launch calls it replaces.  plan.valid stays false for shapes it does not cover (callers keep the
+// per-layer path).  w_slab: the layers' folded weights back to back [n_layers][9][C][C]; bias_slab [n_layers][C].
+// x: tower input (also the first block's residual), t / y: scratch of the same size; the last layer writes the
+// fused heads' planes to feat (required) instead of an activation tensor.
+struct ConvTowerPlan {
+    bool valid = false;
+    int C = 0, n_layers = 0;
+    int64_t max_batch = 0;
+    const float* bias = nullptr;
+    void* impl = nullptr;
+};
+// w0 (optional): the network's first layer, folded [9][C][64] with its bias in the K dimension (conv0_bias_in_k_kernel);
+// a launch with x0 (its input tiles [tile][y][board][x][64]) then runs it as layer 0 and writes its output to x.
+int conv_tower_plan(ConvTowerPlan& plan, const __nv_bfloat16* w_slab, const float* bias_slab, int C, int n_layers, int64_t max_batch,
+                    const __nv_bfloat16* w0 = nullptr);
+int conv_tower_launch(const ConvTowerPlan& plan, __nv_bfloat16* x, __nv_bfloat16* t, __nv_bfloat16* y, int64_t B, cudaStream_t s,
+                      const ConvHeadW& head, float* feat, const int* n_dev = nullptr, int max_ctas = 0, int64_t cap_boards = 0,
+                      const __nv_bfloat16* x0 = nullptr);
+void conv_tower_destroy(ConvTowerPlan& plan);
 void conv_tc_destroy(ConvTcPlan& plan);
 
 }  // namespace rvs

@@ -1281,6 +1281,9 @@ int rvs_engine_set_option(rvs_engine* h, int32_t option, int64_t value) {
     case RVS_OPT_NET_PIPELINE:
         h->net_pipeline = value != 0;
         return 0;
+    case RVS_OPT_NET_TOWER:
+        h->net_tower = value != 0;
+        return 0;
     default:
         return fail(-1, "rvs_engine_set_option: unknown option %d", option);
     }

@@ -80,6 +80,7 @@ struct rvs_engine {
     int lanes_per_game = 0; // wave-1 kernels: 0 = choose by the number of games (rvs_engine_set_lanes_per_game)
     int net_graph = 0;      // RVS_OPT_NET_GRAPH
     int net_max_ctas = 0;   // RVS_OPT_NET_MAX_CTAS
+    int net_tower = 1;      // RVS_OPT_NET_TOWER (persistent whole-network kernel where the shape allows it)
     int net_pipeline = 0;   // RVS_OPT_NET_PIPELINE (measured slower than lockstep on B200, DESIGN.md K4: opt-in)
     uint64_t epoch = 0;     // set_positions calls since create / reset: game id of slot g = g + epoch * G
     unsigned long long* pinned_count = nullptr;  // pinned host word for the sample count of the synchronous drains

@@ -64,6 +64,7 @@ struct NetState {
     ConvLayer* tower = nullptr;  // 2*blocks layers (weights / biases are slices of the two slabs below)
     __nv_bfloat16* tower_w = nullptr;  // [2*blocks][9][C][C]: one slab, so that ONE TMA descriptor covers every layer
     float* tower_bias = nullptr;       // [2*blocks][C]
+    ConvTowerPlan tower_tc;            // persistent whole-network kernel (C = 128), rvs_conv_tc.cu
     // heads (BN folded), f32
     float *pw = nullptr, *pb = nullptr;      // policy conv [2][C], bias [2]
     float *pfw = nullptr, *pfb = nullptr;    // policy fc TRANSPOSED [128][65], [65]
@@ -463,12 +464,13 @@ int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s, cons
     __nv_bfloat16* x0 = n->x0 + off * 64 * 64;
     __nv_bfloat16 *x = n->a + off * 64 * C, *t = n->b + off * 64 * C, *y = n->c + off * 64 * C;
     float* feat = n->feat + off * 192;
+    const bool whole_net = n->tower_tc.valid && h->net_tower && n->conv0.tc.valid;  // first layer + tower + head planes in ONE launch
     if (n->conv0.tc.valid) {  // first layer on the tensor cores: planes -> bf16 tiles -> tcgen05
         const int64_t tiles = (B + 1) / 2;
         // (the wave-1 search's tree step kernel writes the tiles itself: tiles_written)
         if (!tiles_written) RVS_LAUNCH(planes_tiles_kernel, grid_for(tiles * 128, 256), 256, 0, s, bits, B, tiles, (uint4*)x0, n_dev);
         TL_MARK("planes", s);
-        if ((rc = conv_tc_launch(n->conv0.tc, x0, nullptr, x, n->conv0.bias, B, s, nullptr, nullptr, n_dev, mc, cap, 0, tiles_written ? 1 : 0))) return rc;
+        if (!whole_net && (rc = conv_tc_launch(n->conv0.tc, x0, nullptr, x, n->conv0.bias, B, s, nullptr, nullptr, n_dev, mc, cap, 0, tiles_written ? 1 : 0))) return rc;
         TL_MARK("conv0", s);
     } else {  // network.py:97, fused with the leaf encoding (CUDA cores)
         const int tiles = (int)((B + 1) / 2);
@@ -477,6 +479,10 @@ int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s, cons
         else RVS_LAUNCH(conv0_bits_kernel<256>, tiles, 256, 0, s, bits, B, n->w0f, n->b0f, x, n_dev);
     }
     bool fused_head = false;
+    if (whole_net) {  // first layer + all ResBlocks (network.py:97-101) + the heads' 1x1 convs in one persistent launch
+        if ((rc = conv_tower_launch(n->tower_tc, x, t, y, B, s, n->head, feat, n_dev, mc, cap, x0))) return rc;
+        fused_head = true;
+    } else
     for (int i = 0; i < n->blocks; ++i) {  // ResBlock (network.py:23-28)
         const ConvLayer& c1 = n->tower[2 * i];
         const ConvLayer& c2 = n->tower[2 * i + 1];
@@ -553,6 +559,7 @@ void rvs_net_destroy(rvs::NetState* n) {
     for (void* q : n->allocs) cudaFree(q);
     if (n->flat) cudaFree(n->flat);
     for (int i = 0; i < 2 * n->blocks; ++i) conv_tc_destroy(n->tower[i].tc);
+    conv_tower_destroy(n->tower_tc);
     conv_tc_destroy(n->conv0.tc);
     delete[] n->tower;
     delete n;
@@ -750,6 +757,7 @@ int rvs_engine_load_weights(rvs_engine* h, const float* flat, int64_t n_floats, 
     if (C == 128) {  // 128 filters: the first layer runs on the tensor cores too (64 -> 128 variant, one K = 16 step per tap)
         if ((rc = conv_tc_plan(n->conv0.tc, n->conv0.w, C, n->max_batch, 64))) return rc;
     }
+    if ((rc = conv_tower_plan(n->tower_tc, n->tower_w, n->tower_bias, C, 2 * blocks, n->max_batch, C == 128 ? n->conv0.w : nullptr))) return rc;  // valid for C = 128
     RVS_CUDA(cudaStreamSynchronize(s));
     if (C <= 128) {  // host copy of the folded 1x1 head weights for the fused last-layer epilogue (kernel parameter)
         float hw[3 * 128 + 4];

@@ -72,6 +72,8 @@ extern "C" {
                                     ping-pong on two streams so that the tree kernel of one half runs beside the tower of
                                     the other.  Measured on B200 (5x128, 4096 games): 8 % SLOWER than lockstep -- every
                                     tower launch has ~6 us of fixed cost, which the split doubles */
+#define RVS_OPT_NET_TOWER 7      /* RVS_EVAL_NN, 128 filters: 1 = first layer + residual tower + head planes run as ONE persistent
+                                    launch (default), 0 = one launch per layer.  Bit-identical results. */
 
 const char *rvs_last_error(void);
 int rvs_version(void);

@@ -240,3 +240,28 @@ def test_tcgen05_tower_matches_torch_emulation(az, nb, nf, n):
     if nb == 1:
         assert dv <= 0.01
 
+
+@pytest.mark.parametrize("nb,boards", [(5, 1), (5, 3), (5, 64), (5, 300), (5, 701), (2, 1500), (5, 4096), (7, 9000)])
+def test_tower_kernel_matches_per_layer(az, nb, boards):
+    """the persistent whole-tower kernel (conv_tower_kernel: every layer of the 128-filter tower in one launch, each
+    CTA pair re-reading the tiles it stored itself, weights swapped in place) computes exactly what the chain of
+    per-layer launches computes: same MMA order, same epilogue -> identical bits.  Batch sizes cover one tile per
+    CTA (no tile rotation), odd board counts (half-empty last tile), and 1 .. 31 tiles per CTA and layer."""
+    L = az._lib
+    net = _build(az, nb, 128, "bn")
+    rng = np.random.default_rng(boards)
+    occ = rng.integers(0, 2**63, boards, dtype=np.int64)
+    pick = rng.integers(0, 2**63, boards, dtype=np.int64)
+    bl, wh = (occ & pick).astype(np.uint64), (occ & ~pick).astype(np.uint64)
+    sd = rng.integers(1, 3, boards).astype(np.uint8)
+    eng = az.Engine(boards, 8, 1, evaluator=az.EVAL_NN, net_blocks=nb, net_filters=128)
+    az.RvsNetwork.from_module(net).attach(eng)
+    out = {}
+    for tower in (1, 0, 1):
+        eng.set_option(L.OPT_NET_TOWER, tower)
+        out.setdefault(tower, []).append(eng.predict(bl, wh, sd))
+    for lg, v in out[1]:
+        assert np.array_equal(lg, out[0][0][0])
+        assert np.array_equal(v, out[0][0][1])
+    assert np.isfinite(out[1][0][0]).all() and np.abs(out[1][0][0]).max() > 0
+    eng.close()

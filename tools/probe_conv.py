@@ -9,7 +9,7 @@ import numpy as np, torch
 import alphazero_reversi_b200 as az
 
 az._lib.LIB_PATH = sys.argv[1]
-tower = 0
+tower = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 nb = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 B = int(sys.argv[4]) if len(sys.argv) > 4 else 4096
 torch.manual_seed(42)
@@ -20,6 +20,7 @@ occ = rng.integers(0, 2**63, B, dtype=np.int64); pick = rng.integers(0, 2**63, B
 bl = torch.from_numpy(occ & pick).to(dev); wh = torch.from_numpy(occ & ~pick).to(dev)
 sd = torch.ones(B, dtype=torch.uint8, device=dev)
 eng = az.Engine(B, 100, 1, evaluator=az.EVAL_NN, net_blocks=nb, net_filters=128)
+eng.set_option(az._lib.OPT_NET_TOWER, tower)
 rn.attach(eng)
 for _ in range(3): eng.predict(bl, wh, sd)
 torch.cuda.synchronize()
@@ -48,3 +49,11 @@ for name, col, rows in names:
     v = rows[:, col]
     print(f"  {name:36s} mean {v.mean():9.0f}  min {v.min():8d}  max {v.max():8d} cycles   per tile {v.mean() / max(1, lead[:, 7].mean()):7.1f}")
 
+if tower:
+    buf2 = (C.c_longlong * (148 * 48))()
+    L.rvs_debug_conv_layers.argtypes = [C.c_void_p]
+    assert L.rvs_debug_conv_layers(buf2) == 0
+    t = np.frombuffer(buf2, dtype=np.int64).reshape(148, 48)[0::2]
+    nl = 2 * nb + 2
+    d = np.diff(t[:, :nl], axis=1)
+    print("MMA issuer, cycles per layer (mean over CTA pairs):", " ".join(f"{x:.0f}" for x in d.mean(axis=0)))

@@ -17,6 +17,8 @@ bl = torch.from_numpy(occ & pick).to(dev); wh = torch.from_numpy(occ & ~pick).to
 sd = torch.ones(B, dtype=torch.uint8, device=dev)
 eng = az.Engine(B, 100, 1, evaluator=az.EVAL_NN, net_blocks=nb, net_filters=nf)
 rn.attach(eng)
+import os
+if os.environ.get('RVS_TOWER') is not None: eng.set_option(az._lib.OPT_NET_TOWER, int(os.environ['RVS_TOWER']))
 for _ in range(3): eng.predict(bl, wh, sd)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -25,6 +25,8 @@ for name, opts in (("lockstep (graph off, pipeline off)", {L.OPT_NET_PIPELINE: 0
     for k, v in opts.items():
         eng.set_option(k, v)
     rn.attach(eng)
+    import os
+    if os.environ.get('RVS_TOWER') is not None: eng.set_option(L.OPT_NET_TOWER, int(os.environ['RVS_TOWER']))
     eng.set_positions(pb, pw, ps)
     eng.search(100, 1)
     v = eng.root_visits()
