@@ -576,8 +576,11 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// 160 registers x 320 threads leave 14 K registers of the SM free: one CTA of the tree step (72 x 128) or of the heads
+// kernel (48 x 256) fits beside a resident CTA of this kernel, which is what lets the two half-batches of a pipelined
+// search overlap (rvs_net_search_w1)
 template <int C>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTowerThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(160)
 conv_tower_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant__ CUtensorMap m1,
                   const __grid_constant__ CUtensorMap m2, const __grid_constant__ CUtensorMap s0,
                   const __grid_constant__ CUtensorMap s1, const __grid_constant__ CUtensorMap s2,
@@ -887,7 +890,12 @@ conv_tower_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant_
                     // slots alternate so that the partner may still read tile g while tile g + 1 is being summed
                     float* xch = reinterpret_cast<float*>(stg_gen + (size_t)(4 + (ew & 3)) * 2048 + (size_t)(g & 1) * 512);
                     if (hh == 1) { xch[lane] = hd0; xch[32 + lane] = hd1; xch[64 + lane] = hd2; }
-                    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");  // the two warps of quarter q
+                    // the two warps of quarter q; constant ids, so that the kernel reserves 5 of the SM's 16 named barriers and
+                    // not all of them (a register id did: then no CTA that uses __syncthreads could be resident beside this one)
+                    if (q == 0) asm volatile("bar.sync 1, 64;" ::: "memory");
+                    else if (q == 1) asm volatile("bar.sync 2, 64;" ::: "memory");
+                    else if (q == 2) asm volatile("bar.sync 3, 64;" ::: "memory");
+                    else asm volatile("bar.sync 4, 64;" ::: "memory");
                     if (hh == 0 && live) {  // feat[board][plane*64 + px], plane 0/1 policy, 2 value
                         hd0 += xch[lane]; hd1 += xch[32 + lane]; hd2 += xch[64 + lane];
                         const int y = row >> 4, b = (row >> 3) & 1, x = row & 7;

@@ -1341,10 +1341,16 @@ int rvs_engine_process_mapped(rvs_engine* h, const float* probs, const float* va
 }
 
 int rvs_engine_nn_step(rvs_engine* h, int g0, int g1, int flags, const float* probs, const float* values, int* rows,
-                       uint64_t* bits_out, int* n_cur, int* n_next, void* tiles_out, cudaStream_t s) {
+                       uint64_t* bits_out, int* n_cur, int* n_next, void* tiles_out, cudaStream_t s, bool pdl) {
     if (g1 <= g0) return 0;
     const int grid = (g1 - g0 + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    if (h->cfg.rules == RVS_RULES_STRICT) RVS_LAUNCH_PDL(nn_step_kernel<RULES_STRICT>, grid, kBlock, 0, s, h->v, g0, g1, flags, probs, values, rows, bits_out, n_cur, n_next, (uint4*)tiles_out);
+    // pdl = false (pipelined half-batches): a plain launch.  A dependent launched early becomes RESIDENT and waits; beside
+    // the other half's whole-network CTAs only one small CTA fits per SM, and a squatting one keeps the other half's tree
+    // step / heads out.
+    if (!pdl) {
+        if (h->cfg.rules == RVS_RULES_STRICT) RVS_LAUNCH(nn_step_kernel<RULES_STRICT>, grid, kBlock, 0, s, h->v, g0, g1, flags, probs, values, rows, bits_out, n_cur, n_next, (uint4*)tiles_out);
+        else RVS_LAUNCH(nn_step_kernel<RULES_REF>, grid, kBlock, 0, s, h->v, g0, g1, flags, probs, values, rows, bits_out, n_cur, n_next, (uint4*)tiles_out);
+    } else if (h->cfg.rules == RVS_RULES_STRICT) RVS_LAUNCH_PDL(nn_step_kernel<RULES_STRICT>, grid, kBlock, 0, s, h->v, g0, g1, flags, probs, values, rows, bits_out, n_cur, n_next, (uint4*)tiles_out);
     else RVS_LAUNCH_PDL(nn_step_kernel<RULES_REF>, grid, kBlock, 0, s, h->v, g0, g1, flags, probs, values, rows, bits_out, n_cur, n_next, (uint4*)tiles_out);
     h->launches++;
     return 0;

@@ -81,7 +81,7 @@ struct rvs_engine {
     int net_graph = 0;      // RVS_OPT_NET_GRAPH
     int net_max_ctas = 0;   // RVS_OPT_NET_MAX_CTAS
     int net_tower = 1;      // RVS_OPT_NET_TOWER (persistent whole-network kernel where the shape allows it)
-    int net_pipeline = 0;   // RVS_OPT_NET_PIPELINE (measured slower than lockstep on B200, DESIGN.md K4: opt-in)
+    int net_pipeline = 1;   // RVS_OPT_NET_PIPELINE (takes effect where the whole-network kernel runs: rvs_net_search_w1)
     uint64_t epoch = 0;     // set_positions calls since create / reset: game id of slot g = g + epoch * G
     unsigned long long* pinned_count = nullptr;  // pinned host word for the sample count of the synchronous drains
     int waves_done = 0;     // waves processed since begin_search (root noise goes in after the first)
@@ -135,4 +135,4 @@ void rvs_net_destroy(rvs::NetState* n);
 // one fused tree step (process pending leaf | select next | encode) of the wave-1 NN search for games [g0, g1);
 // tiles_out (optional): bf16 input tiles of the tensor-core first layer, written by the same kernel
 int rvs_engine_nn_step(rvs_engine* h, int g0, int g1, int flags, const float* probs, const float* values, int* rows,
-                       uint64_t* bits_out, int* n_cur, int* n_next, void* tiles_out, cudaStream_t s);
+                       uint64_t* bits_out, int* n_cur, int* n_next, void* tiles_out, cudaStream_t s, bool pdl = true);

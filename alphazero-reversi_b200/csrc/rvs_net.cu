@@ -171,8 +171,10 @@ __global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restr
     }
     __shared__ float w1x1[3 * 256];                    // [3][C] (C <= 256)
     __shared__ __align__(16) float featT[192][kHB];    // [0,128): policy planes channel-major (ch*64+px); [128,192): value plane
-    __shared__ float hid[kHB][256];
+    __shared__ float vpart[8][kHB];                    // value_fc2 partial sums per warp
     __shared__ float lg[kHB][68];
+    // (11.5 KB of shared memory and <= 48 registers: a CTA of this kernel fits beside a resident whole-network CTA, so the
+    // heads of one half-batch can run under the tower of the other, rvs_net_search_w1)
     const int t = threadIdx.x;
     const int64_t board0 = (int64_t)blockIdx.x * kHB;
     if (feat_in) {  // (1') the last tower layer already produced the three head planes (fused epilogue)
@@ -229,8 +231,15 @@ __global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restr
                 acc[6] = fmaf(w[u], f1.z, acc[6]); acc[7] = fmaf(w[u], f1.w, acc[7]);
             }
         }
+        // value_fc2 (network.py:114) folded in: this thread's hidden unit times its fc2 weight, summed over the warp here
+        // and over the eight warps in (3) -- a fixed order, and no [boards][256] hidden buffer in shared memory
+        const float w2 = v2w[t];
 #pragma unroll
-        for (int b = 0; b < kHB; ++b) hid[b][t] = fmaxf(acc[b], 0.f);
+        for (int b = 0; b < kHB; ++b) {
+            float pv = w2 * fmaxf(acc[b], 0.f);
+            for (int o = 16; o; o >>= 1) pv += __shfl_xor_sync(0xffffffffu, pv, o);
+            if ((t & 31) == 0) vpart[t >> 5][b] = pv;
+        }
     }
     if (t < 130) {  // (2b) policy_fc: view(batch,-1) is channel-major (network.py:107); weights [128][65];
                     // thread = (logit o, half of the boards)
@@ -258,9 +267,6 @@ __global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restr
         const int w = t >> 5, l = t & 31;
         const int64_t board = board0 + w;
         if (board < B) {
-            float v2[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v2[i] = v2w[l + 32 * i];
             float m = fmaxf(lg[w][l], lg[w][l + 32]);
             if (l == 0) m = fmaxf(m, lg[w][64]);
             for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -279,11 +285,12 @@ __global__ void __launch_bounds__(256) heads_kernel(const __nv_bfloat16* __restr
                 lo[l + 32] = lg[w][l + 32];
                 if (l == 0) lo[64] = lg[w][64];
             }
-            float acc = 0.f;
+            if (l == 0) {
+                float acc = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc = fmaf(v2[i], hid[w][l + 32 * i], acc);
-            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (l == 0) values[board] = tanhf(acc + v2b[0]);
+                for (int i = 0; i < 8; ++i) acc += vpart[i][w];
+                values[board] = tanhf(acc + v2b[0]);
+            }
         }
     }
 }
@@ -451,7 +458,7 @@ __global__ void __launch_bounds__(256) encode_positions_kernel(const uint64_t* _
 // values (+ off).  `off` (even: whole tiles) and `cap` select a sub-range of every buffer: the half-batches of a
 // pipelined search run their own forward passes on their own streams.
 int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s, const int* n_dev = nullptr, int64_t off = 0,
-                int64_t cap = 0, bool tiles_written = false) {
+                int64_t cap = 0, bool tiles_written = false, bool pdl_heads = true, int max_ctas = -1) {
     NetState* n = h->net;
     if (!n || !n->loaded) return fail(-7, "network weights not loaded: call rvs_engine_load_weights first");
     if (cap <= 0) cap = n->max_batch - off;
@@ -459,7 +466,7 @@ int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s, cons
     if (B == 0) return 0;
     int rc;
     const int C = n->C;
-    const int mc = h->net_max_ctas;
+    const int mc = max_ctas >= 0 ? max_ctas : h->net_max_ctas;
     const uint64_t* bits = n->bits + off * 3;
     __nv_bfloat16* x0 = n->x0 + off * 64 * 64;
     __nv_bfloat16 *x = n->a + off * 64 * C, *t = n->b + off * 64 * C, *y = n->c + off * 64 * C;
@@ -494,11 +501,19 @@ int net_forward(rvs_engine* h, int64_t B, bool want_logits, cudaStream_t s, cons
         __nv_bfloat16* tmp = x; x = y; y = tmp;
     }
     TL_MARK("tower", s);
-    RVS_LAUNCH_PDL(heads_kernel, (int)((B + kHB - 1) / kHB), 256, 0, s, (const __nv_bfloat16*)x, fused_head ? (const float*)feat : (const float*)nullptr, C, B,
-                   (const float*)n->pw, (const float*)n->pb, (const float*)n->pfw, (const float*)n->pfb, (const float*)n->vw, (const float*)n->vb,
-                   (const float*)n->v1w, (const float*)n->v1b, (const float*)n->v2w, (const float*)n->v2b,
-                   want_logits ? n->logits + off * 65 : (float*)nullptr, n->probs + off * 65, n->values + off, n_dev,
-                   n_dev ? (unsigned long long*)(h->v.stats + ST_NNEVALS) : (unsigned long long*)nullptr);
+    if (pdl_heads) {
+        RVS_LAUNCH_PDL(heads_kernel, (int)((B + kHB - 1) / kHB), 256, 0, s, (const __nv_bfloat16*)x, fused_head ? (const float*)feat : (const float*)nullptr, C, B,
+                       (const float*)n->pw, (const float*)n->pb, (const float*)n->pfw, (const float*)n->pfb, (const float*)n->vw, (const float*)n->vb,
+                       (const float*)n->v1w, (const float*)n->v1b, (const float*)n->v2w, (const float*)n->v2b,
+                       want_logits ? n->logits + off * 65 : (float*)nullptr, n->probs + off * 65, n->values + off, n_dev,
+                       n_dev ? (unsigned long long*)(h->v.stats + ST_NNEVALS) : (unsigned long long*)nullptr);
+    } else {  // pipelined half-batches: see rvs_engine_nn_step
+        RVS_LAUNCH(heads_kernel, (int)((B + kHB - 1) / kHB), 256, 0, s, (const __nv_bfloat16*)x, fused_head ? (const float*)feat : (const float*)nullptr, C, B,
+                       (const float*)n->pw, (const float*)n->pb, (const float*)n->pfw, (const float*)n->pfb, (const float*)n->vw, (const float*)n->vb,
+                       (const float*)n->v1w, (const float*)n->v1b, (const float*)n->v2w, (const float*)n->v2b,
+                       want_logits ? n->logits + off * 65 : (float*)nullptr, n->probs + off * 65, n->values + off, n_dev,
+                       n_dev ? (unsigned long long*)(h->v.stats + ST_NNEVALS) : (unsigned long long*)nullptr);
+    }
     TL_MARK("heads", s);
     return 0;
 }
@@ -589,7 +604,12 @@ static int rvs_net_search_w1(rvs_engine* h, int32_t num_sims, cudaStream_t s) {
     NetState* n = h->net;
     int rc;
     const int G = h->v.G;
-    const bool two = h->net_pipeline && G >= 512;
+    // Two half-batches pay when the network of a half is ONE launch (the whole-network kernel) and the halves are big enough
+    // to fill the tensor-core grid; that grid then leaves 12 SMs to the other half's tree step / heads (measured on B200,
+    // 5x128, 4096 games: lockstep 6.85, halves on 148 / 140 / 136 / 132 / 124 CTAs 6.74 / 7.03 / 7.24 / 7.16 / 7.03 M sims/s --
+    // beside a resident whole-network CTA the small kernels make little progress, on SMs of their own they do).
+    const bool two = h->net_pipeline && G >= 2048 && n->tower_tc.valid && h->net_tower && n->conv0.tc.valid;
+    const int mc = h->net_max_ctas > 0 ? h->net_max_ctas : (two ? kNumSMs - 12 : 0);
     if (two && !n->side) {
         RVS_CUDA(cudaStreamCreateWithFlags(&n->side, cudaStreamNonBlocking));
         RVS_CUDA(cudaEventCreateWithFlags(&n->ev_fork, cudaEventDisableTiming));
@@ -619,10 +639,10 @@ static int rvs_net_search_w1(rvs_engine* h, int32_t num_sims, cudaStream_t s) {
             const int flags = (w > 0 ? 1 : 0) | (w < num_sims ? 2 : 0) | (w == 1 ? 4 : 0);
             void* tiles = n->conv0.tc.valid ? (void*)(n->x0 + off * 64 * 64) : nullptr;  // first layer on the tensor cores
             if ((rc = rvs_engine_nn_step(h, g0[hf], g1[hf], flags, n->probs + off * 65, n->values + off, n->rows, n->bits + off * 3,
-                                         cur, nxt, tiles, st[hf])))
+                                         cur, nxt, tiles, st[hf], !two)))
                 return rc;
             TL_MARK("tree", st[hf]);
-            if (w < num_sims && (rc = net_forward(h, cap, false, st[hf], cur, off, cap, tiles != nullptr))) return rc;
+            if (w < num_sims && (rc = net_forward(h, cap, false, st[hf], cur, off, cap, tiles != nullptr, !two, mc))) return rc;
         }
     }
 #ifdef RVS_TIMELINE

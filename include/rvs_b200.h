@@ -68,10 +68,10 @@ extern "C" {
                                     value (0 = no limit); with n slots, game ids 0 .. limit-1 are each played exactly once */
 #define RVS_OPT_NET_MAX_CTAS 5   /* RVS_EVAL_NN: cap of the persistent tcgen05 grids (0 = all SMs); leaves SMs to the tree
                                     kernels of the other half-batch when a search is pipelined */
-#define RVS_OPT_NET_PIPELINE 6   /* RVS_EVAL_NN, wave 1: 0 = one lockstep batch per wave (default), 1 = two half-batches
-                                    ping-pong on two streams so that the tree kernel of one half runs beside the tower of
-                                    the other.  Measured on B200 (5x128, 4096 games): 8 % SLOWER than lockstep -- every
-                                    tower launch has ~6 us of fixed cost, which the split doubles */
+#define RVS_OPT_NET_PIPELINE 6   /* RVS_EVAL_NN, wave 1: 1 (default) = two half-batches ping-pong on two streams, so that the
+                                    tree step and the heads of one half run beside the whole-network kernel of the other
+                                    (128 filters, >= 2048 games; the tensor-core grid then leaves 12 SMs free unless
+                                    RVS_OPT_NET_MAX_CTAS says otherwise).  0 = one lockstep batch per wave.  Identical results. */
 #define RVS_OPT_NET_TOWER 7      /* RVS_EVAL_NN, 128 filters: 1 = first layer + residual tower + head planes run as ONE persistent
                                     launch (default), 0 = one launch per layer.  Bit-identical results. */
 

@@ -112,9 +112,13 @@ def _midgame_roots(g, seed):
             np.array([r[2] for r in roots], dtype=np.uint8))
 
 
-@pytest.mark.parametrize("K,graph,pipeline,S", [(1, 0, 0, 64), (1, 0, 1, 64), (1, 1, 0, 64), (8, 0, 0, 64), (8, 1, 0, 64), (32, 0, 0, 96),
-                                                (64, 0, 0, 200), (64, 1, 0, 200)])
-def test_nn_search_consistency(az, K, graph, pipeline, S):
+@pytest.mark.parametrize("K,graph,pipeline,S,nb,nf,g", [(1, 0, 0, 64, 2, 64, 48), (1, 0, 1, 64, 2, 64, 48), (1, 1, 0, 64, 2, 64, 48),
+                                                        (8, 0, 0, 64, 2, 64, 48), (8, 1, 0, 64, 2, 64, 48), (32, 0, 0, 96, 2, 64, 48),
+                                                        (64, 0, 0, 200, 2, 64, 48), (64, 1, 0, 200, 2, 64, 48),
+                                                        # 128 filters: the whole-network kernel inside the search, lockstep and as
+                                                        # two pipelined half-batches (>= 2048 games, odd split)
+                                                        (1, 0, 0, 40, 1, 128, 301), (1, 0, 1, 24, 1, 128, 2305), (8, 0, 0, 32, 1, 128, 301)])
+def test_nn_search_consistency(az, K, graph, pipeline, S, nb, nf, g):
     """The fused NN search (select -> compaction + de-duplication of the leaf batch -> tower -> heads + softmax
     -> slot -> row remap -> expand/backup, all on the device; optionally as a replayed CUDA graph / as two
     pipelined half-batches) against the SAME search driven through the external select / process path and fed
@@ -122,10 +126,8 @@ def test_nn_search_consistency(az, K, graph, pipeline, S):
     fused path consumes).  Same priors, same values, same tree code => visit counts identical in EVERY game
     -- waves of 8 / 32 / 64 contain many duplicate leaves (reference wave semantics), so a wrong remap row
     cannot hide."""
-    nb, nf = 2, 64
     net = _build(az, nb, nf, "bn")
     rn = az.RvsNetwork.from_module(net)
-    g = 48
     rb, rw, rs = _midgame_roots(g, 3)
     eng = az.Engine(g, S, K, evaluator=az.EVAL_NN, net_blocks=nb, net_filters=nf)
     eng.set_option(az._lib.OPT_NET_GRAPH, graph)
@@ -164,13 +166,13 @@ def test_nn_search_consistency(az, K, graph, pipeline, S):
 def test_pipelined_half_batches_equal_lockstep(az):
     """RVS_OPT_NET_PIPELINE: two half-batches ping-pong on two streams (tree kernel of one half beside the tower of
     the other).  Per-game results cannot depend on the split; odd game counts exercise the tile-boundary split."""
-    net = _build(az, 2, 64, "bn")
+    net = _build(az, 1, 128, "bn")  # 128 filters: the pipelined path runs where the whole-network kernel does (>= 2048 games)
     rn = az.RvsNetwork.from_module(net)
-    for g in (1001, 512, 2050):
+    for g in (1001, 2049, 4100):
         rb, rw, rs = _midgame_roots(g, 11)
         out = []
         for pipe in (0, 1):
-            eng = az.Engine(g, 30, 1, evaluator=az.EVAL_NN, net_blocks=2, net_filters=64, seed=9)
+            eng = az.Engine(g, 30, 1, evaluator=az.EVAL_NN, net_blocks=1, net_filters=128, seed=9)
             eng.set_option(az._lib.OPT_NET_PIPELINE, pipe)
             rn.attach(eng)
             eng.set_positions(rb, rw, rs)
