@@ -562,6 +562,9 @@ __device__ __forceinline__ int posmod(int x, int n) { const int r = x % n; retur
 // is then 1280 B, not a whole number of swizzle atoms, which the tensor core does not mind (the swizzle acts on absolute
 // address bits, the descriptor's stride between 8-row groups is 1280 B); the 15 KB per stage this saves against 16
 // slots are what pays for the epilogue's staging buffers.
+#ifndef RVS_TOWER_GROUP
+#define RVS_TOWER_GROUP 4
+#endif
 constexpr int kTowerXS = 10;
 constexpr int kTowerABytes = 10 * 2 * kTowerXS * 128;  // 25 KB
 constexpr int kTowerStaging = 8 * 2048;                // per epilogue warp: 32 rows x 64 B (32 of the 64 channels it converts)
@@ -657,28 +660,47 @@ conv_tower_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant_
     pdl_wait();
     if (ta.n_boards_dev) n_tiles = (__ldcg(ta.n_boards_dev) + 1) >> 1;
     const int n = (n_tiles + 2 * n_pairs - 1) / (2 * n_pairs);  // tiles per CTA and layer (same in both CTAs of a pair)
-    const int rot = n >= 8 ? 4 : (n >= 4 ? 2 : 0);             // rotation of the tile order between layers
-    // tile slot visited at position i of layer l: (sa * i + sb) mod n; next layer = this one reversed, rotated by `rot`
-    auto next_order = [&](int& sa, int& sb) { sb = posmod(sa * (n - 1 - rot) + sb, n); sa = -sa; };
+    // DEPTH FIRST over groups of 4..7 tiles: a group goes through ALL layers before the next group starts.  The live
+    // activations of the whole grid are then (group size) x 3 buffers x 32 KB x 148 CTAs ~ 60 MB, which stays in the 126 MB
+    // L2 -- layer by layer over all 14 tiles of a CTA, every layer wrote and re-read 67 MB (+ 67 MB of residual) and the
+    // 5x128 forward moved ~1.5 GB through HBM.  The chip is power limited under tensor load: with the stores switched off
+    // the same cycles ran 17 % faster in time (tools/probe_conv.py), i.e. DRAM traffic is paid for in SM clock.  The price
+    // is one weight reload (144 KB per CTA from L2, hidden under the group's last tile) per layer and GROUP.
+    const int ngrp = (n + RVS_TOWER_GROUP / 2) / RVS_TOWER_GROUP > 0 ? (n + RVS_TOWER_GROUP / 2) / RVS_TOWER_GROUP : 1;
+    auto group_first = [&](int gi) { return n * gi / ngrp; };  // group gi = tile slots [group_first(gi), group_first(gi + 1))
+    // Tile order inside a group.  A layer may only load a tile that the previous layer has STORED (and published), so the
+    // first tiles a layer visits must be ones the previous layer finished early:
+    //   * 3..7 tiles (the normal case): every layer walks the group in the SAME order -- the tile a layer starts with was
+    //     stored ng - 1 >= 2 tiles before the previous layer ended (L2 locality is no concern for 3 x 96 KB x ng per CTA);
+    //   * >= 8 tiles (RVS_TOWER_GROUP raised): consecutive layers walk in opposite directions (most recently written tiles
+    //     are still in L2), rotated by 4, and tiles are published two tiles late (rot_of);
+    //   * 1..2 tiles (tiny batches): same order, every tile published at once.
+    auto rot_of = [](int ng) { return ng >= 8 ? 4 : 0; };
+    // tile slot visited at position i of a layer: (sa * i + sb) mod ng
+    auto next_order = [&](int& sa, int& sb, int ng, int rot) { if (rot > 0) { sb = posmod(sa * (ng - 1 - rot) + sb, ng); sa = -sa; } };
 
     if (warp == 0) {
         if (lane == 0) {  // ===== TMA producer (both CTAs): own tiles, own half of the weight rows =====
             long long p_done = 0, p_empty = 0, p_wempty = 0; (void)p_done; (void)p_empty; (void)p_wempty;
-            int sa = -1, sb = n - 1, pa = 0, pb = 0;  // layer 0 walks downwards: the previous kernel stored the high tiles last
-            int xi = 0, ti = 1, yi = 2;
             int stage = 0, sph = 0;      // activation stage ring (two stages)
-            int wuse0 = 0, wuse1 = 0;    // layers that have used weight half 0 / 1 so far (= loads of that half issued)
+            int wuse0 = 0, wuse1 = 0;    // layer visits that have used weight half 0 / 1 so far (= loads of that half issued)
+            uint32_t tcount = 0, lbase = 0, lbase_prev = 0;  // tiles issued so far; at the start of this / the previous layer visit
+            for (int gi = 0; gi < ngrp; ++gi) {
+            const int sl0 = group_first(gi), ng = group_first(gi + 1) - sl0, rot = rot_of(ng);
+            int sa = rot > 0 ? -1 : 1, sb = rot > 0 ? ng - 1 : 0, pa = 0, pb = 0;
+            int xi = 0, ti = 1, yi = 2;
             for (int L = 0; L < nL; ++L) {
+                lbase_prev = lbase; lbase = tcount;
                 const bool first = has0 && L == 0;
                 const int l = L - has0;  // tower layer
                 const int in_idx = (l & 1) ? ti : xi;
                 const CUtensorMap* amap = first ? &mx0 : (in_idx == 0 ? &m0 : (in_idx == 1 ? &m1 : &m2));
                 const int kcs = first ? 1 : 2;
-                for (int i = 0; i < n; ++i) {
-                    const int slot = posmod(sa * i + sb, n);
-                    const int tile = (slot * n_pairs + pair) * 2 + (int)rank;  // may be >= n_tiles: TMA zero-fills
+                for (int i = 0; i < ng; ++i, ++tcount) {
+                    const int slot = posmod(sa * i + sb, ng);
+                    const int tile = ((sl0 + slot) * n_pairs + pair) * 2 + (int)rank;  // may be >= n_tiles: TMA zero-fills
                     if (L > 0) {  // this tile was stored by the CTA's own epilogue warps in the previous layer
-                        const uint32_t need = (uint32_t)((L - 1) * n + posmod(pa * (slot - pb), n) + 1);
+                        const uint32_t need = lbase_prev + (uint32_t)posmod(pa * (slot - pb), ng) + 1u;
                         PROBE_T0();
                         for (int w = 0; w < 8; ++w) {
                             uint32_t v;
@@ -695,8 +717,8 @@ conv_tower_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant_
                         if (rank == 0) mbar_expect_tx(FULL(stage), 2 * kABytesX);
                         tma2_load_5d(amap, FULL(stage), a_s + stage * kABytesX, kc * 64, -1, 0, -1, tile);
                         if (++stage == 2) { stage = 0; sph ^= 1; }
-                        if (i == 0 && L > 0) {
-                            // bring in this layer's half kc once the MMAs of the last layer that used it are done
+                        if (i == 0 && (L > 0 || gi > 0)) {
+                            // bring in this layer's half kc once the MMAs of the last layer visit that used it are done
                             const int used = kc == 0 ? wuse0 : wuse1;
                             if (used > 0) { PROBE_T0(); mbar_wait_cluster(WEMPTY(kc), (used - 1) & 1); PROBE_ADD(p_wempty); }
                             load_weights(L, kc);
@@ -706,8 +728,9 @@ conv_tower_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant_
                 wuse0 += 1;
                 if (kcs == 2) wuse1 += 1;
                 pa = sa; pb = sb;
-                next_order(sa, sb);
+                next_order(sa, sb, ng, rot);
                 if (!first && (l & 1)) { const int tmp = xi; xi = yi; yi = tmp; }
+            }
             }
 #ifdef RVS_CONV_PROBE
             g_conv_probe[blockIdx.x * 16 + 0] = p_empty;
@@ -724,14 +747,16 @@ conv_tower_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant_
 #endif
             int stage = 0, sph = 0;
             int wuse0 = 0, wuse1 = 0;
+            for (int gi = 0; gi < ngrp; ++gi) {
+            const int ng = group_first(gi + 1) - group_first(gi);
             for (int L = 0; L < nL; ++L) {
 #ifdef RVS_CONV_PROBE
-                if (L < 47) g_conv_layer[blockIdx.x * 48 + L] = clock64() - p_start;
+                if (gi == 0 && L < 47) g_conv_layer[blockIdx.x * 48 + L] = clock64() - p_start;
 #endif
                 const bool first = has0 && L == 0;
                 const int kcs = first ? 1 : 2;
                 const int ksteps = first ? 1 : 4;  // first layer: only channels 0..15 of its input tiles are non-zero
-                for (int i = 0; i < n; ++i, ++g) {
+                for (int i = 0; i < ng; ++i, ++g) {
                     const int acc = g & 1;
                     { PROBE_T0(); mbar_wait_cluster(ACC_EMPTY(acc), ((g >> 1) & 1) ^ 1); PROBE_ADD(p_acc); }
                     tc_fence_after();
@@ -760,7 +785,7 @@ conv_tower_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant_
                             }
                         }
                         tc2_commit_mc(EMPTY(stage));
-                        if (i == n - 1) tc2_commit_mc(WEMPTY(kc));
+                        if (i == ng - 1) tc2_commit_mc(WEMPTY(kc));
                         if (++stage == 2) { stage = 0; sph ^= 1; }
                     }
                     tc2_commit_mc(ACC_FULL(acc));
@@ -768,13 +793,14 @@ conv_tower_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant_
                 wuse0 += 1;
                 if (kcs == 2) wuse1 += 1;
             }
+            }
 #ifdef RVS_CONV_PROBE
             g_conv_probe[blockIdx.x * 16 + 1] = p_w;
             g_conv_probe[blockIdx.x * 16 + 2] = p_acc;
             g_conv_probe[blockIdx.x * 16 + 3] = p_full;
             g_conv_probe[blockIdx.x * 16 + 4] = clock64() - p_start;
             g_conv_probe[blockIdx.x * 16 + 7] = n * nL;
-            if (nL < 48) g_conv_layer[blockIdx.x * 48 + nL] = clock64() - p_start;
+            if (nL < 48) g_conv_layer[blockIdx.x * 48 + nL] = (clock64() - p_start) / ngrp;  // (per group, roughly)
 #endif
         }
     } else {  // ===== epilogue (both CTAs, own tiles) =====
@@ -791,9 +817,8 @@ conv_tower_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant_
         const uint32_t stg_blk = stg_base + (uint32_t)ew * 2048u;             // 32 rows x 64 B, SWIZZLE_64B
         const uint32_t stg = stg_blk + (uint32_t)lane * 64u;                  // this thread's staging row
         const uint32_t sw = (uint32_t)((lane >> 1) & 3);                      // 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3)
-        int sa = -1, sb = n - 1;
-        int xi = 0, ti = 1, yi = 2;
         uint32_t g = 0;
+        int lv = 0;  // layer visits so far (bias row rotation)
         bool pending = false;  // TMA stores of the previous tile not yet known complete (and not yet published)
         long long p_af = 0, p_e0 = 0, p_ld = 0, p_ms = 0, p_pub = 0, p_res = 0; (void)p_af; (void)p_e0; (void)p_ld; (void)p_ms; (void)p_pub; (void)p_res;
 #ifdef RVS_CONV_PROBE
@@ -804,7 +829,7 @@ conv_tower_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant_
         // have landed".  With enough tiles per CTA the tile order gives the next layer a head start of rot >= 4 tiles,
         // and publishing runs two tiles late: a TMA store then has two tile times to complete and is never waited for
         // (waiting for the previous tile's store at every tile cost the short first-layer tiles ~6000 cycles each).
-        const bool lag2 = rot >= 4;
+        bool lag2 = false;
         auto publish = [&](uint32_t tiles_issued, bool flush) {
             if (lane == 0) {
                 uint32_t upto = tiles_issued;
@@ -820,22 +845,29 @@ conv_tower_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant_
             }
             __syncwarp();
         };
-        for (int L = 0; L < nL; ++L) {
+        for (int gi = 0; gi < ngrp; ++gi) {
+        const int sl0 = group_first(gi), ng = group_first(gi + 1) - sl0, rot = rot_of(ng);
+        if (pending && lag2 != (rot >= 4)) { publish(g, true); pending = false; }  // the lag changes with the group size
+        lag2 = rot >= 4;
+        int sa = rot > 0 ? -1 : 1, sb = rot > 0 ? ng - 1 : 0;
+        const bool defer = ng >= 3;  // publish a tile at the top of a later tile (its stores have landed by then)
+        int xi = 0, ti = 1, yi = 2;
+        for (int L = 0; L < nL; ++L, ++lv) {
             const bool first = has0 && L == 0;
             const int l = L - has0;  // tower layer (-1: the first convolution, whose folded bias rides in its K dimension)
             const bool is_head = ta.head && L == nL - 1;
             const __nv_bfloat16* residual = (!first && (l & 1)) ? ta.buf[xi] : nullptr;
             const int oi = first ? xi : ((l & 1) ? yi : ti);
             const CUtensorMap* omap = oi == 0 ? &s0 : (oi == 1 ? &s1 : &s2);
-            float* sbl = sbias + (L % 3) * C;
+            float* sbl = sbias + (lv % 3) * C;
             // every epilogue warp writes the whole (identical) bias row: no barrier between the warps is needed, and
             // three rotating rows keep a warp that is a layer ahead off the row a slower warp still reads
             for (int j = lane; j < C; j += 32) sbl[j] = first ? 0.f : ta.bias[l * C + j];
             __syncwarp();
-            for (int i = 0; i < n; ++i, ++g) {
+            for (int i = 0; i < ng; ++i, ++g) {
                 const int acc = g & 1;
-                const int slot = posmod(sa * i + sb, n);
-                const int tile = (slot * n_pairs + pair) * 2 + (int)rank;
+                const int slot = posmod(sa * i + sb, ng);
+                const int tile = ((sl0 + slot) * n_pairs + pair) * 2 + (int)rank;
                 const size_t off = ((size_t)tile * kTileRows + row) * C;
                 const bool live = tile < n_tiles;
 #ifdef RVS_CONV_PROBE
@@ -905,7 +937,7 @@ conv_tower_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant_
                         fp[128] = fmaxf(hd2 + head.b[2], 0.f);
                     }
                     if (lane == 0) { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-                    if (rot > 0) pending = true;
+                    if (defer) pending = true;
                     continue;
                 }
                 uint32_t res[32];  // this warp's 64 channels of the residual row
@@ -969,11 +1001,12 @@ conv_tower_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant_
 #ifdef RVS_CONV_PROBE
                 p_ms += clock64();
 #endif
-                if (rot > 0) pending = true;      // published at the top of a later tile: by then the stores have landed
-                else publish(g + 1, true);        // few tiles per CTA: the next layer needs this tile at once
+                if (defer) pending = true;        // published at the top of a later tile: by then the stores have landed
+                else publish(g + 1, true);        // one or two tiles per group: the next layer needs this tile at once
             }
-            next_order(sa, sb);
+            next_order(sa, sb, ng, rot);
             if (!first && (l & 1)) { const int tmp = xi; xi = yi; yi = tmp; }
+        }
         }
         publish(g, true);  // nothing may be in flight when the CTA exits
 #ifdef RVS_CONV_PROBE
