@@ -169,12 +169,13 @@ def main():
                     units=n1, unit_name="simulation")[0]
     k16 = summarise("k1g_16k", "ncu_selfplay_k1g_16k_r2.txt", f"selfplay_k1g_kernel, 16384 games ({lpg16} lanes per game), launch of {n16 // 100} game-plies x 100 simulations (tools/probe_selfplay.py 16384 0 2)",
                     units=n16, unit_name="simulation")[0]
-    c128 = summarise("conv128", "ncu_conv_tc2_128_r2.txt", "conv3x3_tc2_kernel<128,128>: two consecutive tower layers (plain, then with residual) of a 5x128 forward on 4096 boards (tools/probe_net.py 5 128 4096 predict)")
+    t128 = summarise("tower128", "ncu_conv_tower_128_r2.txt", "conv_tower_kernel<128>: the whole 5x128 network up to the head planes (first layer + 10 tower layers) in ONE persistent launch on 4096 boards (tools/probe_net.py 5 128 4096 predict)")[0]
+    c128 = summarise("conv128", "ncu_conv_tc2_128_r2.txt", "conv3x3_tc2_kernel<128,128> (the per-layer path, RVS_OPT_NET_TOWER = 0): two consecutive tower layers (plain, then with residual) of a 5x128 forward on 4096 boards (RVS_TOWER=0 tools/probe_net.py 5 128 4096 predict)")
     c256 = summarise("conv256", "ncu_conv_tc2s_256_r2.txt", "conv3x3_tc2s_kernel (256 filters, streamed weights): two consecutive tower layers of a 20x256 forward on 4096 boards (tools/probe_net.py 20 256 4096 predict)")
-    aux = summarise("nnaux", "ncu_nn_aux_r2.txt", "the small kernels of one wave of the 5x128 NN search on 4096 games (tools/probe_nn_wave.py): first layer, heads, tree step")
+    aux = summarise("nnaux", "ncu_nn_aux_r2.txt", "the small kernels of the 5x128 NN search on 4096 games, two half-batches of 2048 (tools/probe_nn_wave.py): heads, tree step")
     brd = summarise("board", "ncu_board_k1_r2.txt", "K1 streaming kernels on 4 Mi arbitrary disc sets (tools/probe_board.py 4194304)")
     launches("launches_bench_r2.csv", "launches_bench_r2.txt", "python bench.py --steps 2 --warmup 1 --min-seconds 0 --no-cpu --no-big")
-    launches("launches_nnwave_r2.csv", "launches_nnwave_r2.txt", "two waves of the 5x128 NN search, 4096 games (tools/probe_nn_wave.py, --launch-skip 1700 -c 28)")
+    launches("launches_nnwave_r2.csv", "launches_nnwave_r2.txt", "four waves of the 5x128 NN search, 4096 games as two pipelined half-batches (tools/probe_nn_wave.py, --launch-skip 800 -c 24)")
     for f in ("bench_r2_1gpu.json", "bench_r2_reference_arm.json"):
         if os.path.exists(os.path.join(SRC, f)):
             shutil.copy(os.path.join(SRC, f), os.path.join(OUT, f))
@@ -190,6 +191,11 @@ def main():
         "selfplay_k1g_kernel_16384": {"sims_in_launch": n16, "lanes_per_game": lpg16, "warp_inst_per_sim": k16["warp_inst_per_unit"],
                                       "issue_active_pct": k16["issue_active_pct"], "alu_pipe_active_pct": k16["alu_pipe_pct"],
                                       "dram_bytes_per_sim": k16["dram_bytes_per_unit"], "source": "profiles/ncu_selfplay_k1g_16k_r2.txt"},
+        "conv_tower_kernel_128": {"dram_bytes_per_launch": t128["dram_bytes"], "us": t128["us"], "tensor_pipe_active_pct": t128["tensor_pipe_pct"], "boards": boards,
+                                  "flop": boards * 2 * (64 * 9 * 16 * 128 + 10 * 64 * 9 * 128 * 128),
+                                  "algorithmic_bytes": boards * 64 * (64 * 2 + 192 * 4 / 64) + 11 * 9 * 128 * 128 * 2,
+                                  "note": "algorithmic bytes = input tiles in + head planes out + weights once: inter-layer activations need not leave the chip "
+                                          "(they go through L2: depth-first tile groups); flop counts the first layer at the K = 16 it runs"},
         "conv3x3_tc2_kernel_128": [{"dram_bytes_per_launch": c["dram_bytes"], "us": c["us"], "tensor_pipe_active_pct": c["tensor_pipe_pct"],
                                     "boards": boards, "algorithmic_bytes": boards * 64 * 128 * 2 * (2 + i) + 9 * 128 * 128 * 2,
                                     "layer": "plain" if i == 0 else "with residual"} for i, c in enumerate(c128)],

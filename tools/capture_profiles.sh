@@ -32,12 +32,14 @@ if [ "$WHAT" = ncu ] || [ "$WHAT" = all ]; then
   cap k1g -k regex:selfplay_k1g -s 3 -c 1 -- python bench.py --steps 2 --warmup 3 --steps-per-launch 2 --min-seconds 0 --no-cpu --no-big --no-nn
   # the many-games regime (16384 games, automatic lanes per game)
   cap k1g_16k -k regex:selfplay_k1g -s 1 -c 1 -- python tools/probe_selfplay.py 16384 0 2
-  # tower layers: 128 filters (plain + residual layer) and 256 filters
-  cap conv128 -k regex:conv3x3_tc2_kernel -s 34 -c 2 -- python tools/probe_net.py 5 128 4096 predict
+  # 128 filters: the whole-network kernel (first layer + tower + head planes, one launch per forward) ...
+  cap tower128 -k regex:conv_tower_kernel -s 3 -c 1 -- python tools/probe_net.py 5 128 4096 predict
+  # ... and the per-layer kernel it replaces (RVS_OPT_NET_TOWER = 0: plain + residual layer); 256 filters
+  cap conv128 -k regex:conv3x3_tc2_kernel -s 34 -c 2 -- env RVS_TOWER=0 python tools/probe_net.py 5 128 4096 predict
   cap conv256 -k regex:conv3x3_tc2s -s 122 -c 2 -- python tools/probe_net.py 20 256 4096 predict
   # the small kernels of an NN wave (tree step incl. input tiles, first layer, heads)
-  cap nnaux -k "regex:heads_kernel|nn_step_kernel|conv3x3_tc2_kernel<128, 64" --launch-skip 300 -c 3 -- python tools/probe_nn_wave.py
-  $NCU --metrics gpu__time_duration.sum --launch-skip 1700 -c 28 --csv --log-file $O/launches_nnwave_r2.csv \
+  cap nnaux -k "regex:heads_kernel|nn_step_kernel" --launch-skip 300 -c 4 -- python tools/probe_nn_wave.py
+  $NCU --metrics gpu__time_duration.sum --launch-skip 800 -c 24 --csv --log-file $O/launches_nnwave_r2.csv \
       python tools/probe_nn_wave.py > /dev/null 2>&1
   # board kernels
   cap board -k "regex:legal_masks|apply_moves" -c 2 -- python tools/probe_board.py 4194304
