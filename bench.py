@@ -301,18 +301,21 @@ def run_ours(args):
     barrier()
     e0.record()
     if persistent:
-        # K steps = K x N_GAMES game-plies, issued as persistent launches of `ppl` steps each (x reps, see above)
-        used = []
-        for r in range(reps):
-            done = 0
-            while done < args.steps:
-                n = min(ppl, args.steps - done)
-                ev = ks[r * args.steps + done]
-                ev[0].record()
-                eng.selfplay(N_SIMS, plies=N_GAMES * n, temperature=1.0, recycle=True, stream=stream)
-                ev[1].record()
-                used.append(ev)
-                done += n
+        # K x reps steps = K x reps x N_GAMES game-plies, issued as persistent launches of `ppl` steps each: the launch size
+        # is the engine's business (a self-play farm calls rvs_engine_selfplay with a large ply budget), the timed region is
+        # exactly K x reps steps.  A launch ends with a tail of about one early-game ply, so short launches cost throughput:
+        # 20 / 50 / 100 / 400 steps per launch give 2.75 / 2.84 / 2.88 / 2.91e8 sims/s.
+        used, launch_steps = [], []
+        done, total = 0, args.steps * reps
+        while done < total:
+            n = min(ppl, total - done)
+            ev = ks[len(used)]
+            ev[0].record()
+            eng.selfplay(N_SIMS, plies=N_GAMES * n, temperature=1.0, recycle=True, stream=stream)
+            ev[1].record()
+            used.append(ev)
+            launch_steps.append(n)
+            done += n
         ks = used
     else:
         for i in range(args.steps * reps):
@@ -581,7 +584,7 @@ def run_ours(args):
         kcap = (cap or {}).get("selfplay_k1g_kernel", {}) if persistent else {}
         traffic = args.traffic  # DRAM bytes per launch of the dominant kernel, from the committed ncu capture
         if traffic is None and kcap.get("dram_bytes_per_step") is not None:
-            traffic = kcap["dram_bytes_per_step"] * min(ppl, args.steps)
+            traffic = kcap["dram_bytes_per_step"] * (total_steps / len(ks) if persistent else 1)
         # The binding roof of the dominant kernel is the ISSUE rate, not HBM (rollouts are register resident; DRAM
         # traffic is a few % of peak): achieved = warp instructions per simulation (ncu smsp__inst_executed.sum /
         # simulations of the committed capture, stamped with the hash of the kernel sources) x measured sims/s;
@@ -629,7 +632,7 @@ def run_ours(args):
                                       "kernel_source_hash": cap.get("kernel_source_hash"), "current_hash": kernel_source_hash(),
                                       "issue_active_pct_under_ncu": kcap.get("issue_active_pct"),
                                       "alu_pipe_active_pct_under_ncu": kcap.get("alu_pipe_active_pct")} if cap else None),
-                         "steps_per_launch": min(ppl, args.steps) if persistent else 1,
+                         "steps_per_launch": (total_steps / len(ks)) if persistent else 1,
                          "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms * len(ks) / ms,
                          "hbm": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                                  "peak_source": which, "algorithmic_bytes_per_sim": d["tree_bytes"] / max(1, d["sims"])},
@@ -816,7 +819,7 @@ def main():
     ap.add_argument("--presteps", type=int, default=5, help="untimed plies that spread games over all phases")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--wave", type=int, default=1, help="MCTS batch_size per game (reference default 64)")
-    ap.add_argument("--steps-per-launch", type=int, default=50,
+    ap.add_argument("--steps-per-launch", type=int, default=100,
                     help="persistent self-play: steps (x4096 game-plies) per launch")
     ap.add_argument("--lockstep", action="store_true", help="wave 1 through search+play launches per ply")
     ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per launch of the search kernel")
