@@ -747,6 +747,10 @@ conv_tower_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant_
 #endif
             int stage = 0, sph = 0;
             int wuse0 = 0, wuse1 = 0;
+            if (n == 0) {  // empty batch (every game of a wave finished): the weight loads requested above must still land
+                mbar_wait_cluster(WFULL(0), 0);  // before the pair's shared memory is given up
+                if (!has0) mbar_wait_cluster(WFULL(1), 0);
+            }
             for (int gi = 0; gi < ngrp; ++gi) {
             const int ng = group_first(gi + 1) - group_first(gi);
             for (int L = 0; L < nL; ++L) {

@@ -267,3 +267,26 @@ def test_tower_kernel_matches_per_layer(az, nb, boards):
         assert np.array_equal(v, out[0][0][1])
     assert np.isfinite(out[1][0][0]).all() and np.abs(out[1][0][0]).max() > 0
     eng.close()
+
+
+@pytest.mark.parametrize("g", [64, 2304])
+def test_nn_search_on_finished_games_has_an_empty_batch(az, g):
+    """every root is terminal: the tree step claims no batch row, the network kernels see a batch of ZERO boards (device-side
+    count) in every wave -- lockstep (64 games) and as two pipelined half-batches (2304) -- and must neither hang nor leave
+    work in flight; the engine answers a normal search afterwards."""
+    net = _build(az, 1, 128, "bn")
+    rn = az.RvsNetwork.from_module(net)
+    eng = az.Engine(g, 16, 1, evaluator=az.EVAL_NN, net_blocks=1, net_filters=128)
+    rn.attach(eng)
+    full = np.full(g, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)
+    eng.set_positions(full, np.zeros(g, dtype=np.uint64), np.ones(g, dtype=np.uint8))
+    eng.search(16, 1)
+    assert int(eng.root_visits().sum()) == 0
+    assert eng.stats()["nn_evals"] == 0
+    rb, rw, rs = _midgame_roots(g, 5)
+    eng.set_positions(rb, rw, rs)
+    eng.search(16, 1)
+    v = eng.root_visits()
+    st = eng.stats()
+    assert st["overflow"] == 0 and st["nn_evals"] > 0 and int(v.sum()) > 0
+    eng.close()
