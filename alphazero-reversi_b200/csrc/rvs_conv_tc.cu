@@ -525,25 +525,26 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_const
 
 
 // =============================================================================================
-// Whole residual tower in ONE persistent kernel (C = 128).
+// The whole network up to the head planes in ONE persistent kernel (C = 128): first layer, residual tower, fused heads'
+// 1x1 convolutions.
 //
 // A tile is two whole boards, so a 3x3 convolution never reads across tiles, and every layer maps tile slot `it`
-// of pair p to the same CTA: a CTA only ever consumes activations it produced itself.  The tower therefore needs NO
+// of pair p to the same CTA: a CTA only ever consumes activations it produced itself.  The network therefore needs NO
 // grid-wide synchronisation between layers: each CTA pair walks its own tiles through all layers, and the only
 // cross-layer dependencies are inside the CTA --
-//   * input tile of layer l  <- the CTA's own epilogue stores of layer l-1: per-epilogue-warp counters in shared
-//     memory (`done`), published after a generic->async proxy fence because the stores are generic-proxy writes and
-//     the TMA loads that read them back are async-proxy reads;
+//   * input tile of layer l  <- the CTA's own epilogue stores of layer l-1 (TMA stores from a staging block): per-
+//     epilogue-warp counters in shared memory (`done`), published once the bulk group has completed; the TMA producer
+//     thread polls them before it loads the tile;
 //   * the resident weights of layer l replace those of layer l-1 in place, one 64-channel half at a time: the half
 //     read by the kc = 0 MMAs of the previous layer's last tile is reloaded while its kc = 1 MMAs run (WEMPTY /
 //     WFULL barriers per half), so the tensor pipe does not drain at a layer boundary.
 // Compared with one launch per layer (conv3x3_tc2_kernel) this removes, per layer: the launch gap, the serial weight
 // prologue (the next layer's CTA cannot become resident before this one frees its 224 KB of shared memory: ~1800
 // cycles waiting for weights + ~1500 for the first activation box, tools/probe_conv.py), and the tail where early
-// CTAs idle until the slowest one finishes.  The arithmetic (MMA order, epilogue) is the per-layer kernel's, so
-// the results are bit-identical to it (tests/test_gpu_net.py::test_tower_kernel_matches_per_layer).
-// Tile order: consecutive layers walk the CTA's tiles in opposite directions (the most recently written tiles are
-// still in L2), rotated by two so that the first tile a layer needs was stored two epilogues ago.
+// CTAs idle until the slowest one finishes; and it lets the tiles go DEPTH FIRST through the layers in small groups,
+// so that the activations between layers stay in L2 (see `ngrp` below).  The arithmetic (MMA order, epilogue) is the
+// per-layer kernel's, so the results are bit-identical to it (tests/test_gpu_net.py::
+// test_tower_kernel_matches_per_layer, tools/stress_tower.py).
 // =============================================================================================
 struct TowerArgs {
     __nv_bfloat16* buf[3];   // x (block input / residual), t (mid), y (block output); roles rotate per block
