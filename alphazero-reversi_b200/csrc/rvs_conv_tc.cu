@@ -660,7 +660,11 @@ conv_tower_kernel(const __grid_constant__ CUtensorMap m0, const __grid_constant_
     }
     pdl_wait();
     if (ta.n_boards_dev) n_tiles = (__ldcg(ta.n_boards_dev) + 1) >> 1;
-    const int n = (n_tiles + 2 * n_pairs - 1) / (2 * n_pairs);  // tiles per CTA and layer (same in both CTAs of a pair)
+    // Tiles of this CTA (same in both CTAs of a pair): pair p owns the tile pairs p, p + n_pairs, ...  Pairs do not pad
+    // their share to a common length: a pair that is one tile short just finishes earlier -- no MMAs on zero-filled
+    // tiles, and in a pipelined search the other half-batch's CTA takes the SM over at once.
+    const int tile_pairs = (n_tiles + 1) >> 1;
+    const int n = pair < tile_pairs ? (tile_pairs - pair + n_pairs - 1) / n_pairs : 0;
     // DEPTH FIRST over groups of 4..7 tiles: a group goes through ALL layers before the next group starts.  The live
     // activations of the whole grid are then (group size) x 3 buffers x 32 KB x 148 CTAs ~ 60 MB, which stays in the 126 MB
     // L2 -- layer by layer over all 14 tiles of a CTA, every layer wrote and re-read 67 MB (+ 67 MB of residual) and the

@@ -117,7 +117,8 @@ def _midgame_roots(g, seed):
                                                         (64, 0, 0, 200, 2, 64, 48), (64, 1, 0, 200, 2, 64, 48),
                                                         # 128 filters: the whole-network kernel inside the search, lockstep and as
                                                         # two pipelined half-batches (>= 2048 games, odd split)
-                                                        (1, 0, 0, 40, 1, 128, 301), (1, 0, 1, 24, 1, 128, 2305), (8, 0, 0, 32, 1, 128, 301)])
+                                                        (1, 0, 0, 40, 1, 128, 301), (1, 0, 1, 24, 1, 128, 2305), (8, 0, 0, 32, 1, 128, 301),
+                                                        (8, 1, 0, 64, 1, 128, 301)])  # ... and inside a replayed CUDA graph
 def test_nn_search_consistency(az, K, graph, pipeline, S, nb, nf, g):
     """The fused NN search (select -> compaction + de-duplication of the leaf batch -> tower -> heads + softmax
     -> slot -> row remap -> expand/backup, all on the device; optionally as a replayed CUDA graph / as two
