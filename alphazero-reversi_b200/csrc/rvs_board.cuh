@@ -240,9 +240,13 @@ RVS_HD uint64_t brev64(uint64_t x) {
 #endif
 }
 
-// Shifts of the direction scans.  Writing x << s as a multiply by 2^s (IMAD.WIDE.U32 + IMAD on
-// the FMA pipe instead of two ALU-pipe SHF) was measured on B200 and is ~15% SLOWER end to end
-// (lockstep wave-1 step 4.9 ms -> 5.8 ms): kept behind RVS_SHL_MUL for the record only.
+// Shifts of the direction scans.  The shift amount is per lane (a register), so x << s costs two ALU-pipe SHF, and the
+// ALU pipe (LOP3 + SHF, one warp instruction per two cycles) is what the rollout saturates.  HYBRID form (default on the
+// device): the low word is one IMAD on the otherwise idle FMA pipe (lo * 2^s), the high word one funnel shift --
+// 14 of the ~94 ALU instructions of a rollout ply move over: +2 % at 4096 games, +8 % at 16 384 (same-box A/B on
+// B200, gpurun_out/ab_k2_s4.log).  Writing the WHOLE shift as multiplies (IMAD.WIDE.U32 + IMAD, RVS_SHL_MUL) puts two
+// dependent FMA-pipe instructions on the flood chain and was ~15 % SLOWER end to end (round 1); RVS_SHL_PLAIN keeps the
+// two-SHF form for A/B runs.
 struct DirLane {
     uint32_t m1, m2;  // 2^s and 2^(2s)
     int s, s2;      // |shift| in {1, 7, 8, 9} and twice that
@@ -284,6 +288,16 @@ RVS_HD uint64_t shl_mul(uint64_t x, uint32_t m) {
 #if defined(RVS_SHL_MUL)
 RVS_HD uint64_t sh1(const DirLane& L, uint64_t x) { return shl_mul(x, L.m1); }
 RVS_HD uint64_t sh2(const DirLane& L, uint64_t x) { return shl_mul(x, L.m2); }
+#elif !defined(RVS_SHL_PLAIN) && defined(__CUDA_ARCH__)
+// low word on the FMA pipe (one IMAD), high word one funnel shift on the ALU pipe
+__device__ __forceinline__ uint64_t shl_hyb(uint64_t x, uint32_t m, int s) {
+    uint32_t lo;
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(lo) : "r"((uint32_t)x), "r"(m));
+    const uint32_t hi = __funnelshift_l((uint32_t)x, (uint32_t)(x >> 32), s);
+    return ((uint64_t)hi << 32) | lo;
+}
+RVS_HD uint64_t sh1(const DirLane& L, uint64_t x) { return shl_hyb(x, L.m1, L.s); }
+RVS_HD uint64_t sh2(const DirLane& L, uint64_t x) { return shl_hyb(x, L.m2, L.s2); }
 #else
 RVS_HD uint64_t sh1(const DirLane& L, uint64_t x) { return x << L.s; }
 RVS_HD uint64_t sh2(const DirLane& L, uint64_t x) { return x << L.s2; }
@@ -315,6 +329,28 @@ RVS_HD uint64_t flip_raw(const DirLane& L, uint64_t Pd, uint64_t Od, uint64_t mv
     x |= sh2(L, x) & Om2;
     const uint64_t end = sh1(L, x) & ~x & Pm;
     return end ? x : 0ULL;
+}
+// The same scan without the flood.  flip_ray = the cells the scan of move square `sqd` (working domain) can touch:
+// sqd + s, sqd + 2s, ... (at most 7: six cells to pass through and the one that closes the line), cut before the
+// first cell that leaves the board or lies outside fm (such a cell can neither be passed nor close a line).
+// flip_carry: with every non-ray bit and every opponent cell set, adding 1 ripples a carry from bit 0 through the
+// move square and along the run of opponent cells; it stops on the first ray cell that is not an opponent disc
+// (or runs off the top when there is none).  That cell closes the line iff it holds a disc of the mover, and the
+// ray cells below it are the flips.  Equal to flip_raw for every position (tests/test_capi_cpu.py checks the host
+// build on random positions; the GPU parity tests cover the kernels).
+RVS_HD uint64_t flip_ray(const DirLane& L, int sqd) {
+    uint64_t R = 0;
+    for (int i = 1; i <= 7; ++i) {
+        const int c = sqd + i * L.s;
+        if (c > 63 || !((L.fm >> c) & 1ULL)) break;
+        R |= 1ULL << c;
+    }
+    return R;
+}
+RVS_HD uint64_t flip_carry(uint64_t R, uint64_t Pd, uint64_t Od) {
+    const uint64_t X = (Od | ~R) + 1ULL;
+    const uint64_t of = X & R & Pd;
+    return of ? (of - 1ULL) & R : 0ULL;
 }
 RVS_HD uint64_t flip_part(const DirLane& L, uint64_t Pd, uint64_t Od, uint64_t mvd) {
     return to_dom(flip_raw(L, Pd, Od, mvd), L.neg);

@@ -48,6 +48,15 @@ uint64_t hc_flips_sliced(uint64_t P, uint64_t O, int idx, int rules) {
     }
     return v;
 }
+// the table form of the 8-lane groups: ray of the move square + carry ripple (flip_ray / flip_carry)
+uint64_t hc_flips_carry(uint64_t P, uint64_t O, int idx, int rules) {
+    uint64_t v = 0;
+    for (int d = 0; d < 8; ++d) {
+        const DirLane L = rules == RULES_STRICT ? make_dir<RULES_STRICT>(d) : make_dir<RULES_REF>(d);
+        v |= to_dom(flip_carry(flip_ray(L, L.neg ? 63 - idx : idx), to_dom(P, L.neg), to_dom(O, L.neg)), L.neg);
+    }
+    return v;
+}
 int hc_nth_set_bit(uint64_t m, int k) { return nth_set_bit(m, k); }
 uint64_t hc_stream_seed(uint64_t s, uint64_t a, uint64_t b) { return stream_seed(s, a, b); }
 // Dirichlet root noise (rvs_noise.cuh): the product's formulas against the oracle's restatement

@@ -41,6 +41,7 @@ struct Grp {
     uint32_t lutd;       // the table for own-domain row bytes: odd lanes of 8-lane groups see their row bit-reversed
                          // (lut + 2048: lutr[byte * 8 + j] = lut[rev8(byte) * 8 + j])
     uint32_t gather;     // shared-window address: 3 x 64-byte exchange buffers of the group (grp_or64_own8)
+    uint32_t rays;       // LPG == 8: shared-window address of this lane's column of the flip-ray table (ray_init), else 0
     uint32_t path;       // shared-window address: int[kMaxPath + 1] nodes of the current path; the extra word
                          // is the group's broadcast slot (grp_nth_set_bit)
                          // (32-bit shared addresses: a generic pointer costs an S2R + LEA per access)
@@ -64,12 +65,28 @@ __device__ __forceinline__ void lut_init(uint8_t* lut, int tid, int nthreads) {
     }
 }
 
+// Flip-ray table of the 8-lane groups (flip_ray / flip_carry in rvs_board.cuh): row sqd (the move square in the
+// lane's own domain) holds the ray of every direction lane, 16 bytes apart, twice: groups 0 / 2 of a warp read the
+// copy at +0, groups 1 / 3 the copy at +8, so the 16 lanes the LSU serves together (two groups, LDS.64) touch 32
+// distinct banks whatever their squares are.  64 rows x 128 bytes.
+constexpr int kRayWords64 = 64 * 16;
+template <int RULES>
+__device__ __forceinline__ void ray_init(uint64_t* rays, int tid, int nthreads) {
+    for (int e = tid; e < 64 * 8; e += nthreads) {
+        const int sqd = e >> 3, dir = e & 7;
+        const uint64_t R = flip_ray(make_dir<RULES>(dir), sqd);
+        rays[sqd * 16 + dir * 2] = R;
+        rays[sqd * 16 + dir * 2 + 1] = R;
+    }
+}
+
 // word offset of the 3 x 16-word exchange buffers of 8-lane group gi inside the CTA's gather array (kGatherWords words)
 constexpr int kGatherWords = 264;
-__device__ __forceinline__ int gather_off(int gi) { return gi == 0 ? 0 : (gi == 1 ? 68 : (gi == 2 ? 144 : 212)); }
+__device__ __forceinline__ int gather_off(int gi) { return gi == 0 ? 0 : (gi == 1 ? 144 : (gi == 2 ? 68 : 212)); }
 
 template <int RULES, int LPG>
-__device__ __forceinline__ Grp<LPG> make_grp(int lane32, const uint8_t* lut, int* path, const void* gather = nullptr) {
+__device__ __forceinline__ Grp<LPG> make_grp(int lane32, const uint8_t* lut, int* path, const void* gather = nullptr,
+                                             const uint64_t* rays = nullptr) {
     Grp<LPG> g;
     g.sh = lane32 & ~(LPG - 1);
     g.lane = lane32 & (LPG - 1);
@@ -82,9 +99,12 @@ __device__ __forceinline__ Grp<LPG> make_grp(int lane32, const uint8_t* lut, int
     g.lut = (uint32_t)__cvta_generic_to_shared(lut);
     g.lutd = g.lut + (own_rev ? 256u * 8u : 0u);
     g.path = (uint32_t)__cvta_generic_to_shared(path);
-    // 8-lane groups: the four groups of a warp read their exchange buffers with the same LDS.128 instructions, so
-    // the buffers start 4 / 16 / 20 banks apart (kGatherOff): the 8 distinct 16-byte chunks of one load instruction
-    // (4 groups x 2 domains) then cover all 32 banks once -- no bank conflicts
+    g.rays = rays ? (uint32_t)__cvta_generic_to_shared(rays) + 16u * (uint32_t)g.lane + 8u * (uint32_t)((lane32 >> 3) & 1) : 0u;
+    // 8-lane groups: the four groups of a warp access their exchange buffers with the same instructions, which the LSU
+    // serves half a warp (two groups) at a time.  The buffers of groups 0 / 1 / 2 / 3 start at banks 0 / 16 / 4 / 20
+    // (gather_off): the two 64-byte stores of a half warp (STS.64, 16 banks each) and the four distinct 16-byte chunks
+    // of a half warp's LDS.128 (2 groups x 2 domains) then never share a bank.  (With starts 0 / 4 / 16 / 20 the loads
+    // were conflict-free but every STS.64 took 4 wavefronts instead of 2: ncu, round 2.)
     g.gather = gather ? (uint32_t)__cvta_generic_to_shared(gather) + 4u * (uint32_t)gather_off(lane32 >> 3) : 0u;
 #pragma unroll
     for (int j = 0; j < Grp<LPG>::ND; ++j) g.d[j] = make_dir<RULES>(g.lane * Grp<LPG>::ND + j);
@@ -94,6 +114,13 @@ __device__ __forceinline__ Grp<LPG> make_grp(int lane32, const uint8_t* lut, int
 __device__ __forceinline__ unsigned lds_u8(uint32_t a) {
     unsigned v;
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+// the load only for lanes with p (the others get 0): 32 scattered byte loads are a ~5-way bank conflict, the one lane
+// per group that holds the square is not
+__device__ __forceinline__ unsigned lds_u8_if(uint32_t a, bool p) {
+    unsigned v = 0;
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q ld.shared.u8 %0, [%1]; }" : "+r"(v) : "r"(a), "r"((unsigned)p));
     return v;
 }
 __device__ __forceinline__ int lds_s32(uint32_t a) {
@@ -199,7 +226,7 @@ __device__ __forceinline__ NthPrep grp_nth_prep(const Grp<LPG>& g, uint64_t md, 
         const unsigned byte = __byte_perm((unsigned)md, (unsigned)(md >> 32), (unsigned)g.bsh) & 0xFFu;  // one PRMT
         const int j = k - popc64(md & g.belowd);
         r.hit = (unsigned)j < (unsigned)__popc(byte);
-        r.pos = g.lane * 8 + (int)lds_u8(g.lutd + byte * 8 + (j & 7));
+        r.pos = g.lane * 8 + (int)lds_u8_if(g.lutd + byte * 8 + (j & 7), r.hit);
     } else {
         unsigned slice = grp_slice(g, md);
         int j = k - popc64(md & g.below);
@@ -285,8 +312,11 @@ template <int LPG>
 __device__ __forceinline__ MoveOut grp_flip(const Grp<LPG>& g, const GBoard& c, int idx) {
     MoveOut m;
     if constexpr (Grp<LPG>::ND == 1) {  // everything in the lane's own domain
-        const uint64_t mv = 1ULL << (idx ^ g.flip63);
-        const uint64_t f = grp_or64_own8<0>(g, flip_raw(g.d[0], c.P[0], c.O[0], mv));
+        const int sqd = idx ^ g.flip63;
+        const uint64_t mv = 1ULL << sqd;
+        uint64_t R;  // this lane's ray of the move square: one table load instead of the five-step flood
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(R) : "r"(g.rays + 128u * (uint32_t)sqd));
+        const uint64_t f = grp_or64_own8<0>(g, flip_carry(R, c.P[0], c.O[0]));
         m.P[0] = c.P[0] ^ (mv | f); m.P[1] = 0ULL;
         m.O[0] = c.O[0] ^ f;        m.O[1] = 0ULL;
     } else {

@@ -34,6 +34,8 @@ def hc():
     L.hc_legal_sliced.argtypes = [C.c_uint64, C.c_uint64, C.c_int]
     L.hc_flips_sliced.restype = C.c_uint64
     L.hc_flips_sliced.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int]
+    L.hc_flips_carry.restype = C.c_uint64
+    L.hc_flips_carry.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int]
     L.hc_nth_set_bit.argtypes = [C.c_uint64, C.c_int]
     L.hc_stream_seed.restype = C.c_uint64
     L.hc_stream_seed.argtypes = [C.c_uint64] * 3
@@ -103,6 +105,31 @@ def test_direction_sliced_formulas_match_oracle(hc, rules):
             idx = (m & -m).bit_length() - 1
             m &= m - 1
             assert hc.hc_flips_sliced(P, O, idx, rules) == orc.flips(P, O, idx, rules)
+
+
+@pytest.mark.parametrize("rules", [orc.RULES_REF, orc.RULES_STRICT])
+def test_ray_table_carry_flips_match_oracle(hc, rules):
+    """the 8-lane groups' flips (ray of the move square + carry ripple, rvs_board.cuh: flip_ray / flip_carry):
+    every EMPTY square of every position -- legal moves and the phantom ones the search never plays -- including
+    dense endgame boards where runs reach the 6-cell limit"""
+    import random
+    rng = random.Random(77 + rules)
+    pos = list(rand_positions(6000, 57 + rules))
+    for _ in range(3000):  # dense boards: 50-63 discs
+        occ = orc.M64
+        for _ in range(rng.randrange(1, 14)):
+            occ &= ~(1 << rng.randrange(64))
+        P = rng.getrandbits(64) & occ
+        pos.append((P, occ & ~P))
+    n = 0
+    for P, O in pos:
+        E = ~(P | O) & orc.M64
+        while E:
+            idx = (E & -E).bit_length() - 1
+            E &= E - 1
+            assert hc.hc_flips_carry(P, O, idx, rules) == orc.flips(P, O, idx, rules), (hex(P), hex(O), idx)
+            n += 1
+    assert n > 100000
 
 
 @pytest.mark.parametrize("rules", [orc.RULES_REF, orc.RULES_STRICT])
