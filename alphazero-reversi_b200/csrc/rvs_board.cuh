@@ -336,7 +336,7 @@ RVS_HD uint64_t flip_raw(const DirLane& L, uint64_t Pd, uint64_t Od, uint64_t mv
 // flip_carry: with every non-ray bit and every opponent cell set, adding 1 ripples a carry from bit 0 through the
 // move square and along the run of opponent cells; it stops on the first ray cell that is not an opponent disc
 // (or runs off the top when there is none).  That cell closes the line iff it holds a disc of the mover, and the
-// ray cells below it are the flips.  Equal to flip_raw for every position (tests/test_capi_cpu.py checks the host
+// opponent ray cells the ripple cleared are the flips.  Equal to flip_raw for every position (tests/test_capi_cpu.py checks the host
 // build on random positions; the GPU parity tests cover the kernels).
 RVS_HD uint64_t flip_ray(const DirLane& L, int sqd) {
     uint64_t R = 0;
@@ -349,8 +349,9 @@ RVS_HD uint64_t flip_ray(const DirLane& L, int sqd) {
 }
 RVS_HD uint64_t flip_carry(uint64_t R, uint64_t Pd, uint64_t Od) {
     const uint64_t X = (Od | ~R) + 1ULL;
-    const uint64_t of = X & R & Pd;
-    return of ? (of - 1ULL) & R : 0ULL;
+    const uint64_t closed = X & R & Pd;  // the cell the carry stopped on, if it is a ray cell with a disc of the mover
+    const uint64_t run = Od & R & ~X;    // the opponent cells the carry went through (cleared by the ripple)
+    return closed ? run : 0ULL;
 }
 RVS_HD uint64_t flip_part(const DirLane& L, uint64_t Pd, uint64_t Od, uint64_t mvd) {
     return to_dom(flip_raw(L, Pd, Od, mvd), L.neg);

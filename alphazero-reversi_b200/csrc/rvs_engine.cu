@@ -553,7 +553,7 @@ constexpr int kMaxWarpsG = kNumSMs * 16;  // 16 one-warp CTAs per SM (__launch_b
 template <int RULES, int EVAL, int LPG, int MINB>
 __global__ void __launch_bounds__(kBlockG, MINB) search_k1g_kernel(EngineView ev, int S) {
     constexpr int GPB = kBlockG / LPG;
-    __shared__ uint8_t lut[kLutBytes];
+    __shared__ __align__(16) uint8_t lut[kLutBytes];
     __shared__ int spath[GPB][kMaxPath + 1];
     __shared__ __align__(16) unsigned sgather[LPG == 8 ? kGatherWords : 4];  // 3 x 64-byte exchange buffers per 8-lane group (gather_off)
     __shared__ __align__(16) uint64_t srays[LPG == 8 ? kRayWords64 : 2];  // flip-ray table of the 8-lane groups (ray_init)
@@ -608,7 +608,7 @@ template <int RULES, int EVAL, int LPG, int MINB>
 __global__ void __launch_bounds__(kBlockG, MINB) selfplay_k1g_kernel(EngineView ev, int S, float temperature,
                                                                    unsigned long long budget, int recycle) {
     constexpr int GPB = kBlockG / LPG;
-    __shared__ uint8_t lut[kLutBytes];
+    __shared__ __align__(16) uint8_t lut[kLutBytes];
     __shared__ int spath[GPB][kMaxPath + 1];
     __shared__ __align__(16) unsigned sgather[LPG == 8 ? kGatherWords : 4];  // 3 x 64-byte exchange buffers per 8-lane group (gather_off)
     __shared__ __align__(16) uint64_t srays[LPG == 8 ? kRayWords64 : 2];  // flip-ray table of the 8-lane groups (ray_init)

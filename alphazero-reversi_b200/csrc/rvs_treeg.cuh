@@ -43,7 +43,7 @@ struct Grp {
     uint32_t gather;     // shared-window address: 3 x 64-byte exchange buffers of the group (grp_or64_own8)
     uint32_t rays;       // LPG == 8: shared-window address of this lane's column of the flip-ray table (ray_init), else 0
     uint32_t path;       // shared-window address: int[kMaxPath + 1] nodes of the current path; the extra word
-                         // is the group's broadcast slot (grp_nth_set_bit)
+                         // is the broadcast slot of the 4- and 2-lane groups (grp_nth_post)
                          // (32-bit shared addresses: a generic pointer costs an S2R + LEA per access)
     DirLane d[ND];       // this lane's directions; d[j].neg == (j & 1) when ND >= 2
 };
@@ -244,15 +244,23 @@ __device__ __forceinline__ NthPrep grp_nth_prep(const Grp<LPG>& g, uint64_t md, 
     }
     return r;
 }
-// exactly one lane of the group holds the bit: it posts the square in the group's shared slot
-// (STS -> LDS is ~45 cycles shorter than ballot + find-first-set + SHFL on the critical path)
+// exactly one lane of the group holds the bit.  8-lane groups learn the square through ONE warp-wide OR reduction
+// (REDUX.OR): the squares of the four groups ride in the four bytes of the reduced word.  Same-box A/B on B200 at
+// 4096 games: +1.9 % over posting the square through a shared slot (STS -> LDS round trip, two warp barriers), which
+// in turn was ~45 cycles shorter than ballot + find-first-set + SHFL.  Smaller groups keep the shared slot: the eight
+// groups of LPG == 4 would need two reductions, measured 2.4 % SLOWER at 16 384 games.
 template <int LPG>
 __device__ __forceinline__ int grp_nth_post(const Grp<LPG>& g, const NthPrep& p) {
-    if (p.hit) sts_s32(g.path + 4 * kMaxPath, p.pos);
-    __syncwarp();
-    const int sq = lds_s32(g.path + 4 * kMaxPath);
-    __syncwarp();
-    return sq;
+    if constexpr (LPG == 8) {
+        const unsigned all = __reduce_or_sync(kFull, p.hit ? (unsigned)p.pos << g.sh : 0u);  // g.sh = 8 x group index
+        return (int)((all >> g.sh) & 0x3Fu);
+    } else {
+        if (p.hit) sts_s32(g.path + 4 * kMaxPath, p.pos);
+        __syncwarp();
+        const int sq = lds_s32(g.path + 4 * kMaxPath);
+        __syncwarp();
+        return sq;
+    }
 }
 
 // A position held by a group: side to move / opponent in the normal [0] and the bit-reversed [1]
