@@ -76,7 +76,11 @@ struct WaveScratch {
 
 // MCTSNode.ucb_score (mcts.py:96-114) for a visited child without a valid cache
 __device__ __forceinline__ float score_child(int N, float W, int VL, float P, int turn, float c_puct, float sq) {
-    float q = __fdiv_rn(W, (float)(N > 1 ? N : 1));
+    // W == 0 (draws, or wins and losses that cancel: ~19 % of the evaluations, ncu) would send the IEEE division down
+    // its slow path (a call); +-0 / n = +-0, so the quotient is W itself
+    const bool wz = W == 0.0f;
+    float q = __fdiv_rn(wz ? 1.0f : W, (float)(N > 1 ? N : 1));
+    q = wz ? W : q;
     float u = __fmul_rn(c_puct, P);
     u = __fmul_rn(u, sq);
     u = __fdiv_rn(u, (float)(1 + N + VL));

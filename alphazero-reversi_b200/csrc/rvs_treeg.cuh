@@ -240,7 +240,7 @@ __device__ __forceinline__ NthPrep grp_nth_prep(const Grp<LPG>& g, uint64_t md, 
             slice = next ? slice >> 8 : slice;
             row = next ? q + 1 : row;
         }
-        r.pos = (g.lane * RPL + row) * 8 + (int)lds_u8(g.lut + (slice & 0xFFu) * 8 + (j & 7));
+        r.pos = (g.lane * RPL + row) * 8 + (int)lds_u8_if(g.lut + (slice & 0xFFu) * 8 + (j & 7), r.hit);
     }
     return r;
 }
@@ -503,6 +503,55 @@ __device__ __forceinline__ void unstage_root(TreeCtxG<LPG>& cx) {
     }
 }
 
+// LAZY CHILD ROWS.  node.expand (mcts.py:141-161) creates one child per legal move, but with 100 simulations per move
+// ~70 % of the expanded nodes are never selected again, so their children are never looked at: 4096 games x ~900 rows x
+// 32 B per ply is the 126 MB L2 once over (ncu: L2 hit rate 52 %, the child-row loads of the scan wait ~280 cycles on
+// average).  With the uniform prior of the built-in evaluators an unvisited child carries no information beyond its
+// square, so expanding a node (other than the root, whose rows are staged) only records the legal mask in the node's
+// cold row {P, mask lo, meta | kLazyKids, mask hi}; the rows are created -- in the same ascending square order, with
+// the same contents -- by materialize_g the first time a traverse descends through the node.  Searches are unchanged
+// node for node; only row indices differ, and those are not observable.
+constexpr int kLazyKids = 1 << 20;  // cold.z: the children of this node exist only as the legal mask in cold.y / cold.w
+constexpr float kUniformPrior = 1.0f / 65.0f;
+
+// child rows of `lm` at fc, fc + 1, ... (lane l creates the children whose squares lie in its rows)
+template <int LPG>
+__device__ __forceinline__ void create_children_g(TreeCtxG<LPG>& cx, int fc, uint64_t lm, float prior, int turn) {
+    const Grp<LPG>& g = cx.g;
+    unsigned slice = grp_slice(g, lm);
+    int i = fc + popc64(lm & g.below);
+    while (slice) {
+        const int sq = g.lane * 8 * Grp<LPG>::RPL + (__ffs(slice) - 1);
+        slice &= slice - 1;
+        cx.hot[i] = make_int4(0, 0, 0, 0);
+        cx.cold[i] = make_int4(__float_as_int(prior), -1, (sq << 8) | (turn << 16), 0);
+        ++i;
+    }
+}
+
+// the traverse is about to scan the children of `node` (cold row c, group-uniform): create them if they are still lazy
+template <int LPG>
+__device__ __forceinline__ void materialize_g(TreeCtxG<LPG>& cx, int node, int4& c, bool& going, bool lazy) {
+    if (lazy) {
+        const uint64_t lm = (uint64_t)(unsigned)c.y | ((uint64_t)(unsigned)c.w << 32);
+        const int nc = c.z & 0xFF;
+        if (cx.n_nodes + nc > cx.cap) {
+            cx.overflow |= 1;
+            going = false;  // the node stays a leaf of this simulation
+        } else {
+            const int fc = cx.n_nodes;
+            create_children_g(cx, fc, lm, kUniformPrior, 3 - ((c.z >> 16) & 3));  // mcts.py:618
+            c.y = fc;
+            c.w = 0;
+            c.z &= ~kLazyKids;
+            if (cx.g.lane == 0) *cold_at(cx, node) = c;
+            cx.n_nodes += nc;
+            cx.bytes += 32u * (unsigned)nc;
+        }
+    }
+    __syncwarp();
+}
+
 // MCTS._backpropagate_path (mcts.py:625-640): lane l owns path nodes l, l+LPG, ...
 template <int LPG>
 __device__ __forceinline__ void backup_path_g(TreeCtxG<LPG>& cx, int plen, float v, bool act) {
@@ -544,6 +593,10 @@ __device__ __forceinline__ int select_one_g(TreeCtxG<LPG>& cx, GBoard& b, int& p
         const int nchild = c.z & 0xFF;
         going = going && nchild != 0 && !(h.z & kTerminal);
         if (!__any_sync(kFull, going)) break;
+        {
+            const bool lazy = going && (c.z & kLazyKids);
+            if (__any_sync(kFull, lazy)) materialize_g(cx, node, c, going, lazy);
+        }
         if (going) {
             h.z += 1;  // node.virtual_loss += 1 (mcts.py:416)
             if (g.lane == 0) reinterpret_cast<int*>(hot_at(cx, node))[2] = h.z;
@@ -626,20 +679,21 @@ __device__ __forceinline__ void expand_node_g(TreeCtxG<LPG>& cx, int node, uint6
         const int nc = popc64(lm);
         if ((c.z & 0xFF) != 0) {
             // 'if action not in self.children' (mcts.py:154): already expanded, nothing to add
+        } else if (node != 0 && prior == kUniformPrior) {
+            // lazy: the legal mask stands for the children until a traverse needs their rows (materialize_g)
+            if (g.lane == 0) {
+                c.y = (int)(unsigned)lm;
+                c.w = (int)(unsigned)(lm >> 32);
+                c.z = (c.z & ~0xFF) | nc | kLazyKids;
+                *cp = c;
+            }
+            cx.created += (unsigned)nc;
+            cx.bytes += 32u;
         } else if (cx.n_nodes + nc > cx.cap) {
             cx.overflow |= 1;
         } else {
             const int fc = cx.n_nodes;
-            const int turn = 3 - ((c.z >> 16) & 3);  // mcts.py:618
-            unsigned slice = grp_slice(g, lm);
-            int i = fc + popc64(lm & g.below);
-            while (slice) {
-                const int sq = g.lane * 8 * Grp<LPG>::RPL + (__ffs(slice) - 1);
-                slice &= slice - 1;
-                cx.hot[i] = make_int4(0, 0, 0, 0);
-                cx.cold[i] = make_int4(__float_as_int(prior), -1, (sq << 8) | (turn << 16), 0);
-                ++i;
-            }
+            create_children_g(cx, fc, lm, prior, 3 - ((c.z >> 16) & 3));  // mcts.py:618
             if (g.lane == 0) {
                 c.y = fc;
                 c.z = (c.z & ~0xFF) | nc;
@@ -684,7 +738,7 @@ __device__ __forceinline__ void simulate_one_g(TreeCtxG<LPG>& cx, const GBoard& 
         }
         v = code == 1 ? 1.0f : (code == 2 ? -1.0f : 0.0f);
     }
-    expand_node_g(cx, node, lm, 1.0f / 65.0f, eval);  // ends with __syncwarp(): the flag above is visible
+    expand_node_g(cx, node, lm, kUniformPrior, eval);  // ends with __syncwarp(): the flag above is visible
     backup_path_g(cx, plen, v, act);
 }
 

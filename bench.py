@@ -200,13 +200,24 @@ def generation_leg(az, dist, dev, rank, world, local, games, barrier):
     s1 = eng.stats()
     if s1["overflow"] or s1["samples_dropped"] or s1["stalled"]:
         raise SystemExit(f"generation leg: engine error counters non-zero: {s1}")
+    # the same gather once more with the GPU otherwise idle (untimed for `wall`): what NVLink does for this message when
+    # the send / receive kernels do not have to wait for SMs behind the next generation's persistent network kernel
+    alone_ms = 0.0
+    if dist is not None:
+        barrier()
+        a0, a1 = E(), E()
+        a0.record()
+        azd.gather_packed(mine, dst=0)
+        a1.record()
+        torch.cuda.synchronize()
+        alone_ms = a0.elapsed_time(a1)
     eng.close()
-    vals = torch.tensor([wall * 1e3, b0.elapsed_time(b1), b1.elapsed_time(g1), c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
+    vals = torch.tensor([wall * 1e3, b0.elapsed_time(b1), b1.elapsed_time(g1), c0.elapsed_time(c1), alone_ms], dtype=torch.float64, device=dev)
     sums = torch.tensor([float(k), float(st["sims"] - s0["sims"]), float(st["games_finished"])], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    wall_ms, bc_ms, sp_ms, ga_ms = vals.tolist()
+    wall_ms, bc_ms, sp_ms, ga_ms, alone_ms = vals.tolist()
     samples, sims, finished = sums.tolist()
     if rank != 0:
         return None
@@ -219,9 +230,12 @@ def generation_leg(az, dist, dev, rank, world, local, games, barrier):
             "selfplay_s": sp_ms * 1e-3, "sims_per_sec": sims / (wall_ms * 1e-3),
             "broadcast_ms": bc_ms, "broadcast_bytes": int(flat.numel() * 4),
             "gather_ms": ga_ms, "gather_bytes": int(nbytes), "gather_gbs": (nbytes / (ga_ms * 1e-3) / 1e9) if ga_ms > 0 else None,
+            "gather_alone_ms": alone_ms, "gather_alone_gbs": (nbytes / (alone_ms * 1e-3) / 1e9) if alone_ms > 0 else None,
             "collective_share": (bc_ms + ga_ms) / wall_ms,
             "overlap": "gather on a side stream, concurrent with the first ply of the next generation on the main stream; "
-                       "times are device events (max over ranks), wall is the host clock from before the broadcast to the end of the gather"}
+                       "times are device events (max over ranks), wall is the host clock from before the broadcast to the end of the gather; "
+                       "gather_ms is the overlapped gather (its NCCL kernels share the SMs with the running search), gather_alone_* the "
+                       "same message repeated on an idle GPU"}
 
 
 def run_ours(args):

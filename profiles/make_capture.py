@@ -104,9 +104,12 @@ def sims_in_launch(name):
         if not m:
             continue
         lpg = int(m.group(1))
-        for (fl, ln, txt), v in st["line_inst"].items():
-            if "++cx.sims" in txt and fl == "rvs_treeg.cuh":
-                return v * (32 // lpg), lpg
+        # one warp instruction per simulation is attributed to either line (the compiler folds the counter increment
+        # into the backup call in some instantiations; where both survive their counts are equal)
+        for anchor in ("++cx.sims", "backup_path_g(cx, plen, v, act)"):
+            for (fl, ln, txt), v in st["line_inst"].items():
+                if anchor in txt and fl == "rvs_treeg.cuh" and v > 0:
+                    return v * (32 // lpg), lpg
     raise SystemExit(f"{name}: cannot find the simulation counter line")
 
 
