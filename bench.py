@@ -37,7 +37,8 @@ METRIC = "mcts_sims_per_sec"
 UNIT = "sims/s"
 # algorithmic HBM bytes per simulation of the fused search kernel (DESIGN.md "K2 roofline"):
 #   32 B per child row scanned on the way down + 32 B per path node at backup (hot row read +
-#   write) + 32 B per child row created + 24 B leaf record; the rollout itself is register
+#   write) + 32 B per child row created (when a traverse first needs it: lazy child rows; 32 B
+#   for the legal mask an expansion records) + 24 B leaf record; the rollout itself is register
 #   resident (0 B).  Measured per run from the engine's counters, see algorithmic_bytes().
 
 
