@@ -355,7 +355,8 @@ __device__ __noinline__ int play_game(const EngineView& ev, int g, float tempera
         if (e != 1.0)
             for (int i = 0; i < 65; ++i) pi[i] = pow(pi[i], e);
         const double s = np_sum65(pi);
-        for (int i = 0; i < 65; ++i) pi[i] = __ddiv_rn(pi[i], s);
+        for (int i = 0; i < 65; ++i)
+            if (pi[i] != 0.0) pi[i] = __ddiv_rn(pi[i], s);  // 0 / s = 0: skip the ~55 illegal squares (their division takes the slow path)
     }
     int mv = 0;
     const int ply = ev.ply[g];
@@ -370,6 +371,7 @@ __device__ __noinline__ int play_game(const EngineView& ev, int g, float tempera
         double run = 0.0;
         mv = 64;
         for (int i = 0; i < 65; ++i) {
+            if (pi[i] == 0.0) continue;  // run does not change, and run / acc > u was false for the previous entry (0 > u at the start)
             run = __dadd_rn(run, pi[i]);
             if (__ddiv_rn(run, acc) > u) { mv = i; break; }
         }

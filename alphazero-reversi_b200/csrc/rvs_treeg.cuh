@@ -602,7 +602,10 @@ __device__ __forceinline__ int select_one_g(TreeCtxG<LPG>& cx, GBoard& b, int& p
             if (g.lane == 0) reinterpret_cast<int*>(hot_at(cx, node))[2] = h.z;
             cx.bytes += 32u * (unsigned)nchild;
         }
-        const float sq = __fsqrt_rn((float)h.x);
+        // a node with children has been backed up at least once (N >= 1); groups that are not descending any more
+        // still execute this line, and sqrt(0) would take the IEEE square root's slow path (a call, 33 % of the
+        // level steps of a warp: ncu)
+        const float sq = __fsqrt_rn((float)(going ? h.x : 1));
         const int fc = c.y;
         const int nscan = going ? nchild : 0;
         unsigned best_key = key_floor;
