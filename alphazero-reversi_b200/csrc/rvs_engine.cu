@@ -555,16 +555,15 @@ constexpr int kMaxWarpsG = kNumSMs * 16;  // 16 one-warp CTAs per SM (__launch_b
 template <int RULES, int EVAL, int LPG, int MINB>
 __global__ void __launch_bounds__(kBlockG, MINB) search_k1g_kernel(EngineView ev, int S) {
     constexpr int GPB = kBlockG / LPG;
-    __shared__ __align__(16) uint8_t lut[kLutBytes];
+    __shared__ __align__(16) uint8_t lut[LutCfg<LPG>::kBytes];
     __shared__ int spath[GPB][kMaxPath + 1];
     __shared__ __align__(16) unsigned sgather[LPG == 8 ? kGatherWords : 4];  // 3 x 64-byte exchange buffers per 8-lane group (gather_off)
-    __shared__ __align__(16) uint64_t srays[LPG == 8 ? kRayWords64 : 2];  // flip-ray table of the 8-lane groups (ray_init)
-    lut_init(lut, threadIdx.x, kBlockG);
-    if (LPG == 8) ray_init<RULES>(srays, threadIdx.x, kBlockG);
+    __shared__ __align__(16) uint64_t srays[RayCfg<LPG>::kWords64];  // flip-ray table (ray_init)
+    lut_init<LPG>(lut, threadIdx.x, kBlockG);
+    ray_init<RULES, LPG>(srays, threadIdx.x, kBlockG);
     __syncthreads();
     const int n_groups = gridDim.x * GPB;
-    const Grp<LPG> grp = make_grp<RULES, LPG>(threadIdx.x & 31, lut, spath[threadIdx.x / LPG], LPG == 8 ? sgather : nullptr,
-                                               LPG == 8 ? srays : nullptr);
+    const Grp<LPG> grp = make_grp<RULES, LPG>(threadIdx.x & 31, lut, spath[threadIdx.x / LPG], LPG == 8 ? sgather : nullptr, srays);
     __shared__ int4 sstage[GPB][2 * (1 + StageCfg<LPG>::kRows) + 2];  // hot node rows of each group's search
     for (int slot = blockIdx.x * GPB + (int)threadIdx.x / LPG; __any_sync(kFull, slot < ev.G); slot += n_groups) {
         const bool act = slot < ev.G;
@@ -610,18 +609,17 @@ template <int RULES, int EVAL, int LPG, int MINB>
 __global__ void __launch_bounds__(kBlockG, MINB) selfplay_k1g_kernel(EngineView ev, int S, float temperature,
                                                                    unsigned long long budget, int recycle) {
     constexpr int GPB = kBlockG / LPG;
-    __shared__ __align__(16) uint8_t lut[kLutBytes];
+    __shared__ __align__(16) uint8_t lut[LutCfg<LPG>::kBytes];
     __shared__ int spath[GPB][kMaxPath + 1];
     __shared__ __align__(16) unsigned sgather[LPG == 8 ? kGatherWords : 4];  // 3 x 64-byte exchange buffers per 8-lane group (gather_off)
-    __shared__ __align__(16) uint64_t srays[LPG == 8 ? kRayWords64 : 2];  // flip-ray table of the 8-lane groups (ray_init)
-    lut_init(lut, threadIdx.x, kBlockG);
-    if (LPG == 8) ray_init<RULES>(srays, threadIdx.x, kBlockG);
+    __shared__ __align__(16) uint64_t srays[RayCfg<LPG>::kWords64];  // flip-ray table (ray_init)
+    lut_init<LPG>(lut, threadIdx.x, kBlockG);
+    ray_init<RULES, LPG>(srays, threadIdx.x, kBlockG);
     __syncthreads();
     const int n_groups = gridDim.x * GPB;
     const int slot0 = blockIdx.x * GPB + (int)threadIdx.x / LPG;
     const int n_mine = slot0 < ev.G ? (ev.G - slot0 + n_groups - 1) / n_groups : 0;  // slots of this group
-    const Grp<LPG> grp = make_grp<RULES, LPG>(threadIdx.x & 31, lut, spath[threadIdx.x / LPG], LPG == 8 ? sgather : nullptr,
-                                               LPG == 8 ? srays : nullptr);
+    const Grp<LPG> grp = make_grp<RULES, LPG>(threadIdx.x & 31, lut, spath[threadIdx.x / LPG], LPG == 8 ? sgather : nullptr, srays);
     __shared__ int4 sstage[GPB][2 * (1 + StageCfg<LPG>::kRows) + 2];  // hot node rows of each group's search
     bool quit = n_mine == 0;
     int k = 0, idle = 0;  // current slot of the round-robin; consecutive slots found parked / finished

@@ -41,7 +41,7 @@ struct Grp {
     uint32_t lutd;       // the table for own-domain row bytes: odd lanes of 8-lane groups see their row bit-reversed
                          // (lut + 2048: lutr[byte * 8 + j] = lut[rev8(byte) * 8 + j])
     uint32_t gather;     // shared-window address: 3 x 64-byte exchange buffers of the group (grp_or64_own8)
-    uint32_t rays;       // LPG == 8: shared-window address of this lane's column of the flip-ray table (ray_init), else 0
+    uint32_t rays;       // shared-window address of this lane's first column of the flip-ray table (ray_init)
     uint32_t path;       // shared-window address: int[kMaxPath + 1] nodes of the current path; the extra word
                          // is the broadcast slot of the 4- and 2-lane groups (grp_nth_post)
                          // (32-bit shared addresses: a generic pointer costs an S2R + LEA per access)
@@ -50,9 +50,11 @@ struct Grp {
 
 // lut[0 .. 2048): select-in-byte; lut[2048 .. 4096): the same for a bit-reversed byte (positions still count from
 // the least significant bit of the NORMAL byte)
-constexpr int kLutBytes = 2 * 256 * 8;
+template <int LPG>
+struct LutCfg { static constexpr int kBytes = (LPG == 8 ? 2 : 1) * 256 * 8; };  // the reversed-byte table only serves 8-lane groups
+template <int LPG>
 __device__ __forceinline__ void lut_init(uint8_t* lut, int tid, int nthreads) {
-    for (int e = tid; e < kLutBytes; e += nthreads) {
+    for (int e = tid; e < LutCfg<LPG>::kBytes; e += nthreads) {
         unsigned b = (unsigned)(e >> 3) & 0xFFu;
         if (e >= 256 * 8) b = __brev(b) >> 24;
         int j = e & 7, pos = 0;
@@ -65,18 +67,29 @@ __device__ __forceinline__ void lut_init(uint8_t* lut, int tid, int nthreads) {
     }
 }
 
-// Flip-ray table of the 8-lane groups (flip_ray / flip_carry in rvs_board.cuh): row sqd (the move square in the
-// lane's own domain) holds the ray of every direction lane, 16 bytes apart, twice: groups 0 / 2 of a warp read the
-// copy at +0, groups 1 / 3 the copy at +8, so the 16 lanes the LSU serves together (two groups, LDS.64) touch 32
-// distinct banks whatever their squares are.  64 rows x 128 bytes.
-constexpr int kRayWords64 = 64 * 16;
-template <int RULES>
+// Flip-ray table (flip_ray / flip_carry in rvs_board.cuh): row sqd (the move square in the working domain of the
+// direction) holds the ray of every direction.
+//   LPG == 8: 64 rows x 128 bytes, the eight direction lanes 16 bytes apart, each entry twice: groups 0 / 2 of a warp
+//             read the copy at +0, groups 1 / 3 the copy at +8, so the 16 lanes the LSU serves together (two groups,
+//             LDS.64) touch 32 distinct banks whatever their squares are;
+//   LPG < 8:  64 rows x 64 bytes [sqd][direction]; a lane reads its 8 / LPG directions (even ones at row idx, odd
+//             ones -- right shifts, bit-reversed boards -- at row 63 - idx).
+template <int LPG>
+struct RayCfg {
+    static constexpr int kWords64 = LPG == 8 ? 64 * 16 : 64 * 8;
+    static constexpr unsigned kRowBytes = LPG == 8 ? 128u : 64u;
+};
+template <int RULES, int LPG>
 __device__ __forceinline__ void ray_init(uint64_t* rays, int tid, int nthreads) {
     for (int e = tid; e < 64 * 8; e += nthreads) {
         const int sqd = e >> 3, dir = e & 7;
         const uint64_t R = flip_ray(make_dir<RULES>(dir), sqd);
-        rays[sqd * 16 + dir * 2] = R;
-        rays[sqd * 16 + dir * 2 + 1] = R;
+        if constexpr (LPG == 8) {
+            rays[sqd * 16 + dir * 2] = R;
+            rays[sqd * 16 + dir * 2 + 1] = R;
+        } else {
+            rays[e] = R;
+        }
     }
 }
 
@@ -99,7 +112,9 @@ __device__ __forceinline__ Grp<LPG> make_grp(int lane32, const uint8_t* lut, int
     g.lut = (uint32_t)__cvta_generic_to_shared(lut);
     g.lutd = g.lut + (own_rev ? 256u * 8u : 0u);
     g.path = (uint32_t)__cvta_generic_to_shared(path);
-    g.rays = rays ? (uint32_t)__cvta_generic_to_shared(rays) + 16u * (uint32_t)g.lane + 8u * (uint32_t)((lane32 >> 3) & 1) : 0u;
+    g.rays = !rays ? 0u
+             : (uint32_t)__cvta_generic_to_shared(rays) +
+                   (LPG == 8 ? 16u * (uint32_t)g.lane + 8u * (uint32_t)((lane32 >> 3) & 1) : 8u * (uint32_t)(Grp<LPG>::ND * g.lane));
     // 8-lane groups: the four groups of a warp access their exchange buffers with the same instructions, which the LSU
     // serves half a warp (two groups) at a time.  The buffers of groups 0 / 1 / 2 / 3 start at banks 0 / 16 / 4 / 20
     // (gather_off): the two 64-byte stores of a half warp (STS.64, 16 banks each) and the four distinct 16-byte chunks
@@ -323,17 +338,20 @@ __device__ __forceinline__ MoveOut grp_flip(const Grp<LPG>& g, const GBoard& c, 
         const int sqd = idx ^ g.flip63;
         const uint64_t mv = 1ULL << sqd;
         uint64_t R;  // this lane's ray of the move square: one table load instead of the five-step flood
-        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(R) : "r"(g.rays + 128u * (uint32_t)sqd));
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(R) : "r"(g.rays + RayCfg<LPG>::kRowBytes * (uint32_t)sqd));
         const uint64_t f = grp_or64_own8<0>(g, flip_carry(R, c.P[0], c.O[0]));
         m.P[0] = c.P[0] ^ (mv | f); m.P[1] = 0ULL;
         m.O[0] = c.O[0] ^ f;        m.O[1] = 0ULL;
     } else {
         const uint64_t mvn = 1ULL << idx, mvr = 1ULL << (63 - idx);
         uint64_t fn = 0, fr = 0;
+        const uint32_t rown = g.rays + RayCfg<LPG>::kRowBytes * (uint32_t)idx, rowr = g.rays + RayCfg<LPG>::kRowBytes * (uint32_t)(63 - idx);
 #pragma unroll
         for (int j = 0; j < Grp<LPG>::ND; ++j) {
-            if (dir_neg(g, j)) fr |= flip_raw(g.d[j], c.P[1], c.O[1], mvr);
-            else fn |= flip_raw(g.d[j], c.P[0], c.O[0], mvn);
+            uint64_t R;
+            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(R) : "r"((dir_neg(g, j) ? rowr : rown) + 8u * (uint32_t)j));
+            if (dir_neg(g, j)) fr |= flip_carry(R, c.P[1], c.O[1]);
+            else fn |= flip_carry(R, c.P[0], c.O[0]);
         }
         const uint64_t f = grp_or64<LPG>(fn | brev64(fr));
         const uint64_t fb = brev64(f);
@@ -447,7 +465,7 @@ struct TreeCtxG {
 
 // rows a group can stage: the root + its children (REF rules: up to ~33 legal squares incl. phantom moves)
 template <int LPG>
-struct StageCfg { static constexpr int kRows = LPG == 8 ? 32 : (LPG == 4 ? 24 : 0); };
+struct StageCfg { static constexpr int kRows = LPG == 8 ? 32 : (LPG == 4 ? 16 : 0); };  // LPG == 4: 16 one-warp CTAs per SM must fit
 
 // address of a node's hot / cold row: the staged copy when the node is the root or one of its staged children.
 // One generic-space access serves both cases, so groups of a warp that sit at different tree levels do not diverge.
