@@ -404,7 +404,7 @@ def run_ours(args):
         return steps_, wall
 
     depth = max(1, args.e2e_depth)
-    e2e_steps, e2e_ms = measure_e2e(depth, args.e2e_lanes if args.e2e_lanes else (4 if depth >= 3 else 0))
+    e2e_steps, e2e_ms = measure_e2e(depth, args.e2e_lanes if args.e2e_lanes else (2 if depth >= 12 else (4 if depth >= 3 else 0)))
     e2e1_steps, e2e1_ms = measure_e2e(1, 0) if depth != 1 else (e2e_steps, e2e_ms)
 
     # ---- config-1 side metric: register-resident uniform-random playouts ------------------
@@ -839,8 +839,8 @@ def main():
     ap.add_argument("--lockstep", action="store_true", help="wave 1 through search+play launches per ply")
     ap.add_argument("--traffic", type=float, default=None, help="ncu dram bytes per launch of the search kernel")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-depth", type=int, default=8, help="engine handles pipelined in the e2e leg")
-    ap.add_argument("--e2e-lanes", type=int, default=0, help="lanes per game of the e2e engines (0: 4 when pipelined)")
+    ap.add_argument("--e2e-depth", type=int, default=16, help="engine handles pipelined in the e2e leg")
+    ap.add_argument("--e2e-lanes", type=int, default=0, help="lanes per game of the e2e engines (0: 2 from 12 handles, 4 from 3)")
     ap.add_argument("--no-big", action="store_true", help="skip the 16384-game side measurement")
     ap.add_argument("--no-nn", action="store_true", help="skip the config-3 (ResNet) side measurement")
     ap.add_argument("--min-seconds", type=float, default=0.5, help="floor of the timed region (the K steps are repeated)")
