@@ -633,23 +633,28 @@ __device__ __forceinline__ int select_one_g(TreeCtxG<LPG>& cx, GBoard& b, int& p
             const int i = base + g.lane;
             int4 ch = make_int4(0, 0, 0, 0), cc = make_int4(0, 0, 0, 0);
             unsigned key = 0;
-            if (i < nscan) {
-                int4* hp = hot_at(cx, fc + i);
+            // uniform control flow: the score of a visited child without a valid cache is computed by the whole warp
+            // whenever any lane needs it (lanes that do not get harmless operands), instead of a divergent branch per
+            // lane with its reconvergence points
+            const bool in = i < nscan;
+            int4* hp = hot_at(cx, fc + i);
+            if (in) {
                 ch = *hp;
                 cc = *cold_at(cx, fc + i);
-                float score;
-                if (ch.x == 0) {
-                    score = INFINITY;  // mcts.py:96-97
-                } else if (ch.z & kCacheValid) {
-                    score = __int_as_float(ch.w);  // mcts.py:99-100
-                } else {
-                    score = score_child(ch.x, __int_as_float(ch.y), ch.z & kVLMask, __int_as_float(cc.x),
-                                        (cc.z >> 16) & 3, cx.c_puct, sq);
-                    ch.w = __float_as_int(score);
+            }
+            const bool need = in && ch.x != 0 && !(ch.z & kCacheValid);
+            if (__any_sync(kFull, need)) {
+                const float s = score_child(need ? ch.x : 1, need ? __int_as_float(ch.y) : 1.0f, need ? (ch.z & kVLMask) : 0,
+                                            need ? __int_as_float(cc.x) : 1.0f, (cc.z >> 16) & 3, cx.c_puct, need ? sq : 1.0f);
+                if (need) {
+                    ch.w = __float_as_int(s);
                     ch.z |= kCacheValid;
                     reinterpret_cast<int2*>(hp)[1] = make_int2(ch.z, ch.w);
                 }
-                key = (score == score) ? ordered_key(score) : 0u;
+            }
+            {
+                const float score = ch.x == 0 ? INFINITY : __int_as_float(ch.w);  // mcts.py:96-100
+                key = in ? ((score == score) ? ordered_key(score) : 0u) : 0u;
             }
             const unsigned mx = grp_max<LPG>(key);
             const unsigned bal = __ballot_sync(kFull, key == mx) >> g.sh;  // never empty inside the group: mx is one of its keys

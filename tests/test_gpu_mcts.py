@@ -318,3 +318,35 @@ def test_wave1_800_simulations_vs_oracle(az, lpg, evaluator):
         ov, *_ = orc.mcts_search((int(bl[g]), int(wh[g]), int(sd[g])), S, 1, evaluator=evaluator, seed=55, game_id=g)
         assert np.array_equal(v[g], ov), g
     eng.close()
+
+
+@pytest.mark.parametrize("lpg", [8, 4, 2])
+def test_small_node_pool_overflows_cleanly(az, lpg):
+    """A node pool that is too small for the search (nodes_per_game = 48 rows for 100 simulations): the wave-1 group
+    kernels create child rows lazily, when a traverse first descends through an expanded node, so the pool runs out in
+    the middle of a descent.  The search must flag the overflow, stay inside the pool (the neighbouring games' trees
+    are compared with the oracle) and still back every simulation up to the root."""
+    n, S = 64, 100
+    bl, wh, sd = _random_roots(n, 999)
+    small = az.Engine(n, S, 1, evaluator=az.EVAL_ROLLOUT, seed=5, nodes_per_game=48)
+    small.set_lanes_per_game(lpg)
+    small.set_positions(bl, wh, sd)
+    small.search(S, 1)
+    v = small.root_visits()
+    st = small.stats()
+    assert st["overflow"] > 0 and st["sims"] == n * S
+    lm = az.board_ops.legal_masks(bl, wh, sd)
+    for g in range(n):
+        assert int(v[g].sum()) == (S - 1 if int(lm[g]) else 0), g
+    small.close()
+    # the same engine size with the default (worst-case) pool: no overflow and exact visit counts
+    eng = az.Engine(n, S, 1, evaluator=az.EVAL_ROLLOUT, seed=5)
+    eng.set_lanes_per_game(lpg)
+    eng.set_positions(bl, wh, sd)
+    eng.search(S, 1)
+    v = eng.root_visits()
+    assert eng.stats()["overflow"] == 0
+    for g in range(0, n, 7):
+        ov, *_ = orc.mcts_search((int(bl[g]), int(wh[g]), int(sd[g])), S, 1, evaluator=1, seed=5, game_id=g)
+        assert np.array_equal(v[g], ov), g
+    eng.close()
