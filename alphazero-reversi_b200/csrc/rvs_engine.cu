@@ -469,7 +469,7 @@ __device__ __forceinline__ void flush_stats_g(const EngineView& ev, const TreeCt
 
 template <int LPG>
 __device__ __forceinline__ TreeCtxG<LPG> make_ctx_g(const EngineView& ev, int g, const Grp<LPG>& grp) {
-    return TreeCtxG<LPG>{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.cap, 1, ev.c_puct, 0, 0, 0, 0, 0, 0, grp, nullptr, 0, 0u};
+    return TreeCtxG<LPG>{ev.hot + (size_t)g * ev.cap, ev.cold + (size_t)g * ev.cap, ev.brd + (size_t)g * ev.cap, ev.cap, 1, ev.c_puct, 0, 0, 0, 0, 0, 0, grp, nullptr, 0, 0u};
 }
 
 template <int LPG>
@@ -848,7 +848,8 @@ int rvs_engine_create(const rvs_engine_config* cfg, rvs_engine** out) {
     if ((rc = dalloc(h, &v.black, G)) || (rc = dalloc(h, &v.white, G)) || (rc = dalloc(h, &v.side, G)) ||
         (rc = dalloc(h, &v.flags, G)) || (rc = dalloc(h, &v.game_id, G)) || (rc = dalloc(h, &v.ply, G)) ||
         (rc = dalloc(h, &v.live, G)) || (rc = dalloc(h, &v.finished, G)) || (rc = dalloc(h, &v.hot, GN)) ||
-        (rc = dalloc(h, &v.cold, GN)) || (rc = dalloc(h, &v.n_nodes, G)) || (rc = dalloc(h, &v.order, G)) || (rc = dalloc(h, &v.w_node, GK)) ||
+        (rc = dalloc(h, &v.cold, GN)) ||
+        (rc = dalloc(h, &v.brd, (cfg->evaluator == RVS_EVAL_E0 || cfg->evaluator == RVS_EVAL_ROLLOUT) ? GN : (size_t)1)) || (rc = dalloc(h, &v.n_nodes, G)) || (rc = dalloc(h, &v.order, G)) || (rc = dalloc(h, &v.w_node, GK)) ||
         (rc = dalloc(h, &v.w_plen, GK)) || (rc = dalloc(h, &v.w_path, GK * kMaxPath)) || (rc = dalloc(h, &v.w_black, GK)) ||
         (rc = dalloc(h, &v.w_white, GK)) || (rc = dalloc(h, &v.w_sf, GK)) || (rc = dalloc(h, &v.w_lm, GK)) ||
         (rc = dalloc(h, &v.w_val, GK)) || (rc = dalloc(h, &v.w_sides, GK)) || (rc = dalloc(h, &v.s_black, G * 64)) || (rc = dalloc(h, &v.s_white, G * 64)) ||

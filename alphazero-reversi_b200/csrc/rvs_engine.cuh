@@ -26,6 +26,7 @@ struct EngineView {
     uint64_t* game_id; int* ply; uint8_t* live; uint8_t* finished;
     // trees
     int4* hot; int4* cold; int* n_nodes;
+    int4* brd;   // wave-1 group kernels with a built-in evaluator: stored positions of the visited nodes (rvs_treeg.cuh); else 1 row
     int* order;  // slots sorted by game phase (disc count): the four games of a warp have similar rollout lengths
     // wave scratch [G*kmax]
     int* w_node; int* w_plen; int* w_path; uint64_t* w_black; uint64_t* w_white; uint16_t* w_sf;

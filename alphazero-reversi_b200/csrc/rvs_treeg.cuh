@@ -449,6 +449,7 @@ template <int LPG>
 struct TreeCtxG {
     int4* hot;
     int4* cold;
+    int4* brd;  // position of every visited node {black, white} (select_one_g); its side to move sits in hot.z
     int cap;
     int n_nodes;
     float c_puct;
@@ -590,7 +591,16 @@ __device__ __forceinline__ void backup_path_g(TreeCtxG<LPG>& cx, int plen, float
     __syncwarp();
 }
 
-// MCTS._traverse (mcts.py:409-444); the path is left in cx.g.path[0..plen)
+// hot.z bits of a node whose position is stored in cx.brd (set when the node is first reached as a leaf)
+constexpr int kBoardWhite = 1 << 20;  // WHITE is to move in the stored position
+constexpr int kHasBoard = 1 << 21;
+
+// MCTS._traverse (mcts.py:409-444); the path is left in cx.g.path[0..plen).
+// `b` enters as the root position and leaves as the position of the leaf.  The reference replays game.make_move along
+// the whole path in every simulation (mcts.py:439).  Here the position of a node is stored the first time the node
+// is reached (cx.brd, 16 bytes), so the descent itself touches no board: the leaf's position is its parent's stored
+// position plus ONE move (none for a terminal leaf, whose stored value is backed up) -- the same position, since
+// make_move is deterministic, including its auto-passes.
 template <int LPG>
 __device__ __forceinline__ int select_one_g(TreeCtxG<LPG>& cx, GBoard& b, int& plen, int& leaf_vlf, uint64_t& leaf_lm, bool act) {
     const Grp<LPG>& g = cx.g;
@@ -605,7 +615,7 @@ __device__ __forceinline__ int select_one_g(TreeCtxG<LPG>& cx, GBoard& b, int& p
     }
     const unsigned key_floor = ordered_key(-INFINITY);
     bool going = act;
-    bool have_lm = false;  // the last applied move already produced the leaf's legal mask
+    int parent = 0, parent_z = 0, mv = 0;  // the node above the current one, its hot.z, and the move that leads here
     leaf_lm = 0;
     while (true) {
         const int nchild = c.z & 0xFF;
@@ -668,15 +678,14 @@ __device__ __forceinline__ int select_one_g(TreeCtxG<LPG>& cx, GBoard& b, int& p
             }
         }
         if (going && best_i < 0) { cx.overflow |= 2; going = false; }
-        const uint64_t lm_next = grp_apply_move(g, b, (bc.z >> 8) & 0x3F, going);  // game.make_move(*next_move) (mcts.py:439)
         if (going) {
-            leaf_lm = lm_next;
-            have_lm = true;
-            ++cx.steps;
-            node = fc + best_i;
-            h = bh;
-            c = bc;
             if (plen < kMaxPath) {
+                parent = node;
+                parent_z = h.z;
+                mv = (bc.z >> 8) & 0x3F;  // next_move (mcts.py:439)
+                node = fc + best_i;
+                h = bh;
+                c = bc;
                 if (g.lane == 0) sts_s32(g.path + 4 * plen, node);
                 ++plen;
             } else {
@@ -685,9 +694,32 @@ __device__ __forceinline__ int select_one_g(TreeCtxG<LPG>& cx, GBoard& b, int& p
             }
         }
     }
-    if (__any_sync(kFull, act && !have_lm)) {  // the root itself is the leaf (first simulation of a search)
+    // the leaf's position: game.make_move(*next_move) on the parent's stored position (mcts.py:439)
+    const bool step = act && node != 0 && !(h.z & kTerminal);
+    if (__any_sync(kFull, step)) {
+        if (step && parent != 0) {
+            const int4 pb = cx.brd[parent];
+            const uint64_t black = (uint64_t)(unsigned)pb.x | ((uint64_t)(unsigned)pb.y << 32);
+            const uint64_t white = (uint64_t)(unsigned)pb.z | ((uint64_t)(unsigned)pb.w << 32);
+            b = gboard_load(g, Board{black, white, (uint8_t)((parent_z & kBoardWhite) ? 2 : 1), 0});
+            cx.bytes += 16;
+        }
+        const uint64_t lm = grp_apply_move(g, b, mv, step);
+        if (step) {
+            leaf_lm = lm;
+            ++cx.steps;
+            h.z = (h.z & ~kBoardWhite) | kHasBoard | (b.side == 2 ? kBoardWhite : 0);
+            if (g.lane == 0) {  // lane 0 works in the normal domain
+                const uint64_t black = b.side == 1 ? b.P[0] : b.O[0], white = b.side == 1 ? b.O[0] : b.P[0];
+                cx.brd[node] = make_int4((int)(unsigned)black, (int)(unsigned)(black >> 32), (int)(unsigned)white, (int)(unsigned)(white >> 32));
+                reinterpret_cast<int*>(hot_at(cx, node))[2] = h.z;
+            }
+            cx.bytes += 16;
+        }
+    }
+    if (__any_sync(kFull, act && node == 0)) {  // the root itself is the leaf (first simulation of a search)
         const uint64_t lm0 = grp_legal<LPG, 2>(g, b.P, b.O);
-        if (!have_lm) leaf_lm = lm0;
+        if (act && node == 0) leaf_lm = lm0;
     }
     leaf_vlf = h.z;
     __syncwarp();

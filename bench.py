@@ -623,7 +623,9 @@ def run_ours(args):
                        "games_per_gpu": N_GAMES, "sims_per_move": N_SIMS, "wave": wave, "c_puct": 1.0, "temperature": 1.0,
                        "schedule": ("persistent work-conserving self-play launches" if persistent else "lockstep search+play per ply"),
                        "parallelism": f"games sharded x{world}, no data-path collective",
-                       "cache": "node pools 446 MB per GPU (> 126 MB L2), rewritten every step"},
+                       "cache": "node pools 669 MB per GPU (> 126 MB L2); every step rebuilds all 4096 trees from their roots, nothing a step "
+                                "reads was produced by an earlier step except the 18-byte game positions (the rows a step touches, ~25 MB of "
+                                "DRAM traffic under ncu, stay L2 resident by design: lazy child rows)"},
             "board_steps_per_sec": bsteps / (ms * 1e-3),
             "unique_evals_per_sec": evals / (ms * 1e-3),
             "playout_board_steps_per_sec": po_rate,

@@ -3,7 +3,7 @@
 # launch list of the same command and one `--set full` capture per dominant kernel.  The reports are exported to
 # CSV / text on the box (gpurun brings back at most 64 MiB) into gpurun_out/cap_r2/;
 # `python profiles/make_capture.py` turns them into profiles/*_r2.*
-#   usage: gpurun --timeout 2400 -- tools/capture_profiles.sh [bench|ncu|all]
+#   usage: gpurun --timeout 2400 -- tools/capture_profiles.sh [bench|ncu|k1g|all]
 set -u
 WHAT=${1:-all}
 O=gpurun_out/cap_r2
@@ -23,6 +23,12 @@ cap() {  # cap <name> <ncu filter args...> -- <command...>
 if [ "$WHAT" = bench ] || [ "$WHAT" = all ]; then
   python bench.py --steps 20 --warmup 5 > $O/bench_r2_1gpu.json 2> $O/bench_r2_1gpu.err
   python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_r2_reference_arm.json 2> $O/bench_r2_reference_arm.err
+fi
+if [ "$WHAT" = k1g ]; then  # only the wave-1 group kernel changed: refresh its captures (the others stay in $O)
+  $NCU --metrics gpu__time_duration.sum -c 600 --csv --log-file $O/launches_bench_r2.csv \
+      python bench.py --steps 2 --warmup 1 --min-seconds 0 --no-cpu --no-big > $O/launches_bench_r2.log 2>&1
+  cap k1g -k regex:selfplay_k1g -s 3 -c 1 -- python bench.py --steps 2 --warmup 3 --steps-per-launch 2 --min-seconds 0 --no-cpu --no-big --no-nn
+  cap k1g_16k -k regex:selfplay_k1g -s 1 -c 1 -- python tools/probe_selfplay.py 16384 0 2
 fi
 if [ "$WHAT" = ncu ] || [ "$WHAT" = all ]; then
   # launch list of the bench command (short: ncu serialises and replays)
