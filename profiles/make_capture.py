@@ -104,12 +104,14 @@ def sims_in_launch(name):
         if not m:
             continue
         lpg = int(m.group(1))
-        # one warp instruction per simulation is attributed to either line (the compiler folds the counter increment
-        # into the backup call in some instantiations; where both survive their counts are equal)
-        for anchor in ("++cx.sims", "backup_path_g(cx, plen, v, act)"):
-            for (fl, ln, txt), v in st["line_inst"].items():
-                if anchor in txt and fl == "rvs_treeg.cuh" and v > 0:
-                    return v * (32 // lpg), lpg
+        # lines of simulate_one_g that execute once per simulation; the compiler attributes ONE warp instruction to at
+        # least one of them in every instantiation (and two to some), so the smallest positive count is the number of
+        # warp-level simulations
+        cands = [v for (fl, ln, txt), v in st["line_inst"].items()
+                 if fl == "rvs_treeg.cuh" and v > 0 and any(a in txt for a in ("++cx.sims", "backup_path_g(cx, plen, v, act)",
+                                                                              "expand_node_g(cx, node, lm, kUniformPrior, eval)"))]
+        if cands:
+            return min(cands) * (32 // lpg), lpg
     raise SystemExit(f"{name}: cannot find the simulation counter line")
 
 
