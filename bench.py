@@ -233,10 +233,14 @@ def generation_leg(az, dist, dev, rank, world, local, games, barrier):
             "gather_ms": ga_ms, "gather_bytes": int(nbytes), "gather_gbs": (nbytes / (ga_ms * 1e-3) / 1e9) if ga_ms > 0 else None,
             "gather_alone_ms": alone_ms, "gather_alone_gbs": (nbytes / (alone_ms * 1e-3) / 1e9) if alone_ms > 0 else None,
             "collective_share": (bc_ms + ga_ms) / wall_ms,
+            "collective_exposed_ms": max(0.0, wall_ms - sp_ms), "collective_exposed_share": max(0.0, wall_ms - sp_ms) / wall_ms,
             "overlap": "gather on a side stream, concurrent with the first ply of the next generation on the main stream; "
                        "times are device events (max over ranks), wall is the host clock from before the broadcast to the end of the gather; "
-                       "gather_ms is the overlapped gather (its NCCL kernels share the SMs with the running search), gather_alone_* the "
-                       "same message repeated on an idle GPU"}
+                       "gather_ms is the overlapped gather on the receiving rank: it starts when rank 0 has finished ITS games and ends when "
+                       "the slowest rank has sent its samples, so it mostly measures the skew between the ranks' self-play times "
+                       "(tested: an NCCL high-priority stream does not shorten it); gather_alone_* is the same message repeated on "
+                       "idle GPUs; collective_exposed_* = wall minus the slowest rank's self-play (the weight broadcast plus what "
+                       "remains of drain + gather after the last rank has finished playing)"}
 
 
 def run_ours(args):
