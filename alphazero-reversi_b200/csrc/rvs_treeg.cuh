@@ -18,9 +18,15 @@
 // :544-623 process, :625-640 backup); only the work distribution differs:
 //   * children are scanned LPG per step (first chunk / lowest lane keeps ties = first-max rule),
 //   * the path lives in shared memory (64 ints per game) instead of one node per lane,
-//   * expansion: lane l creates the children whose squares lie in its 8/LPG board rows,
-//   * the k-th legal square of a rollout ply is found by the lane whose rows hold it, through a
-//     256 x 8 select-in-byte table in shared memory, and broadcast with one ballot + one shuffle.
+//   * expansion: lane l creates the children whose squares lie in its 8/LPG board rows -- LAZILY: an expanded node
+//     keeps only its legal mask until a traverse first descends through it (materialize_g),
+//   * the position of a node is stored when the node is first reached (cx.brd), so a traverse applies one move per
+//     simulation instead of replaying make_move along the path (select_one_g),
+//   * flips come from a shared table of rays + one carry ripple instead of a flood (flip_ray / flip_carry),
+//   * the k-th legal square of a rollout ply is found by the lane whose rows hold it, through a 256 x 8
+//     select-in-byte table in shared memory, and reaches the group through one warp-wide REDUX.OR (8-lane groups)
+//     or a shared slot (grp_nth_post).
+// None of this changes a search: visit counts, root N and root W stay bit-identical to the oracle (tests/test_gpu_mcts.py).
 #pragma once
 #include "rvs_tree.cuh"
 
